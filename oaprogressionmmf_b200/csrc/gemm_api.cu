@@ -1,0 +1,195 @@
+// gemm_api.cu — host launchers + C-ABI entry points for the tcgen05 GEMM / implicit-GEMM kernels.
+#include <mutex>
+
+#include "../../include/koa_b200.h"
+#include "gemm_tc.cuh"
+#include "koa_internal.h"
+#include "koa_tma.h"
+
+using namespace koa;
+
+static WgradDesc s_wgrad_desc = {8192u, 1024u, 2048u};
+
+extern "C" int koa_version(void) { return 1; }
+
+extern "C" int koa_debug_flag(unsigned int* out) {
+  unsigned int zero = 0;
+  KOA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_koa_debug_flag, sizeof(unsigned int)));
+  KOA_CHECK_CUDA(cudaMemcpyToSymbol(g_koa_debug_flag, &zero, sizeof(unsigned int)));
+  return 0;
+}
+
+extern "C" int koa_debug_set_wgrad_desc(unsigned int lbo, unsigned int sbo, unsigned int k_adv) {
+  s_wgrad_desc.lbo = lbo;
+  s_wgrad_desc.sbo = sbo;
+  s_wgrad_desc.k_adv = k_adv;
+  return 0;
+}
+
+static EpiParams to_epi(const koa_epilogue_t* e) {
+  EpiParams p;
+  p.out = e->out;
+  p.ldo = e->ldo;
+  p.out_fp32 = e->out_fp32;
+  p.act = e->act;
+  p.bias = e->bias;
+  p.pre_out = (bf16*)e->pre_out_bf16;
+  p.aux = (const bf16*)e->aux_bf16;
+  p.res_f32 = e->residual_f32;
+  p.add_bf16 = (const bf16*)e->add_bf16;
+  p.mask_bf16 = (const bf16*)e->mask_bf16;
+  p.out_bf16_copy = (bf16*)e->out_bf16_copy;
+  p.col_sum = e->col_sum;
+  p.col_sumsq = e->col_sumsq;
+  return p;
+}
+
+static int check_epi(const koa_epilogue_t* ep, int n) {
+  KOA_REQUIRE(ep != nullptr && ep->out != nullptr, "epilogue/out must not be NULL");
+  KOA_REQUIRE(n % 32 == 0, "tcgen05 GEMM path needs N %% 32 == 0 (got %d)", n);
+  KOA_REQUIRE(ep->ldo >= n && ep->ldo % 8 == 0, "ldo (%d) must be >= N and a multiple of 8", ep->ldo);
+  KOA_REQUIRE(ep->act != KOA_ACT_GELU_GRAD || ep->aux_bf16 != nullptr, "KOA_ACT_GELU_GRAD needs aux_bf16");
+  KOA_REQUIRE((ep->col_sum == nullptr) == (ep->col_sumsq == nullptr), "col_sum and col_sumsq go together");
+  return 0;
+}
+
+template <int BN, int STAGES, bool IM2COL>
+static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
+                         const EpiParams& ep, cudaStream_t st) {
+  constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_kmajor_kernel<BN, STAGES, IM2COL>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  KOA_CHECK_CUDA(attr_err);
+  const long long tiles = (long long)koa_cdiv(m, BM) * koa_cdiv(n, BN);
+  KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
+  gemm_kmajor_kernel<BN, STAGES, IM2COL><<<(unsigned)tiles, kGemmThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+
+template <bool IM2COL>
+static int dispatch_kmajor(const CUtensorMap& ta, const void* b, int m, int n, int k, const ConvGeom& g,
+                           const EpiParams& ep, cudaStream_t st) {
+  const int num_kb = koa_cdiv(k, BK);
+  const bool bn128 = (n % 128 == 0);
+  CUtensorMap tb;
+  int rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, bn128 ? 128 : 64);
+  if (rc) return rc;
+  if (bn128) {
+    if (num_kb <= 2) return launch_kmajor<128, 2, IM2COL>(ta, tb, m, n, k, g, ep, st);
+    return launch_kmajor<128, 4, IM2COL>(ta, tb, m, n, k, g, ep, st);
+  }
+  if (num_kb <= 2) return launch_kmajor<64, 2, IM2COL>(ta, tb, m, n, k, g, ep, st);
+  return launch_kmajor<64, 4, IM2COL>(ta, tb, m, n, k, g, ep, st);
+}
+
+int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep, cudaStream_t st) {
+  int rc = check_epi(ep, n);
+  if (rc) return rc;
+  KOA_REQUIRE(m > 0 && n > 0 && k > 0, "empty GEMM %dx%dx%d", m, n, k);
+  KOA_REQUIRE(k % 8 == 0, "GEMM K (%d) must be a multiple of 8 (16-byte TMA pitch)", k);
+  CUtensorMap ta;
+  rc = koa_tmap_2d_bf16(&ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)k * 2, 64, 128);
+  if (rc) return rc;
+  ConvGeom g = {1, 1, 1, 0, 1, 1};
+  return dispatch_kmajor<false>(ta, b, m, n, k, g, to_epi(ep), st);
+}
+
+int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_in, int cin, int cout, int filt_r,
+                          int filt_s, int stride, int pad, const koa_epilogue_t* ep, cudaStream_t st) {
+  int rc = check_epi(ep, cout);
+  if (rc) return rc;
+  KOA_REQUIRE(cin % 64 == 0, "implicit-GEMM conv needs Cin %% 64 == 0 (got %d)", cin);
+  KOA_REQUIRE(stride >= 1 && pad >= 0 && filt_r >= 1 && filt_s >= 1, "bad conv geometry");
+  const int hout = (h + 2 * pad - filt_r) / stride + 1;
+  const int wout = (w_in + 2 * pad - filt_s) / stride + 1;
+  KOA_REQUIRE(hout > 0 && wout > 0, "empty conv output");
+  const long long m = (long long)n_img * hout * wout;
+  KOA_REQUIRE(m < 2147483647LL, "too many output pixels");
+  CUtensorMap ta;
+  rc = koa_tmap_im2col_bf16(&ta, x, n_img, h, w_in, cin, filt_r, filt_s, stride, pad, 128);
+  if (rc) return rc;
+  ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64};
+  return dispatch_kmajor<true>(ta, w, (int)m, cout, filt_r * filt_s * cin, g, to_epi(ep), st);
+}
+
+template <int BN, int STAGES, bool IM2COL>
+static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, int cin, int pixels, int taps,
+                        const ConvGeom& g, float* dw, cudaStream_t st) {
+  constexpr size_t smem = wgrad_smem_bytes<BN, STAGES>();
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_wgrad_kernel<BN, STAGES, IM2COL>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  KOA_CHECK_CUDA(attr_err);
+  const int tiles = koa_cdiv(cout, BM) * koa_cdiv(cin, BN) * taps;
+  const int num_kb = koa_cdiv(pixels, BK);
+  // Split the pixel (reduction) range so that the grid covers the machine a few times over.
+  int splits = koa_cdiv(4 * koa_num_sms(), tiles);
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  int kb_per_split = koa_cdiv(num_kb, splits);
+  if (kb_per_split < 4 && num_kb >= 4) kb_per_split = 4;
+  splits = koa_cdiv(num_kb, kb_per_split);
+  dim3 grid((unsigned)tiles, (unsigned)splits);
+  gemm_wgrad_kernel<BN, STAGES, IM2COL>
+      <<<grid, kGemmThreads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+
+int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, cudaStream_t st) {
+  KOA_REQUIRE(pixels > 0 && cout > 0 && cin > 0, "empty wgrad");
+  KOA_REQUIRE(cout % 8 == 0 && cin % 64 == 0, "wgrad needs Cout %% 8 == 0 and Cin %% 64 == 0 (got %d, %d)", cout, cin);
+  CUtensorMap ta, tb;
+  int rc = koa_tmap_2d_bf16(&ta, dy, (uint64_t)cout, (uint64_t)pixels, (uint64_t)cout * 2, 64, 64);
+  if (rc) return rc;
+  rc = koa_tmap_2d_bf16(&tb, x, (uint64_t)cin, (uint64_t)pixels, (uint64_t)cin * 2, 64, 64);
+  if (rc) return rc;
+  ConvGeom g = {1, 1, 1, 0, 1, 1};
+  if (cin % 128 == 0) return launch_wgrad<128, 4, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
+  return launch_wgrad<64, 4, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
+}
+
+int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int cin, int cout,
+                          int filt_r, int filt_s, int stride, int pad, cudaStream_t st) {
+  KOA_REQUIRE(cout % 8 == 0 && cin % 64 == 0, "wgrad needs Cout %% 8 == 0 and Cin %% 64 == 0 (got %d, %d)", cout, cin);
+  const int hout = (h + 2 * pad - filt_r) / stride + 1;
+  const int wout = (w_in + 2 * pad - filt_s) / stride + 1;
+  const long long pixels = (long long)n_img * hout * wout;
+  KOA_REQUIRE(pixels > 0 && pixels < 2147483647LL, "bad pixel count");
+  CUtensorMap ta, tb;
+  int rc = koa_tmap_2d_bf16(&ta, dy, (uint64_t)cout, (uint64_t)pixels, (uint64_t)cout * 2, 64, 64);
+  if (rc) return rc;
+  rc = koa_tmap_im2col_bf16(&tb, x, n_img, h, w_in, cin, filt_r, filt_s, stride, pad, 64);
+  if (rc) return rc;
+  ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64};
+  const int taps = filt_r * filt_s;
+  if (cin % 128 == 0) return launch_wgrad<128, 4, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
+  return launch_wgrad<64, 4, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
+}
+
+// ------------------------------------ C ABI ----------------------------------------------------
+extern "C" int koa_gemm_bf16(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep,
+                             void* stream) {
+  return koa_gemm_launch(a, b, m, n, k, ep, (cudaStream_t)stream);
+}
+extern "C" int koa_conv_fprop_bf16(const void* x, const void* w, int n_img, int h, int w_in, int cin, int cout,
+                                   int filt_r, int filt_s, int stride, int pad, const koa_epilogue_t* ep,
+                                   void* stream) {
+  return koa_conv_fprop_launch(x, w, n_img, h, w_in, cin, cout, filt_r, filt_s, stride, pad, ep, (cudaStream_t)stream);
+}
+extern "C" int koa_gemm_wgrad_bf16(const void* dy, const void* x, float* dw, int pixels, int cout, int cin,
+                                   void* stream) {
+  return koa_gemm_wgrad_launch(dy, x, dw, pixels, cout, cin, (cudaStream_t)stream);
+}
+extern "C" int koa_conv_wgrad_bf16(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int cin,
+                                   int cout, int filt_r, int filt_s, int stride, int pad, void* stream) {
+  return koa_conv_wgrad_launch(dy, x, dw, n_img, h, w_in, cin, cout, filt_r, filt_s, stride, pad, (cudaStream_t)stream);
+}
