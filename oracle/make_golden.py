@@ -1,0 +1,213 @@
+"""Generates tests/golden/*.json from the UNMODIFIED reference (build container only).
+
+    python oracle/make_golden.py            # needs /root/reference; writes tests/golden/
+
+For every reference model class this script
+  1. builds ``koafusion.models.dict_models[name]`` from /root/reference with ``pretrained=False``,
+  2. checks that ``oracle.koa_oracle.model_param_spec`` lists exactly the reference's state_dict keys
+     and shapes, in order,
+  3. loads seeded weights (``make_state_dict``) and seeded inputs (``make_inputs``),
+  4. records eval-mode logits (after BN running stats were perturbed by the seeded init), one
+     train-mode step with FocalLoss (logits, loss, per-parameter gradient L2 norm and three sampled
+     gradient values, updated BN running statistics of the first/last BN layer), and a
+     "sensitised" eval run (pos_embedding / cls_token scaled by 0.02).
+The fixtures are small (no weights): both sides regenerate weights/inputs from (spec, seed).
+The 3-MRI extension models have no reference class; their fixtures are produced from a composition of
+the reference's own FeaT + dict_fes blocks, assembled the way _xrNmrMcP.py:40-179,209-255 does.
+"""
+from __future__ import annotations
+
+import importlib.util
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import koa_oracle as ko  # noqa: E402
+
+
+class AttrDict(dict):
+    """item + attribute access, as the reference reads its OmegaConf config both ways."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+def to_attr(d):
+    if isinstance(d, dict):
+        return AttrDict({k: to_attr(v) for k, v in d.items()})
+    if isinstance(d, (list, tuple)):
+        return [to_attr(v) for v in d]
+    return d
+
+
+def load_ref_focal_loss():
+    spec = importlib.util.spec_from_file_location("ref_losses", os.path.join(REF, "koafusion/various/_losses.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.FocalLoss(gamma=2)
+
+
+# Small but structurally complete cases (CPU seconds each). Sizes must be keys of the reference's
+# spatial lookup table (_xrNmrMcP.py:104-105): 32/64/... for images.
+CASES = {
+    "XR1Cnn": dict(kw=dict(xr_size=64), batch=3),
+    "XR1Cnn_r18": dict(model="XR1Cnn", kw=dict(xr_size=64, xr_arch="resnet18"), batch=2),
+    "MR1CnnTrf": dict(kw=dict(mr_size=64, slices=(4,), depth=2), batch=2),
+    "MR2CnnTrf": dict(kw=dict(mr_size=32, slices=(3, 2), depth=1), batch=2),
+    "XR1MR1CnnTrf": dict(kw=dict(xr_size=64, mr_size=32, slices=(3,), depth=1), batch=2),
+    "XR1MR2CnnTrf": dict(kw=dict(xr_size=64, mr_size=32, slices=(3, 2), depth=1), batch=2),
+    "XR1MR2C1CnnTrf": dict(kw=dict(xr_size=64, mr_size=32, slices=(3, 2), depth=1), batch=2),
+    "MR3CnnTrf": dict(kw=dict(mr_size=32, slices=(3, 2, 2), depth=1), batch=2),
+    "XR1MR3C1CnnTrf": dict(kw=dict(xr_size=64, mr_size=32, slices=(3, 2, 2), depth=1), batch=2),
+}
+
+
+def build_extension_model(name, cfg):
+    """3-MRI pattern extension assembled from the reference's own blocks."""
+    from einops import rearrange, repeat
+    from koafusion.models._core_fes import dict_fes
+    from koafusion.models._core_trf import FeaT
+    from koafusion.models._xrNmrMcP import FeatC1
+    from torch import nn
+
+    agg = cfg["agg"]
+    ns = agg["num_slices"]
+
+    def fe(arch):
+        return nn.Sequential(*list(dict_fes[arch](pretrained=False).children())[:-1])
+
+    def feat(n, with_cls):
+        return FeaT(num_patches=n, patch_dim=2048, emb_dim=2048, depth=agg["depth"], heads=agg["heads"],
+                    mlp_dim=agg["mlp_dim"], num_classes=cfg["output_channels"], emb_dropout=agg["emb_dropout"],
+                    with_cls=with_cls, mlp_dropout=agg["mlp_dropout"])
+
+    class Ext(nn.Module):
+        def __init__(self):
+            super().__init__()
+            mr = cfg["fe"]["mr"]["arch"]
+            if name == "XR1MR3C1CnnTrf":
+                self._fe0 = fe(cfg["fe"]["xr"]["arch"])
+                self._fe1, self._fe2, self._fe3 = fe(mr), fe(mr), fe(mr)
+                self._fe4 = FeatC1(config=cfg["fe"]["clin"])
+                self._agg_1, self._agg_2, self._agg_3 = feat(ns[1], False), feat(ns[2], False), feat(ns[3], False)
+                self._agg_final = feat(1 + ns[1] + ns[2] + ns[3] + ns[4], True)
+            else:
+                self._fe1, self._fe2, self._fe3 = fe(mr), fe(mr), fe(mr)
+                self._agg_1, self._agg_2, self._agg_3 = feat(ns[0], False), feat(ns[1], False), feat(ns[2], False)
+                self._agg_final = feat(ns[0] + ns[1] + ns[2], True)
+
+        def forward(self, *ins):
+            def mri(fe_, agg_, vol):
+                b = vol.shape[0]
+                t = rearrange(vol, "b ch r c s -> (b s) ch r c")
+                t = repeat(t, "bs ch r c -> bs (k ch) r c", k=3)
+                t = rearrange(fe_(t), "(b s) ch d0 d1 -> b (s d0 d1) ch", b=b)
+                return agg_(t)[1]
+
+            parts = []
+            vols = ins
+            if name == "XR1MR3C1CnnTrf":
+                x = repeat(ins[0], "b ch r c -> b (k ch) r c", k=3)
+                parts.append(rearrange(self._fe0(x), "b ch d0 d1 -> b (d0 d1) ch"))
+                vols = ins[1:4]
+            parts.append(mri(self._fe1, self._agg_1, vols[0]))
+            parts.append(mri(self._fe2, self._agg_2, vols[1]))
+            parts.append(mri(self._fe3, self._agg_3, vols[2]))
+            if name == "XR1MR3C1CnnTrf":
+                parts.append(self._fe4(ins[4]))
+            out, _, _ = self._agg_final(torch.cat(parts, dim=1))
+            return {"main": rearrange(out, "b head cls -> b (head cls)")}
+
+    return Ext()
+
+
+def run_case(case_name, case):
+    from koafusion.models import dict_models
+
+    name = case.get("model", case_name)
+    cfg = ko.make_config(name, **case["kw"])
+    acfg = to_attr(cfg)
+    torch.manual_seed(778)
+    if name in dict_models:
+        model = dict_models[name](config=acfg, path_weights=None)
+    else:
+        model = build_extension_model(name, acfg)
+
+    spec = ko.model_param_spec(name, cfg)
+    ref_sd = model.state_dict()
+    assert [k for k, _ in spec] == list(ref_sd.keys()), f"{name}: key order mismatch"
+    for k, shp in spec:
+        assert tuple(ref_sd[k].shape) == tuple(shp), f"{name}: shape mismatch at {k}"
+
+    seed_w, seed_x = 1000 + len(case_name), 2000 + len(case_name)
+    out = dict(case=case_name, model=name, config_kwargs=case["kw"], batch=case["batch"], seed_weights=seed_w,
+               seed_inputs=seed_x, num_keys=len(spec))
+    inputs, target = ko.make_inputs(name, cfg, case["batch"], seed_x)
+
+    def logits_of(m, ins):
+        r = m(*ins)
+        return r["main"] if isinstance(r, dict) else r
+
+    # eval mode
+    model.load_state_dict(ko.make_state_dict(spec, seed_w), strict=True)
+    model.eval()
+    with torch.no_grad():
+        out["eval_logits"] = logits_of(model, inputs).tolist()
+    # sensitised eval
+    model.load_state_dict(ko.make_state_dict(spec, seed_w, pos_scale=0.02), strict=True)
+    with torch.no_grad():
+        out["eval_logits_sensitised"] = logits_of(model, inputs).tolist()
+    # one training step (dropout is 0 in these configs)
+    model.load_state_dict(ko.make_state_dict(spec, seed_w, pos_scale=0.02), strict=True)
+    model.train()
+    model.zero_grad()
+    logits = logits_of(model, inputs)
+    loss = load_ref_focal_loss()(logits, target)
+    loss.backward()
+    out["train_logits"] = logits.detach().tolist()
+    out["train_loss"] = float(loss)
+    grads = {}
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            grads[k] = None
+        else:
+            flat = p.grad.flatten()
+            idx = [0, flat.numel() // 2, flat.numel() - 1]
+            grads[k] = dict(norm=float(flat.norm()), samples=[float(flat[i]) for i in idx])
+    out["grads"] = grads
+    sd_after = model.state_dict()
+    bn_keys = [k for k in sd_after if k.endswith("running_mean") or k.endswith("running_var")]
+    picks = bn_keys[:2] + bn_keys[-2:]
+    out["bn_after"] = {k: dict(sum=float(sd_after[k].sum()), first=float(sd_after[k].flatten()[0])) for k in picks}
+    out["num_batches_tracked_after"] = int(sd_after[[k for k in sd_after if k.endswith("num_batches_tracked")][0]])
+    return out
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    only = sys.argv[1:]
+    for case_name, case in CASES.items():
+        if only and case_name not in only:
+            continue
+        t0 = time.time()
+        res = run_case(case_name, case)
+        path = os.path.join(ROOT, "tests", "golden", f"{case_name}.json")
+        with open(path, "w") as f:
+            json.dump(res, f, indent=1)
+        print(f"{case_name}: {time.time() - t0:.1f}s -> {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
+if __name__ == "__main__":
+    main()
