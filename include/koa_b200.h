@@ -81,6 +81,89 @@ int koa_conv_wgrad_bf16(const void* dy, const void* x, float* dw, int n_img, int
 /* Test/debug knob: MN-major shared-memory descriptor strides used by the wgrad kernels. */
 int koa_debug_set_wgrad_desc(unsigned int lbo_bytes, unsigned int sbo_bytes, unsigned int k_adv_bytes);
 
+
+/* ---- whole feature extractor (per-slice CNN) ---------------------------------------------------- */
+/* Replaces `self._feK(t_inK)` of every model class, i.e. nn.Sequential(*resnet.children()[:-1])
+ * (koafusion/models/_xrNmrMcP.py:40-59,218-220; _mrN_cnn_trf.py:20-28,121; _xr1mrN.py:19-33,132-133;
+ * _xr1_cnn.py:15-19,66) together with the einops rearrange/repeat in front of it (_xrNmrMcP.py:209-213)
+ * and its autograd backward (koafusion/run/train_prog_fus.py:165). */
+enum { KOA_ARCH_RESNET18 = 0, KOA_ARCH_RESNET34 = 1, KOA_ARCH_RESNET50 = 2, KOA_ARCH_RESNEXT50_32X4D = 3 };
+
+typedef struct koa_fe_desc {
+  int arch;          /* KOA_ARCH_* */
+  int n_img;         /* number of 2-D images = batch * slices */
+  int h, w;          /* image size */
+  int slices;        /* > 0: input is a (B,1,R,C,S) slice-innermost volume; 0: input is [n_img][h][w] */
+  int with_gap;      /* 1: features [n_img][C]; 0: [n_img][h_out*w_out][C] (tokens per position) */
+  int training;      /* BatchNorm batch statistics + running-stat update (1) or running statistics (0) */
+  int need_backward; /* keep what koa_fe_backward needs and pack data-gradient weights */
+  const float* input_for_backward; /* slices == 0 only: the [n_img][h][w] input again, for the stem wgrad */
+} koa_fe_desc_t;
+
+size_t koa_fe_workspace_bytes(const koa_fe_desc_t* d);
+int koa_fe_out_shape(const koa_fe_desc_t* d, int* channels, int* h, int* w);
+int koa_fe_num_units(const koa_fe_desc_t* d); /* conv+BN units; params has 5, grads 3 entries per unit */
+/* params[5*u + {0..4}] = conv weight, bn weight, bn bias, running_mean, running_var of unit u in
+ * state_dict order (fp32, PyTorch layout). running_* are updated in place when training. */
+int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params, const float* input, void* workspace,
+                   float* feat, void* stream);
+/* grads[3*u + {0,1,2}] = d conv weight, d bn weight, d bn bias (fp32, accumulated into; NULL skips). */
+int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params, void* const* grads, void* workspace,
+                    const float* dfeat, void* stream);
+int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, size_t* offset, size_t* bytes);
+
+/* ---- whole token transformer (FeaT) --------------------------------------------------------------- */
+/* Replaces FeaT.forward / Transformer / Attention / FeedForward (koafusion/models/_core_trf.py:118-205)
+ * and their autograd backward. Tables follow the reference state_dict order (see feat_engine.cu). */
+typedef struct koa_feat_desc {
+  int batch, n_patches, dim, depth, heads, mlp_dim, num_classes;
+  int with_cls;      /* prepend the learned CLS token */
+  int compute_head;  /* run mlp_head0 on token 0 (dead compute for the per-sequence transformers) */
+  int training;
+  int need_backward;
+  float emb_dropout, mlp_dropout; /* must be 0 here; dropout is applied by koa_dropout_* around the call */
+} koa_feat_desc_t;
+
+size_t koa_feat_workspace_bytes(const koa_feat_desc_t* d);
+int koa_feat_num_params(const koa_feat_desc_t* d);
+int koa_feat_probs_offset(const koa_feat_desc_t* d, int layer, size_t* offset, size_t* bytes);
+int koa_feat_forward(const koa_feat_desc_t* d, const void* const* params, const float* tokens, void* workspace,
+                     float* states_out, float* logits_out, void* stream);
+int koa_feat_backward(const koa_feat_desc_t* d, const void* const* params, void* const* grads, void* workspace,
+                      const float* d_states, const float* d_logits, float* d_tokens, void* stream);
+
+/* ---- single operators ------------------------------------------------------------------------------ */
+/* Small dense layers on CUDA cores, fp32: y = act(x[m,k] . w[n,k]^T + b). Used where N or K is too small
+ * for tcgen05 tiles: FeatC1 Linear(9->2048)+GELU (koafusion/models/_xrNmrMcP.py:15-19; the input is three
+ * z-scores and three one-hot pairs, so the product is a gather/scale of weight columns), the XR1Cnn head
+ * (koafusion/models/_xr1_cnn.py:31-39) and mlp_head0.4 (koafusion/models/_core_trf.py:115). `pre` (optional)
+ * receives the pre-activation for backward. */
+int koa_linear_small_fwd(const float* x, const float* w, const float* b, float* y, float* pre, int m, int n, int k,
+                         int act, void* stream);
+/* dx (may be NULL) is overwritten; dw / db (may be NULL) are accumulated into. scratch: m*n floats. */
+int koa_linear_small_bwd(const float* dy, const float* pre, const float* x, const float* w, float* scratch, float* dx,
+                         float* dw, float* db, int m, int n, int k, int act, void* stream);
+/* FocalLoss(gamma, reduction="mean") and its gradient w.r.t. the logits (koafusion/various/_losses.py:89-108). */
+int koa_focal_loss(const float* logits, const long long* target, float* loss, float* dlogits, int batch, int classes,
+                   float gamma, void* stream);
+/* nn.LayerNorm over the last dim, eps 1e-5 (koafusion/models/_core_trf.py:111,190,192). */
+int koa_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32, float* mean,
+                      float* rstd, int rows, int d, void* stream);
+int koa_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, float* dx,
+                      float* dgamma, float* dbeta, int rows, int d, void* stream);
+/* softmax(Q K^T * scale) V per (batch, head) on a packed bf16 qkv buffer (koafusion/models/_core_trf.py:170-180). */
+int koa_attention_fwd(const void* qkv, void* out, float* probs, int batch, int n, int heads, int head_dim, float scale,
+                      void* stream);
+int koa_attention_bwd(const void* qkv, const float* probs, const void* dout, void* dqkv, int batch, int n, int heads,
+                      int head_dim, float scale, void* stream);
+/* (B,1,R,C,S) -> [B*S][R*C]: einops "b ch r c s -> (b s) ch r c" (koafusion/models/_xrNmrMcP.py:209-210). */
+int koa_stem_pack(const float* vol, float* img, int batch, int rc, int slices, void* stream);
+/* nn.MaxPool2d(3, 2, 1) on NHWC bf16 (koafusion/models/_torchvision.py:174); idx keeps the winning tap. */
+int koa_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, void* stream);
+int koa_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, void* stream);
+/* per-channel sum / sum of squares of a bf16 [rows][c] tensor (stand-alone BatchNorm statistics). */
+int koa_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,10 +37,50 @@ class Epilogue(C.Structure):
     ]
 
 
+class FeDesc(C.Structure):
+    """Mirror of ``koa_fe_desc_t``."""
+
+    _fields_ = [
+        ("arch", C.c_int),
+        ("n_img", C.c_int),
+        ("h", C.c_int),
+        ("w", C.c_int),
+        ("slices", C.c_int),
+        ("with_gap", C.c_int),
+        ("training", C.c_int),
+        ("need_backward", C.c_int),
+        ("input_for_backward", C.c_void_p),
+    ]
+
+
+class FeatDesc(C.Structure):
+    """Mirror of ``koa_feat_desc_t``."""
+
+    _fields_ = [
+        ("batch", C.c_int),
+        ("n_patches", C.c_int),
+        ("dim", C.c_int),
+        ("depth", C.c_int),
+        ("heads", C.c_int),
+        ("mlp_dim", C.c_int),
+        ("num_classes", C.c_int),
+        ("with_cls", C.c_int),
+        ("compute_head", C.c_int),
+        ("training", C.c_int),
+        ("need_backward", C.c_int),
+        ("emb_dropout", C.c_float),
+        ("mlp_dropout", C.c_float),
+    ]
+
+
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2, 3
+ARCH_IDS = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnext50_32x4d": 3}
 
 _P = C.c_void_p
 _I = C.c_int
+_F = C.c_float
+_PP = C.POINTER(C.c_void_p)
+_SZ = C.POINTER(C.c_size_t)
 
 # name -> (restype, argtypes). Every symbol declared in include/koa_b200.h must appear here;
 # tests/test_abi.py cross-checks the two lists.
@@ -53,7 +93,37 @@ SIGNATURES = {
     "koa_conv_fprop_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_gemm_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "koa_conv_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "koa_fe_workspace_bytes": (C.c_size_t, [C.POINTER(FeDesc)]),
+    "koa_fe_out_shape": (_I, [C.POINTER(FeDesc), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "koa_fe_num_units": (_I, [C.POINTER(FeDesc)]),
+    "koa_fe_forward": (_I, [C.POINTER(FeDesc), _PP, _P, _P, _P, _P]),
+    "koa_fe_backward": (_I, [C.POINTER(FeDesc), _PP, _PP, _P, _P, _P]),
+    "koa_fe_debug_offset": (_I, [C.POINTER(FeDesc), _I, _I, _SZ, _SZ]),
+    "koa_feat_workspace_bytes": (C.c_size_t, [C.POINTER(FeatDesc)]),
+    "koa_feat_num_params": (_I, [C.POINTER(FeatDesc)]),
+    "koa_feat_probs_offset": (_I, [C.POINTER(FeatDesc), _I, _SZ, _SZ]),
+    "koa_feat_forward": (_I, [C.POINTER(FeatDesc), _PP, _P, _P, _P, _P, _P]),
+    "koa_feat_backward": (_I, [C.POINTER(FeatDesc), _PP, _PP, _P, _P, _P, _P, _P]),
+    "koa_linear_small_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "koa_linear_small_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "koa_focal_loss": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
+    "koa_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "koa_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "koa_attention_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "koa_attention_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "koa_stem_pack": (_I, [_P, _P, _I, _I, _I, _P]),
+    "koa_maxpool_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "koa_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "koa_col_stats": (_I, [_P, _P, _P, C.c_longlong, _I, _P]),
 }
+
+
+def ptr_table(tensors):
+    """ctypes void* array of device pointers (None -> NULL)."""
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
 
 _lib = None
 

@@ -1,0 +1,1025 @@
+// elementwise.cu — HBM-bound kernels of the koafusion hot path: parameter packing, BatchNorm
+// (finalize / apply / backward), max-pool, global average pool, LayerNorm, token assembly, bias
+// gradients, small linears. All activations are NHWC bf16 with C a multiple of 8; every thread moves
+// 16-byte vectors and per-channel reductions go registers -> shared memory -> one atomic per block.
+#include "koa_common.cuh"
+#include "koa_internal.h"
+#include "koa_kernels.h"
+
+using namespace koa;
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(long long work_items, int threads = kThreads, int max_blocks = 148 * 16) {
+  long long b = (work_items + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(q.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(q.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(q.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(q.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  q.x = pack_bf16x2(f[0], f[1]); q.y = pack_bf16x2(f[2], f[3]);
+  q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
+  return q;
+}
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameter packing
+// ------------------------------------------------------------------------------------------------
+// dst[o][r][s][i] (bf16) = src[o][i][r][s] (fp32);  transpose: dst[i][R-1-r][S-1-s][o] (data-gradient form).
+__global__ void pack_conv_w_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int cout, int cin, int fr,
+                                   int fs, int dgrad_form) {
+  const long long total = (long long)cout * cin * fr * fs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int s = (int)(t % fs); t /= fs;
+    const int r = (int)(t % fr); t /= fr;
+    const int ci = (int)(t % cin); t /= cin;
+    const int co = (int)t;
+    const float v = src[i];
+    long long d;
+    if (!dgrad_form) d = (((long long)co * fr + r) * fs + s) * cin + ci;
+    else d = (((long long)ci * fr + (fr - 1 - r)) * fs + (fs - 1 - s)) * cout + co;
+    dst[d] = __float2bfloat16_rn(v);
+  }
+}
+
+// Grouped 3x3 conv weights [C][Cg][3][3] -> block-diagonal dense per 64-channel chunk:
+// dst[o][r][s][j] with j in [0,64) the input channel inside o's chunk (zero outside o's group).
+// dgrad_form: dst[i][2-r][2-s][j] with j the output channel inside i's chunk.
+__global__ void pack_grouped_w_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int c, int cg, int dgrad_form) {
+  const long long total = (long long)c * 9 * 64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int j = (int)(t % 64); t /= 64;
+    const int tap = (int)(t % 9); t /= 9;
+    const int row = (int)t;  // output channel (fprop form) or input channel (dgrad form)
+    const int chunk = row / 64;
+    const int other = chunk * 64 + j;  // the channel on the other side
+    float v = 0.0f;
+    if (other / cg == row / cg) {
+      if (!dgrad_form) {
+        v = src[((long long)row * cg + (other % cg)) * 9 + tap];
+      } else {
+        v = src[((long long)other * cg + (row % cg)) * 9 + (8 - tap)];
+      }
+    }
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// grad[o][ig][r][s] (fp32) = dense[o][r][s][(o % 64) / cg * cg + ig]   (diagonal blocks of the chunked gradient)
+__global__ void unpack_grouped_dw_kernel(const float* __restrict__ dense, float* __restrict__ grad, int c, int cg) {
+  const long long total = (long long)c * cg * 9;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int tap = (int)(t % 9); t /= 9;
+    const int ig = (int)(t % cg); t /= cg;
+    const int o = (int)t;
+    const int j = ((o % 64) / cg) * cg + ig;
+    grad[i] = dense[((long long)o * 9 + tap) * 64 + j];
+  }
+}
+
+// grad[o][i][r][s] (fp32) = src[o][r][s][i] (fp32)
+__global__ void unpack_conv_dw_kernel(const float* __restrict__ src, float* __restrict__ dst, int cout, int cin, int fr,
+                                      int fs) {
+  const long long total = (long long)cout * cin * fr * fs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int s = (int)(t % fs); t /= fs;
+    const int r = (int)(t % fr); t /= fr;
+    const int ci = (int)(t % cin); t /= cin;
+    const int co = (int)t;
+    dst[i] = src[(((long long)co * fr + r) * fs + s) * cin + ci];
+  }
+}
+
+// bf16 copy and bf16 transpose of a row-major fp32 matrix [rows][cols].
+__global__ void pack_matrix_kernel(const float* __restrict__ src, bf16* __restrict__ dst, bf16* __restrict__ dst_t,
+                                   int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = by + j, c = bx + threadIdx.x;
+    float v = 0.0f;
+    if (r < rows && c < cols) {
+      v = src[(long long)r * cols + c];
+      if (dst != nullptr) dst[(long long)r * cols + c] = __float2bfloat16_rn(v);
+    }
+    tile[j][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (dst_t != nullptr) {
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int c = bx + j, r = by + threadIdx.x;
+      if (r < rows && c < cols) dst_t[(long long)c * rows + r] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    }
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    load8f(src + i * 8, f);
+    *reinterpret_cast<uint4*>(dst + i * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm
+// ------------------------------------------------------------------------------------------------
+// Per-channel affine coefficients from batch statistics (training) or running statistics (eval):
+//   y_hat = (y - mean) * invstd ;  out = y * scale + shift with scale = gamma*invstd, shift = beta - mean*scale.
+// Training also updates running_mean / running_var (momentum 0.1, unbiased variance), as nn.BatchNorm2d.
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   int c, double count, int training, float eps, float momentum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  float mean, var;
+  if (training) {
+    const double m = (double)sum[i] / count;
+    double v = (double)sumsq[i] / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = (float)m;
+    var = (float)v;
+    const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+    run_mean[i] = (1.0f - momentum) * run_mean[i] + momentum * mean;
+    run_var[i] = (1.0f - momentum) * run_var[i] + momentum * (float)unbiased;
+  } else {
+    mean = run_mean[i];
+    var = run_var[i];
+  }
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[i] * invstd;
+  scale[i] = sc;
+  shift[i] = beta[i] - mean * sc;
+  mean_out[i] = mean;
+  invstd_out[i] = invstd;
+}
+
+// Per-channel sum / sum of squares of a bf16 [rows][c] tensor (stand-alone form of the statistics the
+// GEMM epilogue produces; used for layers whose producer is not a tcgen05 GEMM and by the tests).
+__global__ void col_stats_kernel(const bf16* __restrict__ y, float* __restrict__ sum, float* __restrict__ sumsq,
+                                 long long rows, int c) {
+  extern __shared__ float sm[];
+  const int cg = c / 8;                 // channel groups of 8
+  const int lanes = blockDim.x / cg;    // row lanes per block
+  const int g = threadIdx.x % cg;
+  const int rl = threadIdx.x / cg;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (rl < lanes) {
+    for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(y + r * c + g * 8), f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s[u] += f[u]; q[u] += f[u] * f[u]; }
+    }
+  }
+  float* ssum = sm;
+  float* ssq = sm + c;
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) sm[i] = 0.0f;
+  __syncthreads();
+  if (rl < lanes) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { atomicAdd(&ssum[g * 8 + u], s[u]); atomicAdd(&ssq[g * 8 + u], q[u]); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) { atomicAdd(&sum[i], ssum[i]); atomicAdd(&sumsq[i], ssq[i]); }
+}
+
+// out = [relu]( y*scale + shift  +  (res | y2*scale2 + shift2) )
+__global__ void bn_act_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                              const bf16* __restrict__ res, const bf16* __restrict__ y2, const float* __restrict__ scale2,
+                              const float* __restrict__ shift2, bf16* __restrict__ out, long long rows, int c, int relu) {
+  const int cg = c / 8;
+  const long long total = rows * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    float f[8], sc[8], sh[8];
+    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
+    load8f(scale + g * 8, sc);
+    load8f(shift + g * 8, sh);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f[u] = f[u] * sc[u] + sh[u];
+    if (res != nullptr) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(res + i * 8), r);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] += r[u];
+    } else if (y2 != nullptr) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(y2 + i * 8), r);
+      load8f(scale2 + g * 8, sc);
+      load8f(shift2 + g * 8, sh);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] += r[u] * sc[u] + sh[u];
+    }
+    if (relu) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.0f);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+  }
+}
+
+// Backward reduction: dz = dout * (act > 0) [if act != NULL]; accumulates per channel
+//   sum_dz, sum_dz_xhat (xhat from y/mean/invstd) and optionally sum_dz_xhat2 for a second BN
+//   (the downsample branch that shares dz).
+__global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ act,
+                                     const bf16* __restrict__ y, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, const bf16* __restrict__ y2,
+                                     const float* __restrict__ mean2, const float* __restrict__ invstd2,
+                                     float* __restrict__ sum_dz, float* __restrict__ sum_dzx,
+                                     float* __restrict__ sum_dzx2, long long rows, int c) {
+  extern __shared__ float sm[];
+  const int cg = c / 8;
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x % cg;
+  const int rl = threadIdx.x / cg;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float mu[8], is[8], mu2[8], is2[8];
+  load8f(mean + g * 8, mu);
+  load8f(invstd + g * 8, is);
+  if (y2 != nullptr) { load8f(mean2 + g * 8, mu2); load8f(invstd2 + g * 8, is2); }
+  if (rl < lanes) {
+    for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
+      const long long off = r * c + g * 8;
+      float dz[8], yy[8];
+      unpack8(*reinterpret_cast<const uint4*>(dout + off), dz);
+      if (act != nullptr) {
+        float m[8];
+        unpack8(*reinterpret_cast<const uint4*>(act + off), m);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dz[u] = m[u] > 0.0f ? dz[u] : 0.0f;
+      }
+      unpack8(*reinterpret_cast<const uint4*>(y + off), yy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a[u] += dz[u]; b[u] += dz[u] * (yy[u] - mu[u]) * is[u]; }
+      if (y2 != nullptr) {
+        unpack8(*reinterpret_cast<const uint4*>(y2 + off), yy);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) b2[u] += dz[u] * (yy[u] - mu2[u]) * is2[u];
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < 3 * c; i += blockDim.x) sm[i] = 0.0f;
+  __syncthreads();
+  if (rl < lanes) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      atomicAdd(&sm[g * 8 + u], a[u]);
+      atomicAdd(&sm[c + g * 8 + u], b[u]);
+      if (y2 != nullptr) atomicAdd(&sm[2 * c + g * 8 + u], b2[u]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    atomicAdd(&sum_dz[i], sm[i]);
+    atomicAdd(&sum_dzx[i], sm[c + i]);
+    if (y2 != nullptr) atomicAdd(&sum_dzx2[i], sm[2 * c + i]);
+  }
+}
+
+// dgamma = sum_dz_xhat, dbeta = sum_dz (accumulated into the fp32 gradient tensors), and the per-channel
+// coefficients of the apply pass: dy = k0 * dz - k1 - k2 * y  (training: batch statistics take part in
+// the gradient; eval: k1 = k2 = 0).
+//   dy = gamma*invstd * (dz - sum_dz/m - xhat*sum_dzx/m),  xhat = (y - mean)*invstd
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ k0, float* __restrict__ k1,
+                                       float* __restrict__ k2, int c, double count, int training) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float g = gamma[i], is = invstd[i], mu = mean[i];
+  const float sdz = sum_dz[i], sdzx = sum_dzx[i];
+  if (dgamma != nullptr) dgamma[i] += sdzx;
+  if (dbeta != nullptr) dbeta[i] += sdz;
+  const float s = g * is;
+  k0[i] = s;
+  if (training) {
+    const float a = (float)((double)sdz / count);
+    const float b = (float)((double)sdzx / count);
+    // dy = s*dz - s*a - s*b*xhat = s*dz - (s*a - s*b*is*mu) - (s*b*is)*y
+    k2[i] = s * b * is;
+    k1[i] = s * a - s * b * is * mu;
+  } else {
+    k1[i] = 0.0f;
+    k2[i] = 0.0f;
+  }
+}
+
+// dy = k0*dz - k1 - k2*y (and the same for a second BN sharing dz); optionally stores dz itself.
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ act,
+                                    const bf16* __restrict__ y, const float* __restrict__ k0,
+                                    const float* __restrict__ k1, const float* __restrict__ k2, bf16* __restrict__ dy,
+                                    const bf16* __restrict__ y2, const float* __restrict__ k0b,
+                                    const float* __restrict__ k1b, const float* __restrict__ k2b, bf16* __restrict__ dy2,
+                                    long long rows, int c) {
+  const int cg = c / 8;
+  const long long total = rows * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    float dz[8], yy[8], a[8], b[8], cc[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dout + i * 8), dz);
+    if (act != nullptr) {
+      float m[8];
+      unpack8(*reinterpret_cast<const uint4*>(act + i * 8), m);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dz[u] = m[u] > 0.0f ? dz[u] : 0.0f;
+    }
+    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), yy);
+    load8f(k0 + g * 8, a); load8f(k1 + g * 8, b); load8f(k2 + g * 8, cc);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) o[u] = a[u] * dz[u] - b[u] - cc[u] * yy[u];
+    *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+    if (y2 != nullptr) {
+      unpack8(*reinterpret_cast<const uint4*>(y2 + i * 8), yy);
+      load8f(k0b + g * 8, a); load8f(k1b + g * 8, b); load8f(k2b + g * 8, cc);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = a[u] * dz[u] - b[u] - cc[u] * yy[u];
+      *reinterpret_cast<uint4*>(dy2 + i * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pooling
+// ------------------------------------------------------------------------------------------------
+// 3x3 stride-2 pad-1 max pool, first maximum in scan order wins (as ATen); idx = r*3+s of the winner.
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, uint8_t* __restrict__ idx,
+                                   int n, int h, int w, int c, int ho, int wo) {
+  const int cg = c / 8;
+  const long long total = (long long)n * ho * wo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int ow = (int)(t % wo); t /= wo;
+    const int oh = (int)(t % ho); t /= ho;
+    const int ni = (int)t;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { best[u] = -INFINITY; bi[u] = 0; }
+    bool first = true;
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= h) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= w) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + (((long long)ni * h + ih) * w + iw) * c + g * 8), f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (first || f[u] > best[u]) { best[u] = f[u]; bi[u] = r * 3 + s; }
+        }
+        first = false;
+      }
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(best);
+    uint2 packed;
+    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + i * 8) = packed;
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ idx, bf16* __restrict__ dx,
+                                   int n, int h, int w, int c, int ho, int wo) {
+  const int cg = c / 8;
+  const long long total = (long long)n * h * w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int iw = (int)(t % w); t /= w;
+    const int ih = (int)(t % h); t /= h;
+    const int ni = (int)t;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // windows (oh, ow) with 2*oh-1 <= ih <= 2*oh+1
+    for (int oh = (ih) / 2; oh <= (ih + 1) / 2; ++oh) {
+      if (oh < 0 || oh >= ho) continue;
+      const int r = ih - (oh * 2 - 1);
+      if (r < 0 || r > 2) continue;
+      for (int ow = (iw) / 2; ow <= (iw + 1) / 2; ++ow) {
+        if (ow < 0 || ow >= wo) continue;
+        const int s = iw - (ow * 2 - 1);
+        if (s < 0 || s > 2) continue;
+        const long long o = (((long long)ni * ho + oh) * wo + ow) * cg + g;
+        const uint2 packed = *reinterpret_cast<const uint2*>(idx + o * 8);
+        float d[8];
+        unpack8(*reinterpret_cast<const uint4*>(dout + o * 8), d);
+        const int me = r * 3 + s;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t word = u < 4 ? packed.x : packed.y;
+          const int sel = (word >> ((u & 3) * 8)) & 0xff;
+          if (sel == me) acc[u] += d[u];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+  }
+}
+
+// Global average pool over hw positions: x [n][hw][c] bf16 -> feat [n][c] fp32
+__global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ feat, int n, int hw, int c) {
+  const int cg = c / 8;
+  const long long total = (long long)n * cg;
+  const float inv = 1.0f / (float)hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long ni = i / cg;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < hw; ++p) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + (ni * hw + p) * c + g * 8), f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += f[u];
+    }
+    float* dst = feat + ni * c + g * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+  }
+}
+
+__global__ void gap_bwd_kernel(const float* __restrict__ dfeat, bf16* __restrict__ dx, int n, int hw, int c) {
+  const int cg = c / 8;
+  const long long total = (long long)n * hw * cg;
+  const float inv = 1.0f / (float)hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    const long long ni = i / ((long long)cg * hw);
+    float f[8];
+    load8f(dfeat + ni * c + g * 8, f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) f[u] *= inv;
+    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(f);
+  }
+}
+
+// dst[n][2*oh][2*ow][c] = src[n][oh][ow][c], zero elsewhere (dst is h x w). Used to express the data
+// gradient of a stride-2 3x3 convolution as a stride-1 convolution.
+__global__ void zero_insert2_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int n, int h, int w, int c,
+                                    int ho, int wo) {
+  const int cg = c / 8;
+  const long long total = (long long)n * h * w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int iw = (int)(t % w); t /= w;
+    const int ih = (int)(t % h); t /= h;
+    const int ni = (int)t;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if ((ih & 1) == 0 && (iw & 1) == 0 && (ih >> 1) < ho && (iw >> 1) < wo)
+      v = *reinterpret_cast<const uint4*>(src + ((((long long)ni * ho + (ih >> 1)) * wo + (iw >> 1)) * cg + g) * 8);
+    *reinterpret_cast<uint4*>(dst + i * 8) = v;
+  }
+}
+
+// dx[n][2*oh][2*ow][c] += src[n][oh][ow][c]  (data gradient of a 1x1 stride-2 convolution)
+__global__ void scatter_add2_kernel(const bf16* __restrict__ src, bf16* __restrict__ dx, int n, int h, int w, int c,
+                                    int ho, int wo) {
+  const int cg = c / 8;
+  const long long total = (long long)n * ho * wo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int ow = (int)(t % wo); t /= wo;
+    const int oh = (int)(t % ho); t /= ho;
+    const int ni = (int)t;
+    bf16* p = dx + ((((long long)ni * h + oh * 2) * w + ow * 2) * cg + g) * 8;
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const uint4*>(p), a);
+    unpack8(*reinterpret_cast<const uint4*>(src + i * 8), b);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] += b[u];
+    *reinterpret_cast<uint4*>(p) = pack8(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transformer pieces
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (d % 256 == 0, d <= 4096); one warp per row; fp32 in, bf16 and/or fp32 out.
+template <int MAXV>
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, bf16* __restrict__ out_bf16,
+                                     float* __restrict__ out_f32, float* __restrict__ mean_out,
+                                     float* __restrict__ rstd_out, int rows, int d, long long x_row_stride, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (long long)warp * x_row_stride;
+  const int nv = d / 256;  // 8-float vectors per lane
+  float v[MAXV][8];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      load8f(xr + (i * 32 + lane) * 8, v[i]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[i][u];
+    }
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.0f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { const float t = v[i][u] - mean; q += t * t; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+  if (lane == 0) {
+    if (mean_out != nullptr) mean_out[warp] = mean;
+    if (rstd_out != nullptr) rstd_out[warp] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const int col = (i * 32 + lane) * 8;
+      float g[8], b[8], o[8];
+      load8f(gamma + col, g);
+      load8f(beta + col, b);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = (v[i][u] - mean) * rstd * g[u] + b[u];
+      if (out_bf16 != nullptr) *reinterpret_cast<uint4*>(out_bf16 + (long long)warp * d + col) = pack8(o);
+      if (out_f32 != nullptr) {
+        float* dst = out_f32 + (long long)warp * d + col;
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
+// LayerNorm backward. dx = rstd * (dy*g - mean(dy*g) - xhat*mean(dy*g*xhat)) [+ dres]; dgamma/dbeta are
+// accumulated per block in shared memory and flushed with one atomic per column per block.
+// dx is written as fp32 (row stride dx_row_stride) and optionally as a bf16 copy.
+template <int MAXV>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, const float* __restrict__ dres,
+                                     float* __restrict__ dx, bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int rows, int d, long long x_row_stride,
+                                     long long dx_row_stride) {
+  extern __shared__ float sm[];  // [2][d]
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.0f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int nv = d / 256;
+  float ag[MAXV][8], ab[MAXV][8];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { ag[i][u] = 0.0f; ab[i][u] = 0.0f; }
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* xr = x + (long long)row * x_row_stride;
+    const float* dyr = dy + (long long)row * d;
+    float xh[MAXV][8], dg[MAXV][8];
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 8;
+        float xv[8], dv[8], g[8];
+        load8f(xr + col, xv);
+        load8f(dyr + col, dv);
+        load8f(gamma + col, g);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          xh[i][u] = (xv[u] - mu) * rs;
+          dg[i][u] = dv[u] * g[u];
+          s1 += dg[i][u];
+          s2 += dg[i][u] * xh[i][u];
+          ag[i][u] += dv[u] * xh[i][u];
+          ab[i][u] += dv[u];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)d;
+    s2 = warp_sum(s2) / (float)d;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (i < nv) {
+        const int col = (i * 32 + lane) * 8;
+        float o[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = rs * (dg[i][u] - s1 - xh[i][u] * s2);
+        if (dres != nullptr) {
+          float r[8];
+          load8f(dres + (long long)row * dx_row_stride + col, r);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) o[u] += r[u];
+        }
+        float* dst = dx + (long long)row * dx_row_stride + col;
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        if (dx_bf16 != nullptr) *reinterpret_cast<uint4*>(dx_bf16 + (long long)row * d + col) = pack8(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (i < nv) {
+      const int col = (i * 32 + lane) * 8;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { atomicAdd(&sm[col + u], ag[i][u]); atomicAdd(&sm[d + col + u], ab[i][u]); }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(&dgamma[i], sm[i]);
+    atomicAdd(&dbeta[i], sm[d + i]);
+  }
+}
+
+// x[b][t][:] = (t < n_cls ? cls[t] : emb[b][t - n_cls]) + pos[t]      (FeaT: CLS concat + pos-embedding add)
+__global__ void token_assemble_kernel(const float* __restrict__ emb, const float* __restrict__ cls,
+                                      const float* __restrict__ pos, float* __restrict__ x, int batch, int n_tok,
+                                      int n_cls, int d) {
+  const int dv = d / 4;
+  const long long total = (long long)batch * n_tok * dv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int v = (int)(t % dv); t /= dv;
+    const int tok = (int)(t % n_tok); t /= n_tok;
+    const int b = (int)t;
+    float4 a;
+    if (tok < n_cls) a = reinterpret_cast<const float4*>(cls + (long long)tok * d)[v];
+    else a = reinterpret_cast<const float4*>(emb + ((long long)b * (n_tok - n_cls) + (tok - n_cls)) * d)[v];
+    const float4 p = reinterpret_cast<const float4*>(pos + (long long)tok * d)[v];
+    reinterpret_cast<float4*>(x)[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+  }
+}
+
+// Backward of token assembly: dpos[t] += sum_b dx[b][t]; dcls[t] += sum_b dx[b][t] (t < n_cls);
+// demb (bf16, [B*(n_tok-n_cls)][d]) = dx rows of the patch tokens.
+__global__ void token_assemble_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dpos, float* __restrict__ dcls,
+                                          bf16* __restrict__ demb, int batch, int n_tok, int n_cls, int d) {
+  const long long total = (long long)n_tok * d;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tok = (int)(i / d);
+    const int col = (int)(i % d);
+    float s = 0.0f;
+    for (int b = 0; b < batch; ++b) {
+      const float v = dx[((long long)b * n_tok + tok) * d + col];
+      s += v;
+      if (tok >= n_cls) demb[((long long)b * (n_tok - n_cls) + (tok - n_cls)) * d + col] = __float2bfloat16_rn(v);
+    }
+    dpos[i] += s;
+    if (tok < n_cls) dcls[i] += s;
+  }
+}
+
+// out[c] += sum_rows x[r][c]  for bf16 or fp32 x (bias gradients)
+template <typename T>
+__global__ void col_sum_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows, int c, long long ld) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= c) return;
+  float s = 0.0f;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) {
+    if constexpr (sizeof(T) == 2) s += __bfloat162float(x[r * ld + col]);
+    else s += x[r * ld + col];
+  }
+  atomicAdd(&out[col], s);
+}
+
+// Small dense layers on CUDA cores (N or K too small/ragged for the tcgen05 path):
+//   y[m][n] = act(sum_k x[m][k] * w[n][k] + b[n]); one warp per output element.
+__global__ void linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                        const float* __restrict__ b, float* __restrict__ y, float* __restrict__ pre,
+                                        int m, int n, int k, long long x_row_stride, int act) {
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)m * n) return;
+  const int mi = (int)(warp / n), ni = (int)(warp % n);
+  float s = 0.0f;
+  for (int i = lane; i < k; i += 32) s += x[mi * x_row_stride + i] * w[(long long)ni * k + i];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (b != nullptr) s += b[ni];
+    if (pre != nullptr) pre[warp] = s;
+    if (act == KOA_ACT_GELU) s = gelu_erf(s);
+    else if (act == KOA_ACT_RELU) s = fmaxf(s, 0.0f);
+    y[warp] = s;
+  }
+}
+// dpre = dy * act'(pre) (in place on a scratch copy `dpre`); dx[m][k] = sum_n dpre[m][n] w[n][k];
+// dw[n][k] += sum_m dpre[m][n] x[m][k]; db[n] += sum_m dpre[m][n].
+__global__ void linear_small_dpre_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
+                                         float* __restrict__ dpre, long long total, int act) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float g = dy[i];
+    if (act == KOA_ACT_GELU) g *= gelu_erf_grad(pre[i]);
+    else if (act == KOA_ACT_RELU) g = pre[i] > 0.0f ? g : 0.0f;
+    dpre[i] = g;
+  }
+}
+__global__ void linear_small_dx_kernel(const float* __restrict__ dpre, const float* __restrict__ w, float* __restrict__ dx,
+                                       int m, int n, int k, long long dx_row_stride, int accumulate) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)m * k) return;
+  const int mi = (int)(i / k), ki = (int)(i % k);
+  float s = 0.0f;
+  for (int j = 0; j < n; ++j) s += dpre[(long long)mi * n + j] * w[(long long)j * k + ki];
+  float* dst = dx + mi * dx_row_stride + ki;
+  *dst = accumulate ? *dst + s : s;
+}
+__global__ void linear_small_dw_kernel(const float* __restrict__ dpre, const float* __restrict__ x, float* __restrict__ dw,
+                                       float* __restrict__ db, int m, int n, int k, long long x_row_stride) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)n * k) return;
+  const int ni = (int)(i / k), ki = (int)(i % k);
+  float s = 0.0f, sb = 0.0f;
+  for (int j = 0; j < m; ++j) {
+    const float g = dpre[(long long)j * n + ni];
+    s += g * x[j * x_row_stride + ki];
+    sb += g;
+  }
+  dw[i] += s;
+  if (ki == 0 && db != nullptr) db[ni] += sb;
+}
+
+// Focal loss (gamma, mean reduction) on [b][classes] fp32 logits with int64 targets; also d(loss)/d(logits).
+__global__ void focal_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                  float* __restrict__ loss, float* __restrict__ dlogits, int batch, int classes,
+                                  float gamma) {
+  __shared__ float sacc;
+  if (threadIdx.x == 0) sacc = 0.0f;
+  __syncthreads();
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    const float* z = logits + (long long)b * classes;
+    float mx = -INFINITY;
+    for (int j = 0; j < classes; ++j) mx = fmaxf(mx, z[j]);
+    float se = 0.0f;
+    for (int j = 0; j < classes; ++j) se += expf(z[j] - mx);
+    const int t = (int)target[b];
+    const float logpt = z[t] - mx - logf(se);
+    const float pt = expf(logpt);
+    const float om = 1.0f - pt;
+    const float l = -powf(om, gamma) * logpt;
+    atomicAdd(&sacc, l);
+    if (dlogits != nullptr) {
+      // dl/dlogpt = gamma*(1-pt)^(gamma-1)*pt*logpt - (1-pt)^gamma ; dlogpt/dz_j = [j==t] - p_j
+      const float dl = gamma * powf(om, gamma - 1.0f) * pt * logpt - powf(om, gamma);
+      for (int j = 0; j < classes; ++j) {
+        const float pj = expf(z[j] - mx) / se;
+        dlogits[(long long)b * classes + j] = dl * ((j == t ? 1.0f : 0.0f) - pj) / (float)batch;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *loss = sacc / (float)batch;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Launchers (declared in koa_kernels.h)
+// ------------------------------------------------------------------------------------------------
+#define KOA_REQ_C8(c) KOA_REQUIRE((c) % 8 == 0, "channel count %d must be a multiple of 8", (c))
+
+int koa_k_pack_conv_w(const float* src, void* dst, int cout, int cin, int fr, int fs, int dgrad_form, cudaStream_t st) {
+  const long long total = (long long)cout * cin * fr * fs;
+  pack_conv_w_kernel<<<grid_for(total), kThreads, 0, st>>>(src, (bf16*)dst, cout, cin, fr, fs, dgrad_form);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_pack_grouped_w(const float* src, void* dst, int c, int cg, int dgrad_form, cudaStream_t st) {
+  KOA_REQUIRE(c % 64 == 0 && cg >= 1 && 64 % cg == 0, "grouped conv packing needs C %% 64 == 0 and Cg | 64 (C=%d Cg=%d)", c, cg);
+  pack_grouped_w_kernel<<<grid_for((long long)c * 9 * 64), kThreads, 0, st>>>(src, (bf16*)dst, c, cg, dgrad_form);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_unpack_grouped_dw(const float* dense, float* grad, int c, int cg, cudaStream_t st) {
+  unpack_grouped_dw_kernel<<<grid_for((long long)c * cg * 9), kThreads, 0, st>>>(dense, grad, c, cg);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_unpack_conv_dw(const float* src, float* dst, int cout, int cin, int fr, int fs, cudaStream_t st) {
+  unpack_conv_dw_kernel<<<grid_for((long long)cout * cin * fr * fs), kThreads, 0, st>>>(src, dst, cout, cin, fr, fs);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_pack_matrix(const float* src, void* dst, void* dst_t, int rows, int cols, cudaStream_t st) {
+  dim3 grid(koa_cdiv(cols, 32), koa_cdiv(rows, 32)), block(32, 8);
+  pack_matrix_kernel<<<grid, block, 0, st>>>(src, (bf16*)dst, (bf16*)dst_t, rows, cols);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_cast_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
+  KOA_REQUIRE(n % 8 == 0, "cast length must be a multiple of 8");
+  cast_f32_bf16_kernel<<<grid_for(n / 8), kThreads, 0, st>>>(src, (bf16*)dst, n / 8);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* run_mean,
+                      float* run_var, float* scale, float* shift, float* mean, float* invstd, int c, double count,
+                      int training, cudaStream_t st) {
+  bn_finalize_kernel<<<koa_cdiv(c, 128), 128, 0, st>>>(sum, sumsq, gamma, beta, run_mean, run_var, scale, shift, mean,
+                                                       invstd, c, count, training, 1e-5f, 0.1f);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+static int reduce_threads(int c) { return (c / 8) > kThreads ? (c / 8) : kThreads; }
+static int check_reduce_c(int c) {
+  KOA_REQ_C8(c);
+  const int cg = c / 8;
+  KOA_REQUIRE(cg <= 1024 && (reduce_threads(c) % cg) == 0, "per-channel reduction needs C/8 to divide %d (C=%d)", kThreads, c);
+  return 0;
+}
+int koa_k_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, cudaStream_t st) {
+  int rc = check_reduce_c(c);
+  if (rc) return rc;
+  const int threads = reduce_threads(c);
+  const int lanes = threads / (c / 8);
+  col_stats_kernel<<<grid_for(rows, lanes, 148 * 4), threads, 2 * c * sizeof(float), st>>>((const bf16*)y, sum, sumsq, rows, c);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_bn_act(const void* y, const float* scale, const float* shift, const void* res, const void* y2,
+                 const float* scale2, const float* shift2, void* out, long long rows, int c, int relu, cudaStream_t st) {
+  KOA_REQ_C8(c);
+  bn_act_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
+                                                               (const bf16*)y2, scale2, shift2, (bf16*)out, rows, c, relu);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
+                        const void* y2, const float* mean2, const float* invstd2, float* sum_dz, float* sum_dzx,
+                        float* sum_dzx2, long long rows, int c, cudaStream_t st) {
+  int rc = check_reduce_c(c);
+  if (rc) return rc;
+  const int threads = reduce_threads(c);
+  const int lanes = threads / (c / 8);
+  bn_bwd_reduce_kernel<<<grid_for(rows, lanes, 148 * 4), threads, 3 * c * sizeof(float), st>>>(
+      (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean, invstd, (const bf16*)y2, mean2, invstd2, sum_dz,
+      sum_dzx, sum_dzx2, rows, c);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_bn_bwd_finalize(const float* sum_dz, const float* sum_dzx, const float* gamma, const float* mean,
+                          const float* invstd, float* dgamma, float* dbeta, float* k0, float* k1, float* k2, int c,
+                          double count, int training, cudaStream_t st) {
+  bn_bwd_finalize_kernel<<<koa_cdiv(c, 128), 128, 0, st>>>(sum_dz, sum_dzx, gamma, mean, invstd, dgamma, dbeta, k0, k1,
+                                                           k2, c, count, training);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const float* k0, const float* k1,
+                       const float* k2, void* dy, const void* y2, const float* k0b, const float* k1b, const float* k2b,
+                       void* dy2, long long rows, int c, cudaStream_t st) {
+  KOA_REQ_C8(c);
+  bn_bwd_apply_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)dout, (const bf16*)act, (const bf16*)y,
+                                                                     k0, k1, k2, (bf16*)dy, (const bf16*)y2, k0b, k1b,
+                                                                     k2b, (bf16*)dy2, rows, c);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, cudaStream_t st) {
+  KOA_REQ_C8(c);
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), kThreads, 0, st>>>((const bf16*)x, (bf16*)out,
+                                                                                      (uint8_t*)idx, n, h, w, c, ho, wo);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, cudaStream_t st) {
+  KOA_REQ_C8(c);
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx,
+                                                                                    (bf16*)dx, n, h, w, c, ho, wo);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_gap_fwd(const void* x, float* feat, int n, int hw, int c, cudaStream_t st) {
+  KOA_REQ_C8(c);
+  gap_fwd_kernel<<<grid_for((long long)n * (c / 8)), kThreads, 0, st>>>((const bf16*)x, feat, n, hw, c);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_gap_bwd(const float* dfeat, void* dx, int n, int hw, int c, cudaStream_t st) {
+  KOA_REQ_C8(c);
+  gap_bwd_kernel<<<grid_for((long long)n * hw * (c / 8)), kThreads, 0, st>>>(dfeat, (bf16*)dx, n, hw, c);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_zero_insert2(const void* src, void* dst, int n, int h, int w, int c, int ho, int wo, cudaStream_t st) {
+  KOA_REQ_C8(c);
+  zero_insert2_kernel<<<grid_for((long long)n * h * w * (c / 8)), kThreads, 0, st>>>((const bf16*)src, (bf16*)dst, n, h, w,
+                                                                                     c, ho, wo);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_scatter_add2(const void* src, void* dx, int n, int h, int w, int c, int ho, int wo, cudaStream_t st) {
+  KOA_REQ_C8(c);
+  scatter_add2_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), kThreads, 0, st>>>((const bf16*)src, (bf16*)dx, n, h,
+                                                                                       w, c, ho, wo);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                        float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st) {
+  KOA_REQUIRE(d % 256 == 0 && d <= 4096, "LayerNorm width %d must be a multiple of 256 and <= 4096", d);
+  const int blocks = koa_cdiv((long long)rows * 32, kThreads);
+  if (d <= 2048)
+    layernorm_fwd_kernel<8><<<blocks, kThreads, 0, st>>>(x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d,
+                                                         x_row_stride, 1e-5f);
+  else
+    layernorm_fwd_kernel<16><<<blocks, kThreads, 0, st>>>(x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d,
+                                                          x_row_stride, 1e-5f);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                        const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int rows, int d,
+                        long long x_row_stride, long long dx_row_stride, cudaStream_t st) {
+  KOA_REQUIRE(d % 256 == 0 && d <= 2048, "LayerNorm backward width %d must be a multiple of 256 and <= 2048", d);
+  int blocks = koa_cdiv(rows, kThreads / 32);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  layernorm_bwd_kernel<8><<<blocks, kThreads, 2 * d * sizeof(float), st>>>(dy, x, gamma, mean, rstd, dres, dx,
+                                                                           (bf16*)dx_bf16, dgamma, dbeta, rows, d,
+                                                                           x_row_stride, dx_row_stride);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_token_assemble(const float* emb, const float* cls, const float* pos, float* x, int batch, int n_tok, int n_cls,
+                         int d, cudaStream_t st) {
+  KOA_REQUIRE(d % 4 == 0, "token width must be a multiple of 4");
+  token_assemble_kernel<<<grid_for((long long)batch * n_tok * (d / 4)), kThreads, 0, st>>>(emb, cls, pos, x, batch, n_tok,
+                                                                                          n_cls, d);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_token_assemble_bwd(const float* dx, float* dpos, float* dcls, void* demb, int batch, int n_tok, int n_cls, int d,
+                             cudaStream_t st) {
+  token_assemble_bwd_kernel<<<grid_for((long long)n_tok * d), kThreads, 0, st>>>(dx, dpos, dcls, (bf16*)demb, batch, n_tok,
+                                                                                n_cls, d);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_col_sum(const void* x, int is_bf16, float* out, long long rows, int c, long long ld, cudaStream_t st) {
+  int ysplit = (int)((rows + 63) / 64);
+  if (ysplit > 64) ysplit = 64;
+  if (ysplit < 1) ysplit = 1;
+  dim3 grid(koa_cdiv(c, 128), ysplit);
+  if (is_bf16) col_sum_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)x, out, rows, c, ld);
+  else col_sum_kernel<float><<<grid, 128, 0, st>>>((const float*)x, out, rows, c, ld);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_linear_small_fwd(const float* x, const float* w, const float* b, float* y, float* pre, int m, int n, int k,
+                           long long x_row_stride, int act, cudaStream_t st) {
+  const long long warps = (long long)m * n;
+  linear_small_fwd_kernel<<<koa_cdiv(warps * 32, kThreads), kThreads, 0, st>>>(x, w, b, y, pre, m, n, k, x_row_stride, act);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_linear_small_bwd(const float* dy, const float* pre, const float* x, const float* w, float* dpre_scratch,
+                           float* dx, float* dw, float* db, int m, int n, int k, long long x_row_stride,
+                           long long dx_row_stride, int act, int accumulate_dx, cudaStream_t st) {
+  const long long total = (long long)m * n;
+  linear_small_dpre_kernel<<<grid_for(total), kThreads, 0, st>>>(dy, pre, dpre_scratch, total, act);
+  KOA_LAUNCH_CHECK();
+  if (dx != nullptr) {
+    linear_small_dx_kernel<<<koa_cdiv((long long)m * k, kThreads), kThreads, 0, st>>>(dpre_scratch, w, dx, m, n, k,
+                                                                                     dx_row_stride, accumulate_dx);
+    KOA_LAUNCH_CHECK();
+  }
+  if (dw != nullptr) {
+    linear_small_dw_kernel<<<koa_cdiv((long long)n * k, kThreads), kThreads, 0, st>>>(dpre_scratch, x, dw, db, m, n, k,
+                                                                                     x_row_stride);
+    KOA_LAUNCH_CHECK();
+  }
+  return 0;
+}
+int koa_k_focal_loss(const float* logits, const long long* target, float* loss, float* dlogits, int batch, int classes,
+                     float gamma, cudaStream_t st) {
+  focal_loss_kernel<<<1, 128, 0, st>>>(logits, target, loss, dlogits, batch, classes, gamma);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}

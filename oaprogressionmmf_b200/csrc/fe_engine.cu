@@ -1,0 +1,502 @@
+// fe_engine.cu — whole-network forward / backward of the per-slice CNN feature extractors
+// (ResNet-18/34/50, ResNeXt-50-32x4d without `fc`; koafusion/models/_torchvision.py:227-239 and the
+// torchvision twins picked by koafusion/models/_core_fes.py:6-15).
+//
+// One C call runs every layer of the extractor on one stream:
+//   stem pack -> 7x7 stem (CUDA cores) -> BN/ReLU -> max-pool -> [bottleneck | basic] blocks -> GAP
+// Convolutions are tcgen05 implicit GEMMs (gemm_api.cu) that also emit the BatchNorm batch statistics;
+// BN-apply/ReLU/residual, pooling and the BN backward are the HBM-bound kernels of elementwise.cu.
+// Activations are NHWC bf16; everything needed by backward stays in the caller-provided workspace whose
+// layout is a pure function of the descriptor (koa_fe_workspace_bytes / koa_fe_debug_offset).
+#include <algorithm>
+#include <vector>
+
+#include "../../include/koa_b200.h"
+#include "koa_common.cuh"
+#include "koa_internal.h"
+#include "koa_kernels.h"
+
+#define KOA_TRY(x)          \
+  do {                      \
+    int rc_ = (x);          \
+    if (rc_) return rc_;    \
+  } while (0)
+
+namespace {
+
+struct Unit {
+  int cin, cout, k, stride, pad, groups;
+  int hin, win, hout, wout;
+  long long rows_in, rows_out;
+  size_t w_fwd, w_dgrad, dw_scratch, y;
+  size_t fstat;  // forward batch statistics: sum, sumsq            (zeroed by forward)
+  size_t bstat;  // backward reductions: sum_dz, sum_dz_xhat         (zeroed by backward)
+  size_t coef;   // scale, shift, mean, invstd, k0, k1, k2
+  int idx;  // position in the params (x5) / grads (x3) tables
+};
+struct Block {
+  int kind;  // 0 bottleneck, 1 basic
+  int u1, u2, u3, ud;
+  size_t a1, a2, out;
+  size_t in;  // activation feeding the block
+  int stride;
+};
+struct Plan {
+  int n_img, h, w, out_c, out_h, out_w;
+  std::vector<Unit> units;
+  std::vector<Block> blocks;
+  size_t img, wfold, dwfold, a0, p0, idx0;
+  size_t fstat_begin, fstat_end;   // contiguous fp32 regions zeroed at the start of forward / backward
+  size_t bstat_begin, bstat_end;
+  size_t g[2], t[5];               // backward scratch (block gradients ping-pong + temporaries)
+  size_t total;
+};
+
+enum { S_SUM = 0, S_SUMSQ, S_SDZ, S_SDZX, S_SCALE, S_SHIFT, S_MEAN, S_INVSTD, S_K0, S_K1, S_K2 };
+constexpr int COEF_SLOTS = 7;
+
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  }
+};
+
+int build_plan(const koa_fe_desc_t* d, Plan& p) {
+  KOA_REQUIRE(d != nullptr, "null descriptor");
+  KOA_REQUIRE(d->arch >= 0 && d->arch <= 3, "unknown feature-extractor arch %d", d->arch);
+  KOA_REQUIRE(d->n_img > 0 && d->h >= 32 && d->w >= 32, "bad input geometry n=%d h=%d w=%d", d->n_img, d->h, d->w);
+  const bool bottleneck = d->arch >= 2;
+  const int layers_r18[4] = {2, 2, 2, 2}, layers_r50[4] = {3, 4, 6, 3};
+  const int* layers = d->arch == 0 ? layers_r18 : layers_r50;
+  const int groups = d->arch == 3 ? 32 : 1;
+  const int width_per_group = d->arch == 3 ? 4 : 64;
+  const int expansion = bottleneck ? 4 : 1;
+  p.n_img = d->n_img; p.h = d->h; p.w = d->w;
+  p.units.clear(); p.blocks.clear();
+  Bump ws;
+  const long long n = d->n_img;
+  auto conv_out = [](int x, int k, int s, int pad) { return (x + 2 * pad - k) / s + 1; };
+
+  auto add_unit = [&](int cin, int cout, int k, int stride, int pad, int grp, int hin, int win) {
+    Unit u{};
+    u.cin = cin; u.cout = cout; u.k = k; u.stride = stride; u.pad = pad; u.groups = grp;
+    u.hin = hin; u.win = win; u.hout = conv_out(hin, k, stride, pad); u.wout = conv_out(win, k, stride, pad);
+    u.rows_in = n * hin * win; u.rows_out = n * u.hout * u.wout;
+    u.idx = (int)p.units.size();
+    p.units.push_back(u);
+    return u.idx;
+  };
+
+  // ---- topology -------------------------------------------------------------------------------
+  const int stem = add_unit(3, 64, 7, 2, 3, 1, d->h, d->w);
+  int ch = p.units[stem].hout, cw = p.units[stem].wout;
+  const int ph = conv_out(ch, 3, 2, 1), pw = conv_out(cw, 3, 2, 1);
+  int inplanes = 64, hh = ph, ww = pw;
+  for (int li = 0; li < 4; ++li) {
+    const int planes = 64 << li;
+    for (int bi = 0; bi < layers[li]; ++bi) {
+      const int stride = (li > 0 && bi == 0) ? 2 : 1;
+      Block b{};
+      b.kind = bottleneck ? 0 : 1;
+      b.stride = stride;
+      b.u3 = -1; b.ud = -1;
+      const int outc = planes * expansion;
+      if (bottleneck) {
+        const int width = (planes * width_per_group / 64) * groups;
+        b.u1 = add_unit(inplanes, width, 1, 1, 0, 1, hh, ww);
+        b.u2 = add_unit(width, width, 3, stride, 1, groups, hh, ww);
+        b.u3 = add_unit(width, outc, 1, 1, 0, 1, p.units[b.u2].hout, p.units[b.u2].wout);
+      } else {
+        b.u1 = add_unit(inplanes, planes, 3, stride, 1, 1, hh, ww);
+        b.u2 = add_unit(planes, planes, 3, 1, 1, 1, p.units[b.u1].hout, p.units[b.u1].wout);
+      }
+      if (bi == 0 && (stride != 1 || inplanes != outc)) b.ud = add_unit(inplanes, outc, 1, stride, 0, 1, hh, ww);
+      p.blocks.push_back(b);
+      inplanes = outc;
+      hh = p.units[b.u2].hout; ww = p.units[b.u2].wout;
+    }
+  }
+  p.out_c = inplanes; p.out_h = hh; p.out_w = ww;
+  for (const Unit& u : p.units) {
+    if (u.idx == stem) continue;
+    KOA_REQUIRE(u.cin % 64 == 0 && u.cout % 64 == 0, "unit %d: channels must be multiples of 64", u.idx);
+    if (u.groups > 1) KOA_REQUIRE(u.cin == u.cout && 64 % (u.cin / u.groups) == 0, "unit %d: unsupported grouping", u.idx);
+    if (u.stride == 2 && u.k == 3) KOA_REQUIRE(u.hin % 2 == 0 && u.win % 2 == 0, "stride-2 3x3 conv needs even input size (got %dx%d)", u.hin, u.win);
+  }
+
+  // ---- workspace --------------------------------------------------------------------------------
+  p.img = ws.take((size_t)n * d->h * d->w * 4);
+  p.wfold = ws.take(49 * 64 * 4);
+  for (Unit& u : p.units) {
+    if (u.idx == stem) continue;
+    const size_t wcount = u.groups > 1 ? (size_t)u.cout * 9 * 64 : (size_t)u.cout * u.k * u.k * u.cin;
+    u.w_fwd = ws.take(wcount * 2);
+    u.w_dgrad = ws.take(wcount * 2);
+    u.dw_scratch = (u.k > 1) ? ws.take(wcount * 4) : 0;
+  }
+  for (Unit& u : p.units) u.y = ws.take((size_t)u.rows_out * u.cout * 2);
+  const Unit& us = p.units[stem];
+  p.a0 = ws.take((size_t)us.rows_out * 64 * 2);
+  p.p0 = ws.take((size_t)n * ph * pw * 64 * 2);
+  p.idx0 = ws.take((size_t)n * ph * pw * 64);
+  size_t prev = p.p0;
+  size_t max_act = (size_t)us.rows_out * 64;
+  for (Block& b : p.blocks) {
+    const Unit& u1 = p.units[b.u1];
+    const Unit& u2 = p.units[b.u2];
+    b.in = prev;
+    b.a1 = ws.take((size_t)u1.rows_out * u1.cout * 2);
+    if (b.kind == 0) {
+      b.a2 = ws.take((size_t)u2.rows_out * u2.cout * 2);
+      const Unit& u3 = p.units[b.u3];
+      b.out = ws.take((size_t)u3.rows_out * u3.cout * 2);
+      max_act = std::max(max_act, (size_t)u3.rows_out * u3.cout);
+    } else {
+      b.a2 = 0;
+      b.out = ws.take((size_t)u2.rows_out * u2.cout * 2);
+    }
+    max_act = std::max(max_act, (size_t)u1.rows_in * u1.cin);
+    max_act = std::max(max_act, (size_t)u1.rows_in * u1.cout);  // zero-inserted / pre-stride tensors
+    max_act = std::max(max_act, (size_t)u2.rows_in * u2.cout);
+    prev = b.out;
+  }
+  p.fstat_begin = ws.off;
+  for (Unit& u : p.units) u.fstat = ws.take((size_t)2 * u.cout * 4);
+  p.fstat_end = ws.off;
+  p.bstat_begin = ws.off;
+  p.dwfold = ws.take(49 * 64 * 4);
+  for (Unit& u : p.units) u.bstat = ws.take((size_t)2 * u.cout * 4);
+  p.bstat_end = ws.off;
+  for (Unit& u : p.units) u.coef = ws.take((size_t)COEF_SLOTS * u.cout * 4);
+  for (int i = 0; i < 2; ++i) p.g[i] = ws.take(max_act * 2);
+  for (int i = 0; i < 5; ++i) p.t[i] = ws.take(max_act * 2);
+  p.total = ws.off;
+  return 0;
+}
+
+inline uint8_t* at(void* ws, size_t off) { return reinterpret_cast<uint8_t*>(ws) + off; }
+inline float* bn_slot(void* ws, const Unit& u, int slot) {
+  if (slot <= S_SUMSQ) return reinterpret_cast<float*>(at(ws, u.fstat)) + (size_t)slot * u.cout;
+  if (slot <= S_SDZX) return reinterpret_cast<float*>(at(ws, u.bstat)) + (size_t)(slot - S_SDZ) * u.cout;
+  return reinterpret_cast<float*>(at(ws, u.coef)) + (size_t)(slot - S_SCALE) * u.cout;
+}
+
+struct ParamView {
+  const void* const* params;
+  const float* w(const Unit& u) const { return (const float*)params[u.idx * 5 + 0]; }
+  const float* gamma(const Unit& u) const { return (const float*)params[u.idx * 5 + 1]; }
+  const float* beta(const Unit& u) const { return (const float*)params[u.idx * 5 + 2]; }
+  float* run_mean(const Unit& u) const { return (float*)params[u.idx * 5 + 3]; }
+  float* run_var(const Unit& u) const { return (float*)params[u.idx * 5 + 4]; }
+};
+
+int pack_unit_weights(const Unit& u, const ParamView& pv, void* ws, bool need_dgrad, cudaStream_t st) {
+  if (u.groups > 1) {
+    KOA_TRY(koa_k_pack_grouped_w(pv.w(u), at(ws, u.w_fwd), u.cout, u.cin / u.groups, 0, st));
+    if (need_dgrad) KOA_TRY(koa_k_pack_grouped_w(pv.w(u), at(ws, u.w_dgrad), u.cout, u.cin / u.groups, 1, st));
+    return 0;
+  }
+  KOA_TRY(koa_k_pack_conv_w(pv.w(u), at(ws, u.w_fwd), u.cout, u.cin, u.k, u.k, 0, st));
+  if (need_dgrad) KOA_TRY(koa_k_pack_conv_w(pv.w(u), at(ws, u.w_dgrad), u.cout, u.cin, u.k, u.k, 1, st));
+  return 0;
+}
+
+// y = conv(x) (+ batch statistics when training)
+int conv_forward(const Plan& p, const Unit& u, const void* x, void* ws, int training, cudaStream_t st) {
+  koa_epilogue_t ep{};
+  ep.out = at(ws, u.y);
+  ep.ldo = u.cout;
+  if (training) {
+    ep.col_sum = bn_slot(ws, u, S_SUM);
+    ep.col_sumsq = bn_slot(ws, u, S_SUMSQ);
+  }
+  if (u.groups > 1)
+    return koa_conv_grouped_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.stride, &ep, st);
+  if (u.k == 1 && u.stride == 1) return koa_gemm_launch(x, at(ws, u.w_fwd), (int)u.rows_out, u.cout, u.cin, &ep, st);
+  return koa_conv_fprop_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, &ep, st);
+}
+
+int bn_finalize(const Unit& u, const ParamView& pv, void* ws, int training, cudaStream_t st) {
+  return koa_k_bn_finalize(bn_slot(ws, u, S_SUM), bn_slot(ws, u, S_SUMSQ), pv.gamma(u), pv.beta(u), pv.run_mean(u),
+                           pv.run_var(u), bn_slot(ws, u, S_SCALE), bn_slot(ws, u, S_SHIFT), bn_slot(ws, u, S_MEAN),
+                           bn_slot(ws, u, S_INVSTD), u.cout, (double)u.rows_out, training, st);
+}
+
+// a = relu(bn(y))
+int bn_relu(const Unit& u, void* ws, size_t a_off, cudaStream_t st) {
+  return koa_k_bn_act(at(ws, u.y), bn_slot(ws, u, S_SCALE), bn_slot(ws, u, S_SHIFT), nullptr, nullptr, nullptr, nullptr,
+                      at(ws, a_off), u.rows_out, u.cout, 1, st);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" size_t koa_fe_workspace_bytes(const koa_fe_desc_t* d) {
+  Plan p;
+  if (build_plan(d, p)) return 0;
+  return p.total;
+}
+
+extern "C" int koa_fe_out_shape(const koa_fe_desc_t* d, int* channels, int* h, int* w) {
+  Plan p;
+  KOA_TRY(build_plan(d, p));
+  *channels = p.out_c; *h = p.out_h; *w = p.out_w;
+  return 0;
+}
+
+extern "C" int koa_fe_num_units(const koa_fe_desc_t* d) {
+  Plan p;
+  if (build_plan(d, p)) return -1;
+  return (int)p.units.size();
+}
+
+// what: 0 raw conv output y of unit `index`; 1 block output of block `index`; 2 a1 of block; 3 a2 of block;
+// 4 stem activation a0; 5 pooled p0; 6 BN coefficients (scale, shift, mean, invstd, k0, k1, k2) of unit `index`.
+extern "C" int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, size_t* offset, size_t* bytes) {
+  Plan p;
+  KOA_TRY(build_plan(d, p));
+  if (what == 0 || what == 6) {
+    KOA_REQUIRE(index >= 0 && index < (int)p.units.size(), "unit index out of range");
+    const Unit& u = p.units[index];
+    if (what == 0) { *offset = u.y; *bytes = (size_t)u.rows_out * u.cout * 2; }
+    else { *offset = u.coef; *bytes = (size_t)COEF_SLOTS * u.cout * 4; }
+    return 0;
+  }
+  if (what >= 1 && what <= 3) {
+    KOA_REQUIRE(index >= 0 && index < (int)p.blocks.size(), "block index out of range");
+    const Block& b = p.blocks[index];
+    const Unit& last = p.units[b.kind == 0 ? b.u3 : b.u2];
+    const Unit& u1 = p.units[b.u1];
+    const Unit& u2 = p.units[b.u2];
+    if (what == 1) { *offset = b.out; *bytes = (size_t)last.rows_out * last.cout * 2; }
+    if (what == 2) { *offset = b.a1; *bytes = (size_t)u1.rows_out * u1.cout * 2; }
+    if (what == 3) { *offset = b.a2; *bytes = (size_t)u2.rows_out * u2.cout * 2; }
+    return 0;
+  }
+  if (what == 4) { *offset = p.a0; *bytes = (size_t)p.units[0].rows_out * 64 * 2; return 0; }
+  if (what == 5) { *offset = p.p0; *bytes = p.idx0 - p.p0; return 0; }
+  koa_set_error("unknown debug selector %d", what);
+  return KOA_ERR_ARG;
+}
+
+extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params, const float* input, void* ws,
+                              float* feat, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan p;
+  KOA_TRY(build_plan(d, p));
+  KOA_REQUIRE(params != nullptr && input != nullptr && ws != nullptr && feat != nullptr, "null pointer argument");
+  const ParamView pv{params};
+  const int training = d->training;
+  const bool need_dgrad = d->need_backward != 0;
+  KOA_CHECK_CUDA(cudaMemsetAsync(at(ws, p.fstat_begin), 0, p.fstat_end - p.fstat_begin, st));
+
+  // ---- stem ---------------------------------------------------------------------------------------
+  const Unit& us = p.units[0];
+  const float* img = input;
+  if (d->slices > 0) {  // (B,1,R,C,S) slice-innermost volume
+    KOA_REQUIRE(d->n_img % d->slices == 0, "n_img must be batch * slices");
+    KOA_TRY(koa_k_stem_pack(input, (float*)at(ws, p.img), d->n_img / d->slices, d->h * d->w, d->slices, st));
+    img = (const float*)at(ws, p.img);
+  }
+  KOA_TRY(koa_k_stem_fold_w(pv.w(us), (float*)at(ws, p.wfold), st));
+  KOA_TRY(koa_k_stem_conv_fwd(img, (const float*)at(ws, p.wfold), at(ws, us.y), training ? bn_slot(ws, us, S_SUM) : nullptr,
+                              training ? bn_slot(ws, us, S_SUMSQ) : nullptr, p.n_img, d->h, d->w, st));
+  KOA_TRY(bn_finalize(us, pv, ws, training, st));
+  KOA_TRY(bn_relu(us, ws, p.a0, st));
+  KOA_TRY(koa_k_maxpool_fwd(at(ws, p.a0), at(ws, p.p0), at(ws, p.idx0), p.n_img, us.hout, us.wout, 64, st));
+
+  // ---- residual blocks --------------------------------------------------------------------------
+  for (const Block& b : p.blocks) {
+    const Unit& u1 = p.units[b.u1];
+    const Unit& u2 = p.units[b.u2];
+    const void* x = at(ws, b.in);
+    KOA_TRY(pack_unit_weights(u1, pv, ws, need_dgrad, st));
+    KOA_TRY(conv_forward(p, u1, x, ws, training, st));
+    KOA_TRY(bn_finalize(u1, pv, ws, training, st));
+    KOA_TRY(bn_relu(u1, ws, b.a1, st));
+    KOA_TRY(pack_unit_weights(u2, pv, ws, need_dgrad, st));
+    KOA_TRY(conv_forward(p, u2, at(ws, b.a1), ws, training, st));
+    KOA_TRY(bn_finalize(u2, pv, ws, training, st));
+    const Unit* last = &u2;
+    if (b.kind == 0) {
+      const Unit& u3 = p.units[b.u3];
+      KOA_TRY(bn_relu(u2, ws, b.a2, st));
+      KOA_TRY(pack_unit_weights(u3, pv, ws, need_dgrad, st));
+      KOA_TRY(conv_forward(p, u3, at(ws, b.a2), ws, training, st));
+      KOA_TRY(bn_finalize(u3, pv, ws, training, st));
+      last = &u3;
+    }
+    if (b.ud >= 0) {
+      const Unit& ud = p.units[b.ud];
+      KOA_TRY(pack_unit_weights(ud, pv, ws, need_dgrad, st));
+      KOA_TRY(conv_forward(p, ud, x, ws, training, st));
+      KOA_TRY(bn_finalize(ud, pv, ws, training, st));
+      KOA_TRY(koa_k_bn_act(at(ws, last->y), bn_slot(ws, *last, S_SCALE), bn_slot(ws, *last, S_SHIFT), nullptr,
+                           at(ws, ud.y), bn_slot(ws, ud, S_SCALE), bn_slot(ws, ud, S_SHIFT), at(ws, b.out),
+                           last->rows_out, last->cout, 1, st));
+    } else {
+      KOA_TRY(koa_k_bn_act(at(ws, last->y), bn_slot(ws, *last, S_SCALE), bn_slot(ws, *last, S_SHIFT), x, nullptr, nullptr,
+                           nullptr, at(ws, b.out), last->rows_out, last->cout, 1, st));
+    }
+  }
+  // ---- head: global average pool (with_gap) or the raw NHWC map as tokens -------------------------
+  const Block& lb = p.blocks.back();
+  const int hw = p.out_h * p.out_w;
+  if (d->with_gap) KOA_TRY(koa_k_gap_fwd(at(ws, lb.out), feat, p.n_img, hw, p.out_c, st));
+  else KOA_TRY(koa_k_gap_fwd(at(ws, lb.out), feat, p.n_img * hw, 1, p.out_c, st));
+  return 0;
+}
+
+namespace {
+
+// BatchNorm backward of one unit (optionally two units sharing the incoming gradient):
+// reduce -> finalize (dgamma/dbeta + coefficients) -> apply.
+int bn_backward(const Unit& u, const Unit* u_b, const ParamView& pv, void* const* grads, void* ws, const void* dout,
+                const void* act_mask, void* dy, void* dy_b, int training, cudaStream_t st) {
+  KOA_TRY(koa_k_bn_bwd_reduce(dout, act_mask, at(ws, u.y), bn_slot(ws, u, S_MEAN), bn_slot(ws, u, S_INVSTD),
+                              u_b ? at(ws, u_b->y) : nullptr, u_b ? bn_slot(ws, *u_b, S_MEAN) : nullptr,
+                              u_b ? bn_slot(ws, *u_b, S_INVSTD) : nullptr, bn_slot(ws, u, S_SDZ), bn_slot(ws, u, S_SDZX),
+                              u_b ? bn_slot(ws, *u_b, S_SDZX) : nullptr, u.rows_out, u.cout, st));
+  KOA_TRY(koa_k_bn_bwd_finalize(bn_slot(ws, u, S_SDZ), bn_slot(ws, u, S_SDZX), pv.gamma(u), bn_slot(ws, u, S_MEAN),
+                                bn_slot(ws, u, S_INVSTD), (float*)grads[u.idx * 3 + 1], (float*)grads[u.idx * 3 + 2],
+                                bn_slot(ws, u, S_K0), bn_slot(ws, u, S_K1), bn_slot(ws, u, S_K2), u.cout,
+                                (double)u.rows_out, training, st));
+  if (u_b) {
+    KOA_TRY(koa_k_bn_bwd_finalize(bn_slot(ws, u, S_SDZ), bn_slot(ws, *u_b, S_SDZX), pv.gamma(*u_b),
+                                  bn_slot(ws, *u_b, S_MEAN), bn_slot(ws, *u_b, S_INVSTD), (float*)grads[u_b->idx * 3 + 1],
+                                  (float*)grads[u_b->idx * 3 + 2], bn_slot(ws, *u_b, S_K0), bn_slot(ws, *u_b, S_K1),
+                                  bn_slot(ws, *u_b, S_K2), u_b->cout, (double)u_b->rows_out, training, st));
+  }
+  return koa_k_bn_bwd_apply(dout, act_mask, at(ws, u.y), bn_slot(ws, u, S_K0), bn_slot(ws, u, S_K1), bn_slot(ws, u, S_K2),
+                            dy, u_b ? at(ws, u_b->y) : nullptr, u_b ? bn_slot(ws, *u_b, S_K0) : nullptr,
+                            u_b ? bn_slot(ws, *u_b, S_K1) : nullptr, u_b ? bn_slot(ws, *u_b, S_K2) : nullptr, dy_b,
+                            u.rows_out, u.cout, st);
+}
+
+// dW of one unit into the fp32 gradient tensor (PyTorch layout [Cout][Cin/g][k][k]).
+int conv_wgrad(const Plan& p, const Unit& u, const void* x, const void* dy, void* const* grads, void* ws, cudaStream_t st) {
+  float* gw = (float*)grads[u.idx * 3 + 0];
+  if (gw == nullptr) return 0;
+  if (u.k == 1 && u.stride == 1) return koa_gemm_wgrad_launch(dy, x, gw, (int)u.rows_out, u.cout, u.cin, st);
+  if (u.k == 1) return koa_conv_wgrad_launch(dy, x, gw, p.n_img, u.hin, u.win, u.cin, u.cout, 1, 1, u.stride, 0, st);
+  float* scratch = (float*)at(ws, u.dw_scratch);
+  if (u.groups > 1) {
+    KOA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)u.cout * 9 * 64 * 4, st));
+    KOA_TRY(koa_conv_grouped_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.stride, st));
+    return koa_k_unpack_grouped_dw(scratch, gw, u.cout, u.cin / u.groups, st);
+  }
+  KOA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)u.cout * u.k * u.k * u.cin * 4, st));
+  KOA_TRY(koa_conv_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, st));
+  return koa_k_unpack_conv_dw(scratch, gw, u.cout, u.cin, u.k, u.k, st);
+}
+
+// dx = data gradient of unit u given dy. `ep` carries the output pointer (+ optional fused addends).
+// tmp: scratch for the zero-inserted dy of stride-2 3x3 convolutions.
+int conv_dgrad(const Plan& p, const Unit& u, const void* dy, void* ws, koa_epilogue_t* ep, void* tmp, cudaStream_t st) {
+  ep->ldo = u.cin;
+  if (u.k == 1) {
+    // 1x1: dx[rows_out, cin] = dy[rows_out, cout] . W[cout, cin]; B operand = W^T stored [cin][cout]
+    return koa_gemm_launch(dy, at(ws, u.w_dgrad), (int)u.rows_out, u.cin, u.cout, ep, st);
+  }
+  const void* src = dy;
+  if (u.stride == 2) {
+    KOA_TRY(koa_k_zero_insert2(dy, tmp, p.n_img, u.hin, u.win, u.cout, u.hout, u.wout, st));
+    src = tmp;
+  }
+  if (u.groups > 1) return koa_conv_grouped_launch(src, at(ws, u.w_dgrad), p.n_img, u.hin, u.win, u.cout, 1, ep, st);
+  return koa_conv_fprop_launch(src, at(ws, u.w_dgrad), p.n_img, u.hin, u.win, u.cout, u.cin, u.k, u.k, 1, u.pad, ep, st);
+}
+
+}  // namespace
+
+extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params, void* const* grads, void* ws,
+                               const float* dfeat, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan p;
+  KOA_TRY(build_plan(d, p));
+  KOA_REQUIRE(params != nullptr && grads != nullptr && ws != nullptr && dfeat != nullptr, "null pointer argument");
+  KOA_REQUIRE(d->need_backward, "forward was not run with need_backward");
+  const ParamView pv{params};
+  const int training = d->training;
+  const int hw = p.out_h * p.out_w;
+  KOA_CHECK_CUDA(cudaMemsetAsync(at(ws, p.bstat_begin), 0, p.bstat_end - p.bstat_begin, st));
+  int cur = 0;  // p.g[cur] holds the gradient w.r.t. the current block's output
+  if (d->with_gap) KOA_TRY(koa_k_gap_bwd(dfeat, at(ws, p.g[cur]), p.n_img, hw, p.out_c, st));
+  else KOA_TRY(koa_k_cast_bf16(dfeat, at(ws, p.g[cur]), (long long)p.n_img * hw * p.out_c, st));
+
+  for (int bi = (int)p.blocks.size() - 1; bi >= 0; --bi) {
+    const Block& b = p.blocks[bi];
+    const Unit& u1 = p.units[b.u1];
+    const Unit& u2 = p.units[b.u2];
+    const Unit* u3 = b.kind == 0 ? &p.units[b.u3] : nullptr;
+    const Unit* ud = b.ud >= 0 ? &p.units[b.ud] : nullptr;
+    const Unit& last = u3 ? *u3 : u2;
+    void* g_out = at(ws, p.g[cur]);
+    void* g_in = at(ws, p.g[cur ^ 1]);
+    void* x = at(ws, b.in);
+    void* dy_last = at(ws, p.t[0]);
+    void* dy_down = at(ws, p.t[1]);
+    // out = relu(bn_last(y_last) + identity): dz = g_out * (out > 0)
+    KOA_TRY(bn_backward(last, ud, pv, grads, ws, g_out, at(ws, b.out), dy_last, ud ? dy_down : nullptr, training, st));
+    void* d_a1 = at(ws, p.t[3]);
+    if (u3) {
+      KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2), dy_last, grads, ws, st));
+      void* d_a2 = at(ws, p.t[2]);
+      koa_epilogue_t ep{};
+      ep.out = d_a2;
+      KOA_TRY(conv_dgrad(p, *u3, dy_last, ws, &ep, nullptr, st));
+      KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, at(ws, b.a2), d_a2, nullptr, training, st));  // in place -> dy2
+      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1), d_a2, grads, ws, st));
+      koa_epilogue_t ep2{};
+      ep2.out = d_a1;
+      KOA_TRY(conv_dgrad(p, u2, d_a2, ws, &ep2, at(ws, p.t[4]), st));
+    } else {
+      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1), dy_last, grads, ws, st));
+      koa_epilogue_t ep2{};
+      ep2.out = d_a1;
+      KOA_TRY(conv_dgrad(p, u2, dy_last, ws, &ep2, at(ws, p.t[4]), st));
+    }
+    KOA_TRY(bn_backward(u1, nullptr, pv, grads, ws, d_a1, at(ws, b.a1), d_a1, nullptr, training, st));  // in place -> dy1
+    KOA_TRY(conv_wgrad(p, u1, x, d_a1, grads, ws, st));
+    // gradient w.r.t. the block input = dgrad(conv1) + identity path
+    {
+      koa_epilogue_t ep{};
+      ep.out = g_in;
+      if (!ud) {  // identity: + g_out masked by out > 0
+        ep.add_bf16 = g_out;
+        ep.mask_bf16 = at(ws, b.out);
+      }
+      KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
+    }
+    if (ud) {
+      KOA_TRY(conv_wgrad(p, *ud, x, dy_down, grads, ws, st));
+      if (ud->stride == 1) {
+        koa_epilogue_t ep{};
+        ep.out = g_in;
+        ep.add_bf16 = g_in;  // accumulate in place
+        KOA_TRY(conv_dgrad(p, *ud, dy_down, ws, &ep, nullptr, st));
+      } else {
+        koa_epilogue_t ep{};
+        ep.out = at(ws, p.t[2]);
+        KOA_TRY(conv_dgrad(p, *ud, dy_down, ws, &ep, nullptr, st));
+        KOA_TRY(koa_k_scatter_add2(at(ws, p.t[2]), g_in, p.n_img, ud->hin, ud->win, ud->cin, ud->hout, ud->wout, st));
+      }
+    }
+    cur ^= 1;
+  }
+  // ---- stem -----------------------------------------------------------------------------------------
+  const Unit& us = p.units[0];
+  void* d_a0 = at(ws, p.t[0]);
+  KOA_TRY(koa_k_maxpool_bwd(at(ws, p.g[cur]), at(ws, p.idx0), d_a0, p.n_img, us.hout, us.wout, 64, st));
+  KOA_TRY(bn_backward(us, nullptr, pv, grads, ws, d_a0, at(ws, p.a0), d_a0, nullptr, training, st));
+  if (grads[0] != nullptr) {
+    const float* img = d->slices > 0 ? (const float*)at(ws, p.img) : d->input_for_backward;
+    KOA_REQUIRE(img != nullptr, "stem weight gradient needs the input image (input_for_backward)");
+    KOA_TRY(koa_k_stem_wgrad(img, d_a0, (float*)at(ws, p.dwfold), p.n_img, d->h, d->w, st));
+    KOA_TRY(koa_k_stem_unfold_dw((const float*)at(ws, p.dwfold), (float*)grads[0], st));
+  }
+  return 0;
+}

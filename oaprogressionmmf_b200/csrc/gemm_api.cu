@@ -95,7 +95,7 @@ int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa
   CUtensorMap ta;
   rc = koa_tmap_2d_bf16(&ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)k * 2, 64, 128);
   if (rc) return rc;
-  ConvGeom g = {1, 1, 1, 0, 1, 1};
+  ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
   return dispatch_kmajor<false>(ta, b, m, n, k, g, to_epi(ep), st);
 }
 
@@ -113,7 +113,7 @@ int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_
   CUtensorMap ta;
   rc = koa_tmap_im2col_bf16(&ta, x, n_img, h, w_in, cin, filt_r, filt_s, stride, pad, 128);
   if (rc) return rc;
-  ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64};
+  ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64, 0};
   return dispatch_kmajor<true>(ta, w, (int)m, cout, filt_r * filt_s * cin, g, to_epi(ep), st);
 }
 
@@ -128,7 +128,7 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   });
   KOA_CHECK_CUDA(attr_err);
-  const int tiles = koa_cdiv(cout, BM) * koa_cdiv(cin, BN) * taps;
+  const int tiles = (g.grouped ? 1 : koa_cdiv(cout, BM)) * koa_cdiv(cin, BN) * taps;
   const int num_kb = koa_cdiv(pixels, BK);
   // Split the pixel (reduction) range so that the grid covers the machine a few times over.
   int splits = koa_cdiv(4 * koa_num_sms(), tiles);
@@ -152,7 +152,7 @@ int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, 
   if (rc) return rc;
   rc = koa_tmap_2d_bf16(&tb, x, (uint64_t)cin, (uint64_t)pixels, (uint64_t)cin * 2, 64, 64);
   if (rc) return rc;
-  ConvGeom g = {1, 1, 1, 0, 1, 1};
+  ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
   if (cin % 128 == 0) return launch_wgrad<128, 4, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
   return launch_wgrad<64, 4, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
 }
@@ -169,10 +169,45 @@ int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, i
   if (rc) return rc;
   rc = koa_tmap_im2col_bf16(&tb, x, n_img, h, w_in, cin, filt_r, filt_s, stride, pad, 64);
   if (rc) return rc;
-  ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64};
+  ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64, 0};
   const int taps = filt_r * filt_s;
   if (cin % 128 == 0) return launch_wgrad<128, 4, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
   return launch_wgrad<64, 4, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
+}
+
+// Grouped 3x3 convolution (ResNeXt, koafusion/models/_torchvision.py:110,327-328) as a block-diagonal dense
+// convolution per 64-channel chunk: w is [C][3][3][64] (koa_k_pack_grouped_w), K = 576 per output chunk.
+int koa_conv_grouped_launch(const void* x, const void* w, int n_img, int h, int w_in, int c, int stride,
+                            const koa_epilogue_t* ep, cudaStream_t st) {
+  int rc = check_epi(ep, c);
+  if (rc) return rc;
+  KOA_REQUIRE(c % 64 == 0, "grouped conv needs C %% 64 == 0 (got %d)", c);
+  const int hout = (h + 2 - 3) / stride + 1, wout = (w_in + 2 - 3) / stride + 1;
+  const long long m = (long long)n_img * hout * wout;
+  KOA_REQUIRE(m > 0 && m < 2147483647LL, "bad pixel count");
+  CUtensorMap ta, tb;
+  rc = koa_tmap_im2col_bf16(&ta, x, n_img, h, w_in, c, 3, 3, stride, 1, 128);
+  if (rc) return rc;
+  rc = koa_tmap_2d_bf16(&tb, w, 576, (uint64_t)c, 576 * 2, 64, 64);
+  if (rc) return rc;
+  ConvGeom g = {hout, wout, stride, 1, 3, 1, 1};
+  return launch_kmajor<64, 4, true>(ta, tb, (int)m, c, 576, g, to_epi(ep), st);
+}
+
+// dw[C][9][64] += per-chunk dense weight gradient of the grouped convolution.
+int koa_conv_grouped_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int c,
+                                  int stride, cudaStream_t st) {
+  KOA_REQUIRE(c % 64 == 0, "grouped conv needs C %% 64 == 0 (got %d)", c);
+  const int hout = (h + 2 - 3) / stride + 1, wout = (w_in + 2 - 3) / stride + 1;
+  const long long pixels = (long long)n_img * hout * wout;
+  KOA_REQUIRE(pixels > 0 && pixels < 2147483647LL, "bad pixel count");
+  CUtensorMap ta, tb;
+  int rc = koa_tmap_2d_bf16(&ta, dy, (uint64_t)c, (uint64_t)pixels, (uint64_t)c * 2, 64, 64);
+  if (rc) return rc;
+  rc = koa_tmap_im2col_bf16(&tb, x, n_img, h, w_in, c, 3, 3, stride, 1, 64);
+  if (rc) return rc;
+  ConvGeom g = {hout, wout, stride, 1, 3, c / 64, 1};
+  return launch_wgrad<64, 4, true>(ta, tb, c, c, (int)pixels, 9, g, dw, st);
 }
 
 // ------------------------------------ C ABI ----------------------------------------------------

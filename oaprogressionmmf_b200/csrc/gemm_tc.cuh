@@ -16,6 +16,7 @@ struct ConvGeom {
   int stride, pad;  // convolution stride / padding
   int filt_s;       // filter width (taps are enumerated r-major: tap = r * filt_s + s)
   int cin_blocks;   // Cin / 64
+  int grouped;      // 1: block-diagonal (grouped) 3x3 conv, output chunk n_t only reads input chunk n_t
 };
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_GELU_GRAD = 3 };
@@ -44,20 +45,6 @@ template <int BN, int STAGES>
 constexpr size_t gemm_smem_bytes() {
   return 1024 /*align slack*/ + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 +
          2 * BN * sizeof(float);
-}
-
-// Reduce v[0..31] across the 32 lanes of a warp so that lane L ends with the column-L total in v[0].
-__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = upper ? v[i] : v[i + off];
-      const float keep = upper ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
 }
 
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiParams& ep, long long row_off, int n,
@@ -247,7 +234,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const int cb = kb - tap * g.cin_blocks;
           const int fr = tap / g.filt_s;
           const int fs = tap - fr * g.filt_s;
-          tma_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], cb * 64, pw, ph, pn, (uint16_t)fs, (uint16_t)fr);
+          const int c0 = g.grouped ? n_t * 64 : cb * 64;
+          tma_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], c0, pw, ph, pn, (uint16_t)fs, (uint16_t)fr);
         } else {
           tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
         }
@@ -326,6 +314,8 @@ template <int BN, int STAGES, bool B_IM2COL>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int cout, int cin,
                   int pixels, int taps, ConvGeom g, float* __restrict__ dw, int kb_per_split, WgradDesc wd) {
+  // g.grouped: dw is [C][taps][64] (per-64-channel-chunk dense blocks); tile n_t pairs input chunk n_t with
+  // output chunk n_t only (BN must be 64; the upper 64 accumulator rows are discarded).
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t BOX_BYTES = 64 * BK * 2;  // one {64 channels x 64 pixels} TMA box
@@ -342,12 +332,12 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (cin + BN - 1) / BN;
-  const int m_tiles = (cout + BM - 1) / BM;
+  const int m_tiles = g.grouped ? 1 : (cout + BM - 1) / BM;
   int t = blockIdx.x;
   const int n_t = t % n_tiles; t /= n_tiles;
   const int m_t = t % m_tiles; t /= m_tiles;
   const int tap = t;
-  const int m0 = m_t * BM;
+  const int m0 = g.grouped ? n_t * 64 : m_t * BM;
   const int n0 = n_t * BN;
   const int num_kb_total = (pixels + BK - 1) / BK;
   const int kb_begin = blockIdx.y * kb_per_split;
@@ -427,8 +417,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_wait(tmem_full_bar, 0, 0x600);
     tc_fence_after();
     const int row = m0 + q * 32 + lane;  // output channel
-    const bool row_ok = row < cout;
-    float* dst_row = dw + ((long long)row * taps + tap) * cin;
+    const bool row_ok = g.grouped ? (q * 32 + lane) < 64 : row < cout;
+    const int ldw = g.grouped ? 64 : cin;
+    const int col0 = g.grouped ? 0 : n0;
+    float* dst_row = dw + ((long long)row * taps + tap) * ldw;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= cin) break;
@@ -436,7 +428,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
       if (row_ok) {
-        float* dst = dst_row + n0 + c0;
+        float* dst = dst_row + col0 + c0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),

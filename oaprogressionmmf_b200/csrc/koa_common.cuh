@@ -239,6 +239,20 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Reduce v[0..31] across the 32 lanes of a warp so that lane L ends with the column-L total in v[0].
+__device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 }  // namespace koa
 
 #endif  // __CUDACC__

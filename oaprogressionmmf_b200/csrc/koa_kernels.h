@@ -1,0 +1,75 @@
+// koa_kernels.h — typed launchers of the HBM-bound / CUDA-core kernels (elementwise.cu, stem.cu,
+// attention.cu). Internal to libkoa_b200.so; the engines (fe_engine.cu, feat_engine.cu) and the
+// per-op C ABI wrappers (ops_api.cu) are built from these.
+#pragma once
+#include <cuda_runtime.h>
+
+// ---- parameter packing --------------------------------------------------------------------------
+int koa_k_pack_conv_w(const float* src, void* dst, int cout, int cin, int fr, int fs, int dgrad_form, cudaStream_t st);
+int koa_k_pack_grouped_w(const float* src, void* dst, int c, int cg, int dgrad_form, cudaStream_t st);
+int koa_k_unpack_grouped_dw(const float* dense, float* grad, int c, int cg, cudaStream_t st);
+int koa_k_unpack_conv_dw(const float* src, float* dst, int cout, int cin, int fr, int fs, cudaStream_t st);
+int koa_k_pack_matrix(const float* src, void* dst, void* dst_t, int rows, int cols, cudaStream_t st);
+int koa_k_cast_bf16(const float* src, void* dst, long long n, cudaStream_t st);
+
+// ---- BatchNorm ------------------------------------------------------------------------------------
+int koa_k_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* run_mean,
+                      float* run_var, float* scale, float* shift, float* mean, float* invstd, int c, double count,
+                      int training, cudaStream_t st);
+int koa_k_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, cudaStream_t st);
+int koa_k_bn_act(const void* y, const float* scale, const float* shift, const void* res, const void* y2,
+                 const float* scale2, const float* shift2, void* out, long long rows, int c, int relu, cudaStream_t st);
+int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
+                        const void* y2, const float* mean2, const float* invstd2, float* sum_dz, float* sum_dzx,
+                        float* sum_dzx2, long long rows, int c, cudaStream_t st);
+int koa_k_bn_bwd_finalize(const float* sum_dz, const float* sum_dzx, const float* gamma, const float* mean,
+                          const float* invstd, float* dgamma, float* dbeta, float* k0, float* k1, float* k2, int c,
+                          double count, int training, cudaStream_t st);
+int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const float* k0, const float* k1,
+                       const float* k2, void* dy, const void* y2, const float* k0b, const float* k1b, const float* k2b,
+                       void* dy2, long long rows, int c, cudaStream_t st);
+
+// ---- pooling / resampling -------------------------------------------------------------------------
+int koa_k_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, cudaStream_t st);
+int koa_k_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, cudaStream_t st);
+int koa_k_gap_fwd(const void* x, float* feat, int n, int hw, int c, cudaStream_t st);
+int koa_k_gap_bwd(const float* dfeat, void* dx, int n, int hw, int c, cudaStream_t st);
+int koa_k_zero_insert2(const void* src, void* dst, int n, int h, int w, int c, int ho, int wo, cudaStream_t st);
+int koa_k_scatter_add2(const void* src, void* dx, int n, int h, int w, int c, int ho, int wo, cudaStream_t st);
+
+// ---- transformer pieces ---------------------------------------------------------------------------
+int koa_k_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
+                        float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st);
+int koa_k_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                        const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int rows, int d,
+                        long long x_row_stride, long long dx_row_stride, cudaStream_t st);
+int koa_k_token_assemble(const float* emb, const float* cls, const float* pos, float* x, int batch, int n_tok, int n_cls,
+                         int d, cudaStream_t st);
+int koa_k_token_assemble_bwd(const float* dx, float* dpos, float* dcls, void* demb, int batch, int n_tok, int n_cls, int d,
+                             cudaStream_t st);
+int koa_k_col_sum(const void* x, int is_bf16, float* out, long long rows, int c, long long ld, cudaStream_t st);
+int koa_k_linear_small_fwd(const float* x, const float* w, const float* b, float* y, float* pre, int m, int n, int k,
+                           long long x_row_stride, int act, cudaStream_t st);
+int koa_k_linear_small_bwd(const float* dy, const float* pre, const float* x, const float* w, float* dpre_scratch,
+                           float* dx, float* dw, float* db, int m, int n, int k, long long x_row_stride,
+                           long long dx_row_stride, int act, int accumulate_dx, cudaStream_t st);
+int koa_k_focal_loss(const float* logits, const long long* target, float* loss, float* dlogits, int batch, int classes,
+                     float gamma, cudaStream_t st);
+
+// ---- attention (attention.cu) -----------------------------------------------------------------------
+// qkv: bf16 [B*n][3*D] with feature index = (qkv, head, d); out: bf16 [B*n][D]; probs: fp32 [B][H][n][n].
+int koa_k_attention_fwd(const void* qkv, void* out, float* probs, int batch, int n, int heads, int head_dim, float scale,
+                        cudaStream_t st);
+int koa_k_attention_bwd(const void* qkv, const float* probs, const void* dout, void* dqkv, int batch, int n, int heads,
+                        int head_dim, float scale, cudaStream_t st);
+
+// ---- stem (stem.cu) -----------------------------------------------------------------------------------
+// vol (B,1,R,C,S) fp32 slice-innermost -> img [B*S][R][C] fp32
+int koa_k_stem_pack(const float* vol, float* img, int batch, int rc, int slices, cudaStream_t st);
+// w [64][3][7][7] fp32 -> wfold [49][64] fp32 (sum over the 3 identical input channels)
+int koa_k_stem_fold_w(const float* w, float* wfold, cudaStream_t st);
+int koa_k_stem_conv_fwd(const float* img, const float* wfold, void* y, float* sum, float* sumsq, int n, int h, int w,
+                        cudaStream_t st);
+// dwfold [49][64] accumulated with atomics (caller zeroes); then expanded to dw [64][3][7][7]
+int koa_k_stem_wgrad(const float* img, const void* dy, float* dwfold, int n, int h, int w, cudaStream_t st);
+int koa_k_stem_unfold_dw(const float* dwfold, float* dw, cudaStream_t st);
