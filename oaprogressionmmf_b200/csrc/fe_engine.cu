@@ -254,7 +254,7 @@ extern "C" int koa_fe_num_units(const koa_fe_desc_t* d) {
 }
 
 // what: 0 raw conv output y of unit `index`; 1 block output of block `index`; 2 a1 of block; 3 a2 of block;
-// 4 stem activation a0; 5 pooled p0; 6 BN coefficients (scale, shift, mean, invstd, k0, k1, k2) of unit `index`.
+// 4 stem activation a0; 5 pooled p0; 7 max-pool argmax bytes; 6 BN coefficients (scale, shift, mean, invstd, k0, k1, k2) of unit `index`.
 extern "C" int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, size_t* offset, size_t* bytes) {
   Plan p;
   KOA_TRY(build_plan(d, p));
@@ -277,7 +277,8 @@ extern "C" int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, 
     return 0;
   }
   if (what == 4) { *offset = p.a0; *bytes = (size_t)p.units[0].rows_out * 64 * 2; return 0; }
-  if (what == 5) { *offset = p.p0; *bytes = p.idx0 - p.p0; return 0; }
+  if (what == 5) { *offset = p.p0; *bytes = (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64 * 2; return 0; }
+  if (what == 7) { *offset = p.idx0; *bytes = (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64; return 0; }
   koa_set_error("unknown debug selector %d", what);
   return KOA_ERR_ARG;
 }

@@ -226,6 +226,47 @@ def _is_stem_bn(key: str) -> bool:
 
 
 # ------------------------------------------------------------------------------------------------
+# bf16 storage emulation
+# ------------------------------------------------------------------------------------------------
+# The CUDA path stores activations, activation gradients and GEMM weight operands in bf16 and
+# accumulates in fp32. With ``emulate_bf16=True`` the oracle rounds at exactly those storage points
+# (values stay fp32 tensors), so a comparison against it isolates kernel bugs from the precision
+# choice; the fp32 oracle (default) is the reference semantics. A randomly initialised BatchNorm
+# ResNet amplifies perturbations from block to block, so the two oracles themselves differ by far
+# more than one bf16 ulp at the feature level (measured in tests/test_gpu_parity.py).
+class _RoundAct(torch.autograd.Function):
+    """bf16 round of an activation in forward and of its gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+class _RoundWeight(torch.autograd.Function):
+    """bf16 round of a GEMM weight operand; the gradient reaches the fp32 master weight unrounded."""
+
+    @staticmethod
+    def forward(ctx, w):
+        return w.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _ra(x: Tensor, emulate: bool) -> Tensor:
+    return _RoundAct.apply(x) if emulate else x
+
+
+def _rw(w: Tensor, emulate: bool) -> Tensor:
+    return _RoundWeight.apply(w) if emulate else w
+
+
+# ------------------------------------------------------------------------------------------------
 # Functional forward passes
 # ------------------------------------------------------------------------------------------------
 def _bn(sd: StateDict, p: str, x: Tensor, training: bool) -> Tensor:
@@ -239,32 +280,38 @@ def _bn(sd: StateDict, p: str, x: Tensor, training: bool) -> Tensor:
 
 
 def fe_forward(sd: StateDict, prefix: str, arch: str, x: Tensor, training: bool, with_gap: bool = True,
-               taps: Dict[str, Tensor] | None = None) -> Tensor:
+               taps: Dict[str, Tensor] | None = None, emulate_bf16: bool = False) -> Tensor:
     """``ResNet._forward_impl`` without ``fc`` (_torchvision.py:227-239), blocks per :64-80 / :118-138.
     ``x`` is (N, 3, H, W). ``taps`` (optional) collects block outputs for intermediate parity checks."""
-    x = F.conv2d(x, sd[f"{prefix}.0.weight"], stride=2, padding=3)
-    x = F.relu(_bn(sd, f"{prefix}.1", x, training))
-    if taps is not None:
-        taps[f"{prefix}.stem"] = x
-    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    e = emulate_bf16
+
+    def tap(key, t):
+        if taps is not None:
+            taps[key] = t
+        return t
+
+    def conv(inp, key, **kw):  # conv output is stored in bf16 by the CUDA path
+        return tap(key[:-len(".weight")] + ".y", _ra(F.conv2d(inp, _rw(sd[key], e), **kw), e))
+
+    # the stem runs in fp32 on the fp32 input/weights; only its output is stored in bf16
+    x = tap(f"{prefix}.0.y", _ra(F.conv2d(x, sd[f"{prefix}.0.weight"], stride=2, padding=3), e))
+    x = tap(f"{prefix}.stem", _ra(F.relu(_bn(sd, f"{prefix}.1", x, training)), e))
+    x = tap(f"{prefix}.pool", F.max_pool2d(x, kernel_size=3, stride=2, padding=1))
     for b in fe_block_plan(arch):
         p = f"{prefix}.{b['layer']}.{b['index']}"
         identity = x
         if b["kind"] == "bottleneck":
-            o = F.relu(_bn(sd, f"{p}.bn1", F.conv2d(x, sd[f"{p}.conv1.weight"]), training))
-            o = F.conv2d(o, sd[f"{p}.conv2.weight"], stride=b["stride"], padding=1, groups=b["groups"])
-            o = F.relu(_bn(sd, f"{p}.bn2", o, training))
-            o = _bn(sd, f"{p}.bn3", F.conv2d(o, sd[f"{p}.conv3.weight"]), training)
+            o = tap(f"{p}.a1", _ra(F.relu(_bn(sd, f"{p}.bn1", conv(x, f"{p}.conv1.weight"), training)), e))
+            o = conv(o, f"{p}.conv2.weight", stride=b["stride"], padding=1, groups=b["groups"])
+            o = tap(f"{p}.a2", _ra(F.relu(_bn(sd, f"{p}.bn2", o, training)), e))
+            o = _bn(sd, f"{p}.bn3", conv(o, f"{p}.conv3.weight"), training)
         else:
-            o = F.conv2d(x, sd[f"{p}.conv1.weight"], stride=b["stride"], padding=1)
-            o = F.relu(_bn(sd, f"{p}.bn1", o, training))
-            o = _bn(sd, f"{p}.bn2", F.conv2d(o, sd[f"{p}.conv2.weight"], padding=1), training)
+            o = conv(x, f"{p}.conv1.weight", stride=b["stride"], padding=1)
+            o = tap(f"{p}.a1", _ra(F.relu(_bn(sd, f"{p}.bn1", o, training)), e))
+            o = _bn(sd, f"{p}.bn2", conv(o, f"{p}.conv2.weight", padding=1), training)
         if b["downsample"]:
-            identity = _bn(sd, f"{p}.downsample.1", F.conv2d(x, sd[f"{p}.downsample.0.weight"], stride=b["stride"]),
-                           training)
-        x = F.relu(o + identity)
-        if taps is not None:
-            taps[p] = x
+            identity = _bn(sd, f"{p}.downsample.1", conv(x, f"{p}.downsample.0.weight", stride=b["stride"]), training)
+        x = tap(p, _ra(F.relu(o + identity), e))
     if with_gap:
         x = x.mean(dim=(2, 3), keepdim=True)
     return x

@@ -42,8 +42,8 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False):
-    print(f"== FE {arch} B={n_b} S={slices} {size}x{size} train={train} xr={xr}", flush=True)
+def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False, emulate=False):
+    print(f"== FE {arch} B={n_b} S={slices} {size}x{size} train={train} xr={xr} emulate_bf16={emulate}", flush=True)
     dev = "cuda"
     spec = ko.fe_param_spec(arch, "_fe")
     sd = ko.make_state_dict(spec, 11, device=dev)
@@ -66,7 +66,7 @@ def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False):
     for v in params.values():
         v.requires_grad_(True)
     taps = {}
-    ref = ko.fe_forward(sd, "_fe", arch, imgs, train, True, taps).flatten(1)
+    ref = ko.fe_forward(sd, "_fe", arch, imgs, train, True, taps, emulate_bf16=emulate).flatten(1)
     got = tok.reshape(-1, tok.shape[-1])
     print(f"features rel={rel(got, ref):.3e}  |ref|={ref.norm():.3f} finite={bool(torch.isfinite(got).all())}")
     # intermediates
@@ -102,6 +102,9 @@ def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False):
         gm = mine[k[len("_fe."):]].grad
         e = rel(gm, v.grad)
         worst.append((e, k, float(v.grad.norm())))
+    if os.environ.get("KOA_ALL_GRADS"):
+        for e, k, nrm in reversed(worst):
+            print(f"  grad {k}: rel={e:.3e} |ref|={nrm:.3e}")
     worst.sort(reverse=True)
     for e, k, nrm in worst[:12]:
         print(f"  grad {k}: rel={e:.3e} |ref|={nrm:.3e}")
@@ -111,6 +114,134 @@ def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False):
         msd = enc.state_dict()
         es = [rel(msd[k[len('_fe.'):]], v) for k, v in sd.items() if k.endswith(("running_mean", "running_var"))]
         print(f"  running stats: max rel={max(es):.3e}")
+
+
+def _ws_view(lib, desc, ws, what, index, dtype):
+    off, nb = C.c_size_t(), C.c_size_t()
+    _lib.check(lib.koa_fe_debug_offset(C.byref(desc), what, index, C.byref(off), C.byref(nb)), "dbg")
+    return ws[off.value:off.value + nb.value].view(dtype)
+
+
+def _nhwc_bf16(t):
+    return t.detach().permute(0, 2, 3, 1).contiguous().bfloat16().reshape(-1)
+
+
+def section_fe_teacher(arch, n_b=2, slices=3, size=64, xr=False):
+    """Backward validation with forced-identical forward state: the workspace activations saved by the CUDA
+    forward are overwritten with the bf16-emulating oracle's, then koa_fe_backward runs on them. Removes the
+    ReLU-mask / rounding-avalanche noise of the forward pass from the gradient comparison."""
+    print(f"== FE teacher-forced backward {arch} B={n_b} S={slices} {size}x{size} xr={xr}", flush=True)
+    dev = "cuda"
+    lib = _lib.load()
+    spec = ko.fe_param_spec(arch, "_fe")
+    sd = ko.make_state_dict(spec, 11, device=dev)
+    enc = SliceEncoder(dict_fes[arch](pretrained=False), with_gap=True).to(dev)
+    enc.load_state_dict({k[len("_fe."):]: v.clone() for k, v in sd.items()})
+    enc.train(True)
+    g = torch.Generator().manual_seed(5)
+    if xr:
+        vol = torch.randn(n_b, 1, size, size, generator=g).to(dev)
+        imgs = vol.expand(-1, 3, -1, -1)
+        tok = enc.encode_image(vol)
+    else:
+        vol = torch.randn(n_b, 1, size, size, slices, generator=g).to(dev)
+        imgs = ko._slices_to_images(vol)
+        tok = enc.encode_volume(vol)
+    fn = tok.grad_fn
+    while fn is not None and not hasattr(fn, "ws"):
+        fn = fn.next_functions[0][0] if fn.next_functions else None
+    ws, desc = fn.ws, fn.desc
+    params = {k: v for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+    for v in params.values():
+        v.requires_grad_(True)
+    taps = {}
+    ref = ko.fe_forward(sd, "_fe", arch, imgs, True, True, taps, emulate_bf16=True).flatten(1)
+    # unit order of the engine: stem, then per block conv1, conv2, [conv3], [downsample]
+    ykeys = ["_fe.0.y"]
+    for b in ko.fe_block_plan(arch):
+        p = f"_fe.{b['layer']}.{b['index']}"
+        ykeys += [f"{p}.conv1.y", f"{p}.conv2.y"]
+        if b["kind"] == "bottleneck":
+            ykeys.append(f"{p}.conv3.y")
+        if b["downsample"]:
+            ykeys.append(f"{p}.downsample.0.y")
+    worst_fwd = 0.0
+    for ui, key in enumerate(ykeys):
+        y = taps[key]
+        dst = _ws_view(lib, desc, ws, 0, ui, torch.bfloat16)
+        src = _nhwc_bf16(y)
+        worst_fwd = max(worst_fwd, rel(dst.float(), src.float()))
+        dst.copy_(src)
+        coef = _ws_view(lib, desc, ws, 6, ui, torch.float32).view(7, -1)
+        yf = y.detach()
+        mean = yf.mean(dim=(0, 2, 3))
+        var = yf.var(dim=(0, 2, 3), unbiased=False)
+        coef[2].copy_(mean)
+        coef[3].copy_(torch.rsqrt(var + 1e-5))
+    print(f"  forward raw conv outputs before overwrite: worst rel={worst_fwd:.3e}")
+    _ws_view(lib, desc, ws, 4, 0, torch.bfloat16).copy_(_nhwc_bf16(taps["_fe.stem"]))
+    for bi, b in enumerate(ko.fe_block_plan(arch)):
+        p = f"_fe.{b['layer']}.{b['index']}"
+        _ws_view(lib, desc, ws, 1, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[p]))
+        _ws_view(lib, desc, ws, 2, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[f"{p}.a1"]))
+        if b["kind"] == "bottleneck":
+            _ws_view(lib, desc, ws, 3, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[f"{p}.a2"]))
+    # pooled activation + argmax from the overwritten stem activation
+    a0 = _ws_view(lib, desc, ws, 4, 0, torch.bfloat16)
+    p0 = _ws_view(lib, desc, ws, 5, 0, torch.bfloat16)
+    idx0 = _ws_view(lib, desc, ws, 7, 0, torch.uint8)
+    hs = (size + 6 - 7) // 2 + 1
+    _lib.check(lib.koa_maxpool_fwd(a0.data_ptr(), p0.data_ptr(), idx0.data_ptr(), imgs.shape[0], hs, hs, 64,
+                                   _lib.current_stream()), "maxpool")
+    print(f"  pooled rel vs oracle={rel(p0.float(), _nhwc_bf16(taps['_fe.pool']).float()):.3e}")
+    gy = torch.randn(ref.shape, generator=g).to(dev)
+    got = tok.reshape(-1, tok.shape[-1])
+    (got * gy).sum().backward()
+    (ref * gy).sum().backward()
+    torch.cuda.synchronize()
+    print("  debug flag", hex(_lib.debug_flag()))
+    rows = []
+    mine = dict(enc.named_parameters())
+    for k, v in params.items():
+        rows.append((rel(mine[k[len("_fe."):]].grad, v.grad), k, float(v.grad.norm())))
+    if os.environ.get("KOA_ALL_GRADS"):
+        for e, k, nrm in reversed(rows):
+            print(f"  grad {k}: rel={e:.3e} |ref|={nrm:.3e}")
+    rows.sort(reverse=True)
+    for e, k, nrm in rows[:10]:
+        print(f"  grad {k}: rel={e:.3e} |ref|={nrm:.3e}")
+    es = torch.tensor([r[0] for r in rows])
+    print(f"  grads: max={es.max():.3e} median={es.median():.3e} n={len(rows)}")
+
+
+def section_floor(arch, n_b=2, slices=3, size=64, train=True):
+    """Precision floor with no CUDA-path code involved: fp32 oracle vs bf16-emulating oracle."""
+    print(f"== precision floor (oracle fp32 vs oracle bf16-emulated) {arch} B={n_b} S={slices} {size} train={train}", flush=True)
+    dev = "cuda"
+    spec = ko.fe_param_spec(arch, "_fe")
+    g = torch.Generator().manual_seed(5)
+    vol = torch.randn(n_b, 1, size, size, slices, generator=g).to(dev)
+    imgs = ko._slices_to_images(vol)
+    outs = []
+    gy = None
+    for emu in (False, True):
+        sd = ko.make_state_dict(spec, 11, device=dev)
+        params = {k: v for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+        for v in params.values():
+            v.requires_grad_(True)
+        taps = {}
+        f = ko.fe_forward(sd, "_fe", arch, imgs, train, True, taps, emulate_bf16=emu).flatten(1)
+        if gy is None:
+            gy = torch.randn(f.shape, generator=g).to(dev)
+        (f * gy).sum().backward()
+        outs.append((f.detach(), {k: v.grad for k, v in params.items()}, taps))
+    (f0, g0, t0), (f1, g1, t1) = outs
+    print(f"  features rel={rel(f1, f0):.3e}")
+    for b in ko.fe_block_plan(arch):
+        p = f"_fe.{b['layer']}.{b['index']}"
+        print(f"  block {b['layer']}.{b['index']} out rel={rel(t1[p], t0[p]):.3e}")
+    es = torch.tensor([rel(g1[k], g0[k]) for k in g0])
+    print(f"  grads: max={es.max():.3e} median={es.median():.3e}")
 
 
 def section_feat(b=2, n_p=5, dim=2048, depth=2, heads=8, with_cls=True, head=True):
@@ -219,6 +350,24 @@ def main():
     if "fe" in args.sections:
         section_fe(args.arch, train=True)
         section_fe(args.arch, train=False)
+    if "fe_emu" in args.sections:
+        section_fe(args.arch, train=True, emulate=True)
+        section_fe(args.arch, train=False, emulate=True)
+        section_fe(args.arch, n_b=4, slices=16, size=128, train=True, emulate=True)
+    if "fe_tf" in args.sections:
+        section_fe_teacher(args.arch)
+        section_fe_teacher(args.arch, n_b=2, slices=8, size=96)
+    if "fe_tf_xr" in args.sections:
+        section_fe_teacher("resnext50_32x4d", n_b=3, size=64, xr=True)
+    if "fe_tf_r18" in args.sections:
+        section_fe_teacher("resnet18")
+    if "floor" in args.sections:
+        section_floor(args.arch, train=True)
+        section_floor(args.arch, train=False)
+    if "fe_eval" in args.sections:
+        section_fe(args.arch, train=False)
+    if "fe_big" in args.sections:
+        section_fe(args.arch, n_b=4, slices=16, size=128, train=True)
     if "fe_xr" in args.sections:
         section_fe("resnext50_32x4d", n_b=3, size=64, train=True, xr=True)
     if "fe_r18" in args.sections:
