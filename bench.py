@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the koafusion hot path on B200: knees/sec for forward + FocalLoss + backward of the fusion
+model (metric of BASELINE.json), one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's algorithm on the host cores (oracle port)
+
+One JSON line on stdout (rank 0). See DESIGN.md "Measurement" for the definitions of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "knees/sec fwd+bwd (XR+3MRI+clin fusion) at 1/2/4/8 B200; % tensor-core roofline"
+
+# Algorithmic GFLOP per knee (2*MAC of convolutions, linears and attention matmuls; backward = 2x forward
+# minus the stem data gradient), BASELINE.md section 2 / SURVEY.md section 8(d).
+FLOPS_FWD_BWD = {"XR1Cnn": 62.06e9, "MR1CnnTrf": 834.5e9, "MR2CnnTrf": 1251.7e9, "XR1MR2CnnTrf": 1279.6e9,
+                 "XR1MR2C1CnnTrf": 1280.2e9, "MR3CnnTrf": 1654.5e9, "XR1MR3C1CnnTrf": 1717.8e9}
+WORKLOAD_DESC = {
+    "XR1MR3C1CnnTrf": "XR 350x350 (ResNeXt-50) + DESS 160x160x64 + TSE 160x160x32 + T2map 160x160x25 (ResNet-50 each) + 9 "
+                      "clinical vars, per-sequence + fusion transformers (D 2048, depth 4); 3-MRI extension of the "
+                      "reference's XR1MR2C1CnnTrf (BASELINE.json config 4)",
+    "XR1MR2C1CnnTrf": "reference full model: XR 350x350 + DESS 160x160x64 + T2map 160x160x25 + clinical (runner.sh:341-363)",
+    "MR1CnnTrf": "DESS 160x160x64 only: per-slice ResNet-50 + slice-aggregation transformer (BASELINE.json config 2)",
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=p.get("bf16_tflops_sustained", 1386.1), burst=p.get("bf16_tflops", 1663.1),
+                    hbm=p.get("hbm_gbs", 6536.4), source="MEASURED_PEAKS.json (sustained bf16 GEMM)")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback of B200_PROFILING.md")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                                          "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:  # noqa: BLE001
+                continue
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def dist_info():
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return ws, rank, local
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm (oracle port, fp32 eager torch) on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step(workload, knees, steps, warmup, threads):
+    from oracle import koa_oracle as ko
+
+    torch.set_num_threads(threads)
+    cfg = ko.make_config(workload)
+    spec = ko.model_param_spec(workload, cfg)
+    sd = ko.make_state_dict(spec, 778)
+    inputs, target = ko.make_inputs(workload, cfg, knees, 779)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ko.train_step(workload, cfg, sd, inputs, target)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args):
+    ws, rank, _ = dist_info()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    knees = args.cpu_knees
+    times = cpu_reference_step(args.workload, knees, max(1, args.steps), max(0, min(args.warmup, 1)), threads)
+    ms = 1e3 * sum(times) / len(times)
+    value = knees / (ms / 1e3)
+    sample = (f"{len(times)} timed steps (after {max(0, min(args.warmup, 1))} warm-up) of zero_grad+forward+FocalLoss+backward on "
+              f"{knees} knee(s) of the same workload, fp32 eager PyTorch restatement of the reference (oracle port)")
+    line = dict(metric=METRIC, value=value, unit="knees/s", impl="reference", n_gpus=args.gpus, steps=len(times),
+                warmup=max(0, min(args.warmup, 1)), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=args.workload, description=WORKLOAD_DESC.get(args.workload, args.workload),
+                            knees_per_step=knees, device="host CPU"),
+                cpu_baseline=dict(value=value, unit="knees/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=value, unit="knees/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from oaprogressionmmf_b200 import _lib
+    from oaprogressionmmf_b200.koamodels import dict_models
+    from oaprogressionmmf_b200.losses import FocalLoss
+    from oaprogressionmmf_b200.synthetic import SyntheticKneeLoader, input_bytes, model_config, to_attr
+
+    ws, rank, local = dist_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU path. Use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    torch.manual_seed(778)
+    cfg = model_config(args.workload)
+    model = dict_models[args.workload](to_attr(cfg), None).to(dev)
+    model.train()
+    # per-sequence transformer heads never receive gradients (dead compute in the reference): exclude them
+    for name, p in model.named_parameters():
+        if ("_agg_1." in name or "_agg_2." in name or "_agg_3." in name) and ".mlp_head0." in name:
+            p.requires_grad_(False)
+    n_params = sum(p.numel() for p in model.parameters())
+    step_model = model
+    if ws > 1:
+        step_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=True,
+                                                               gradient_as_bucket_view=True, static_graph=True)
+    loss_fn = FocalLoss(gamma=2)
+    B = args.batch
+    loader = SyntheticKneeLoader(cfg, B, seed=779 + rank, n_distinct=2, pin=True)
+    host_batches = loader.batches
+    dev_batches = [([t.to(dev) for t in ins], tgt.to(dev)) for ins, tgt in host_batches]
+    h2d_bytes = input_bytes(*host_batches[0])
+
+    def step(ins, tgt):
+        step_model.zero_grad(set_to_none=True)
+        logits = step_model(*ins)["main"]
+        loss = loss_fn(logits, tgt)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(*dev_batches[i % 2])
+    barrier()
+    lib.koa_profile_enable(1)
+    launches0 = lib.koa_launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        loss = step(*dev_batches[i % 2])
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = lib.koa_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = (C.c_double * 6)()
+    lib.koa_profile_read(prof)
+    lib.koa_profile_enable(0)
+    flag = _lib.debug_flag()
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = ws * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end: pinned host inputs -> device copy -> step -> loss read back, every step ----------
+    def e2e_step(i):
+        ins_h, tgt_h = host_batches[i % 2]
+        ins = [t.to(dev, non_blocking=True) for t in ins_h]
+        tgt = tgt_h.to(dev, non_blocking=True)
+        return float(step(ins, tgt).item())
+
+    for i in range(min(2, args.warmup)):
+        e2e_step(i)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        last_loss = e2e_step(i)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = ws * B * args.steps / (float(t.item()) / 1e3)
+
+    if rank != 0:
+        if ws > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    flops_knee = FLOPS_FWD_BWD[args.workload]
+    # dominant kernel family: the tcgen05 GEMM / implicit-GEMM convolution kernels (forward + data gradient),
+    # timed per launch with CUDA events on the launching stream over the timed region
+    k_ms, k_flops, k_n = prof[0], prof[1], prof[2]
+    w_ms, w_flops, w_n = prof[3], prof[4], prof[5]
+    achieved = (k_flops / (k_ms / 1e3)) / 1e12 if k_ms > 0 else 0.0
+    roofline = dict(bound="tensor", kernel="gemm_kmajor_kernel (tcgen05 GEMM / im2col implicit-GEMM conv, fwd + dgrad)",
+                    achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], traffic=None,
+                    peak_source=peaks["source"], avg_launch_ms=k_ms / max(1.0, k_n), launches_timed=int(k_n),
+                    share_of_step=k_ms / ms_total,
+                    wgrad=dict(kernel="gemm_wgrad_kernel (tcgen05 MN-major split-K)",
+                               achieved=(w_flops / (w_ms / 1e3)) / 1e12 if w_ms > 0 else 0.0,
+                               avg_launch_ms=w_ms / max(1.0, w_n), launches_timed=int(w_n), share_of_step=w_ms / ms_total),
+                    whole_step=dict(achieved=value / ws * flops_knee / 1e12, frac=value / ws * flops_knee / 1e12 / peaks["tflops"],
+                                    note="algorithmic FLOPs of the whole step / step time, per GPU"))
+    cpu = None
+    if ws == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        times = cpu_reference_step(args.workload, args.cpu_knees, 1, 0, threads)
+        cpu = dict(value=args.cpu_knees / times[0], unit="knees/s", cores=threads, kind="port",
+                   sample=f"1 step (no warm-up) of forward+FocalLoss+backward on {args.cpu_knees} knee(s) of the same "
+                          f"workload with the fp32 eager PyTorch restatement of the reference (oracle port), {times[0]:.1f} s")
+    line = dict(metric=METRIC, value=value, unit="knees/s", n_gpus=ws, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                config=dict(workload=args.workload, description=WORKLOAD_DESC.get(args.workload, args.workload),
+                            knees_per_gpu=B, global_batch=B * ws, parallelism=f"dp{ws} (knee-wise, one process per GPU)",
+                            params=n_params, step="zero_grad + forward + FocalLoss + backward" +
+                            (" + NCCL gradient all-reduce (DDP buckets overlapped with backward)" if ws > 1 else ""),
+                            dropout=0.0, bn="train mode (batch statistics per GPU)",
+                            l2="working set per step (tens of GB of activations) exceeds the 126 MB L2; two input batches alternate"),
+                roofline=roofline, cpu_baseline=cpu,
+                e2e=dict(value=e2e_value, unit="knees/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
+                gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag)
+    print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="XR1MR3C1CnnTrf", choices=sorted(FLOPS_FWD_BWD))
+    ap.add_argument("--batch", type=int, default=16, help="knees per GPU (runner.sh:342 trains the full model at 16)")
+    ap.add_argument("--cpu-knees", type=int, default=1, help="knees in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,13 @@ const char* koa_last_error(void);
 int koa_version(void);
 /* Reads and clears the device-side diagnostic word (non-zero: a pipeline barrier timed out). */
 int koa_debug_flag(unsigned int* out);
+/* Kernels launched by this library in this process so far. */
+long long koa_launch_count(void);
+/* Optional per-launch CUDA-event timing of the tcgen05 kernel family (used by bench.py for the roofline):
+ * out[cls*3 + {0,1,2}] = device ms, algorithmic FLOPs (2*M*N*K), launches; cls 0 = forward/data-gradient
+ * GEMMs and implicit-GEMM convolutions, cls 1 = weight-gradient GEMMs. Reading synchronises and clears. */
+int koa_profile_enable(int on);
+int koa_profile_read(double* out);
 
 /* ---- fused GEMM epilogue --------------------------------------------------------------------- */
 enum { KOA_ACT_NONE = 0, KOA_ACT_RELU = 1, KOA_ACT_GELU = 2, KOA_ACT_GELU_GRAD = 3 };

@@ -89,6 +89,9 @@ SIGNATURES = {
     "koa_version": (_I, []),
     "koa_debug_flag": (_I, [C.POINTER(C.c_uint)]),
     "koa_debug_set_wgrad_desc": (_I, [C.c_uint, C.c_uint, C.c_uint]),
+    "koa_launch_count": (C.c_longlong, []),
+    "koa_profile_enable": (_I, [_I]),
+    "koa_profile_read": (_I, [C.POINTER(C.c_double)]),
     "koa_gemm_bf16": (_I, [_P, _P, _I, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_conv_fprop_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_gemm_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),

@@ -1,5 +1,6 @@
 // gemm_api.cu — host launchers + C-ABI entry points for the tcgen05 GEMM / implicit-GEMM kernels.
 #include <mutex>
+#include <vector>
 
 #include "../../include/koa_b200.h"
 #include "gemm_tc.cuh"
@@ -9,6 +10,56 @@
 using namespace koa;
 
 static WgradDesc s_wgrad_desc = {8192u, 1024u, 2048u};
+
+// ---- optional profiling of the tcgen05 kernel family -------------------------------------------------
+// When enabled every launch is bracketed by CUDA events on its own stream; koa_profile_read() synchronises
+// and returns device time, algorithmic FLOPs (2*M*N*K) and launch counts per kernel class
+// (0 = fprop/dgrad/linear "kmajor" kernels, 1 = weight-gradient kernels).
+namespace {
+struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+bool s_prof_on = false;
+std::vector<ProfRec> s_prof;
+std::mutex s_prof_mu;
+
+struct ProfScope {
+  cudaStream_t st; int cls; double flops; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(cudaStream_t st_, int cls_, double flops_) : st(st_), cls(cls_), flops(flops_) {
+    if (!s_prof_on) return;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    std::lock_guard<std::mutex> lk(s_prof_mu);
+    s_prof.push_back({a, b, cls, flops});
+  }
+};
+}  // namespace
+
+extern "C" int koa_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(s_prof_mu);
+  s_prof_on = on != 0;
+  for (auto& r : s_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  s_prof.clear();
+  return 0;
+}
+// out[cls*3 + {0,1,2}] = device milliseconds, algorithmic FLOPs, launches for cls in {0,1}; clears the records.
+extern "C" int koa_profile_read(double* out) {
+  KOA_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(s_prof_mu);
+  for (int i = 0; i < 6; ++i) out[i] = 0.0;
+  for (auto& r : s_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    out[r.cls * 3 + 0] += ms;
+    out[r.cls * 3 + 1] += r.flops;
+    out[r.cls * 3 + 2] += 1.0;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  s_prof.clear();
+  return 0;
+}
 
 extern "C" int koa_version(void) { return 1; }
 
@@ -66,7 +117,10 @@ static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
   KOA_CHECK_CUDA(attr_err);
   const long long tiles = (long long)koa_cdiv(m, BM) * koa_cdiv(n, BN);
   KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
-  gemm_kmajor_kernel<BN, STAGES, IM2COL><<<(unsigned)tiles, kGemmThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
+  {
+    ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k);
+    gemm_kmajor_kernel<BN, STAGES, IM2COL><<<(unsigned)tiles, kGemmThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
+  }
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -138,8 +192,13 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
   if (kb_per_split < 4 && num_kb >= 4) kb_per_split = 4;
   splits = koa_cdiv(num_kb, kb_per_split);
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  gemm_wgrad_kernel<BN, STAGES, IM2COL>
-      <<<grid, kGemmThreads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc);
+  {
+    // grouped: only the diagonal 64x64 blocks are algorithmic work
+    const double n_eff = g.grouped ? 64.0 : (double)cin;
+    ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps);
+    gemm_wgrad_kernel<BN, STAGES, IM2COL>
+        <<<grid, kGemmThreads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc);
+  }
   KOA_LAUNCH_CHECK();
   return 0;
 }

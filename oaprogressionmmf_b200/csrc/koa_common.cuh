@@ -40,8 +40,11 @@ void koa_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
+void koa_count_launch();
+
 #define KOA_LAUNCH_CHECK()                                                                \
   do {                                                                                    \
+    koa_count_launch();                                                                   \
     cudaError_t _e = cudaGetLastError();                                                  \
     if (_e != cudaSuccess) {                                                              \
       koa_set_error("%s:%d launch error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e),\

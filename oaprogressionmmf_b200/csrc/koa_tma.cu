@@ -1,6 +1,7 @@
 // koa_tma.cu — TMA tensor-map encoding + library-wide error state.
 #include "koa_tma.h"
 
+#include <atomic>
 #include <mutex>
 #include <stdarg.h>
 #include <string.h>
@@ -17,6 +18,11 @@ void koa_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* koa_last_error(void) { return t_koa_error; }
+
+// Number of kernels this library has launched in this process (every launcher counts itself).
+static std::atomic<long long> s_launches{0};
+void koa_count_launch() { s_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long koa_launch_count(void) { return s_launches.load(std::memory_order_relaxed); }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

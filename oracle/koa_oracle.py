@@ -186,10 +186,18 @@ def _mr1_num_tokens(cfg: dict) -> int:
 
 
 def make_state_dict(spec: Sequence[Tuple[str, Tuple[int, ...]]], seed: int, pos_scale: float = 1.0,
-                    device: str = "cpu") -> "OrderedDict[str, Tensor]":
+                    device: str = "cpu", res_gain: float = 1.0) -> "OrderedDict[str, Tensor]":
     """Seeded, well-conditioned parameter values for a (key, shape) spec. Values are drawn on the CPU
     in spec order from one generator so that the build container (reference + oracle) and the GPU
-    box (oracle + CUDA path) materialise bit-identical weights from (spec, seed)."""
+    box (oracle + CUDA path) materialise bit-identical weights from (spec, seed).
+    ``res_gain`` scales the weight of the last BatchNorm of every residual branch (bn3 of a bottleneck, bn2
+    of a basic block): < 1 gives the near-identity blocks of a trained / zero-init-residual network instead of
+    the perturbation-amplifying dynamics of a freshly initialised BatchNorm ResNet."""
+    last_bn: Dict[str, str] = {}
+    for key, _ in spec:  # name of the last bnK of each block
+        if ".bn" in key and key.endswith(".weight"):
+            blk, name = key.rsplit(".bn", 1)
+            last_bn[blk] = max(last_bn.get(blk, ""), name)
     g = torch.Generator().manual_seed(seed)
     sd: "OrderedDict[str, Tensor]" = OrderedDict()
     for key, shape in spec:
@@ -209,6 +217,10 @@ def make_state_dict(spec: Sequence[Tuple[str, Tuple[int, ...]]], seed: int, pos_
             t = torch.rand(shape, generator=g) + 0.5
         elif is_norm and leaf == "weight":
             t = torch.rand(shape, generator=g) + 0.5
+            if res_gain != 1.0 and ".bn" in key:
+                blk, name = key.rsplit(".bn", 1)
+                if last_bn.get(blk) == name:
+                    t = t * res_gain
         elif is_norm and leaf == "bias":
             t = torch.randn(shape, generator=g) * 0.1
         elif len(shape) == 2:  # nn.Linear weight

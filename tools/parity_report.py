@@ -20,6 +20,7 @@ from oaprogressionmmf_b200 import _lib  # noqa: E402
 from oaprogressionmmf_b200.koamodels import FeaT, SliceEncoder, dict_fes, dict_models  # noqa: E402
 from oracle import koa_oracle as ko  # noqa: E402
 
+RES_GAIN = 1.0
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 
@@ -46,7 +47,7 @@ def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False, emulate=Fal
     print(f"== FE {arch} B={n_b} S={slices} {size}x{size} train={train} xr={xr} emulate_bf16={emulate}", flush=True)
     dev = "cuda"
     spec = ko.fe_param_spec(arch, "_fe")
-    sd = ko.make_state_dict(spec, 11, device=dev)
+    sd = ko.make_state_dict(spec, 11, device=dev, res_gain=RES_GAIN)
     enc = SliceEncoder(dict_fes[arch](pretrained=False), with_gap=True).to(dev)
     enc.load_state_dict({k[len("_fe."):]: v.clone() for k, v in sd.items()})
     enc.train(train)
@@ -134,7 +135,7 @@ def section_fe_teacher(arch, n_b=2, slices=3, size=64, xr=False):
     dev = "cuda"
     lib = _lib.load()
     spec = ko.fe_param_spec(arch, "_fe")
-    sd = ko.make_state_dict(spec, 11, device=dev)
+    sd = ko.make_state_dict(spec, 11, device=dev, res_gain=RES_GAIN)
     enc = SliceEncoder(dict_fes[arch](pretrained=False), with_gap=True).to(dev)
     enc.load_state_dict({k[len("_fe."):]: v.clone() for k, v in sd.items()})
     enc.train(True)
@@ -225,7 +226,7 @@ def section_floor(arch, n_b=2, slices=3, size=64, train=True):
     outs = []
     gy = None
     for emu in (False, True):
-        sd = ko.make_state_dict(spec, 11, device=dev)
+        sd = ko.make_state_dict(spec, 11, device=dev, res_gain=RES_GAIN)
         params = {k: v for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
         for v in params.values():
             v.requires_grad_(True)
@@ -346,7 +347,10 @@ def main():
     ap.add_argument("sections", nargs="*", default=["fe", "feat", "models"])
     ap.add_argument("--arch", default="resnet50")
     ap.add_argument("--cases", nargs="*", default=None)
+    ap.add_argument("--res-gain", type=float, default=1.0)
     args = ap.parse_args()
+    global RES_GAIN
+    RES_GAIN = args.res_gain
     if "fe" in args.sections:
         section_fe(args.arch, train=True)
         section_fe(args.arch, train=False)
@@ -364,6 +368,9 @@ def main():
     if "floor" in args.sections:
         section_floor(args.arch, train=True)
         section_floor(args.arch, train=False)
+    if "floor2" in args.sections:
+        section_floor(args.arch, n_b=4, slices=4, size=64, train=True)
+        section_fe(args.arch, n_b=4, slices=4, size=64, train=True)
     if "fe_eval" in args.sections:
         section_fe(args.arch, train=False)
     if "fe_big" in args.sections:
