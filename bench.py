@@ -220,6 +220,8 @@ def run_ours(args):
     launches = lib.koa_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     prof = (C.c_double * 6)()
+    if args.profile_dump and rank == 0:
+        lib.koa_profile_dump(args.profile_dump.encode())
     lib.koa_profile_read(prof)
     lib.koa_profile_enable(0)
     flag = _lib.debug_flag()
@@ -304,6 +306,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="knees per GPU (runner.sh:342 trains the full model at 16)")
     ap.add_argument("--cpu-knees", type=int, default=1, help="knees in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-dump", default=None, help="write the per-shape tcgen05 kernel timing table to this file")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -44,6 +44,8 @@ long long koa_launch_count(void);
  * GEMMs and implicit-GEMM convolutions, cls 1 = weight-gradient GEMMs. Reading synchronises and clears. */
 int koa_profile_enable(int on);
 int koa_profile_read(double* out);
+/* Writes a per-shape breakdown of the recorded launches to a text file (does not clear the records). */
+int koa_profile_dump(const char* path);
 
 /* ---- fused GEMM epilogue --------------------------------------------------------------------- */
 enum { KOA_ACT_NONE = 0, KOA_ACT_RELU = 1, KOA_ACT_GELU = 2, KOA_ACT_GELU_GRAD = 3 };

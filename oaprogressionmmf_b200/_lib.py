@@ -92,6 +92,7 @@ SIGNATURES = {
     "koa_launch_count": (C.c_longlong, []),
     "koa_profile_enable": (_I, [_I]),
     "koa_profile_read": (_I, [C.POINTER(C.c_double)]),
+    "koa_profile_dump": (_I, [C.c_char_p]),
     "koa_gemm_bf16": (_I, [_P, _P, _I, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_conv_fprop_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_gemm_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),

@@ -857,7 +857,7 @@ int koa_k_col_stats(const void* y, float* sum, float* sumsq, long long rows, int
   if (rc) return rc;
   const int threads = reduce_threads(c);
   const int lanes = threads / (c / 8);
-  col_stats_kernel<<<grid_for(rows, lanes, 148 * 4), threads, 2 * c * sizeof(float), st>>>((const bf16*)y, sum, sumsq, rows, c);
+  col_stats_kernel<<<grid_for(rows, lanes, 148 * 8), threads, 2 * c * sizeof(float), st>>>((const bf16*)y, sum, sumsq, rows, c);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -876,7 +876,7 @@ int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const 
   if (rc) return rc;
   const int threads = reduce_threads(c);
   const int lanes = threads / (c / 8);
-  bn_bwd_reduce_kernel<<<grid_for(rows, lanes, 148 * 4), threads, 3 * c * sizeof(float), st>>>(
+  bn_bwd_reduce_kernel<<<grid_for(rows, lanes, 148 * 8), threads, 3 * c * sizeof(float), st>>>(
       (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean, invstd, (const bf16*)y2, mean2, invstd2, sum_dz,
       sum_dzx, sum_dzx2, rows, c);
   KOA_LAUNCH_CHECK();

@@ -1,5 +1,7 @@
 // gemm_api.cu — host launchers + C-ABI entry points for the tcgen05 GEMM / implicit-GEMM kernels.
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "../../include/koa_b200.h"
@@ -16,14 +18,15 @@ static WgradDesc s_wgrad_desc = {8192u, 1024u, 2048u};
 // and returns device time, algorithmic FLOPs (2*M*N*K) and launch counts per kernel class
 // (0 = fprop/dgrad/linear "kmajor" kernels, 1 = weight-gradient kernels).
 namespace {
-struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+struct ProfRec { cudaEvent_t a, b; int cls; double flops; int m, n, k, tag; };
 bool s_prof_on = false;
 std::vector<ProfRec> s_prof;
 std::mutex s_prof_mu;
 
 struct ProfScope {
-  cudaStream_t st; int cls; double flops; cudaEvent_t a = nullptr, b = nullptr;
-  ProfScope(cudaStream_t st_, int cls_, double flops_) : st(st_), cls(cls_), flops(flops_) {
+  cudaStream_t st; int cls; double flops; int m, n, k, tag; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(cudaStream_t st_, int cls_, double flops_, int m_ = 0, int n_ = 0, int k_ = 0, int tag_ = 0)
+      : st(st_), cls(cls_), flops(flops_), m(m_), n(n_), k(k_), tag(tag_) {
     if (!s_prof_on) return;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, st);
@@ -32,7 +35,7 @@ struct ProfScope {
     if (!a) return;
     cudaEventRecord(b, st);
     std::lock_guard<std::mutex> lk(s_prof_mu);
-    s_prof.push_back({a, b, cls, flops});
+    s_prof.push_back({a, b, cls, flops, m, n, k, tag});
   }
 };
 }  // namespace
@@ -42,6 +45,28 @@ extern "C" int koa_profile_enable(int on) {
   s_prof_on = on != 0;
   for (auto& r : s_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   s_prof.clear();
+  return 0;
+}
+// Per-shape breakdown of the recorded launches as text lines "cls tag m n k launches ms tflops" (does not clear).
+extern "C" int koa_profile_dump(const char* path) {
+  KOA_CHECK_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(s_prof_mu);
+  struct Acc { double ms = 0, flops = 0; long n = 0; };
+  std::map<std::tuple<int, int, int, int, int>, Acc> acc;
+  for (auto& r : s_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    Acc& a = acc[std::make_tuple(r.cls, r.tag, r.m, r.n, r.k)];
+    a.ms += ms; a.flops += r.flops; a.n += 1;
+  }
+  FILE* f = fopen(path, "w");
+  KOA_REQUIRE(f != nullptr, "cannot open %s", path);
+  fprintf(f, "# cls(0=kmajor,1=wgrad) tag(bit0 im2col, 1 stats, 2 add, 3 mask, 4 res_f32, 5 fp32 out, 6 act) m n k launches total_ms tflops\n");
+  for (auto& kv : acc)
+    fprintf(f, "%d %d %d %d %d %ld %.4f %.1f\n", std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first),
+            std::get<3>(kv.first), std::get<4>(kv.first), kv.second.n, kv.second.ms,
+            kv.second.ms > 0 ? kv.second.flops / (kv.second.ms * 1e-3) / 1e12 : 0.0);
+  fclose(f);
   return 0;
 }
 // out[cls*3 + {0,1,2}] = device milliseconds, algorithmic FLOPs, launches for cls in {0,1}; clears the records.
@@ -101,6 +126,7 @@ static int check_epi(const koa_epilogue_t* ep, int n) {
   KOA_REQUIRE(ep->ldo >= n && ep->ldo % 8 == 0, "ldo (%d) must be >= N and a multiple of 8", ep->ldo);
   KOA_REQUIRE(ep->act != KOA_ACT_GELU_GRAD || ep->aux_bf16 != nullptr, "KOA_ACT_GELU_GRAD needs aux_bf16");
   KOA_REQUIRE((ep->col_sum == nullptr) == (ep->col_sumsq == nullptr), "col_sum and col_sumsq go together");
+  KOA_REQUIRE(ep->col_sum == nullptr || n <= kMaxStatCols, "column statistics support N <= %d (got %d)", kMaxStatCols, n);
   return 0;
 }
 
@@ -117,9 +143,12 @@ static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
   KOA_CHECK_CUDA(attr_err);
   const long long tiles = (long long)koa_cdiv(m, BM) * koa_cdiv(n, BN);
   KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
+  const unsigned grid = (unsigned)(tiles < koa_num_sms() ? tiles : koa_num_sms());  // persistent: one CTA per SM
   {
-    ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k);
-    gemm_kmajor_kernel<BN, STAGES, IM2COL><<<(unsigned)tiles, kGemmThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
+    const int flavor = (IM2COL ? 1 : 0) | (ep.col_sum ? 2 : 0) | (ep.add_bf16 ? 4 : 0) | (ep.mask_bf16 ? 8 : 0) |
+                       (ep.res_f32 ? 16 : 0) | (ep.out_fp32 ? 32 : 0) | (ep.act ? 64 : 0);
+    ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, flavor);
+    gemm_kmajor_kernel<BN, STAGES, IM2COL><<<grid, kKmajorThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
   }
   KOA_LAUNCH_CHECK();
   return 0;
@@ -133,12 +162,10 @@ static int dispatch_kmajor(const CUtensorMap& ta, const void* b, int m, int n, i
   CUtensorMap tb;
   int rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, bn128 ? 128 : 64);
   if (rc) return rc;
-  if (bn128) {
-    if (num_kb <= 2) return launch_kmajor<128, 2, IM2COL>(ta, tb, m, n, k, g, ep, st);
-    return launch_kmajor<128, 4, IM2COL>(ta, tb, m, n, k, g, ep, st);
-  }
-  if (num_kb <= 2) return launch_kmajor<64, 2, IM2COL>(ta, tb, m, n, k, g, ep, st);
-  return launch_kmajor<64, 4, IM2COL>(ta, tb, m, n, k, g, ep, st);
+  (void)num_kb;
+  // persistent kernel, one CTA per SM: a deep smem ring lets the TMA producer run ahead across tiles
+  if (bn128) return launch_kmajor<128, 5, IM2COL>(ta, tb, m, n, k, g, ep, st);
+  return launch_kmajor<64, 8, IM2COL>(ta, tb, m, n, k, g, ep, st);
 }
 
 int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep, cudaStream_t st) {
@@ -195,7 +222,7 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
   {
     // grouped: only the diagonal 64x64 blocks are algorithmic work
     const double n_eff = g.grouped ? 64.0 : (double)cin;
-    ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps);
+    ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps, cout, cin * taps, pixels, IM2COL ? 1 : 0);
     gemm_wgrad_kernel<BN, STAGES, IM2COL>
         <<<grid, kGemmThreads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc);
   }
@@ -212,8 +239,8 @@ int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, 
   rc = koa_tmap_2d_bf16(&tb, x, (uint64_t)cin, (uint64_t)pixels, (uint64_t)cin * 2, 64, 64);
   if (rc) return rc;
   ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
-  if (cin % 128 == 0) return launch_wgrad<128, 4, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
-  return launch_wgrad<64, 4, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
+  if (cin % 128 == 0) return launch_wgrad<128, 3, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
+  return launch_wgrad<64, 3, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
 }
 
 int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int cin, int cout,
@@ -230,8 +257,8 @@ int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, i
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64, 0};
   const int taps = filt_r * filt_s;
-  if (cin % 128 == 0) return launch_wgrad<128, 4, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
-  return launch_wgrad<64, 4, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
+  if (cin % 128 == 0) return launch_wgrad<128, 3, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
+  return launch_wgrad<64, 3, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
 }
 
 // Grouped 3x3 convolution (ResNeXt, koafusion/models/_torchvision.py:110,327-328) as a block-diagonal dense
@@ -250,7 +277,7 @@ int koa_conv_grouped_launch(const void* x, const void* w, int n_img, int h, int 
   rc = koa_tmap_2d_bf16(&tb, w, 576, (uint64_t)c, 576 * 2, 64, 64);
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, 1, 3, 1, 1};
-  return launch_kmajor<64, 4, true>(ta, tb, (int)m, c, 576, g, to_epi(ep), st);
+  return launch_kmajor<64, 8, true>(ta, tb, (int)m, c, 576, g, to_epi(ep), st);
 }
 
 // dw[C][9][64] += per-chunk dense weight gradient of the grouped convolution.
@@ -266,7 +293,7 @@ int koa_conv_grouped_wgrad_launch(const void* dy, const void* x, float* dw, int 
   rc = koa_tmap_im2col_bf16(&tb, x, n_img, h, w_in, c, 3, 3, stride, 1, 64);
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, 1, 3, c / 64, 1};
-  return launch_wgrad<64, 4, true>(ta, tb, c, c, (int)pixels, 9, g, dw, st);
+  return launch_wgrad<64, 3, true>(ta, tb, c, c, (int)pixels, 9, g, dw, st);
 }
 
 // ------------------------------------ C ABI ----------------------------------------------------

@@ -37,18 +37,78 @@ struct EpiParams {
   float* col_sumsq;
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;     // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kEpiWarps = 8;          // fprop/dgrad kernel: 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int kKmajorThreads = 64 + 32 * kEpiWarps;
 constexpr int BM = 128;
 constexpr int BK = 64;
 
+constexpr int kMaxStatCols = 2048;  // widest BatchNorm in the networks (layer4 output)
 template <int BN, int STAGES>
 constexpr size_t gemm_smem_bytes() {
-  return 1024 /*align slack*/ + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 +
-         2 * BN * sizeof(float);
+  return 1024 /*align slack*/ + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 +
+         2 * kMaxStatCols * sizeof(float) + kEpiWarps * 2048 /*epilogue staging*/ + 16;
 }
 
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiParams& ep, long long row_off, int n,
-                                               bool row_ok, int lane, float* s_sum, float* s_sumsq, int c_local) {
+// ---- coalesced epilogue stores -------------------------------------------------------------------
+// After tcgen05.ld a thread owns 32 consecutive columns of ONE row, so a direct store would write 16-byte
+// pieces of 32 different rows per instruction (half-filled sectors). Each epilogue warp therefore stages its
+// 32-row sub-tile in a private 2 KB shared-memory buffer ([32 rows][64 bytes], 16-byte pieces XOR-swizzled by
+// (row >> 1) & 3 so both the row-wise writes and the transposed reads are bank-conflict free) and writes it
+// back 8 rows x 64 contiguous bytes per instruction.
+constexpr int kStageBytesPerWarp = 32 * 64;
+
+__device__ __forceinline__ uint32_t stage_off(int row, int piece) {
+  return (uint32_t)(row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+}
+
+// Row-major store of a [32 rows][64 bytes] warp tile: `gbase` points at (first row of the warp, first byte of the
+// 64-byte segment); rows are `pitch_bytes` apart; rows >= rows_valid are skipped.
+__device__ __forceinline__ void stage_flush(const uint8_t* stage, uint8_t* gbase, long long pitch_bytes, int rows_valid,
+                                            int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2);
+    const int piece = lane & 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(row, piece));
+    if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + row * pitch_bytes + piece * 16) = v;
+  }
+  __syncwarp();
+}
+
+// 32 fp32 values of this thread's row -> bf16 -> staged -> coalesced store at column n of a bf16 [M][ld] tensor.
+__device__ __forceinline__ void store_row_bf16(const float (&v)[32], uint8_t* stage, bf16* g, long long ld, long long row0,
+                                               int n, int rows_valid, int lane) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    uint4 q;
+    q.x = pack_bf16x2(v[p * 8 + 0], v[p * 8 + 1]); q.y = pack_bf16x2(v[p * 8 + 2], v[p * 8 + 3]);
+    q.z = pack_bf16x2(v[p * 8 + 4], v[p * 8 + 5]); q.w = pack_bf16x2(v[p * 8 + 6], v[p * 8 + 7]);
+    *reinterpret_cast<uint4*>(stage + stage_off(lane, p)) = q;
+  }
+  stage_flush(stage, reinterpret_cast<uint8_t*>(g + row0 * ld + n), ld * 2, rows_valid, lane);
+}
+
+__device__ __forceinline__ void store_row_f32(const float (&v)[32], uint8_t* stage, float* g, long long ld, long long row0,
+                                              int n, int rows_valid, int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {  // two 16-column halves of 64 bytes each
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      *reinterpret_cast<float4*>(stage + stage_off(lane, p)) =
+          make_float4(v[h * 16 + p * 4 + 0], v[h * 16 + p * 4 + 1], v[h * 16 + p * 4 + 2], v[h * 16 + p * 4 + 3]);
+    stage_flush(stage, reinterpret_cast<uint8_t*>(g + row0 * ld + n + h * 16), ld * 4, rows_valid, lane);
+  }
+}
+
+// Epilogue of one 32-row x 32-column chunk. `row0` = first row of this warp's 32-row group, the thread owns row
+// row0 + lane. `stage` = this warp's 2 KB staging buffer.
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiParams& ep, long long row0, int rows_valid,
+                                               int n, int lane, uint8_t* stage, float* s_sum, float* s_sumsq,
+                                               int c_local) {
+  const bool row_ok = lane < rows_valid;
+  const long long row_off = (row0 + lane) * ep.ldo;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -60,16 +120,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
-  if (ep.pre_out != nullptr && row_ok) {
-    uint4* dst = reinterpret_cast<uint4*>(ep.pre_out + row_off + n);
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 q;
-      q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-      q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-      dst[j / 8] = q;
-    }
-  }
+  if (ep.pre_out != nullptr) store_row_bf16(v, stage, ep.pre_out, ep.ldo, row0, n, rows_valid, lane);
   if (ep.act == ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -124,56 +175,59 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
       for (int u = 0; u < 8; ++u) v[j + u] += a[u];
     }
   }
-  if (row_ok) {
-    if (ep.out_fp32) {
-      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + row_off + n);
+  if (ep.out_fp32) {
+    store_row_f32(v, stage, reinterpret_cast<float*>(ep.out), ep.ldo, row0, n, rows_valid, lane);
+    if (ep.out_bf16_copy != nullptr) store_row_bf16(v, stage, ep.out_bf16_copy, ep.ldo, row0, n, rows_valid, lane);
+  } else {
+    // bf16 output: stage, (statistics from the staged, i.e. rounded, values), coalesced write-back
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) dst[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      if (ep.out_bf16_copy != nullptr) {
-        uint4* d2 = reinterpret_cast<uint4*>(ep.out_bf16_copy + row_off + n);
+    for (int p = 0; p < 4; ++p) {
+      uint4 q;
+      q.x = pack_bf16x2(v[p * 8 + 0], v[p * 8 + 1]); q.y = pack_bf16x2(v[p * 8 + 2], v[p * 8 + 3]);
+      q.z = pack_bf16x2(v[p * 8 + 4], v[p * 8 + 5]); q.w = pack_bf16x2(v[p * 8 + 6], v[p * 8 + 7]);
+      if (!row_ok) q = make_uint4(0, 0, 0, 0);  // rows past M contribute exact zeros to the statistics
+      *reinterpret_cast<uint4*>(stage + stage_off(lane, p)) = q;
+    }
+    if (ep.col_sum != nullptr) {
+      __syncwarp();
+      // lane = (h, p): column pair (2p, 2p+1) over the 16 rows 2i + h; the two lane halves read rows in different
+      // bank halves, each half reads one contiguous 64-byte row per step (conflict free)
+      const int h = lane >> 4, p = lane & 15;
+      float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 q;
-          q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-          q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-          d2[j / 8] = q;
-        }
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + stage_off(2 * i + h, p >> 2) + (p & 3) * 4);
+        const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+        s0 += x0; s1 += x1;
+        q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
       }
-    } else {
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + row_off + n);
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 q;
-        q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-        q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-        dst[j / 8] = q;
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+      if (h == 0) {
+        atomicAdd(&s_sum[c_local + 2 * p], s0); atomicAdd(&s_sum[c_local + 2 * p + 1], s1);
+        atomicAdd(&s_sumsq[c_local + 2 * p], q0); atomicAdd(&s_sumsq[c_local + 2 * p + 1], q1);
       }
     }
-  }
-  if (ep.col_sum != nullptr) {
-    // Statistics of the values as stored (bf16-rounded); rows past M hold exact zeros.
-    float s[32], q[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = row_ok ? bf16_round(v[j]) : 0.0f;
-      s[j] = x;
-      q[j] = x * x;
-    }
-    warp_transpose_reduce32(s, lane);
-    warp_transpose_reduce32(q, lane);
-    atomicAdd(&s_sum[c_local + lane], s[0]);
-    atomicAdd(&s_sumsq[c_local + lane], q[0]);
+    stage_flush(stage, reinterpret_cast<uint8_t*>(reinterpret_cast<bf16*>(ep.out) + row0 * ep.ldo + n), (long long)ep.ldo * 2,
+                rows_valid, lane);
   }
 }
 
 // out[M, N] = A[M, K] * B[N, K]^T with the fused epilogue. A_IM2COL: A rows are the output
 // pixels of a convolution over an NHWC tensor and K enumerates (r, s, cin).
+//
+// Persistent: gridDim.x = min(#tiles, #SMs) CTAs walk the tile list (n-tile fastest, so CTAs running at the
+// same time share their A rows through L2). Three pipelines overlap across tiles:
+//   TMA -> smem ring (STAGES deep, full/empty mbarriers, runs ahead into the next tile),
+//   MMA -> TMEM accumulator ring (2 x BN columns, tmem_full/tmem_empty mbarriers),
+//   epilogue warps drain accumulator i while the MMA of tile i+1 is issued.
 template <int BN, int STAGES, bool A_IM2COL>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kKmajorThreads, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                    int K, ConvGeom g, EpiParams ep) {
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr int ACC = 2;  // TMEM accumulator stages
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
@@ -181,18 +235,20 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [ACC]
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC; // [ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
+  // BatchNorm statistics are accumulated per output column in shared memory over ALL tiles of this CTA and
+  // flushed once at the end: 148 same-address global atomics per column instead of one per tile.
   float* s_sum = reinterpret_cast<float*>(tmem_slot + 4);
-  float* s_sumsq = s_sum + BN;
+  float* s_sumsq = s_sum + kMaxStatCols;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(((uintptr_t)(s_sumsq + kMaxStatCols) + 15) & ~(uintptr_t)15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (N + BN - 1) / BN;
-  const int n_t = blockIdx.x % n_tiles;
-  const int m_t = blockIdx.x / n_tiles;
-  const int m0 = m_t * BM;
-  const int n0 = n_t * BN;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int num_tiles = n_tiles * m_tiles;
   const int num_kb = (K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
@@ -203,10 +259,14 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+#pragma unroll
+    for (int a = 0; a < ACC; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
+    }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, ACC * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -214,87 +274,124 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      int pw = 0, ph = 0, pn = 0;
-      if (A_IM2COL) {
-        const int hw = g.hout * g.wout;
-        pn = m0 / hw;
-        const int rem = m0 - pn * hw;
-        const int oh = rem / g.wout;
-        const int ow = rem - oh * g.wout;
-        pw = ow * g.stride - g.pad;
-        ph = oh * g.stride - g.pad;
-      }
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t phase = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], phase ^ 1, 0x100 + s);
-        mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+      uint32_t it = 0;  // k-block counter across all tiles of this CTA
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_t = tile % n_tiles;
+        const int m0 = (tile / n_tiles) * BM;
+        const int n0 = n_t * BN;
+        int pw = 0, ph = 0, pn = 0;
         if (A_IM2COL) {
-          const int tap = kb / g.cin_blocks;
-          const int cb = kb - tap * g.cin_blocks;
-          const int fr = tap / g.filt_s;
-          const int fs = tap - fr * g.filt_s;
-          const int c0 = g.grouped ? n_t * 64 : cb * 64;
-          tma_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], c0, pw, ph, pn, (uint16_t)fs, (uint16_t)fr);
-        } else {
-          tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+          const int hw = g.hout * g.wout;
+          pn = m0 / hw;
+          const int rem = m0 - pn * hw;
+          const int oh = rem / g.wout;
+          const int ow = rem - oh * g.wout;
+          pw = ow * g.stride - g.pad;
+          ph = oh * g.stride - g.pad;
         }
-        tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], phase ^ 1, 0x100 + s);
+          mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          if (A_IM2COL) {
+            const int tap = kb / g.cin_blocks;
+            const int cb = kb - tap * g.cin_blocks;
+            const int fr = tap / g.filt_s;
+            const int fs = tap - fr * g.filt_s;
+            const int c0 = g.grouped ? n_t * 64 : cb * 64;
+            tma_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], c0, pw, ph, pn, (uint16_t)fs, (uint16_t)fr);
+          } else {
+            tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+          }
+          tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t phase = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], phase, 0x200 + s);
+      uint32_t it = 0, lt = 0;  // k-block counter, local tile counter
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t acc = lt % ACC;
+        const uint32_t acc_phase = (lt / ACC) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, 0x700 + acc);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * B_BYTES), 16, 1024);
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], phase, 0x200 + s);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * B_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 (32 bytes) along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
-          umma_bf16_ss(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 (32 bytes) along K inside the 128-byte swizzle row: +2 in (addr >> 4) units
+            umma_bf16_ss(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&tmem_full_bar[acc]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
-    // Epilogue warps 2..5; TMEM lane quarter is fixed by warp id modulo 4.
+    // Epilogue warps 2..9: the TMEM lane quarter is fixed by warp id modulo 4; the two warps of a quarter take
+    // alternate 32-column chunks of the tile.
     const int q = warp & 3;
-    const int ep_tid = (warp - 2) * 32 + lane;
-    if (ep.col_sum != nullptr) {
-      for (int i = ep_tid; i < 2 * BN; i += 128) s_sum[i] = 0.0f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int e = warp - 2;
+    const int chunk_par = e >> 2;
+    const int ep_tid = e * 32 + lane;
+    constexpr int kEpiThreads = kEpiWarps * 32;
+    uint8_t* stage = s_stage + e * kStageBytesPerWarp;
+    const bool stats = ep.col_sum != nullptr;
+    if (stats) {
+      for (int i = ep_tid; i < 2 * kMaxStatCols; i += kEpiThreads) s_sum[i] = 0.0f;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
-    mbar_wait(tmem_full_bar, 0, 0x300);
-    tc_fence_after();
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < M;
-    const long long row_off = (long long)row * ep.ldo;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * BM;
+      const uint32_t acc = lt % ACC;
+      const uint32_t acc_phase = (lt / ACC) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase, 0x300 + acc);
+      tc_fence_after();
+      const long long row0 = (long long)m0 + q * 32;
+      const int rows_valid = max(0, min(32, M - (int)row0));
+      bool released = false;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= N) break;
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      epilogue_chunk(r, ep, row_off, n0 + c0, row_ok, lane, s_sum, s_sumsq, c0);
-    }
-    if (ep.col_sum != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = ep_tid; i < BN; i += 128) {
-        if (n0 + i < N) {
-          atomicAdd(ep.col_sum + n0 + i, s_sum[i]);
-          atomicAdd(ep.col_sumsq + n0 + i, s_sumsq[i]);
+      for (int c0 = chunk_par * 32; c0 < BN; c0 += 64) {
+        if (n0 + c0 >= N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (c0 + 64 >= BN || n0 + c0 + 64 >= N) {
+          // last TMEM read of this warp for this tile: hand the accumulator back before the global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          released = true;
         }
+        epilogue_chunk(r, ep, row0, rows_valid, n0 + c0, lane, stage, s_sum, s_sumsq, n0 + c0);
+      }
+      if (!released) {  // this warp had no chunk inside N
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
+    }
+    if (stats) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      for (int i = ep_tid; i < N; i += kEpiThreads) {
+        atomicAdd(ep.col_sum + i, s_sum[i]);
+        atomicAdd(ep.col_sumsq + i, s_sumsq[i]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, ACC * BN);
 }
 
 // Weight-gradient GEMM: dW[Cout, tap, Cin] += sum over pixels p of dY[p, Cout] * X[p (shifted by tap), Cin].
