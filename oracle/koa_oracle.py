@@ -387,21 +387,29 @@ def _slices_to_images(vol: Tensor) -> Tensor:
     return vol.permute(0, 4, 1, 2, 3).reshape(b * s, ch, r, c).expand(-1, 3, -1, -1)
 
 
-def _fe_tokens(sd, prefix, arch, images, training, batch, drop_p, taps=None):
+def _fe_tokens(sd, prefix, arch, images, training, batch, drop_p, taps=None, emulate_bf16=False):
     """FE → Dropout2d → tokens "(b s) ch 1 1 -> b s ch" (_xrNmrMcP.py:226-232)."""
-    f = fe_forward(sd, prefix, arch, images, training, True, taps)
+    f = fe_forward(sd, prefix, arch, images, training, True, taps, emulate_bf16=emulate_bf16)
     if drop_p:
         f = F.dropout2d(f, drop_p, training)
     return f.reshape(batch, -1, f.shape[1])
 
 
 def model_forward(name: str, cfg: dict, sd: StateDict, inputs: Sequence[Tensor], training: bool,
-                  taps: Dict[str, Tensor] | None = None) -> Tensor:
-    """Logits (B, output_channels) of ``dict_models[name]`` for positional ``inputs``."""
+                  taps: Dict[str, Tensor] | None = None, emulate_bf16: bool = False) -> Tensor:
+    """Logits (B, output_channels) of ``dict_models[name]`` for positional ``inputs``.
+    ``emulate_bf16`` rounds the feature extractors' stored tensors to bf16 (see ``fe_forward``); it exists to
+    measure the precision floor of bf16 storage with no CUDA-path code involved."""
     agg = cfg["agg"]
+    _tok = globals()["_fe_tokens"]
+
+    def _fe_tokens(*a, **k):  # noqa: F811 - thread the emulation flag through every extractor call below
+        return _tok(*a, emulate_bf16=emulate_bf16, **k)
+
     if name == "XR1Cnn":  # _xr1_cnn.py:48-81
         x = inputs[0]
-        f = fe_forward(sd, "_fe", cfg["fe"]["arch"], x.expand(-1, 3, -1, -1), training, True, taps).flatten(1)
+        f = fe_forward(sd, "_fe", cfg["fe"]["arch"], x.expand(-1, 3, -1, -1), training, True, taps,
+                       emulate_bf16=emulate_bf16).flatten(1)
         f = _dropout(f, agg["dropout"], training)
         f = F.relu(F.linear(f, sd["_agg.1.weight"], sd["_agg.1.bias"]))
         f = _dropout(f, agg["dropout"], training)
@@ -477,14 +485,14 @@ def focal_loss(logits: Tensor, target: Tensor, gamma: float = 2.0) -> Tensor:
 
 
 def train_step(name: str, cfg: dict, sd: StateDict, inputs: Sequence[Tensor], target: Tensor,
-               taps: Dict[str, Tensor] | None = None):
+               taps: Dict[str, Tensor] | None = None, emulate_bf16: bool = False):
     """zero_grad → forward(train) → FocalLoss → backward (koafusion/run/train_prog_fus.py:133-165).
     Returns (logits, loss, {key: grad or None}). BN running stats in ``sd`` are updated in place."""
     params = {k: v for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
     for v in params.values():
         v.requires_grad_(True)
         v.grad = None
-    logits = model_forward(name, cfg, sd, inputs, True, taps)
+    logits = model_forward(name, cfg, sd, inputs, True, taps, emulate_bf16=emulate_bf16)
     loss = focal_loss(logits, target)
     loss.backward()
     grads = {k: v.grad for k, v in params.items()}
