@@ -59,11 +59,15 @@ typedef struct koa_epilogue {
   void* pre_out_bf16;        /* optional bf16 copy of (acc + bias) before the activation */
   const void* aux_bf16;      /* KOA_ACT_GELU_GRAD: pre-activation h; value *= gelu'(h) */
   const float* residual_f32; /* optional fp32 addend */
-  const void* add_bf16;      /* optional bf16 addend ... */
-  const void* mask_bf16;     /* ... gated by mask > 0 when non-NULL (ReLU'd residual gradient) */
+  const void* add_bf16;      /* optional bf16 addend */
+  const void* gate_bf16;     /* optional: the final value is zeroed where gate <= 0 (ReLU backward by the forward
+                                activation, applied after every addend) */
   void* out_bf16_copy;       /* optional bf16 copy of the final value when out is fp32 */
-  float* col_sum;            /* optional per-column sum / sum of squares (BatchNorm batch statistics), */
-  float* col_sumsq;          /* accumulated with atomics: caller zeroes them first */
+  float* col_sum;            /* optional per-column sum / sum of squares of the stored bf16 output (BatchNorm batch */
+  float* col_sumsq;          /* statistics), accumulated with atomics: caller zeroes them first */
+  const void* stat_y;        /* BatchNorm backward form of the statistics: when non-NULL, col_sumsq receives */
+  const float* stat_mean;    /* sum(out * xhat) with xhat = (stat_y - stat_mean) * stat_invstd (stat_y: bf16 */
+  const float* stat_invstd;  /* [M, ldo], the forward conv output), i.e. col_sum / col_sumsq = dbeta / dgamma */
 } koa_epilogue_t;
 
 /* out[M,N] = epilogue(A[M,K] . B[N,K]^T); A, B bf16 row-major. tcgen05/TMEM tiles fed by TMA.

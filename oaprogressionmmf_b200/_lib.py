@@ -30,10 +30,13 @@ class Epilogue(C.Structure):
         ("aux_bf16", C.c_void_p),
         ("residual_f32", C.c_void_p),
         ("add_bf16", C.c_void_p),
-        ("mask_bf16", C.c_void_p),
+        ("gate_bf16", C.c_void_p),
         ("out_bf16_copy", C.c_void_p),
         ("col_sum", C.c_void_p),
         ("col_sumsq", C.c_void_p),
+        ("stat_y", C.c_void_p),
+        ("stat_mean", C.c_void_p),
+        ("stat_invstd", C.c_void_p),
     ]
 
 

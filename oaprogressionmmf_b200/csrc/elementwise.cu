@@ -261,23 +261,39 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
   load8f(invstd + g * 8, is);
   if (y2 != nullptr) { load8f(mean2 + g * 8, mu2); load8f(invstd2 + g * 8, is2); }
   if (rl < lanes) {
-    for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
-      const long long off = r * c + g * 8;
-      float dz[8], yy[8];
-      unpack8(*reinterpret_cast<const uint4*>(dout + off), dz);
-      if (act != nullptr) {
-        float m[8];
-        unpack8(*reinterpret_cast<const uint4*>(act + off), m);
+    const long long stride = (long long)gridDim.x * lanes;
+    const bool has_act = act != nullptr, has_y2 = y2 != nullptr;
+    for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += 4 * stride) {
+      // four rows per iteration: all 16-byte loads are issued before the first use
+      uint4 qd[4], qm[4], qy[4], qz[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) dz[u] = m[u] > 0.0f ? dz[u] : 0.0f;
+      for (int j = 0; j < 4; ++j) {
+        const long long rr = r + j * stride;
+        const bool ok = rr < rows;
+        const long long off = (ok ? rr : r) * c + g * 8;
+        qd[j] = ok ? *reinterpret_cast<const uint4*>(dout + off) : make_uint4(0, 0, 0, 0);
+        qy[j] = *reinterpret_cast<const uint4*>(y + off);
+        if (has_act) qm[j] = *reinterpret_cast<const uint4*>(act + off);
+        if (has_y2) qz[j] = *reinterpret_cast<const uint4*>(y2 + off);
       }
-      unpack8(*reinterpret_cast<const uint4*>(y + off), yy);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { a[u] += dz[u]; b[u] += dz[u] * (yy[u] - mu[u]) * is[u]; }
-      if (y2 != nullptr) {
-        unpack8(*reinterpret_cast<const uint4*>(y2 + off), yy);
+      for (int j = 0; j < 4; ++j) {
+        float dz[8], yy[8];
+        unpack8(qd[j], dz);
+        if (has_act) {
+          float m[8];
+          unpack8(qm[j], m);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) b2[u] += dz[u] * (yy[u] - mu2[u]) * is2[u];
+          for (int u = 0; u < 8; ++u) dz[u] = m[u] > 0.0f ? dz[u] : 0.0f;
+        }
+        unpack8(qy[j], yy);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a[u] += dz[u]; b[u] += dz[u] * (yy[u] - mu[u]) * is[u]; }
+        if (has_y2) {
+          unpack8(qz[j], yy);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) b2[u] += dz[u] * (yy[u] - mu2[u]) * is2[u];
+        }
       }
     }
   }
@@ -462,7 +478,9 @@ __global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ f
   }
 }
 
-__global__ void gap_bwd_kernel(const float* __restrict__ dfeat, bf16* __restrict__ dx, int n, int hw, int c) {
+// dx[n][p][c] = dfeat[n][c] / hw, zeroed where gate <= 0 (gate = the pooled activation: ReLU backward folded in)
+__global__ void gap_bwd_kernel(const float* __restrict__ dfeat, const bf16* __restrict__ gate, bf16* __restrict__ dx, int n,
+                               int hw, int c) {
   const int cg = c / 8;
   const long long total = (long long)n * hw * cg;
   const float inv = 1.0f / (float)hw;
@@ -473,6 +491,12 @@ __global__ void gap_bwd_kernel(const float* __restrict__ dfeat, bf16* __restrict
     load8f(dfeat + ni * c + g * 8, f);
 #pragma unroll
     for (int u = 0; u < 8; ++u) f[u] *= inv;
+    if (gate != nullptr) {
+      float m[8];
+      unpack8(*reinterpret_cast<const uint4*>(gate + i * 8), m);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = m[u] > 0.0f ? f[u] : 0.0f;
+    }
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(f);
   }
 }
@@ -496,9 +520,10 @@ __global__ void zero_insert2_kernel(const bf16* __restrict__ src, bf16* __restri
   }
 }
 
-// dx[n][2*oh][2*ow][c] += src[n][oh][ow][c]  (data gradient of a 1x1 stride-2 convolution)
-__global__ void scatter_add2_kernel(const bf16* __restrict__ src, bf16* __restrict__ dx, int n, int h, int w, int c,
-                                    int ho, int wo) {
+// dx[n][2*oh][2*ow][c] += src[n][oh][ow][c] (data gradient of a 1x1 stride-2 convolution); the addend is zeroed
+// where gate (same layout as dx) <= 0.
+__global__ void scatter_add2_kernel(const bf16* __restrict__ src, const bf16* __restrict__ gate, bf16* __restrict__ dx,
+                                    int n, int h, int w, int c, int ho, int wo) {
   const int cg = c / 8;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -507,10 +532,17 @@ __global__ void scatter_add2_kernel(const bf16* __restrict__ src, bf16* __restri
     const int ow = (int)(t % wo); t /= wo;
     const int oh = (int)(t % ho); t /= ho;
     const int ni = (int)t;
-    bf16* p = dx + ((((long long)ni * h + oh * 2) * w + ow * 2) * cg + g) * 8;
+    const long long o = ((((long long)ni * h + oh * 2) * w + ow * 2) * cg + g) * 8;
+    bf16* p = dx + o;
     float a[8], b[8];
     unpack8(*reinterpret_cast<const uint4*>(p), a);
     unpack8(*reinterpret_cast<const uint4*>(src + i * 8), b);
+    if (gate != nullptr) {
+      float m[8];
+      unpack8(*reinterpret_cast<const uint4*>(gate + o), m);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) b[u] = m[u] > 0.0f ? b[u] : 0.0f;
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) a[u] += b[u];
     *reinterpret_cast<uint4*>(p) = pack8(a);
@@ -922,9 +954,9 @@ int koa_k_gap_fwd(const void* x, float* feat, int n, int hw, int c, cudaStream_t
   KOA_LAUNCH_CHECK();
   return 0;
 }
-int koa_k_gap_bwd(const float* dfeat, void* dx, int n, int hw, int c, cudaStream_t st) {
+int koa_k_gap_bwd(const float* dfeat, const void* gate, void* dx, int n, int hw, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
-  gap_bwd_kernel<<<grid_for((long long)n * hw * (c / 8)), kThreads, 0, st>>>(dfeat, (bf16*)dx, n, hw, c);
+  gap_bwd_kernel<<<grid_for((long long)n * hw * (c / 8)), kThreads, 0, st>>>(dfeat, (const bf16*)gate, (bf16*)dx, n, hw, c);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -935,10 +967,11 @@ int koa_k_zero_insert2(const void* src, void* dst, int n, int h, int w, int c, i
   KOA_LAUNCH_CHECK();
   return 0;
 }
-int koa_k_scatter_add2(const void* src, void* dx, int n, int h, int w, int c, int ho, int wo, cudaStream_t st) {
+int koa_k_scatter_add2(const void* src, const void* gate, void* dx, int n, int h, int w, int c, int ho, int wo,
+                       cudaStream_t st) {
   KOA_REQ_C8(c);
-  scatter_add2_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), kThreads, 0, st>>>((const bf16*)src, (bf16*)dx, n, h,
-                                                                                       w, c, ho, wo);
+  scatter_add2_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), kThreads, 0, st>>>((const bf16*)src, (const bf16*)gate,
+                                                                                       (bf16*)dx, n, h, w, c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
 }

@@ -355,12 +355,14 @@ namespace {
 
 // BatchNorm backward of one unit (optionally two units sharing the incoming gradient):
 // reduce -> finalize (dgamma/dbeta + coefficients) -> apply.
+// `stats_done`: sum_dz / sum_dz_xhat of `u` were already accumulated by the epilogue of the GEMM that produced `dout`.
 int bn_backward(const Unit& u, const Unit* u_b, const ParamView& pv, void* const* grads, void* ws, const void* dout,
-                const void* act_mask, void* dy, void* dy_b, int training, cudaStream_t st) {
-  KOA_TRY(koa_k_bn_bwd_reduce(dout, act_mask, at(ws, u.y), bn_slot(ws, u, S_MEAN), bn_slot(ws, u, S_INVSTD),
-                              u_b ? at(ws, u_b->y) : nullptr, u_b ? bn_slot(ws, *u_b, S_MEAN) : nullptr,
-                              u_b ? bn_slot(ws, *u_b, S_INVSTD) : nullptr, bn_slot(ws, u, S_SDZ), bn_slot(ws, u, S_SDZX),
-                              u_b ? bn_slot(ws, *u_b, S_SDZX) : nullptr, u.rows_out, u.cout, st));
+                const void* act_mask, void* dy, void* dy_b, int training, bool stats_done, cudaStream_t st) {
+  if (!stats_done)
+    KOA_TRY(koa_k_bn_bwd_reduce(dout, act_mask, at(ws, u.y), bn_slot(ws, u, S_MEAN), bn_slot(ws, u, S_INVSTD),
+                                u_b ? at(ws, u_b->y) : nullptr, u_b ? bn_slot(ws, *u_b, S_MEAN) : nullptr,
+                                u_b ? bn_slot(ws, *u_b, S_INVSTD) : nullptr, bn_slot(ws, u, S_SDZ), bn_slot(ws, u, S_SDZX),
+                                u_b ? bn_slot(ws, *u_b, S_SDZX) : nullptr, u.rows_out, u.cout, st));
   KOA_TRY(koa_k_bn_bwd_finalize(bn_slot(ws, u, S_SDZ), bn_slot(ws, u, S_SDZX), pv.gamma(u), bn_slot(ws, u, S_MEAN),
                                 bn_slot(ws, u, S_INVSTD), (float*)grads[u.idx * 3 + 1], (float*)grads[u.idx * 3 + 2],
                                 bn_slot(ws, u, S_K0), bn_slot(ws, u, S_K1), bn_slot(ws, u, S_K2), u.cout,
@@ -411,8 +413,35 @@ int conv_dgrad(const Plan& p, const Unit& u, const void* dy, void* ws, koa_epilo
   return koa_conv_fprop_launch(src, at(ws, u.w_dgrad), p.n_img, u.hin, u.win, u.cout, u.cin, u.k, u.k, 1, u.pad, ep, st);
 }
 
+// Gate an epilogue by the forward activation `act_off` (ReLU backward) and, when `fuse`, let it accumulate the
+// BatchNorm-backward reductions of unit `u` (whose ReLU output `act_off` is) on the values it stores.
+void gate_and_stats(koa_epilogue_t& ep, void* ws, size_t act_off, const Unit* u, bool fuse) {
+  ep.gate_bf16 = at(ws, act_off);
+  if (fuse && u != nullptr) {
+    ep.col_sum = bn_slot(ws, *u, S_SDZ);
+    ep.col_sumsq = bn_slot(ws, *u, S_SDZX);
+    ep.stat_y = at(ws, u->y);
+    ep.stat_mean = bn_slot(ws, *u, S_MEAN);
+    ep.stat_invstd = bn_slot(ws, *u, S_INVSTD);
+  }
+}
+
+bool fuse_bn_bwd_stats() {
+  static const int v = [] {
+    const char* e = getenv("KOA_FUSE_BN_BWD");
+    return e == nullptr ? 1 : atoi(e);
+  }();
+  return v != 0;
+}
+
 }  // namespace
 
+// Backward. The gradient handed from block to block is G_b = dL/d(pre-ReLU residual sum of block b), i.e. the
+// gradient w.r.t. the block output already multiplied by (out_b > 0): the ReLU mask is applied once, by the epilogue
+// that produces the gradient (gate = the forward activation), never re-read by the BatchNorm kernels. The same
+// epilogues accumulate sum(dz) and sum(dz * xhat) of the BatchNorm that follows in backward order, so the separate
+// reduction pass only remains for the BatchNorm pairs that share a gradient (blocks with a downsample branch), for
+// gradients assembled by more than one kernel (stride-2 downsample) and for the stem.
 extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params, void* const* grads, void* ws,
                                const float* dfeat, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -423,10 +452,15 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
   const ParamView pv{params};
   const int training = d->training;
   const int hw = p.out_h * p.out_w;
+  const bool fuse = fuse_bn_bwd_stats();
   KOA_CHECK_CUDA(cudaMemsetAsync(at(ws, p.bstat_begin), 0, p.bstat_end - p.bstat_begin, st));
-  int cur = 0;  // p.g[cur] holds the gradient w.r.t. the current block's output
-  if (d->with_gap) KOA_TRY(koa_k_gap_bwd(dfeat, at(ws, p.g[cur]), p.n_img, hw, p.out_c, st));
-  else KOA_TRY(koa_k_cast_bf16(dfeat, at(ws, p.g[cur]), (long long)p.n_img * hw * p.out_c, st));
+  int cur = 0;  // p.g[cur] holds G of the current block
+  {
+    const Block& lb = p.blocks.back();
+    if (d->with_gap) KOA_TRY(koa_k_gap_bwd(dfeat, at(ws, lb.out), at(ws, p.g[cur]), p.n_img, hw, p.out_c, st));
+    else KOA_TRY(koa_k_gap_bwd(dfeat, at(ws, lb.out), at(ws, p.g[cur]), p.n_img * hw, 1, p.out_c, st));
+  }
+  bool g_stats_done = false;  // the producer of G already reduced it for the last BatchNorm of the current block
 
   for (int bi = (int)p.blocks.size() - 1; bi >= 0; --bi) {
     const Block& b = p.blocks[bi];
@@ -440,59 +474,72 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     void* x = at(ws, b.in);
     void* dy_last = at(ws, p.t[0]);
     void* dy_down = at(ws, p.t[1]);
-    // out = relu(bn_last(y_last) + identity): dz = g_out * (out > 0)
-    KOA_TRY(bn_backward(last, ud, pv, grads, ws, g_out, at(ws, b.out), dy_last, ud ? dy_down : nullptr, training, st));
+    KOA_TRY(bn_backward(last, ud, pv, grads, ws, g_out, nullptr, dy_last, ud ? dy_down : nullptr, training, g_stats_done, st));
     void* d_a1 = at(ws, p.t[3]);
     if (u3) {
       KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2), dy_last, grads, ws, st));
       void* d_a2 = at(ws, p.t[2]);
       koa_epilogue_t ep{};
       ep.out = d_a2;
+      gate_and_stats(ep, ws, b.a2, &u2, fuse);  // dz2 = dgrad * (a2 > 0)
       KOA_TRY(conv_dgrad(p, *u3, dy_last, ws, &ep, nullptr, st));
-      KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, at(ws, b.a2), d_a2, nullptr, training, st));  // in place -> dy2
+      KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, nullptr, d_a2, nullptr, training, fuse, st));  // in place -> dy2
       KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1), d_a2, grads, ws, st));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
+      gate_and_stats(ep2, ws, b.a1, &u1, fuse);
       KOA_TRY(conv_dgrad(p, u2, d_a2, ws, &ep2, at(ws, p.t[4]), st));
     } else {
       KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1), dy_last, grads, ws, st));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
+      gate_and_stats(ep2, ws, b.a1, &u1, fuse);
       KOA_TRY(conv_dgrad(p, u2, dy_last, ws, &ep2, at(ws, p.t[4]), st));
     }
-    KOA_TRY(bn_backward(u1, nullptr, pv, grads, ws, d_a1, at(ws, b.a1), d_a1, nullptr, training, st));  // in place -> dy1
+    KOA_TRY(bn_backward(u1, nullptr, pv, grads, ws, d_a1, nullptr, d_a1, nullptr, training, fuse, st));  // in place -> dy1
     KOA_TRY(conv_wgrad(p, u1, x, d_a1, grads, ws, st));
-    // gradient w.r.t. the block input = dgrad(conv1) + identity path
-    {
+    // G of the previous block = (dgrad(conv1) + identity path) * (x > 0); x is that block's output (or the pooled
+    // stem activation, where the gate is a no-op for the gradient that survives the stem's own ReLU mask).
+    const Block* prev = bi > 0 ? &p.blocks[bi - 1] : nullptr;
+    const Unit* prev_last = prev ? &p.units[prev->kind == 0 ? prev->u3 : prev->u2] : nullptr;
+    const bool single_producer = !(ud && ud->stride != 1);
+    const bool fuse_prev = fuse && prev != nullptr && prev->ud < 0 && single_producer;
+    if (!ud) {
       koa_epilogue_t ep{};
       ep.out = g_in;
-      if (!ud) {  // identity: + g_out masked by out > 0
-        ep.add_bf16 = g_out;
-        ep.mask_bf16 = at(ws, b.out);
-      }
+      ep.add_bf16 = g_out;  // identity path: G of this block
+      gate_and_stats(ep, ws, b.in, prev_last, fuse_prev);
       KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
-    }
-    if (ud) {
+    } else {
       KOA_TRY(conv_wgrad(p, *ud, x, dy_down, grads, ws, st));
       if (ud->stride == 1) {
         koa_epilogue_t ep{};
         ep.out = g_in;
-        ep.add_bf16 = g_in;  // accumulate in place
-        KOA_TRY(conv_dgrad(p, *ud, dy_down, ws, &ep, nullptr, st));
+        KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
+        koa_epilogue_t ep2{};
+        ep2.out = g_in;
+        ep2.add_bf16 = g_in;  // accumulate in place, then gate the sum
+        gate_and_stats(ep2, ws, b.in, prev_last, fuse_prev);
+        KOA_TRY(conv_dgrad(p, *ud, dy_down, ws, &ep2, nullptr, st));
       } else {
         koa_epilogue_t ep{};
-        ep.out = at(ws, p.t[2]);
-        KOA_TRY(conv_dgrad(p, *ud, dy_down, ws, &ep, nullptr, st));
-        KOA_TRY(koa_k_scatter_add2(at(ws, p.t[2]), g_in, p.n_img, ud->hin, ud->win, ud->cin, ud->hout, ud->wout, st));
+        ep.out = g_in;
+        gate_and_stats(ep, ws, b.in, nullptr, false);
+        KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
+        koa_epilogue_t ep2{};
+        ep2.out = at(ws, p.t[2]);
+        KOA_TRY(conv_dgrad(p, *ud, dy_down, ws, &ep2, nullptr, st));
+        KOA_TRY(koa_k_scatter_add2(at(ws, p.t[2]), x, g_in, p.n_img, ud->hin, ud->win, ud->cin, ud->hout, ud->wout, st));
       }
     }
+    g_stats_done = fuse_prev;
     cur ^= 1;
   }
   // ---- stem -----------------------------------------------------------------------------------------
   const Unit& us = p.units[0];
   void* d_a0 = at(ws, p.t[0]);
   KOA_TRY(koa_k_maxpool_bwd(at(ws, p.g[cur]), at(ws, p.idx0), d_a0, p.n_img, us.hout, us.wout, 64, st));
-  KOA_TRY(bn_backward(us, nullptr, pv, grads, ws, d_a0, at(ws, p.a0), d_a0, nullptr, training, st));
+  KOA_TRY(bn_backward(us, nullptr, pv, grads, ws, d_a0, at(ws, p.a0), d_a0, nullptr, training, false, st));
   if (grads[0] != nullptr) {
     const float* img = d->slices > 0 ? (const float*)at(ws, p.img) : d->input_for_backward;
     KOA_REQUIRE(img != nullptr, "stem weight gradient needs the input image (input_for_backward)");

@@ -61,7 +61,7 @@ extern "C" int koa_profile_dump(const char* path) {
   }
   FILE* f = fopen(path, "w");
   KOA_REQUIRE(f != nullptr, "cannot open %s", path);
-  fprintf(f, "# cls(0=kmajor,1=wgrad) tag(bit0 im2col, 1 stats, 2 add, 3 mask, 4 res_f32, 5 fp32 out, 6 act) m n k launches total_ms tflops\n");
+  fprintf(f, "# cls(0=kmajor,1=wgrad) tag(bit0 im2col, 1 stats, 2 add, 3 gate, 4 res_f32, 5 fp32 out, 6 act, 7 bn-bwd stats) m n k launches total_ms tflops\n");
   for (auto& kv : acc)
     fprintf(f, "%d %d %d %d %d %ld %.4f %.1f\n", std::get<0>(kv.first), std::get<1>(kv.first), std::get<2>(kv.first),
             std::get<3>(kv.first), std::get<4>(kv.first), kv.second.n, kv.second.ms,
@@ -113,10 +113,13 @@ static EpiParams to_epi(const koa_epilogue_t* e) {
   p.aux = (const bf16*)e->aux_bf16;
   p.res_f32 = e->residual_f32;
   p.add_bf16 = (const bf16*)e->add_bf16;
-  p.mask_bf16 = (const bf16*)e->mask_bf16;
+  p.gate_bf16 = (const bf16*)e->gate_bf16;
   p.out_bf16_copy = (bf16*)e->out_bf16_copy;
   p.col_sum = e->col_sum;
   p.col_sumsq = e->col_sumsq;
+  p.stat_y = (const bf16*)e->stat_y;
+  p.stat_mean = e->stat_mean;
+  p.stat_invstd = e->stat_invstd;
   return p;
 }
 
@@ -127,17 +130,27 @@ static int check_epi(const koa_epilogue_t* ep, int n) {
   KOA_REQUIRE(ep->act != KOA_ACT_GELU_GRAD || ep->aux_bf16 != nullptr, "KOA_ACT_GELU_GRAD needs aux_bf16");
   KOA_REQUIRE((ep->col_sum == nullptr) == (ep->col_sumsq == nullptr), "col_sum and col_sumsq go together");
   KOA_REQUIRE(ep->col_sum == nullptr || n <= kMaxStatCols, "column statistics support N <= %d (got %d)", kMaxStatCols, n);
+  KOA_REQUIRE(ep->col_sum == nullptr || !ep->out_fp32, "column statistics need a bf16 output");
+  KOA_REQUIRE(ep->stat_y == nullptr || (ep->col_sum != nullptr && ep->stat_mean != nullptr && ep->stat_invstd != nullptr),
+              "stat_y needs col_sum/col_sumsq and stat_mean/stat_invstd");
   return 0;
 }
 
-template <int BN, int STAGES, bool IM2COL>
-static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
-                         const EpiParams& ep, cudaStream_t st) {
+// The convolution flavour of the epilogue (bf16 output, optional addend / gate / statistics) is a separate, leaner
+// instantiation; everything else (bias, activations, fp32 residual stream) takes the full one.
+static bool conv_epilogue(const EpiParams& ep) {
+  return !ep.out_fp32 && ep.act == ACT_NONE && ep.bias == nullptr && ep.pre_out == nullptr && ep.res_f32 == nullptr &&
+         ep.out_bf16_copy == nullptr;
+}
+
+template <int BN, int STAGES, bool IM2COL, bool CONV>
+static int launch_kmajor_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
+                           const EpiParams& ep, cudaStream_t st) {
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_kmajor_kernel<BN, STAGES, IM2COL>,
+    attr_err = cudaFuncSetAttribute(gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   });
   KOA_CHECK_CUDA(attr_err);
@@ -145,13 +158,20 @@ static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
   KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
   const unsigned grid = (unsigned)(tiles < koa_num_sms() ? tiles : koa_num_sms());  // persistent: one CTA per SM
   {
-    const int flavor = (IM2COL ? 1 : 0) | (ep.col_sum ? 2 : 0) | (ep.add_bf16 ? 4 : 0) | (ep.mask_bf16 ? 8 : 0) |
-                       (ep.res_f32 ? 16 : 0) | (ep.out_fp32 ? 32 : 0) | (ep.act ? 64 : 0);
+    const int flavor = (IM2COL ? 1 : 0) | (ep.col_sum ? 2 : 0) | (ep.add_bf16 ? 4 : 0) | (ep.gate_bf16 ? 8 : 0) |
+                       (ep.res_f32 ? 16 : 0) | (ep.out_fp32 ? 32 : 0) | (ep.act ? 64 : 0) | (ep.stat_y ? 128 : 0);
     ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, flavor);
-    gemm_kmajor_kernel<BN, STAGES, IM2COL><<<grid, kKmajorThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
+    gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV><<<grid, kKmajorThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
   }
   KOA_LAUNCH_CHECK();
   return 0;
+}
+
+template <int BN, int STAGES, bool IM2COL>
+static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
+                         const EpiParams& ep, cudaStream_t st) {
+  if (conv_epilogue(ep)) return launch_kmajor_t<BN, STAGES, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
+  return launch_kmajor_t<BN, STAGES, IM2COL, false>(ta, tb, m, n, k, g, ep, st);
 }
 
 template <bool IM2COL>
@@ -165,7 +185,7 @@ static int dispatch_kmajor(const CUtensorMap& ta, const void* b, int m, int n, i
   (void)num_kb;
   // persistent kernel, one CTA per SM: a deep smem ring lets the TMA producer run ahead across tiles
   if (bn128) return launch_kmajor<128, 5, IM2COL>(ta, tb, m, n, k, g, ep, st);
-  return launch_kmajor<64, 8, IM2COL>(ta, tb, m, n, k, g, ep, st);
+  return launch_kmajor<64, 6, IM2COL>(ta, tb, m, n, k, g, ep, st);
 }
 
 int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep, cudaStream_t st) {
@@ -277,7 +297,7 @@ int koa_conv_grouped_launch(const void* x, const void* w, int n_img, int h, int 
   rc = koa_tmap_2d_bf16(&tb, w, 576, (uint64_t)c, 576 * 2, 64, 64);
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, 1, 3, 1, 1};
-  return launch_kmajor<64, 8, true>(ta, tb, (int)m, c, 576, g, to_epi(ep), st);
+  return launch_kmajor<64, 6, true>(ta, tb, (int)m, c, 576, g, to_epi(ep), st);
 }
 
 // dw[C][9][64] += per-chunk dense weight gradient of the grouped convolution.

@@ -31,10 +31,13 @@ struct EpiParams {
   const bf16* aux;        // ACT_GELU_GRAD: pre-activation h; result = v * gelu'(h)
   const float* res_f32;   // optional fp32 addend [M, ldo]
   const bf16* add_bf16;   // optional bf16 addend [M, ldo]
-  const bf16* mask_bf16;  // optional: add_bf16 contributes only where mask > 0
+  const bf16* gate_bf16;  // optional: the final value is zeroed where gate <= 0 (ReLU backward)
   bf16* out_bf16_copy;    // optional bf16 copy of the final value (when out is fp32)
-  float* col_sum;         // optional per-column sum / sum of squares of the bf16-rounded output
-  float* col_sumsq;
+  float* col_sum;         // optional per-column sum of the bf16-rounded output and, in col_sumsq, either its sum of
+  float* col_sumsq;       // squares (forward BatchNorm statistics) or, when stat_y is set, sum of out * xhat(stat_y)
+  const bf16* stat_y;     // BatchNorm backward: forward conv output y [M, ldo]; xhat = (y - mean) * invstd
+  const float* stat_mean;
+  const float* stat_invstd;
 };
 
 constexpr int kGemmThreads = 192;     // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
@@ -44,173 +47,299 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 
 constexpr int kMaxStatCols = 2048;  // widest BatchNorm in the networks (layer4 output)
+
+// ---- coalesced epilogue traffic --------------------------------------------------------------------
+// After tcgen05.ld a thread owns 32 consecutive columns of ONE row, so direct global accesses would touch 16-byte
+// pieces of 32 different rows per instruction (half-filled sectors). Every [32 rows][64 bytes] sub-tile therefore
+// moves between global memory and the row-per-thread register layout through a per-warp shared-memory staging
+// buffer (16-byte pieces XOR-swizzled by (row >> 1) & 3: the row-wise accesses and the transposed ones are both
+// bank-conflict free); the global side is always 8 rows x 64 contiguous bytes per instruction.
+constexpr int kStageBytesPerWarp = 32 * 64;
+constexpr int kStagesPerWarp = 2;
+
 template <int BN, int STAGES>
 constexpr size_t gemm_smem_bytes() {
   return 1024 /*align slack*/ + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 +
-         2 * kMaxStatCols * sizeof(float) + kEpiWarps * 2048 /*epilogue staging*/ + 16;
+         2 * kMaxStatCols * sizeof(float) + 2 * BN * 4 * 2 * sizeof(float) /*per-tile partial statistics*/ +
+         kEpiWarps * kStagesPerWarp * kStageBytesPerWarp + 32;
 }
 
-// ---- coalesced epilogue stores -------------------------------------------------------------------
-// After tcgen05.ld a thread owns 32 consecutive columns of ONE row, so a direct store would write 16-byte
-// pieces of 32 different rows per instruction (half-filled sectors). Each epilogue warp therefore stages its
-// 32-row sub-tile in a private 2 KB shared-memory buffer ([32 rows][64 bytes], 16-byte pieces XOR-swizzled by
-// (row >> 1) & 3 so both the row-wise writes and the transposed reads are bank-conflict free) and writes it
-// back 8 rows x 64 contiguous bytes per instruction.
-constexpr int kStageBytesPerWarp = 32 * 64;
+// ---- shared-memory accessors in the shared state space (generic LD/ST on staging pointers costs a long-scoreboard
+// round trip per access; these compile to LDS / STS) ------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64f(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ uint4 ldg128_nc(const uint8_t* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg128(uint8_t* p, const uint4& v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ uint32_t stage_off(int row, int piece) {
   return (uint32_t)(row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
 }
 
-// Row-major store of a [32 rows][64 bytes] warp tile: `gbase` points at (first row of the warp, first byte of the
-// 64-byte segment); rows are `pitch_bytes` apart; rows >= rows_valid are skipped.
-__device__ __forceinline__ void stage_flush(const uint8_t* stage, uint8_t* gbase, long long pitch_bytes, int rows_valid,
-                                            int lane) {
-  __syncwarp();
+// Per-lane constants of the two access patterns of a [32 rows][64 bytes] staging tile.
+struct LaneMap {
+  uint32_t row_off[4];  // row-per-thread pattern: byte offset of piece p of row `lane`
+  uint32_t co_off;      // coalesced pattern: byte offset of (row lane >> 2, piece lane & 3); rows 8 apart are +512
+  int co_row;           // lane >> 2
+  int co_byte;          // (lane & 3) * 16
+};
+__device__ __forceinline__ LaneMap make_lane_map(int lane) {
+  LaneMap m;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) m.row_off[p] = stage_off(lane, p);
+  m.co_off = stage_off(lane >> 2, lane & 3);  // ((8i + r) >> 1) & 3 == (r >> 1) & 3: the swizzle does not depend on i
+  m.co_row = lane >> 2;
+  m.co_byte = (lane & 3) * 16;
+  return m;
+}
+
+// global -> registers, coalesced (8 rows x 64 contiguous bytes per instruction); rows >= rows_valid read 0.
+__device__ __forceinline__ void tile_ldg(uint4 (&t)[4], const uint8_t* gbase, long long pitch_bytes, int rows_valid,
+                                         const LaneMap& lm) {
+  const uint8_t* p = gbase + lm.co_row * pitch_bytes + lm.co_byte;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int row = i * 8 + (lane >> 2);
-    const int piece = lane & 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(stage + stage_off(row, piece));
-    if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + row * pitch_bytes + piece * 16) = v;
+    t[i] = make_uint4(0, 0, 0, 0);
+    if (i * 8 + lm.co_row < rows_valid) t[i] = ldg128_nc(p + i * 8 * pitch_bytes);
   }
+}
+__device__ __forceinline__ void tile_sts(uint32_t stage, const uint4 (&t)[4], const LaneMap& lm) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sts128(stage + lm.co_off + i * 512, t[i]);
+}
+__device__ __forceinline__ void row_lds(uint4 (&q)[4], uint32_t stage, const LaneMap& lm) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) q[p] = lds128(stage + lm.row_off[p]);
+}
+__device__ __forceinline__ void row_sts(uint32_t stage, const uint4 (&q)[4], const LaneMap& lm) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) sts128(stage + lm.row_off[p], q[p]);
+}
+__device__ __forceinline__ void unpack_row_bf16(float (&f)[32], const uint4 (&q)[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    float2 a;
+    a = unpack_bf16x2(q[p].x); f[p * 8 + 0] = a.x; f[p * 8 + 1] = a.y;
+    a = unpack_bf16x2(q[p].y); f[p * 8 + 2] = a.x; f[p * 8 + 3] = a.y;
+    a = unpack_bf16x2(q[p].z); f[p * 8 + 4] = a.x; f[p * 8 + 5] = a.y;
+    a = unpack_bf16x2(q[p].w); f[p * 8 + 6] = a.x; f[p * 8 + 7] = a.y;
+  }
+}
+__device__ __forceinline__ void pack_row_bf16(uint4 (&q)[4], const float (&v)[32]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    q[p].x = pack_bf16x2(v[p * 8 + 0], v[p * 8 + 1]); q[p].y = pack_bf16x2(v[p * 8 + 2], v[p * 8 + 3]);
+    q[p].z = pack_bf16x2(v[p * 8 + 4], v[p * 8 + 5]); q[p].w = pack_bf16x2(v[p * 8 + 6], v[p * 8 + 7]);
+  }
+}
+// staged coalesced tile -> this thread's row as 32 floats (whole warp; syncs on both sides)
+__device__ __forceinline__ void tile_to_row_bf16(float (&f)[32], uint32_t stage, const uint4 (&t)[4], const LaneMap& lm) {
+  tile_sts(stage, t, lm);
+  __syncwarp();
+  uint4 q[4];
+  row_lds(q, stage, lm);
+  __syncwarp();
+  unpack_row_bf16(f, q);
+}
+
+// Coalesced write-back of a staged [32 rows][64 bytes] tile; rows >= rows_valid are skipped.
+__device__ __forceinline__ void stage_flush(uint32_t stage, uint8_t* gbase, long long pitch_bytes, int rows_valid,
+                                            const LaneMap& lm) {
+  __syncwarp();
+  uint8_t* p = gbase + lm.co_row * pitch_bytes + lm.co_byte;
+  uint4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = lds128(stage + lm.co_off + i * 512);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i * 8 + lm.co_row < rows_valid) stg128(p + i * 8 * pitch_bytes, v[i]);
   __syncwarp();
 }
 
-// 32 fp32 values of this thread's row -> bf16 -> staged -> coalesced store at column n of a bf16 [M][ld] tensor.
-__device__ __forceinline__ void store_row_bf16(const float (&v)[32], uint8_t* stage, bf16* g, long long ld, long long row0,
-                                               int n, int rows_valid, int lane) {
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    uint4 q;
-    q.x = pack_bf16x2(v[p * 8 + 0], v[p * 8 + 1]); q.y = pack_bf16x2(v[p * 8 + 2], v[p * 8 + 3]);
-    q.z = pack_bf16x2(v[p * 8 + 4], v[p * 8 + 5]); q.w = pack_bf16x2(v[p * 8 + 6], v[p * 8 + 7]);
-    *reinterpret_cast<uint4*>(stage + stage_off(lane, p)) = q;
-  }
-  stage_flush(stage, reinterpret_cast<uint8_t*>(g + row0 * ld + n), ld * 2, rows_valid, lane);
+__device__ __forceinline__ void store_row_bf16(const float (&v)[32], uint32_t stage, bf16* g, long long ld, int rows_valid,
+                                               const LaneMap& lm) {
+  uint4 q[4];
+  pack_row_bf16(q, v);
+  row_sts(stage, q, lm);
+  stage_flush(stage, reinterpret_cast<uint8_t*>(g), ld * 2, rows_valid, lm);
 }
 
-__device__ __forceinline__ void store_row_f32(const float (&v)[32], uint8_t* stage, float* g, long long ld, long long row0,
-                                              int n, int rows_valid, int lane) {
+__device__ __forceinline__ void store_row_f32(const float (&v)[32], uint32_t stage, float* g, long long ld, int rows_valid,
+                                              const LaneMap& lm) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {  // two 16-column halves of 64 bytes each
 #pragma unroll
     for (int p = 0; p < 4; ++p)
-      *reinterpret_cast<float4*>(stage + stage_off(lane, p)) =
-          make_float4(v[h * 16 + p * 4 + 0], v[h * 16 + p * 4 + 1], v[h * 16 + p * 4 + 2], v[h * 16 + p * 4 + 3]);
-    stage_flush(stage, reinterpret_cast<uint8_t*>(g + row0 * ld + n + h * 16), ld * 4, rows_valid, lane);
+      sts128(stage + lm.row_off[p], make_uint4(__float_as_uint(v[h * 16 + p * 4 + 0]), __float_as_uint(v[h * 16 + p * 4 + 1]),
+                                               __float_as_uint(v[h * 16 + p * 4 + 2]), __float_as_uint(v[h * 16 + p * 4 + 3])));
+    stage_flush(stage, reinterpret_cast<uint8_t*>(g + h * 16), ld * 4, rows_valid, lm);
   }
 }
 
-// Epilogue of one 32-row x 32-column chunk. `row0` = first row of this warp's 32-row group, the thread owns row
-// row0 + lane. `stage` = this warp's 2 KB staging buffer.
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiParams& ep, long long row0, int rows_valid,
-                                               int n, int lane, uint8_t* stage, float* s_sum, float* s_sumsq,
-                                               int c_local) {
-  const bool row_ok = lane < rows_valid;
-  const long long row_off = (row0 + lane) * ep.ldo;
+// Epilogue of one 32-row x 32-column chunk. The thread owns row row0 + lane of the warp's 32-row group; `n` = first
+// global column; `taddr` = TMEM address of the chunk. `release_bar` (or NULL) is arrived on as soon as the
+// accumulator has been read (last chunk of this warp for the tile). `stage` = shared-space address of this warp's
+// two 2 KB staging buffers; `part` = shared-space address of this tile's partial-statistics slots
+// [BN columns][4 row quarters][2].
+// CONV = true compiles the convolution flavour only (bf16 output, optional addend / gate / statistics; no bias,
+// activation, fp32 paths): fewer live registers and branches for the epilogue-bound small-K layers.
+template <bool CONV>
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint64_t* release_bar, const EpiParams& ep, long long row0,
+                                               int rows_valid, int n, int lane, const LaneMap& lm, uint32_t stage,
+                                               uint32_t part, int c_local, int quarter) {
+  const uint32_t stage1 = stage + kStageBytesPerWarp;
+  const long long tile_off = row0 * ep.ldo + n;  // element offset of this warp tile in every [M, ldo] tensor
+  const long long pitch2 = (long long)ep.ldo * 2;
+  const bool has_add = ep.add_bf16 != nullptr, has_gate = ep.gate_bf16 != nullptr;
+  const bool stats = ep.col_sum != nullptr, bwd = ep.stat_y != nullptr;
+  // issue the global reads of the epilogue operands first: they overlap the TMEM load
+  uint4 t_add[4], t_gate[4], t_y[4];  // t_y doubles as the GELU' operand (never used together with stat_y)
+  if (!CONV && ep.act == ACT_GELU_GRAD) tile_ldg(t_y, reinterpret_cast<const uint8_t*>(ep.aux + tile_off), pitch2, rows_valid, lm);
+  else if (bwd) tile_ldg(t_y, reinterpret_cast<const uint8_t*>(ep.stat_y + tile_off), pitch2, rows_valid, lm);
+  if (has_add) tile_ldg(t_add, reinterpret_cast<const uint8_t*>(ep.add_bf16 + tile_off), pitch2, rows_valid, lm);
+  if (has_gate) tile_ldg(t_gate, reinterpret_cast<const uint8_t*>(ep.gate_bf16 + tile_off), pitch2, rows_valid, lm);
+
+  uint32_t r[32];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+  if (release_bar != nullptr) {  // hand the accumulator back before the global traffic of this chunk
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(release_bar);
+  }
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 
-  if (ep.bias != nullptr) {
+  if (!CONV) {
+    if (ep.bias != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(ep.bias + n + j);
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
     }
-  }
-  if (ep.pre_out != nullptr) store_row_bf16(v, stage, ep.pre_out, ep.ldo, row0, n, rows_valid, lane);
-  if (ep.act == ACT_RELU) {
+    if (ep.pre_out != nullptr) store_row_bf16(v, stage, ep.pre_out + tile_off, ep.ldo, rows_valid, lm);
+    if (ep.act == ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-  } else if (ep.act == ACT_GELU) {
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    } else if (ep.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-  } else if (ep.act == ACT_GELU_GRAD) {
-    if (row_ok) {
-      const uint4* src = reinterpret_cast<const uint4*>(ep.aux + row_off + n);
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (ep.act == ACT_GELU_GRAD) {
+      float h[32];
+      tile_to_row_bf16(h, stage, t_y, lm);
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 q = src[j / 8];
-        const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
-        v[j] *= gelu_erf_grad(a.x); v[j + 1] *= gelu_erf_grad(a.y);
-        v[j + 2] *= gelu_erf_grad(b.x); v[j + 3] *= gelu_erf_grad(b.y);
-        v[j + 4] *= gelu_erf_grad(c.x); v[j + 5] *= gelu_erf_grad(c.y);
-        v[j + 6] *= gelu_erf_grad(d.x); v[j + 7] *= gelu_erf_grad(d.y);
+      for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(h[j]);
+    }
+    if (ep.res_f32 != nullptr) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {  // two 16-column halves of 64 bytes each
+        uint4 t[4], q[4];
+        tile_ldg(t, reinterpret_cast<const uint8_t*>(ep.res_f32 + tile_off + hh * 16), (long long)ep.ldo * 4, rows_valid, lm);
+        tile_sts(stage, t, lm);
+        __syncwarp();
+        row_lds(q, stage, lm);
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          v[hh * 16 + p * 4 + 0] += __uint_as_float(q[p].x); v[hh * 16 + p * 4 + 1] += __uint_as_float(q[p].y);
+          v[hh * 16 + p * 4 + 2] += __uint_as_float(q[p].z); v[hh * 16 + p * 4 + 3] += __uint_as_float(q[p].w);
+        }
       }
     }
   }
-  if (ep.res_f32 != nullptr && row_ok) {
-    const float4* src = reinterpret_cast<const float4*>(ep.res_f32 + row_off + n);
+  if (has_add || has_gate) {  // both operand tiles take one trip through the two staging buffers
+    if (has_add) tile_sts(stage, t_add, lm);
+    if (has_gate) tile_sts(stage1, t_gate, lm);
+    __syncwarp();
+    uint4 qa[4], qg[4];
+    if (has_add) row_lds(qa, stage, lm);
+    if (has_gate) row_lds(qg, stage1, lm);
+    __syncwarp();
+    if (has_add) {
+      float a[32];
+      unpack_row_bf16(a, qa);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = src[j / 4];
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      for (int j = 0; j < 32; ++j) v[j] += a[j];
+    }
+    if (has_gate) {
+      float g[32];
+      unpack_row_bf16(g, qg);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = g[j] > 0.0f ? v[j] : 0.0f;
     }
   }
-  if (ep.add_bf16 != nullptr && row_ok) {
-    const uint4* src = reinterpret_cast<const uint4*>(ep.add_bf16 + row_off + n);
-    const uint4* msk = ep.mask_bf16 ? reinterpret_cast<const uint4*>(ep.mask_bf16 + row_off + n) : nullptr;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const uint4 q = src[j / 8];
-      float a[8];
-      float2 t;
-      t = unpack_bf16x2(q.x); a[0] = t.x; a[1] = t.y;
-      t = unpack_bf16x2(q.y); a[2] = t.x; a[3] = t.y;
-      t = unpack_bf16x2(q.z); a[4] = t.x; a[5] = t.y;
-      t = unpack_bf16x2(q.w); a[6] = t.x; a[7] = t.y;
-      if (msk != nullptr) {
-        const uint4 mq = msk[j / 8];
-        float m[8];
-        t = unpack_bf16x2(mq.x); m[0] = t.x; m[1] = t.y;
-        t = unpack_bf16x2(mq.y); m[2] = t.x; m[3] = t.y;
-        t = unpack_bf16x2(mq.z); m[4] = t.x; m[5] = t.y;
-        t = unpack_bf16x2(mq.w); m[6] = t.x; m[7] = t.y;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] = m[u] > 0.0f ? a[u] : 0.0f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[j + u] += a[u];
-    }
+  if (!CONV && ep.out_fp32) {
+    store_row_f32(v, stage, reinterpret_cast<float*>(ep.out) + tile_off, ep.ldo, rows_valid, lm);
+    if (ep.out_bf16_copy != nullptr) store_row_bf16(v, stage, ep.out_bf16_copy + tile_off, ep.ldo, rows_valid, lm);
+    return;
   }
-  if (ep.out_fp32) {
-    store_row_f32(v, stage, reinterpret_cast<float*>(ep.out), ep.ldo, row0, n, rows_valid, lane);
-    if (ep.out_bf16_copy != nullptr) store_row_bf16(v, stage, ep.out_bf16_copy, ep.ldo, row0, n, rows_valid, lane);
-  } else {
-    // bf16 output: stage, (statistics from the staged, i.e. rounded, values), coalesced write-back
+  // bf16 output: stage, (statistics from the staged, i.e. rounded, values), coalesced write-back
+  uint4 q[4];
+  pack_row_bf16(q, v);
+  if (stats && lane >= rows_valid) {  // rows past M contribute exact zeros to the statistics
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      uint4 q;
-      q.x = pack_bf16x2(v[p * 8 + 0], v[p * 8 + 1]); q.y = pack_bf16x2(v[p * 8 + 2], v[p * 8 + 3]);
-      q.z = pack_bf16x2(v[p * 8 + 4], v[p * 8 + 5]); q.w = pack_bf16x2(v[p * 8 + 6], v[p * 8 + 7]);
-      if (!row_ok) q = make_uint4(0, 0, 0, 0);  // rows past M contribute exact zeros to the statistics
-      *reinterpret_cast<uint4*>(stage + stage_off(lane, p)) = q;
+    for (int p = 0; p < 4; ++p) q[p] = make_uint4(0, 0, 0, 0);
+  }
+  row_sts(stage, q, lm);
+  if (stats) {
+    if (bwd) tile_sts(stage1, t_y, lm);
+    __syncwarp();
+    // lane = (h, p): column pair (2p, 2p+1) over the 16 rows 2i + h; the two lane halves read rows in different
+    // bank halves, each half reads one contiguous 64-byte row per step (conflict free)
+    const int h = lane >> 4, p = lane & 15;
+    float mu0 = 0.0f, mu1 = 0.0f, is0 = 1.0f, is1 = 1.0f;
+    if (bwd) {
+      const float2 mu = __ldg(reinterpret_cast<const float2*>(ep.stat_mean + n + 2 * p));
+      const float2 is = __ldg(reinterpret_cast<const float2*>(ep.stat_invstd + n + 2 * p));
+      mu0 = mu.x; mu1 = mu.y; is0 = is.x; is1 = is.y;
     }
-    if (ep.col_sum != nullptr) {
-      __syncwarp();
-      // lane = (h, p): column pair (2p, 2p+1) over the 16 rows 2i + h; the two lane halves read rows in different
-      // bank halves, each half reads one contiguous 64-byte row per step (conflict free)
-      const int h = lane >> 4, p = lane & 15;
-      float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+    float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+    // row 2i + h, 4 bytes at column pair p: piece p >> 2 (swizzled by ((2i + h) >> 1) & 3 = i & 3), word p & 3
+    const uint32_t base = stage + (uint32_t)(h * 64 + (p & 3) * 4);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + stage_off(2 * i + h, p >> 2) + (p & 3) * 4);
-        const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
-        s0 += x0; s1 += x1;
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t off = (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4);
+      const uint32_t w = lds32(base + off);
+      const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+      s0 += x0; s1 += x1;
+      if (bwd) {
+        const uint32_t wy = lds32(base + kStageBytesPerWarp + off);
+        const float y0 = __uint_as_float(wy << 16), y1 = __uint_as_float(wy & 0xffff0000u);
+        q0 = fmaf(x0, (y0 - mu0) * is0, q0); q1 = fmaf(x1, (y1 - mu1) * is1, q1);
+      } else {
         q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
       }
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-      q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
-      if (h == 0) {
-        atomicAdd(&s_sum[c_local + 2 * p], s0); atomicAdd(&s_sum[c_local + 2 * p + 1], s1);
-        atomicAdd(&s_sumsq[c_local + 2 * p], q0); atomicAdd(&s_sumsq[c_local + 2 * p + 1], q1);
-      }
     }
-    stage_flush(stage, reinterpret_cast<uint8_t*>(reinterpret_cast<bf16*>(ep.out) + row0 * ep.ldo + n), (long long)ep.ldo * 2,
-                rows_valid, lane);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+    if (h == 0) {  // this warp's 32-row partial of columns (c_local + 2p, + 2p + 1): private slot, no atomics
+      const uint32_t dst = part + (uint32_t)(((c_local + 2 * p) * 4 + quarter) * 8);
+      sts64f(dst, s0, q0);
+      sts64f(dst + 32, s1, q1);
+    }
   }
+  stage_flush(stage, reinterpret_cast<uint8_t*>(reinterpret_cast<bf16*>(ep.out) + tile_off), pitch2, rows_valid, lm);
 }
 
 // out[M, N] = A[M, K] * B[N, K]^T with the fused epilogue. A_IM2COL: A rows are the output
@@ -221,7 +350,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
 //   TMA -> smem ring (STAGES deep, full/empty mbarriers, runs ahead into the next tile),
 //   MMA -> TMEM accumulator ring (2 x BN columns, tmem_full/tmem_empty mbarriers),
 //   epilogue warps drain accumulator i while the MMA of tile i+1 is issued.
-template <int BN, int STAGES, bool A_IM2COL>
+template <int BN, int STAGES, bool A_IM2COL, bool CONV_EPI>
 __global__ void __launch_bounds__(kKmajorThreads, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                    int K, ConvGeom g, EpiParams ep) {
@@ -242,7 +371,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // flushed once at the end: 148 same-address global atomics per column instead of one per tile.
   float* s_sum = reinterpret_cast<float*>(tmem_slot + 4);
   float* s_sumsq = s_sum + kMaxStatCols;
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(((uintptr_t)(s_sumsq + kMaxStatCols) + 15) & ~(uintptr_t)15);
+  float* s_part = s_sumsq + kMaxStatCols;  // [2 tiles in flight][BN][4 row quarters][2]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(((uintptr_t)(s_part + 2 * BN * 8) + 15) & ~(uintptr_t)15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -343,7 +473,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int chunk_par = e >> 2;
     const int ep_tid = e * 32 + lane;
     constexpr int kEpiThreads = kEpiWarps * 32;
-    uint8_t* stage = s_stage + e * kStageBytesPerWarp;
+    const uint32_t stage = smem_u32(s_stage) + e * (kStagesPerWarp * kStageBytesPerWarp);
+    const LaneMap lm = make_lane_map(lane);
     const bool stats = ep.col_sum != nullptr;
     if (stats) {
       for (int i = ep_tid; i < 2 * kMaxStatCols; i += kEpiThreads) s_sum[i] = 0.0f;
@@ -359,26 +490,35 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const long long row0 = (long long)m0 + q * 32;
       const int rows_valid = max(0, min(32, M - (int)row0));
+      float* part = s_part + (lt & 1) * (BN * 8);
+      const uint32_t part_s = smem_u32(part);
       bool released = false;
 #pragma unroll 1
       for (int c0 = chunk_par * 32; c0 < BN; c0 += 64) {
         if (n0 + c0 >= N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (c0 + 64 >= BN || n0 + c0 + 64 >= N) {
-          // last TMEM read of this warp for this tile: hand the accumulator back before the global stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-          released = true;
-        }
-        epilogue_chunk(r, ep, row0, rows_valid, n0 + c0, lane, stage, s_sum, s_sumsq, n0 + c0);
+        // last TMEM read of this warp for this tile: the accumulator is handed back inside epilogue_chunk
+        const bool last = (c0 + 64 >= BN || n0 + c0 + 64 >= N);
+        epilogue_chunk<CONV_EPI>(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0,
+                                 last ? &tmem_empty_bar[acc] : nullptr, ep, row0, rows_valid, n0 + c0, lane, lm, stage,
+                                 part_s, c0, q);
+        released = released || last;
       }
       if (!released) {  // this warp had no chunk inside N
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      if (stats) {
+        // Combine the four row-quarter partials of every column of this tile. Column n0 + c is always owned by
+        // epilogue thread c, so the running per-CTA totals need no atomics; `part` is double buffered, which makes
+        // one barrier per tile sufficient.
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        if (ep_tid < BN && n0 + ep_tid < N) {
+          const float4 a = *reinterpret_cast<const float4*>(part + ep_tid * 8);
+          const float4 b = *reinterpret_cast<const float4*>(part + ep_tid * 8 + 4);
+          s_sum[n0 + ep_tid] += (a.x + a.z) + (b.x + b.z);
+          s_sumsq[n0 + ep_tid] += (a.y + a.w) + (b.y + b.w);
+        }
       }
     }
     if (stats) {

@@ -33,9 +33,10 @@ int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const f
 int koa_k_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, cudaStream_t st);
 int koa_k_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, cudaStream_t st);
 int koa_k_gap_fwd(const void* x, float* feat, int n, int hw, int c, cudaStream_t st);
-int koa_k_gap_bwd(const float* dfeat, void* dx, int n, int hw, int c, cudaStream_t st);
+int koa_k_gap_bwd(const float* dfeat, const void* gate, void* dx, int n, int hw, int c, cudaStream_t st);
 int koa_k_zero_insert2(const void* src, void* dst, int n, int h, int w, int c, int ho, int wo, cudaStream_t st);
-int koa_k_scatter_add2(const void* src, void* dx, int n, int h, int w, int c, int ho, int wo, cudaStream_t st);
+int koa_k_scatter_add2(const void* src, const void* gate, void* dx, int n, int h, int w, int c, int ho, int wo,
+                       cudaStream_t st);
 
 // ---- transformer pieces ---------------------------------------------------------------------------
 int koa_k_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,

@@ -1,0 +1,699 @@
+"""Parity of the CUDA path (through the C ABI of libkoa_b200.so) against the oracle, on a real B200.
+
+Three layers of evidence, all ``-m gpu``:
+
+1. **Operators** (``koa_gemm_bf16``, ``koa_conv_fprop_bf16``, ``koa_*_wgrad_bf16``, LayerNorm, attention, max-pool,
+   focal loss, small linears, stem pack): called directly through ctypes on seeded inputs and compared with the
+   same op in fp32 PyTorch on the same (bf16-representable) operands. Tolerances are one bf16 rounding of the output
+   (2^-8 relative per element, 4e-3 relative L2) for bf16 outputs and 1e-4 for fp32 outputs.
+2. **Engines** (``koa_fe_*`` = whole per-slice CNN, ``koa_feat_*`` = whole token transformer): compared with
+   ``oracle.koa_oracle.fe_forward`` / ``feat_forward``. Eval mode is held to BASELINE.json's 1e-2 relative
+   tolerance. Train-mode BatchNorm at random initialisation amplifies *any* perturbation from block to block
+   (the fp32 oracle and the same oracle with activations rounded to bf16 differ by 1e-2 .. 3e-1 at the feature
+   level, depending on the residual gain), so the train-mode bar is "at the bf16 precision floor": the error of
+   the CUDA path against the fp32 oracle must not exceed the error of the bf16-emulating oracle against the fp32
+   oracle by more than a stated factor. The backward pass is additionally checked with the forward state forced
+   to be identical (teacher forcing), which removes the ReLU-mask avalanche from the gradient comparison.
+3. **Models**: the six ``koafusion.models`` classes (+ the two 3-MRI extensions) replayed on the golden fixtures
+   generated from the unmodified reference (``oracle/make_golden.py``): eval logits within 1e-2 relative and
+   identical class predictions, state_dict round trip, gradients present exactly where the reference has them.
+
+Nothing here reads /root/reference; the oracle is the checker, never the thing measured.
+"""
+import ctypes as C
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oaprogressionmmf_b200 import _lib
+from oracle import koa_oracle as ko
+from tests.util import rel, to_attr
+
+pytestmark = pytest.mark.gpu
+
+BF16_REL_L2 = 4e-3      # one bf16 rounding of the output: 2^-9 max, ~1.1e-3 rms per element
+BF16_ELEM = 2.0 ** -7   # per-element bound used with an absolute floor
+LOGIT_TOL = 1e-2        # BASELINE.json: logits within 1e-2 relative error under bf16
+
+
+def _stream():
+    return _lib.current_stream()
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).contiguous()
+
+
+def _randn(*shape, seed=0, scale=1.0, dev="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dev)
+
+
+def _epi(**kw):
+    e = _lib.Epilogue()
+    for k, v in kw.items():
+        setattr(e, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    return e
+
+
+def _close_bf16(got, ref, what):
+    got, ref = got.float(), ref.float()
+    assert torch.isfinite(got).all(), what
+    r = rel(got, ref)
+    assert r < BF16_REL_L2, f"{what}: rel L2 {r:.3e}"
+    bound = BF16_ELEM * ref.abs() + 2e-3 * float(ref.abs().mean() + 1e-12) + 1e-6
+    worst = float(((got - ref).abs() - bound).max())
+    assert worst <= 0, f"{what}: element outside one bf16 rounding by {worst:.3e}"
+
+
+# =====================================================================================================
+# 1. operators
+# =====================================================================================================
+@pytest.mark.parametrize("m,n,k", [(300, 256, 64), (1000, 2048, 2048), (257, 96, 72), (128, 64, 576), (50, 6144, 256),
+                                   (19000, 128, 64)])
+def test_gemm_plain(cuda, m, n, k):
+    """koa_gemm_bf16 == F.linear (reference: _core_trf.py:104,145,148,161,163; 1x1 convs _torchvision.py:29-31)."""
+    lib = _lib.load()
+    a, b = _bf(_randn(m, k, seed=1)), _bf(_randn(n, k, seed=2, scale=k ** -0.5))
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+    ep = _epi(out=out, ldo=n)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "gemm")
+    _close_bf16(out, a.float() @ b.float().t(), f"gemm {m}x{n}x{k}")
+
+
+def test_gemm_empty_and_bad_shapes_are_rejected(cuda):
+    lib = _lib.load()
+    a = torch.zeros(8, 64, dtype=torch.bfloat16, device=cuda)
+    out = torch.zeros(8, 64, dtype=torch.bfloat16, device=cuda)
+    ep = _epi(out=out, ldo=64)
+    assert lib.koa_gemm_bf16(a.data_ptr(), a.data_ptr(), 0, 64, 64, C.byref(ep), _stream()) == -1   # empty
+    assert lib.koa_gemm_bf16(a.data_ptr(), a.data_ptr(), 8, 40, 64, C.byref(ep), _stream()) == -1   # N % 32
+    assert lib.koa_gemm_bf16(a.data_ptr(), a.data_ptr(), 8, 64, 60, C.byref(ep), _stream()) == -1   # K % 8
+    assert b"multiple" in lib.koa_last_error()
+    ep2 = _epi(out=None, ldo=64)
+    assert lib.koa_gemm_bf16(a.data_ptr(), a.data_ptr(), 8, 64, 64, C.byref(ep2), _stream()) == -1  # NULL out
+
+
+def test_gemm_fused_epilogues(cuda):
+    """bias + GELU with the pre-activation copy (ff.net.0), fp32 output + fp32 residual + bf16 copy (to_out / ff.net.3
+    on the residual stream), GELU' gating (backward of ff.net.0), bf16 addend + ReLU gate (identity path of a residual
+    block in backward) with the fused BatchNorm-backward reductions, BatchNorm column statistics (conv forward)."""
+    lib = _lib.load()
+    m, n, k = 333, 256, 192
+    a, b = _bf(_randn(m, k, seed=3)), _bf(_randn(n, k, seed=4, scale=k ** -0.5))
+    acc = a.float() @ b.float().t()
+    bias = _randn(n, seed=5, scale=0.3)
+    # bias + GELU, pre-activation copy
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+    pre = torch.empty_like(out)
+    ep = _epi(out=out, ldo=n, act=_lib.ACT_GELU, bias=bias, pre_out_bf16=pre)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "gemm gelu")
+    _close_bf16(pre, acc + bias, "pre-activation")
+    _close_bf16(out, F.gelu(acc + bias), "gelu")
+    # fp32 out + fp32 residual + bf16 copy
+    res = _randn(m, n, seed=6)
+    out32 = torch.empty(m, n, dtype=torch.float32, device=cuda)
+    cp = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+    ep = _epi(out=out32, ldo=n, out_fp32=1, bias=bias, residual_f32=res, out_bf16_copy=cp)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "gemm res")
+    ref = acc + bias + res
+    assert rel(out32, ref) < 1e-5
+    _close_bf16(cp, ref, "bf16 copy")
+    # GELU' gating: out = acc * gelu'(h)
+    h = _bf(_randn(m, n, seed=7))
+    ep = _epi(out=out, ldo=n, act=_lib.ACT_GELU_GRAD, aux_bf16=h)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "gemm gelu'")
+    hf = h.float().requires_grad_(True)
+    (gp,) = torch.autograd.grad(F.gelu(hf).sum(), hf)
+    _close_bf16(out, acc * gp, "gelu grad")
+    # addend + ReLU-backward gate: out = (acc + add) * (gate > 0)
+    add, gate = _bf(_randn(m, n, seed=8)), _bf(_randn(m, n, seed=9).relu())
+    ep = _epi(out=out, ldo=n, add_bf16=add, gate_bf16=gate)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "gemm add")
+    _close_bf16(out, (acc + add.float()) * (gate.float() > 0), "gated add")
+    # the same with the BatchNorm-backward reductions of the stored values: sum(dz), sum(dz * xhat)
+    y = _bf(_randn(m, n, seed=10) * 2 + 0.5)
+    mean, invstd = _randn(n, seed=11, scale=0.3), torch.rand(n, generator=torch.Generator().manual_seed(12)).to(cuda) + 0.5
+    s = torch.zeros(n, device=cuda)
+    q = torch.zeros(n, device=cuda)
+    ep = _epi(out=out, ldo=n, add_bf16=add, gate_bf16=gate, col_sum=s, col_sumsq=q, stat_y=y, stat_mean=mean,
+              stat_invstd=invstd)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "gemm bn-bwd stats")
+    _close_bf16(out, (acc + add.float()) * (gate.float() > 0), "gated add (stats)")
+    dz = out.float()
+    xhat = (y.float() - mean) * invstd
+    assert torch.allclose(s, dz.sum(0), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(q, (dz * xhat).sum(0), rtol=1e-4, atol=2e-3)
+    # ReLU + column statistics of the stored (rounded) values
+    s = torch.zeros(n, device=cuda)
+    q = torch.zeros(n, device=cuda)
+    ep = _epi(out=out, ldo=n, col_sum=s, col_sumsq=q)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "gemm stats")
+    _close_bf16(out, acc, "stats out")
+    assert torch.allclose(s, out.float().sum(0), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(q, (out.float() ** 2).sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("m,n,k", [(40000, 256, 64), (5000, 64, 576), (777, 2048, 128), (128 * 148 * 3 + 5, 128, 64)])
+def test_gemm_column_statistics_many_tiles(cuda, m, n, k):
+    """Forward BatchNorm statistics fused in the epilogue over many tiles per CTA (persistent kernel, per-CTA running
+    totals in shared memory, one global atomic per column and CTA), ragged last row tile."""
+    lib = _lib.load()
+    a, b = _bf(_randn(m, k, seed=3)), _bf(_randn(n, k, seed=4, scale=k ** -0.5))
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+    s, q = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    ep = _epi(out=out, ldo=n, col_sum=s, col_sumsq=q)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "gemm stats")
+    _close_bf16(out, a.float() @ b.float().t(), "stats out")
+    of = out.double()
+    assert torch.allclose(s.double(), of.sum(0), rtol=1e-4, atol=1e-2 * (m ** 0.5) * 1e-1)
+    assert torch.allclose(q.double(), (of ** 2).sum(0), rtol=1e-4, atol=1e-2)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("n_img,h,w,cin,cout,k,stride,pad", [
+    (3, 20, 20, 64, 64, 3, 1, 1), (2, 20, 20, 128, 128, 3, 2, 1), (5, 10, 10, 256, 512, 1, 2, 0),
+    (2, 40, 40, 64, 256, 3, 1, 1), (7, 5, 5, 512, 512, 3, 1, 1), (1, 6, 10, 64, 96, 3, 1, 1)])
+def test_conv_fprop_and_wgrad(cuda, n_img, h, w, cin, cout, k, stride, pad):
+    """Implicit-GEMM convolution and its weight gradient == nn.Conv2d / autograd (_torchvision.py:23-31,110,211-213)."""
+    lib = _lib.load()
+    x = _bf(_randn(n_img, cin, h, w, seed=11))
+    wt = _bf(_randn(cout, cin, k, k, seed=12, scale=(cin * k * k) ** -0.5))
+    xf, wf = x.float().requires_grad_(True), wt.float().requires_grad_(True)
+    ref = F.conv2d(xf, wf, stride=stride, padding=pad)
+    ho, wo = ref.shape[2], ref.shape[3]
+    x_nhwc = _nhwc(x)
+    w_pack = wt.permute(0, 2, 3, 1).contiguous()  # [Cout][R][S][Cin]
+    out = torch.empty(n_img, ho, wo, cout, dtype=torch.bfloat16, device=cuda)
+    ep = _epi(out=out, ldo=cout)
+    _lib.check(lib.koa_conv_fprop_bf16(x_nhwc.data_ptr(), w_pack.data_ptr(), n_img, h, w, cin, cout, k, k, stride, pad,
+                                       C.byref(ep), _stream()), "conv fprop")
+    _close_bf16(out, _nhwc(ref.detach()), "conv fprop")
+    # weight gradient
+    dy = _bf(_randn(n_img, cout, ho, wo, seed=13))
+    (gw,) = torch.autograd.grad(ref, wf, dy.float())
+    dw = torch.zeros(cout, k, k, cin, dtype=torch.float32, device=cuda)
+    _lib.check(lib.koa_conv_wgrad_bf16(_nhwc(dy).data_ptr(), x_nhwc.data_ptr(), dw.data_ptr(), n_img, h, w, cin, cout, k, k,
+                                       stride, pad, _stream()), "conv wgrad")
+    assert rel(dw, gw.permute(0, 2, 3, 1)) < 1e-4
+
+
+@pytest.mark.parametrize("pixels,cout,cin", [(1000, 256, 64), (64, 64, 64), (4133, 512, 128), (100, 2048, 512)])
+def test_gemm_wgrad(cuda, pixels, cout, cin):
+    lib = _lib.load()
+    dy, x = _bf(_randn(pixels, cout, seed=21)), _bf(_randn(pixels, cin, seed=22))
+    dw = torch.zeros(cout, cin, dtype=torch.float32, device=cuda)
+    _lib.check(lib.koa_gemm_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), pixels, cout, cin, _stream()), "wgrad")
+    assert rel(dw, dy.float().t() @ x.float()) < 1e-4
+    # accumulates (split-K partial sums land with atomics on top of what is there)
+    _lib.check(lib.koa_gemm_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), pixels, cout, cin, _stream()), "wgrad")
+    assert rel(dw, 2 * (dy.float().t() @ x.float())) < 1e-4
+
+
+@pytest.mark.parametrize("rows,d", [(7, 2048), (1472, 2048), (33, 256)])
+def test_layernorm(cuda, rows, d):
+    """nn.LayerNorm(eps 1e-5) forward / backward (_core_trf.py:111,190,192)."""
+    lib = _lib.load()
+    x = _randn(rows, d, seed=31, scale=2.0) + 0.5
+    gamma, beta = _randn(d, seed=32) * 0.2 + 1.0, _randn(d, seed=33) * 0.1
+    o16 = torch.empty(rows, d, dtype=torch.bfloat16, device=cuda)
+    o32 = torch.empty(rows, d, device=cuda)
+    mean, rstd = torch.empty(rows, device=cuda), torch.empty(rows, device=cuda)
+    _lib.check(lib.koa_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), o16.data_ptr(), o32.data_ptr(),
+                                     mean.data_ptr(), rstd.data_ptr(), rows, d, _stream()), "ln fwd")
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (d,), gr, br, 1e-5)
+    assert rel(o32, ref) < 1e-5
+    _close_bf16(o16, ref.detach(), "layernorm bf16 copy")
+    dy = _randn(rows, d, seed=34)
+    ref.backward(dy)
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(d, device=cuda), torch.zeros(d, device=cuda)
+    _lib.check(lib.koa_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                     dx.data_ptr(), dg.data_ptr(), db.data_ptr(), rows, d, _stream()), "ln bwd")
+    assert rel(dx, xr.grad) < 1e-4 and rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("b,n,heads,hd", [(2, 65, 8, 256), (3, 25, 8, 256), (1, 124, 8, 256), (2, 7, 4, 64), (1, 1, 8, 32)])
+def test_attention(cuda, b, n, heads, hd):
+    """softmax(Q K^T * scale) V with the reference's (qkv, head, d) feature split and model-dim scale
+    (_core_trf.py:160,167-182), forward + backward, including the single-token and 124-token (3-MRI) cases."""
+    lib = _lib.load()
+    d = heads * hd
+    scale = float(d) ** -0.5
+    qkv = _bf(_randn(b * n, 3 * d, seed=41))
+    out = torch.empty(b * n, d, dtype=torch.bfloat16, device=cuda)
+    probs = torch.empty(b, heads, n, n, device=cuda)
+    _lib.check(lib.koa_attention_fwd(qkv.data_ptr(), out.data_ptr(), probs.data_ptr(), b, n, heads, hd, scale, _stream()),
+               "attn fwd")
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = qf.view(b, n, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    pr = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    ref = (pr @ v).permute(0, 2, 1, 3).reshape(b * n, d)
+    assert rel(probs, pr) < 1e-4
+    _close_bf16(out, ref.detach(), "attention out")
+    dout = _bf(_randn(b * n, d, seed=42))
+    ref.backward(dout.float())
+    dqkv = torch.empty_like(qkv)
+    _lib.check(lib.koa_attention_bwd(qkv.data_ptr(), probs.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), b, n, heads, hd,
+                                     scale, _stream()), "attn bwd")
+    assert rel(dqkv.float(), qf.grad) < BF16_REL_L2
+
+
+@pytest.mark.parametrize("n,h,w", [(3, 32, 32), (2, 175, 175), (1, 80, 80)])
+def test_maxpool(cuda, n, h, w):
+    """nn.MaxPool2d(3, 2, 1) (_torchvision.py:174) incl. the odd 175 -> 88 XR size; bit exact (pure selection)."""
+    lib = _lib.load()
+    c = 64
+    x = _bf(_randn(n, c, h, w, seed=51))
+    ref, _ = F.max_pool2d(x.float(), 3, 2, 1, return_indices=True)
+    ho, wo = ref.shape[2], ref.shape[3]
+    out = torch.empty(n, ho, wo, c, dtype=torch.bfloat16, device=cuda)
+    idx = torch.empty(n, ho, wo, c, dtype=torch.uint8, device=cuda)
+    _lib.check(lib.koa_maxpool_fwd(_nhwc(x).data_ptr(), out.data_ptr(), idx.data_ptr(), n, h, w, c, _stream()), "pool")
+    assert torch.equal(out.float(), _nhwc(ref))
+    dout = _bf(_randn(n, c, ho, wo, seed=52))
+    xf = x.float().requires_grad_(True)
+    F.max_pool2d(xf, 3, 2, 1).backward(dout.float())
+    dx = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=cuda)
+    _lib.check(lib.koa_maxpool_bwd(_nhwc(dout).data_ptr(), idx.data_ptr(), dx.data_ptr(), n, h, w, c, _stream()), "pool bwd")
+    _close_bf16(dx, _nhwc(xf.grad), "maxpool bwd")  # windows overlap: up to 4 bf16 addends per input pixel
+
+
+@pytest.mark.parametrize("batch", [1, 16, 257])
+def test_focal_loss(cuda, batch):
+    """FocalLoss(gamma 2, mean) and d loss / d logits (various/_losses.py:89-108)."""
+    lib = _lib.load()
+    logits = _randn(batch, 2, seed=61, scale=2.0)
+    target = (torch.rand(batch, generator=torch.Generator().manual_seed(62)) < 0.3).long().to(cuda)
+    loss = torch.empty((), device=cuda)
+    dl = torch.empty_like(logits)
+    _lib.check(lib.koa_focal_loss(logits.data_ptr(), target.data_ptr(), loss.data_ptr(), dl.data_ptr(), batch, 2, 2.0,
+                                  _stream()), "focal")
+    lr = logits.clone().requires_grad_(True)
+    ref = ko.focal_loss(lr, target)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-6 + 1e-5 * abs(float(ref))
+    assert rel(dl, lr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("m,n,k,act", [(16, 2048, 9, _lib.ACT_GELU), (8, 512, 2048, _lib.ACT_RELU), (5, 2, 512, _lib.ACT_NONE)])
+def test_linear_small(cuda, m, n, k, act):
+    """FeatC1 Linear(9 -> 2048)+GELU (_xrNmrMcP.py:15-19), XR1Cnn head (_xr1_cnn.py:31-39)."""
+    lib = _lib.load()
+    x, w, b = _randn(m, k, seed=71), _randn(n, k, seed=72, scale=k ** -0.5), _randn(n, seed=73, scale=0.1)
+    y, pre = torch.empty(m, n, device=cuda), torch.empty(m, n, device=cuda)
+    _lib.check(lib.koa_linear_small_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), pre.data_ptr(), m, n, k, act,
+                                        _stream()), "small fwd")
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    z = F.linear(xr, wr, br)
+    ref = {_lib.ACT_GELU: F.gelu, _lib.ACT_RELU: F.relu, _lib.ACT_NONE: lambda t: t}[act](z)
+    assert rel(y, ref) < 1e-5
+    dy = _randn(m, n, seed=74)
+    ref.backward(dy)
+    dx, dw, db = torch.empty_like(x), torch.zeros_like(w), torch.zeros_like(b)
+    scratch = torch.empty(m, n, device=cuda)
+    _lib.check(lib.koa_linear_small_bwd(dy.data_ptr(), pre.data_ptr(), x.data_ptr(), w.data_ptr(), scratch.data_ptr(),
+                                        dx.data_ptr(), dw.data_ptr(), db.data_ptr(), m, n, k, act, _stream()), "small bwd")
+    assert rel(dx, xr.grad) < 1e-4 and rel(dw, wr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+
+
+def test_stem_pack_is_the_einops_rearrange(cuda):
+    """'b ch r c s -> (b s) ch r c' (_xrNmrMcP.py:209-210): bit exact (pure data movement), ragged slice counts."""
+    lib = _lib.load()
+    for b, r, c, s in [(2, 16, 16, 5), (1, 32, 32, 25), (3, 8, 12, 1)]:
+        vol = _randn(b, 1, r, c, s, seed=81)
+        img = torch.empty(b * s, r, c, device=cuda)
+        _lib.check(lib.koa_stem_pack(vol.data_ptr(), img.data_ptr(), b, r * c, s, _stream()), "stem pack")
+        assert torch.equal(img, ko._slices_to_images(vol)[:, 0])
+
+
+def test_col_stats(cuda):
+    lib = _lib.load()
+    y = _bf(_randn(5000, 256, seed=91) + 0.3)
+    s, q = torch.zeros(256, device=cuda), torch.zeros(256, device=cuda)
+    _lib.check(lib.koa_col_stats(y.data_ptr(), s.data_ptr(), q.data_ptr(), 5000, 256, _stream()), "col stats")
+    assert torch.allclose(s, y.float().sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(q, (y.float() ** 2).sum(0), rtol=1e-4, atol=1e-2)
+
+
+# =====================================================================================================
+# 2. engines
+# =====================================================================================================
+def _fe_pair(arch, dev, seed=11, res_gain=1.0, with_gap=True):
+    from oaprogressionmmf_b200.koamodels import SliceEncoder, dict_fes
+
+    spec = ko.fe_param_spec(arch, "_fe")
+    sd = ko.make_state_dict(spec, seed, device=dev, res_gain=res_gain)
+    enc = SliceEncoder(dict_fes[arch](pretrained=False), with_gap=with_gap).to(dev)
+    enc.load_state_dict({k[len("_fe."):]: v.clone() for k, v in sd.items()})
+    return sd, enc
+
+
+def _leafify(sd):
+    params = {k: v for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+    for v in params.values():
+        v.requires_grad_(True)
+    return params
+
+
+@pytest.mark.parametrize("arch,xr,size,b,s", [("resnet50", False, 64, 2, 3), ("resnet50", False, 160, 1, 2),
+                                              ("resnet18", False, 64, 2, 3), ("resnet34", False, 64, 1, 2),
+                                              ("resnext50_32x4d", True, 64, 3, 0), ("resnext50_32x4d", True, 350, 1, 0)])
+def test_fe_eval_features(cuda, arch, xr, size, b, s):
+    """Whole extractor, eval mode (BatchNorm running statistics): features within 1e-2 of the fp32 oracle, incl. the
+    real 160x160 MRI and the odd 350x350 XR geometry (350 -> 175 -> 88 -> 44 -> 22 -> 11)."""
+    sd, enc = _fe_pair(arch, cuda)
+    enc.eval()
+    if xr:
+        x = _randn(b, 1, size, size, seed=5)
+        imgs = x.expand(-1, 3, -1, -1)
+        with torch.no_grad():
+            tok = enc.encode_image(x)
+    else:
+        x = _randn(b, 1, size, size, s, seed=5)
+        imgs = ko._slices_to_images(x)
+        with torch.no_grad():
+            tok = enc.encode_volume(x)
+    with torch.no_grad():
+        ref = ko.fe_forward(sd, "_fe", arch, imgs, False, True).flatten(1)
+    got = tok.reshape(-1, tok.shape[-1])
+    assert torch.isfinite(got).all()
+    assert rel(got, ref) < LOGIT_TOL, rel(got, ref)
+
+
+def test_fe_reference_call_convention(cuda):
+    """SliceEncoder.forward takes what the reference feeds its nn.Sequential: (N, 3, H, W) with three identical
+    channels, returns (N, C, 1, 1) with GAP and (N, C, h, w) without (_xrNmrMcP.py:47-59,218-220)."""
+    sd, enc = _fe_pair("resnet18", cuda)
+    enc.eval()
+    x = _randn(4, 1, 64, 64, seed=6).expand(-1, 3, -1, -1)
+    with torch.no_grad():
+        got = enc(x)
+        ref = ko.fe_forward(sd, "_fe", "resnet18", x, False, True)
+    assert got.shape == ref.shape == (4, 512, 1, 1)
+    assert rel(got, ref) < LOGIT_TOL
+    sd2, enc2 = _fe_pair("resnet18", cuda, with_gap=False)
+    enc2.eval()
+    with torch.no_grad():
+        got = enc2(x)
+        ref = ko.fe_forward(sd2, "_fe", "resnet18", x, False, False)
+    assert got.shape == ref.shape == (4, 512, 2, 2)
+    assert rel(got, ref) < LOGIT_TOL
+
+
+@pytest.mark.parametrize("arch,res_gain,b,s,size", [("resnet50", 0.1, 4, 4, 64), ("resnet50", 1.0, 4, 4, 64),
+                                                    ("resnet18", 1.0, 2, 3, 64)])
+def test_fe_train_at_bf16_floor(cuda, arch, res_gain, b, s, size):
+    """Train mode (batch statistics, running-stat update, full backward) against the fp32 oracle. The bar is the
+    bf16 precision floor measured in the same test with no CUDA-path code involved (fp32 oracle vs the oracle with
+    every stored activation / GEMM operand rounded to bf16): CUDA-path error <= 1.5 x floor + 2e-3."""
+    x = _randn(b, 1, size, size, s, seed=5)
+    imgs = ko._slices_to_images(x)
+    gy = None
+    runs = {}
+    for tag in ("fp32", "bf16emu"):
+        sd, _ = _fe_pair(arch, cuda, res_gain=res_gain)
+        params = _leafify(sd)
+        f = ko.fe_forward(sd, "_fe", arch, imgs, True, True, None, emulate_bf16=(tag == "bf16emu")).flatten(1)
+        if gy is None:
+            gy = _randn(*f.shape, seed=7)
+        (f * gy).sum().backward()
+        runs[tag] = (f.detach(), {k: v.grad for k, v in params.items()}, sd)
+    sd, enc = _fe_pair(arch, cuda, res_gain=res_gain)
+    enc.train()
+    tok = enc.encode_volume(x)
+    got = tok.reshape(-1, tok.shape[-1])
+    (got * gy).sum().backward()
+    f0, g0, sd0 = runs["fp32"]
+    f1, g1, _ = runs["bf16emu"]
+    floor_f, mine_f = rel(f1, f0), rel(got, f0)
+    assert mine_f <= 1.5 * floor_f + 2e-3, (mine_f, floor_f)
+    mine = dict(enc.named_parameters())
+    floor_g = torch.tensor([rel(g1[k], g0[k]) for k in g0])
+    mine_g = torch.tensor([rel(mine[k[len("_fe."):]].grad, g0[k]) for k in g0])
+    assert torch.isfinite(mine_g).all()
+    assert float(mine_g.median()) <= 1.5 * float(floor_g.median()) + 2e-3, (float(mine_g.median()), float(floor_g.median()))
+    assert float(mine_g.max()) <= 2.0 * float(floor_g.max()) + 2e-3, (float(mine_g.max()), float(floor_g.max()))
+    # running statistics / num_batches_tracked are updated like nn.BatchNorm2d(momentum 0.1)
+    msd = enc.state_dict()
+    for k, v in sd0.items():
+        if k.endswith(("running_mean", "running_var")):
+            assert rel(msd[k[len("_fe."):]], v) < max(2e-2, 2 * floor_f), k
+        if k.endswith("num_batches_tracked"):
+            assert int(msd[k[len("_fe."):]]) == int(v) == 1
+
+
+def _ws_view(lib, desc, ws, what, index, dtype):
+    off, nb = C.c_size_t(), C.c_size_t()
+    _lib.check(lib.koa_fe_debug_offset(C.byref(desc), what, index, C.byref(off), C.byref(nb)), "koa_fe_debug_offset")
+    return ws[off.value:off.value + nb.value].view(dtype)
+
+
+def _nhwc_bf16(t):
+    return t.detach().permute(0, 2, 3, 1).contiguous().bfloat16().reshape(-1)
+
+
+@pytest.mark.parametrize("arch,xr,b,s,size", [("resnet50", False, 2, 3, 64), ("resnet50", False, 2, 8, 96),
+                                              ("resnext50_32x4d", True, 3, 0, 64), ("resnet18", False, 2, 3, 64)])
+def test_fe_backward_teacher_forced(cuda, arch, xr, b, s, size):
+    """koa_fe_backward on a forward state forced to equal the bf16-emulating oracle's (the saved activations in the
+    workspace are overwritten through koa_fe_debug_offset): every parameter gradient within a few bf16 roundings
+    of autograd (median < 2e-2, max < 1e-1 relative L2 over 60-159 tensors; gradients are stored in bf16 between
+    layers, ~150 roundings deep)."""
+    lib = _lib.load()
+    sd, enc = _fe_pair(arch, cuda)
+    enc.train()
+    if xr:
+        x = _randn(b, 1, size, size, seed=5)
+        imgs = x.expand(-1, 3, -1, -1)
+        tok = enc.encode_image(x)
+    else:
+        x = _randn(b, 1, size, size, s, seed=5)
+        imgs = ko._slices_to_images(x)
+        tok = enc.encode_volume(x)
+    fn = tok.grad_fn
+    while fn is not None and not hasattr(fn, "ws"):
+        fn = fn.next_functions[0][0] if fn.next_functions else None
+    ws, desc = fn.ws, fn.desc
+    params = _leafify(sd)
+    taps = {}
+    ref = ko.fe_forward(sd, "_fe", arch, imgs, True, True, taps, emulate_bf16=True).flatten(1)
+    ykeys = ["_fe.0.y"]
+    plan = ko.fe_block_plan(arch)
+    for blk in plan:
+        p = f"_fe.{blk['layer']}.{blk['index']}"
+        ykeys += [f"{p}.conv1.y", f"{p}.conv2.y"]
+        if blk["kind"] == "bottleneck":
+            ykeys.append(f"{p}.conv3.y")
+        if blk["downsample"]:
+            ykeys.append(f"{p}.downsample.0.y")
+    for ui, key in enumerate(ykeys):
+        y = taps[key].detach()
+        _ws_view(lib, desc, ws, 0, ui, torch.bfloat16).copy_(_nhwc_bf16(y))
+        coef = _ws_view(lib, desc, ws, 6, ui, torch.float32).view(7, -1)
+        coef[2].copy_(y.mean(dim=(0, 2, 3)))
+        coef[3].copy_(torch.rsqrt(y.var(dim=(0, 2, 3), unbiased=False) + 1e-5))
+    _ws_view(lib, desc, ws, 4, 0, torch.bfloat16).copy_(_nhwc_bf16(taps["_fe.stem"]))
+    for bi, blk in enumerate(plan):
+        p = f"_fe.{blk['layer']}.{blk['index']}"
+        _ws_view(lib, desc, ws, 1, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[p]))
+        _ws_view(lib, desc, ws, 2, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[f"{p}.a1"]))
+        if blk["kind"] == "bottleneck":
+            _ws_view(lib, desc, ws, 3, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[f"{p}.a2"]))
+    a0 = _ws_view(lib, desc, ws, 4, 0, torch.bfloat16)
+    p0 = _ws_view(lib, desc, ws, 5, 0, torch.bfloat16)
+    idx0 = _ws_view(lib, desc, ws, 7, 0, torch.uint8)
+    hs = (size + 6 - 7) // 2 + 1
+    _lib.check(lib.koa_maxpool_fwd(a0.data_ptr(), p0.data_ptr(), idx0.data_ptr(), imgs.shape[0], hs, hs, 64, _stream()),
+               "maxpool")
+    assert torch.equal(p0.float(), _nhwc_bf16(taps["_fe.pool"]).float())
+    gy = _randn(*ref.shape, seed=7)
+    (tok.reshape(-1, tok.shape[-1]) * gy).sum().backward()
+    (ref * gy).sum().backward()
+    mine = dict(enc.named_parameters())
+    errs = torch.tensor([rel(mine[k[len("_fe."):]].grad, v.grad) for k, v in params.items()])
+    assert torch.isfinite(errs).all()
+    assert float(errs.median()) < 2e-2 and float(errs.max()) < 1e-1, (float(errs.median()), float(errs.max()))
+
+
+@pytest.mark.parametrize("b,n_p,depth,with_cls,head", [(2, 5, 2, True, True), (3, 7, 1, False, False), (2, 64, 1, False, False),
+                                                       (1, 123, 1, True, True), (4, 25, 1, False, True)])
+def test_feat_forward_backward(cuda, b, n_p, depth, with_cls, head):
+    """FeaT (embedding, CLS/pos, pre-norm blocks, head; _core_trf.py:74-205) vs the fp32 oracle: token states, logits,
+    input gradient and every parameter gradient; dead heads keep grad None like the reference."""
+    from oaprogressionmmf_b200.koamodels import FeaT
+
+    dim, heads = 2048, 8
+    spec = ko.feat_param_spec("_agg", n_p, dim, depth, dim, 2, with_cls)
+    sd = ko.make_state_dict(spec, 21, pos_scale=0.5, device=cuda)
+    mod = FeaT(n_p, dim, dim, depth, heads, dim, 2, with_cls=with_cls).to(cuda)
+    mod.load_state_dict({k[len("_agg."):]: v.clone() for k, v in sd.items()})
+    mod.train()
+    tok = _randn(b, n_p, dim, seed=6, scale=0.7).requires_grad_(True)
+    tok_ref = tok.detach().clone().requires_grad_(True)
+    out, states, attns = mod.run(tok, compute_head=head)
+    for v in sd.values():
+        v.requires_grad_(True)
+    out_ref, states_ref = ko.feat_forward(sd, "_agg", tok_ref, depth, heads, 0.0, 0.0, True)
+    assert out.shape == out_ref.shape and states.shape == states_ref.shape and len(attns) == depth
+    assert rel(states, states_ref) < 5e-3
+    gs, go = _randn(*states.shape, seed=8), _randn(*out.shape, seed=9)
+    loss = (states * gs).sum() + ((out * go).sum() if head else 0)
+    loss_ref = (states_ref * gs).sum() + ((out_ref * go).sum() if head else 0)
+    if head:
+        assert rel(out, out_ref) < LOGIT_TOL
+    loss.backward()
+    loss_ref.backward()
+    assert rel(tok.grad, tok_ref.grad) < 1e-2
+    mine = dict(mod.named_parameters())
+    for k, v in sd.items():
+        gm = mine[k[len("_agg."):]].grad
+        if v.grad is None:
+            assert gm is None, k
+            continue
+        assert gm is not None, k
+        assert rel(gm, v.grad) < 1e-2, (k, rel(gm, v.grad))
+
+
+# =====================================================================================================
+# 3. models, on the fixtures generated from the unmodified reference
+# =====================================================================================================
+GOLDEN = sorted(f[:-5] for f in os.listdir(os.path.join(os.path.dirname(__file__), "golden")) if f.endswith(".json"))
+
+
+def _golden_case(case, golden_dir, dev, pos_scale=1.0):
+    from oaprogressionmmf_b200.koamodels import dict_models
+
+    with open(os.path.join(golden_dir, case + ".json")) as f:
+        gold = json.load(f)
+    name = gold["model"]
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in gold["config_kwargs"].items()}
+    cfg = ko.make_config(name, **kw)
+    spec = ko.model_param_spec(name, cfg)
+    inputs, target = ko.make_inputs(name, cfg, gold["batch"], gold["seed_inputs"], device=dev)
+    model = dict_models[name](to_attr(cfg), None).to(dev)
+    model.load_state_dict(ko.make_state_dict(spec, gold["seed_weights"], pos_scale=pos_scale, device=dev), strict=True)
+    return gold, cfg, model, inputs, target
+
+
+@pytest.mark.parametrize("case", GOLDEN)
+def test_model_eval_logits_match_reference(cuda, golden_dir, case):
+    """Eval-mode logits of every model class against the logits the *unmodified reference* produced for the same
+    weights and inputs: within 1e-2 relative (bf16) and identical class predictions."""
+    gold, cfg, model, inputs, _ = _golden_case(case, golden_dir, cuda)
+    model.eval()
+    with torch.no_grad():
+        out = model(*inputs)
+    assert isinstance(out, dict) and list(out) == ["main"]
+    lg = out["main"]
+    ref = torch.tensor(gold["eval_logits"], device=cuda)
+    assert lg.shape == ref.shape
+    # Precision floor of bf16 storage for this case, measured with no CUDA-path code involved: the oracle with every
+    # stored activation / GEMM operand rounded to bf16 against the same reference logits. For the tiny fixtures
+    # (2 knees x 2 logits, 64x64 inputs) the floor itself sits at 0.5e-2 .. 1.1e-2, so the bar is BASELINE.json's
+    # 1e-2 or 1.5 x the floor, whichever is larger (and never above 2e-2).
+    spec = ko.model_param_spec(gold["model"], cfg)
+    sd = ko.make_state_dict(spec, gold["seed_weights"], device=cuda)
+    with torch.no_grad():
+        emu = ko.model_forward(gold["model"], cfg, sd, inputs, training=False, emulate_bf16=True)
+    floor = rel(emu, ref)
+    tol = min(2e-2, max(LOGIT_TOL, 1.5 * floor))
+    assert rel(lg, ref) < tol, (rel(lg, ref), floor)
+    assert bool((lg.argmax(1) == ref.argmax(1)).all())
+
+
+@pytest.mark.parametrize("case", GOLDEN)
+def test_model_train_step_matches_reference_structure(cuda, golden_dir, case):
+    """One train-mode step on the golden case: loss finite and close to the reference's, a gradient for exactly
+    the parameters the reference has one for (None on the dead per-sequence heads), every gradient finite and of
+    the reference's magnitude (tiny train-mode batches sit on the chaotic BatchNorm floor, see module docstring:
+    gradient norms within a factor 4, median within 40 %)."""
+    from oaprogressionmmf_b200.losses import FocalLoss
+
+    # the reference's train step was recorded on the sensitised weights (pos_embedding / cls_token x 0.02, so that
+    # the logits depend on the image features; oracle/make_golden.py)
+    gold, cfg, model, inputs, target = _golden_case(case, golden_dir, cuda, pos_scale=0.02)
+    model.train()
+    lg = model(*inputs)["main"]
+    loss = FocalLoss(gamma=2)(lg, target)
+    loss.backward()
+    assert abs(float(loss) - gold["train_loss"]) < 0.2 * max(gold["train_loss"], 0.1)
+    ratios = []
+    for k, p in model.named_parameters():
+        gref = gold["grads"][k]
+        if gref is None:
+            assert p.grad is None, f"{k}: reference leaves grad None"
+            continue
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+        ratios.append(float(p.grad.norm()) / (gref["norm"] + 1e-30))
+    r = torch.tensor(ratios)
+    assert float(r.min()) > 1 / 4 and float(r.max()) < 4, (float(r.min()), float(r.max()))
+    assert abs(float(r.median()) - 1) < 0.4
+
+
+def test_output_type_main_returns_bare_tensor(cuda, golden_dir):
+    gold, cfg, model, inputs, _ = _golden_case("XR1Cnn_r18", golden_dir, cuda)
+    model.config["output_type"] = "main"
+    model.eval()
+    with torch.no_grad():
+        out = model(*inputs)
+    assert torch.is_tensor(out) and out.shape == (gold["batch"], 2)
+    model.config["output_type"] = "nope"
+    with pytest.raises(ValueError):
+        model(*inputs)
+
+
+def test_full_size_model_step_properties(cuda):
+    """BASELINE.json's full sizes (XR 350^2 + DESS 160^2x64 + T2 160^2x25 + clinical, B = 2), where the oracle is too
+    slow to be the checker: size-independent properties instead. (1) eval logits are invariant to the order of the
+    knees in the batch (no cross-knee leakage through the slice batch); (2) a train step gives finite gradients for
+    every live parameter and None on the dead heads; (3) the backward pass is linear in the loss scale: backward of
+    2*loss doubles every gradient (a power-of-two scale survives the bf16 storage exactly; split-K atomics reorder
+    fp32 sums, hence 1e-3 instead of bit equality)."""
+    from oaprogressionmmf_b200.koamodels import dict_models
+    from oaprogressionmmf_b200.losses import FocalLoss
+
+    name = "XR1MR2C1CnnTrf"
+    cfg = ko.make_config(name)
+    spec = ko.model_param_spec(name, cfg)
+    model = dict_models[name](to_attr(cfg), None).to(cuda)
+    model.load_state_dict(ko.make_state_dict(spec, 778, device=cuda))
+    inputs, target = ko.make_inputs(name, cfg, 2, 779, device=cuda)
+    model.eval()
+    with torch.no_grad():
+        a = model(*inputs)["main"]
+        b = model(*[t.flip(0) for t in inputs])["main"].flip(0)
+    assert torch.isfinite(a).all() and rel(b, a) < 1e-6
+    # backward linearity at full size. Eval-mode BatchNorm keeps the two forward passes bit-identical (train-mode
+    # statistics are summed with atomics whose order varies run to run, and a 2-image batch amplifies that).
+    grads = []
+    for scale in (1.0, 2.0):
+        model.zero_grad(set_to_none=True)
+        (FocalLoss(gamma=2)(model(*inputs)["main"], target) * scale).backward()
+        grads.append({k: (None if p.grad is None else p.grad.clone()) for k, p in model.named_parameters()})
+    for k, g in grads[0].items():
+        dead = ("_agg_1.mlp_head0." in k) or ("_agg_2.mlp_head0." in k)
+        assert (g is None) == dead, k
+        if g is not None:
+            assert torch.isfinite(g).all(), k
+            assert rel(grads[1][k], 2 * g) < 1e-3, k
+    # train mode: finite loss and gradients, BatchNorm buffers updated
+    model.train()
+    model.zero_grad(set_to_none=True)
+    loss = FocalLoss(gamma=2)(model(*inputs)["main"], target)
+    loss.backward()
+    assert torch.isfinite(loss)
+    for k, p in model.named_parameters():
+        dead = ("_agg_1.mlp_head0." in k) or ("_agg_2.mlp_head0." in k)
+        assert (p.grad is None) == dead, k
+        if p.grad is not None:
+            assert torch.isfinite(p.grad).all(), k
+    assert int(model._fe1[1].num_batches_tracked) == 1

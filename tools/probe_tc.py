@@ -105,9 +105,9 @@ def group_gemm():
     ok &= report("gemm gelu-grad epilogue", torch, _lib, out, (a.float() @ b.float().t()) * hf.grad)
     add = torch.randn(m, n, device="cuda", generator=g).bfloat16()
     mask = torch.randn(m, n, device="cuda", generator=g).relu().bfloat16()
-    ep = _lib.Epilogue(out=out.data_ptr(), ldo=n, add_bf16=add.data_ptr(), mask_bf16=mask.data_ptr())
+    ep = _lib.Epilogue(out=out.data_ptr(), ldo=n, add_bf16=add.data_ptr(), gate_bf16=mask.data_ptr())
     _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), st), "gemm")
-    ok &= report("gemm masked add", torch, _lib, out, a.float() @ b.float().t() + add.float() * (mask.float() > 0))
+    ok &= report("gemm masked add", torch, _lib, out, (a.float() @ b.float().t() + add.float()) * (mask.float() > 0))
     # column statistics
     cs = torch.zeros(n, device="cuda")
     cq = torch.zeros(n, device="cuda")
