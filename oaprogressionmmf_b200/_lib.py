@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkoa_b200.so")
+LIB_PATH = os.environ.get("KOA_LIB") or os.path.join(_HERE, "libkoa_b200.so")  # KOA_LIB: A/B builds of the same ABI
 
 
 class KoaError(RuntimeError):
@@ -131,6 +131,27 @@ def ptr_table(tensors):
     for i, t in enumerate(tensors):
         arr[i] = None if t is None else t.data_ptr()
     return arr
+
+def zeros_like_flat(tensors):
+    """Zero-initialised gradient buffers for ``tensors`` (None entries stay None) carved out of ONE flat
+    allocation: a single memset instead of one fill kernel per parameter."""
+    import torch
+
+    live = [t for t in tensors if t is not None]
+    if not live:
+        return [None] * len(tensors)
+    sizes = [(t.numel() + 63) // 64 * 64 for t in live]  # 256-byte aligned slices
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=live[0].device)
+    out, off, it = [], 0, iter(sizes)
+    for t in tensors:
+        if t is None:
+            out.append(None)
+            continue
+        n = next(it)
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += n
+    return out
+
 
 _lib = None
 

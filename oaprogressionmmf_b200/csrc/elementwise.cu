@@ -83,6 +83,51 @@ __global__ void pack_grouped_w_kernel(const float* __restrict__ src, bf16* __res
   }
 }
 
+// Batched form of the two kernels above: one launch packs every convolution of an extractor (both operand forms).
+struct PackJobTable {
+  KoaPackJob job[kKoaMaxPackJobs];
+  long long begin[kKoaMaxPackJobs + 1];  // prefix sums of the per-job work items
+  int n;
+};
+__global__ void pack_fe_weights_kernel(const __grid_constant__ PackJobTable tab) {
+  const long long total = tab.begin[tab.n];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = tab.n - 1;
+    while (lo < hi) {  // last job whose begin <= i
+      const int mid = (lo + hi + 1) >> 1;
+      if (tab.begin[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const KoaPackJob& jb = tab.job[lo];
+    long long t = i - tab.begin[lo];
+    bf16* fwd = reinterpret_cast<bf16*>(jb.fwd);
+    bf16* dg = reinterpret_cast<bf16*>(jb.dgrad);
+    if (jb.cg == 0) {
+      const int fr = jb.k, fs = jb.k, cin = jb.cin, cout = jb.cout;
+      const bf16 v = __float2bfloat16_rn(jb.src[t]);
+      const int s = (int)(t % fs); t /= fs;
+      const int r = (int)(t % fr); t /= fr;
+      const int ci = (int)(t % cin); t /= cin;
+      const int co = (int)t;
+      fwd[(((long long)co * fr + r) * fs + s) * cin + ci] = v;
+      if (dg != nullptr) dg[(((long long)ci * fr + (fr - 1 - r)) * fs + (fs - 1 - s)) * cout + co] = v;
+    } else {
+      const int cg = jb.cg;
+      const long long idx = t;
+      const int j = (int)(t % 64); t /= 64;
+      const int tap = (int)(t % 9); t /= 9;
+      const int row = (int)t;
+      const int other = (row / 64) * 64 + j;
+      float vf = 0.0f, vd = 0.0f;
+      if (other / cg == row / cg) {
+        vf = jb.src[((long long)row * cg + (other % cg)) * 9 + tap];
+        if (dg != nullptr) vd = jb.src[((long long)other * cg + (row % cg)) * 9 + (8 - tap)];
+      }
+      fwd[idx] = __float2bfloat16_rn(vf);
+      if (dg != nullptr) dg[idx] = __float2bfloat16_rn(vd);
+    }
+  }
+}
+
 // grad[o][ig][r][s] (fp32) = dense[o][r][s][(o % 64) / cg * cg + ig]   (diagonal blocks of the chunked gradient)
 __global__ void unpack_grouped_dw_kernel(const float* __restrict__ dense, float* __restrict__ grad, int c, int cg) {
   const long long total = (long long)c * cg * 9;
@@ -844,6 +889,26 @@ int koa_k_pack_conv_w(const float* src, void* dst, int cout, int cin, int fr, in
 int koa_k_pack_grouped_w(const float* src, void* dst, int c, int cg, int dgrad_form, cudaStream_t st) {
   KOA_REQUIRE(c % 64 == 0 && cg >= 1 && 64 % cg == 0, "grouped conv packing needs C %% 64 == 0 and Cg | 64 (C=%d Cg=%d)", c, cg);
   pack_grouped_w_kernel<<<grid_for((long long)c * 9 * 64), kThreads, 0, st>>>(src, (bf16*)dst, c, cg, dgrad_form);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_pack_fe_weights(const KoaPackJob* jobs, int n_jobs, cudaStream_t st) {
+  KOA_REQUIRE(n_jobs > 0 && n_jobs <= kKoaMaxPackJobs, "pack job count %d out of range", n_jobs);
+  PackJobTable tab;
+  tab.n = n_jobs;
+  long long acc = 0;
+  for (int j = 0; j < n_jobs; ++j) {
+    tab.job[j] = jobs[j];
+    tab.begin[j] = acc;
+    if (jobs[j].cg > 0) {
+      KOA_REQUIRE(jobs[j].cout % 64 == 0 && 64 % jobs[j].cg == 0 && jobs[j].k == 3, "unsupported grouped conv packing");
+      acc += (long long)jobs[j].cout * 9 * 64;
+    } else {
+      acc += (long long)jobs[j].cout * jobs[j].cin * jobs[j].k * jobs[j].k;
+    }
+  }
+  tab.begin[n_jobs] = acc;
+  pack_fe_weights_kernel<<<grid_for(acc, kThreads, 148 * 8), kThreads, 0, st>>>(tab);
   KOA_LAUNCH_CHECK();
   return 0;
 }

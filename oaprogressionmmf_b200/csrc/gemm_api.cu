@@ -259,8 +259,8 @@ int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, 
   rc = koa_tmap_2d_bf16(&tb, x, (uint64_t)cin, (uint64_t)pixels, (uint64_t)cin * 2, 64, 64);
   if (rc) return rc;
   ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
-  if (cin % 128 == 0) return launch_wgrad<128, 3, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
-  return launch_wgrad<64, 3, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
+  if (cin % 128 == 0) return launch_wgrad<128, 6, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
+  return launch_wgrad<64, 6, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
 }
 
 int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int cin, int cout,
@@ -277,8 +277,8 @@ int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, i
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64, 0};
   const int taps = filt_r * filt_s;
-  if (cin % 128 == 0) return launch_wgrad<128, 3, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
-  return launch_wgrad<64, 3, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
+  if (cin % 128 == 0) return launch_wgrad<128, 6, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
+  return launch_wgrad<64, 6, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
 }
 
 // Grouped 3x3 convolution (ResNeXt, koafusion/models/_torchvision.py:110,327-328) as a block-diagonal dense
@@ -313,7 +313,7 @@ int koa_conv_grouped_wgrad_launch(const void* dy, const void* x, float* dw, int 
   rc = koa_tmap_im2col_bf16(&tb, x, n_img, h, w_in, c, 3, 3, stride, 1, 64);
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, 1, 3, c / 64, 1};
-  return launch_wgrad<64, 3, true>(ta, tb, c, c, (int)pixels, 9, g, dw, st);
+  return launch_wgrad<64, 6, true>(ta, tb, c, c, (int)pixels, 9, g, dw, st);
 }
 
 // ------------------------------------ C ABI ----------------------------------------------------

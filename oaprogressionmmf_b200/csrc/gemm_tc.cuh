@@ -302,7 +302,11 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint64_t* release
     for (int p = 0; p < 4; ++p) q[p] = make_uint4(0, 0, 0, 0);
   }
   row_sts(stage, q, lm);
+#ifdef KOA_EXP_NO_STATS_LOOP
+  if (false) {
+#else
   if (stats) {
+#endif
     if (bwd) tile_sts(stage1, t_y, lm);
     __syncwarp();
     // lane = (h, p): column pair (2p, 2p+1) over the 16 rows 2i + h; the two lane halves read rows in different
@@ -314,23 +318,35 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint64_t* release
       const float2 is = __ldg(reinterpret_cast<const float2*>(ep.stat_invstd + n + 2 * p));
       mu0 = mu.x; mu1 = mu.y; is0 = is.x; is1 = is.y;
     }
-    float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
-    // row 2i + h, 4 bytes at column pair p: piece p >> 2 (swizzled by ((2i + h) >> 1) & 3 = i & 3), word p & 3
+    // row 2i + h, 4 bytes at column pair p: piece p >> 2 (swizzled by ((2i + h) >> 1) & 3 = i & 3), word p & 3.
+    // All shared-memory reads are issued before the first use (a load-use pair per iteration serialises on the
+    // LDS latency), the two flavours are separate straight-line loops, and each sum has two independent chains.
     const uint32_t base = stage + (uint32_t)(h * 64 + (p & 3) * 4);
+    uint32_t w[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const uint32_t off = (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4);
-      const uint32_t w = lds32(base + off);
-      const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
-      s0 += x0; s1 += x1;
-      if (bwd) {
-        const uint32_t wy = lds32(base + kStageBytesPerWarp + off);
-        const float y0 = __uint_as_float(wy << 16), y1 = __uint_as_float(wy & 0xffff0000u);
-        q0 = fmaf(x0, (y0 - mu0) * is0, q0); q1 = fmaf(x1, (y1 - mu1) * is1, q1);
-      } else {
-        q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+    for (int i = 0; i < 16; ++i) w[i] = lds32(base + (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4));
+    float sa[2] = {0.0f, 0.0f}, sb[2] = {0.0f, 0.0f}, qa[2] = {0.0f, 0.0f}, qb[2] = {0.0f, 0.0f};
+    if (bwd) {
+      uint32_t wy[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        wy[i] = lds32(base + kStageBytesPerWarp + (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float x0 = __uint_as_float(w[i] << 16), x1 = __uint_as_float(w[i] & 0xffff0000u);
+        const float y0 = __uint_as_float(wy[i] << 16), y1 = __uint_as_float(wy[i] & 0xffff0000u);
+        sa[i & 1] += x0; sb[i & 1] += x1;
+        qa[i & 1] = fmaf(x0, (y0 - mu0) * is0, qa[i & 1]); qb[i & 1] = fmaf(x1, (y1 - mu1) * is1, qb[i & 1]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float x0 = __uint_as_float(w[i] << 16), x1 = __uint_as_float(w[i] & 0xffff0000u);
+        sa[i & 1] += x0; sb[i & 1] += x1;
+        qa[i & 1] = fmaf(x0, x0, qa[i & 1]); qb[i & 1] = fmaf(x1, x1, qb[i & 1]);
       }
     }
+    float s0 = sa[0] + sa[1], s1 = sb[0] + sb[1], q0 = qa[0] + qa[1], q1 = qb[0] + qb[1];
     s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
     q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
     if (h == 0) {  // this warp's 32-row partial of columns (c_local + 2p, + 2p + 1): private slot, no atomics
@@ -512,7 +528,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // Combine the four row-quarter partials of every column of this tile. Column n0 + c is always owned by
         // epilogue thread c, so the running per-CTA totals need no atomics; `part` is double buffered, which makes
         // one barrier per tile sufficient.
+#ifndef KOA_EXP_NO_TILE_BARRIER
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+#endif
         if (ep_tid < BN && n0 + ep_tid < N) {
           const float4 a = *reinterpret_cast<const float4*>(part + ep_tid * 8);
           const float4 b = *reinterpret_cast<const float4*>(part + ep_tid * 8 + 4);

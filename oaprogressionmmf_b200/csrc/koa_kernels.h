@@ -9,6 +9,17 @@ int koa_k_pack_conv_w(const float* src, void* dst, int cout, int cin, int fr, in
 int koa_k_pack_grouped_w(const float* src, void* dst, int c, int cg, int dgrad_form, cudaStream_t st);
 int koa_k_unpack_grouped_dw(const float* dense, float* grad, int c, int cg, cudaStream_t st);
 int koa_k_unpack_conv_dw(const float* src, float* dst, int cout, int cin, int fr, int fs, cudaStream_t st);
+// All convolution weights of one extractor in ONE launch: job j converts src (fp32 [Cout][Cin/g][k][k]) into the
+// forward ([Cout][k][k][Cin], or the per-64-channel block-diagonal form of a grouped conv) and, when dgrad != NULL,
+// the data-gradient ([Cin][k'][k'][Cout], taps flipped) bf16 operands.
+struct KoaPackJob {
+  const float* src;
+  void* fwd;
+  void* dgrad;
+  int cout, cin, k, cg;  // cg > 0: grouped 3x3 convolution with cg input channels per group (C = cout = cin)
+};
+constexpr int kKoaMaxPackJobs = 64;
+int koa_k_pack_fe_weights(const KoaPackJob* jobs, int n_jobs, cudaStream_t st);
 int koa_k_pack_matrix(const float* src, void* dst, void* dst_t, int rows, int cols, cudaStream_t st);
 int koa_k_cast_bf16(const float* src, void* dst, long long n, cudaStream_t st);
 

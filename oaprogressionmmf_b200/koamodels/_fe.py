@@ -153,7 +153,7 @@ class _FEFunction(torch.autograd.Function):
         lib = _lib.load()
         enc = ctx.enc
         params = enc._trainable()
-        grads = [torch.zeros_like(p) if p.requires_grad else None for p in params]
+        grads = _lib.zeros_like_flat([p if p.requires_grad else None for p in params])
         gtable = _lib.ptr_table(grads)
         dfeat = dfeat.contiguous().float()
         _lib.check(lib.koa_fe_backward(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(), dfeat.data_ptr(),

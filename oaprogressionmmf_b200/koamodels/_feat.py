@@ -107,17 +107,15 @@ class _FeaTFunction(torch.autograd.Function):
         lib = _lib.load()
         mod = ctx.mod
         params = mod._param_list()
-        grads = [None if (p is None or not p.requires_grad) else torch.zeros_like(p) for p in params]
+        # every table slot the engine accumulates into must exist (also for frozen parameters); the dead head of the
+        # per-sequence transformers gets no slot at all: the reference leaves .grad = None there
+        n_head = 6
+        live = [None if p is None else p for p in params]
         if not ctx.desc.compute_head:
-            # dead head of the per-sequence transformers: the reference leaves .grad = None there
-            for i in range(len(grads) - 6, len(grads)):
-                grads[i] = None
+            live[-n_head:] = [None] * n_head
             d_logits = None
-        # every table slot the engine accumulates into must exist
-        gfull = [g if g is not None else (None if p is None else torch.zeros_like(p)) for g, p in zip(grads, params)]
-        if not ctx.desc.compute_head:
-            for i in range(len(gfull) - 6, len(gfull)):
-                gfull[i] = None
+        gfull = _lib.zeros_like_flat(live)
+        grads = [g if (g is not None and p.requires_grad) else None for g, p in zip(gfull, params)]
         gtable = _lib.ptr_table(gfull)
         d_tokens = torch.empty(ctx.token_shape, dtype=torch.float32, device=ctx.ws.device) if ctx.tokens_need_grad else None
         ds = None if d_states is None else d_states.contiguous().float()
