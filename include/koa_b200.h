@@ -68,6 +68,9 @@ typedef struct koa_epilogue {
   const void* stat_y;        /* BatchNorm backward form of the statistics: when non-NULL, col_sumsq receives */
   const float* stat_mean;    /* sum(out * xhat) with xhat = (stat_y - stat_mean) * stat_invstd (stat_y: bf16 */
   const float* stat_invstd;  /* [M, ldo], the forward conv output), i.e. col_sum / col_sumsq = dbeta / dgamma */
+  float drop_p;              /* > 0: dropout after the activation, before the residual add: value *= mask / (1 - p), */
+  unsigned int drop_site;    /* mask = koa_dropout_mask(drop_seed, drop_site, M, N, drop_p) (counter-based Philox, */
+  unsigned long long drop_seed; /* regenerated in backward instead of stored) */
 } koa_epilogue_t;
 
 /* out[M,N] = epilogue(A[M,K] . B[N,K]^T); A, B bf16 row-major. tcgen05/TMEM tiles fed by TMA.
@@ -134,7 +137,8 @@ typedef struct koa_feat_desc {
   int compute_head;  /* run mlp_head0 on token 0 (dead compute for the per-sequence transformers) */
   int training;
   int need_backward;
-  float emb_dropout, mlp_dropout; /* must be 0 here; dropout is applied by koa_dropout_* around the call */
+  float emb_dropout, mlp_dropout; /* nn.Dropout probabilities (_core_trf.py:105,127,146-149,164); active when training */
+  unsigned long long seed;   /* Philox seed of this call's dropout masks; backward must get the same descriptor */
 } koa_feat_desc_t;
 
 size_t koa_feat_workspace_bytes(const koa_feat_desc_t* d);
@@ -174,6 +178,11 @@ int koa_stem_pack(const float* vol, float* img, int batch, int rc, int slices, v
 /* nn.MaxPool2d(3, 2, 1) on NHWC bf16 (koafusion/models/_torchvision.py:174); idx keeps the winning tap. */
 int koa_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, void* stream);
 int koa_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, void* stream);
+/* Dropout scale factors (0 or 1/(1-p)) of site `site` as an fp32 [rows][cols] tensor: exactly the mask the engines
+ * and koa_gemm_bf16 apply for (seed, site) (nn.Dropout of koafusion/models/_core_trf.py:105,146-149,164 with a
+ * counter-based generator). FeaT sites: 4*layer + {0: to_out, 1: ff GELU, 2: ff out}, 0xE000: embedding, 0xF000: head. */
+int koa_dropout_mask(unsigned long long seed, unsigned int site, long long rows, int cols, float p, float* out,
+                     void* stream);
 /* per-channel sum / sum of squares of a bf16 [rows][c] tensor (stand-alone BatchNorm statistics). */
 int koa_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, void* stream);
 

@@ -37,6 +37,9 @@ class Epilogue(C.Structure):
         ("stat_y", C.c_void_p),
         ("stat_mean", C.c_void_p),
         ("stat_invstd", C.c_void_p),
+        ("drop_p", C.c_float),
+        ("drop_site", C.c_uint),
+        ("drop_seed", C.c_ulonglong),
     ]
 
 
@@ -73,6 +76,7 @@ class FeatDesc(C.Structure):
         ("need_backward", C.c_int),
         ("emb_dropout", C.c_float),
         ("mlp_dropout", C.c_float),
+        ("seed", C.c_ulonglong),
     ]
 
 
@@ -122,6 +126,7 @@ SIGNATURES = {
     "koa_maxpool_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "koa_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "koa_col_stats": (_I, [_P, _P, _P, C.c_longlong, _I, _P]),
+    "koa_dropout_mask": (_I, [C.c_ulonglong, C.c_uint, C.c_longlong, _I, _F, _P, _P]),
 }
 
 

@@ -1115,6 +1115,46 @@ int koa_k_linear_small_bwd(const float* dy, const float* pre, const float* x, co
   }
   return 0;
 }
+namespace {
+__global__ void dropout_mask_kernel(DropSpec d, long long n, float* __restrict__ out) {
+  const long long quads = (n + 3) / 4;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    float s[4];
+    drop_scales4(d, (unsigned long long)q, s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (q * 4 + i < n) out[q * 4 + i] = s[i];
+  }
+}
+__global__ void dropout_apply_kernel(DropSpec d, long long quads, float* __restrict__ x_inplace, const float* __restrict__ x,
+                                     bf16* __restrict__ out_bf16) {
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+    float s[4];
+    drop_scales4(d, (unsigned long long)q, s);
+    const float4 v = *reinterpret_cast<const float4*>((x_inplace ? x_inplace : x) + q * 4);
+    const float4 o = make_float4(v.x * s[0], v.y * s[1], v.z * s[2], v.w * s[3]);
+    if (x_inplace != nullptr) *reinterpret_cast<float4*>(x_inplace + q * 4) = o;
+    if (out_bf16 != nullptr) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y); pk.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(out_bf16 + q * 4) = pk;
+    }
+  }
+}
+}  // namespace
+int koa_k_dropout_mask(unsigned long long seed, unsigned int site, long long n, float p, float* out, cudaStream_t st) {
+  KOA_REQUIRE(n > 0 && p >= 0.0f && p < 1.0f && out != nullptr, "bad dropout mask request");
+  dropout_mask_kernel<<<grid_for((n + 3) / 4), kThreads, 0, st>>>(make_drop_spec(seed, site, p), n, out);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_dropout_apply(float* x_inplace, const float* x, void* out_bf16, unsigned long long seed, unsigned int site,
+                        long long n, float p, cudaStream_t st) {
+  KOA_REQUIRE(n > 0 && n % 4 == 0 && p >= 0.0f && p < 1.0f && (x_inplace != nullptr || x != nullptr), "bad dropout request");
+  dropout_apply_kernel<<<grid_for(n / 4), kThreads, 0, st>>>(make_drop_spec(seed, site, p), n / 4, x_inplace, x, (bf16*)out_bf16);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
 int koa_k_focal_loss(const float* logits, const long long* target, float* loss, float* dlogits, int batch, int classes,
                      float gamma, cudaStream_t st) {
   focal_loss_kernel<<<1, 128, 0, st>>>(logits, target, loss, dlogits, batch, classes, gamma);

@@ -3,7 +3,7 @@
 // torchvision twins picked by koafusion/models/_core_fes.py:6-15).
 //
 // One C call runs every layer of the extractor on one stream:
-//   stem pack -> 7x7 stem (CUDA cores) -> BN/ReLU -> max-pool -> [bottleneck | basic] blocks -> GAP
+//   stem pack -> 7x7 stem (im2col + tensor-core GEMM, K = 49 folded taps) -> BN/ReLU -> max-pool -> [bottleneck | basic] blocks -> GAP
 // Convolutions are tcgen05 implicit GEMMs (gemm_api.cu) that also emit the BatchNorm batch statistics;
 // BN-apply/ReLU/residual, pooling and the BN backward are the HBM-bound kernels of elementwise.cu.
 // Activations are NHWC bf16; everything needed by backward stays in the caller-provided workspace whose
@@ -45,7 +45,7 @@ struct Plan {
   int n_img, h, w, out_c, out_h, out_w;
   std::vector<Unit> units;
   std::vector<Block> blocks;
-  size_t img, wfold, dwfold, a0, p0, idx0;
+  size_t img, wstem, dwstem, a_stem, a0, p0, idx0;
   size_t fstat_begin, fstat_end;   // contiguous fp32 regions zeroed at the start of forward / backward
   size_t bstat_begin, bstat_end;
   size_t g[2], t[5];               // backward scratch (block gradients ping-pong + temporaries)
@@ -129,7 +129,7 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
 
   // ---- workspace --------------------------------------------------------------------------------
   p.img = ws.take((size_t)n * d->h * d->w * 4);
-  p.wfold = ws.take(49 * 64 * 4);
+  p.wstem = ws.take(64 * 64 * 2);
   for (Unit& u : p.units) {
     if (u.idx == stem) continue;
     const size_t wcount = u.groups > 1 ? (size_t)u.cout * 9 * 64 : (size_t)u.cout * u.k * u.k * u.cin;
@@ -139,6 +139,7 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
   }
   for (Unit& u : p.units) u.y = ws.take((size_t)u.rows_out * u.cout * 2);
   const Unit& us = p.units[stem];
+  p.a_stem = ws.take((size_t)us.rows_out * 64 * 2);  // im2col operand of the stem GEMM (kept for its weight gradient)
   p.a0 = ws.take((size_t)us.rows_out * 64 * 2);
   p.p0 = ws.take((size_t)n * ph * pw * 64 * 2);
   p.idx0 = ws.take((size_t)n * ph * pw * 64);
@@ -167,7 +168,7 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
   for (Unit& u : p.units) u.fstat = ws.take((size_t)2 * u.cout * 4);
   p.fstat_end = ws.off;
   p.bstat_begin = ws.off;
-  p.dwfold = ws.take(49 * 64 * 4);
+  p.dwstem = ws.take(64 * 64 * 4);
   for (Unit& u : p.units) u.bstat = ws.take((size_t)2 * u.cout * 4);
   p.bstat_end = ws.off;
   for (Unit& u : p.units) u.coef = ws.take((size_t)COEF_SLOTS * u.cout * 4);
@@ -314,9 +315,19 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
     KOA_TRY(koa_k_stem_pack(input, (float*)at(ws, p.img), d->n_img / d->slices, d->h * d->w, d->slices, st));
     img = (const float*)at(ws, p.img);
   }
-  KOA_TRY(koa_k_stem_fold_w(pv.w(us), (float*)at(ws, p.wfold), st));
-  KOA_TRY(koa_k_stem_conv_fwd(img, (const float*)at(ws, p.wfold), at(ws, us.y), training ? bn_slot(ws, us, S_SUM) : nullptr,
-                              training ? bn_slot(ws, us, S_SUMSQ) : nullptr, p.n_img, d->h, d->w, st));
+  // stem as a tensor-core GEMM: [pixels, 64 (49 taps of the folded grey channel)] x [64, 64]^T
+  KOA_TRY(koa_k_stem_pack_wb(pv.w(us), at(ws, p.wstem), st));
+  KOA_TRY(koa_k_stem_im2col(img, at(ws, p.a_stem), p.n_img, d->h, d->w, st));
+  {
+    koa_epilogue_t ep{};
+    ep.out = at(ws, us.y);
+    ep.ldo = 64;
+    if (training) {
+      ep.col_sum = bn_slot(ws, us, S_SUM);
+      ep.col_sumsq = bn_slot(ws, us, S_SUMSQ);
+    }
+    KOA_TRY(koa_gemm_launch(at(ws, p.a_stem), at(ws, p.wstem), (int)us.rows_out, 64, 64, &ep, st));
+  }
   KOA_TRY(bn_finalize(us, pv, ws, training, st));
   KOA_TRY(bn_relu(us, ws, p.a0, st));
   KOA_TRY(koa_k_maxpool_fwd(at(ws, p.a0), at(ws, p.p0), at(ws, p.idx0), p.n_img, us.hout, us.wout, 64, st));
@@ -549,10 +560,8 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
   KOA_TRY(koa_k_maxpool_bwd(at(ws, p.g[cur]), at(ws, p.idx0), d_a0, p.n_img, us.hout, us.wout, 64, st));
   KOA_TRY(bn_backward(us, nullptr, pv, grads, ws, d_a0, at(ws, p.a0), d_a0, nullptr, training, false, st));
   if (grads[0] != nullptr) {
-    const float* img = d->slices > 0 ? (const float*)at(ws, p.img) : d->input_for_backward;
-    KOA_REQUIRE(img != nullptr, "stem weight gradient needs the input image (input_for_backward)");
-    KOA_TRY(koa_k_stem_wgrad(img, d_a0, (float*)at(ws, p.dwfold), p.n_img, d->h, d->w, st));
-    KOA_TRY(koa_k_stem_unfold_dw((const float*)at(ws, p.dwfold), (float*)grads[0], st));
+    KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64, st));
+    KOA_TRY(koa_k_stem_unfold_dwb((const float*)at(ws, p.dwstem), (float*)grads[0], st));
   }
   return 0;
 }

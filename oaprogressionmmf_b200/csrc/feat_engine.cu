@@ -60,8 +60,8 @@ int build_plan(const koa_feat_desc_t* d, Plan& p) {
   KOA_REQUIRE(d->mlp_dim % 64 == 0, "FeaT mlp_dim %d must be a multiple of 64", d->mlp_dim);
   KOA_REQUIRE(d->heads > 0 && d->dim % d->heads == 0 && (d->dim / d->heads) % 8 == 0 && d->dim / d->heads <= 256,
               "unsupported head split %d / %d", d->dim, d->heads);
-  KOA_REQUIRE(d->emb_dropout == 0.0f && d->mlp_dropout == 0.0f || !d->training,
-              "dropout inside FeaT is applied by the host mirror (koa_dropout_*); pass 0 here");
+  KOA_REQUIRE(d->emb_dropout >= 0.0f && d->emb_dropout < 1.0f && d->mlp_dropout >= 0.0f && d->mlp_dropout < 1.0f,
+              "dropout probabilities must be in [0, 1)");
   p.B = d->batch; p.n_p = d->n_patches; p.n_cls = d->with_cls ? 1 : 0; p.n = p.n_p + p.n_cls;
   KOA_REQUIRE(p.n <= 128, "FeaT supports at most 128 tokens (got %d)", p.n);
   p.D = d->dim; p.depth = d->depth; p.heads = d->heads; p.mlp = d->mlp_dim; p.classes = d->num_classes;
@@ -135,6 +135,25 @@ int linear(const void* a, const void* w, long long m, int n, int k, koa_epilogue
   return koa_gemm_launch(a, w, (int)m, n, k, ep, st);
 }
 
+constexpr unsigned kSiteEmb = 0xE000u, kSiteHead = 0xF000u;
+// dropout layers inside a transformer block (nn.Dropout of to_out / FeedForward, _core_trf.py:146-149,164)
+inline unsigned site_attn_out(int l) { return 4u * l + 0u; }
+inline unsigned site_ff_act(int l) { return 4u * l + 1u; }
+inline unsigned site_ff_out(int l) { return 4u * l + 2u; }
+
+struct Drop {
+  bool emb, mlp;
+  float p_emb, p_mlp;
+  unsigned long long seed;
+  explicit Drop(const koa_feat_desc_t* d)
+      : emb(d->training && d->emb_dropout > 0.0f), mlp(d->training && d->mlp_dropout > 0.0f), p_emb(d->emb_dropout),
+        p_mlp(d->mlp_dropout), seed(d->seed) {}
+  void set(koa_epilogue_t& ep, unsigned site) const {
+    if (!mlp) return;
+    ep.drop_p = p_mlp; ep.drop_site = site; ep.drop_seed = seed;
+  }
+};
+
 __global__ void gelu_bwd_rows_kernel(const float* __restrict__ d, const bf16* __restrict__ pre, bf16* __restrict__ out,
                                      long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
@@ -170,6 +189,7 @@ extern "C" int koa_feat_forward(const koa_feat_desc_t* d, const void* const* par
   const int D = p.D, mlp = p.mlp;
   const bool bw = d->need_backward != 0;
   const float scale = 1.0f / sqrtf((float)D);  // reference quirk: model dim, not head dim (_core_trf.py:160)
+  const Drop drop(d);
 
   KOA_TRY(koa_k_cast_bf16(tokens, at(ws, p.tok_bf16), p.Mp * D, st));
   KOA_TRY(koa_k_pack_matrix(pr.pe_w(), at(ws, p.w_pe), bw ? at(ws, p.w_pe_t) : nullptr, D, D, st));
@@ -180,6 +200,7 @@ extern "C" int koa_feat_forward(const koa_feat_desc_t* d, const void* const* par
   }
   float* x0 = atf(ws, p.depth > 0 ? p.L[0].x_in : p.x_final);
   KOA_TRY(koa_k_token_assemble(atf(ws, p.emb), pr.cls(), pr.pos(), x0, p.B, p.n, p.n_cls, D, st));
+  if (drop.emb) KOA_TRY(koa_k_dropout_apply(x0, nullptr, nullptr, drop.seed, kSiteEmb, p.M * D, drop.p_emb, st));
 
   for (int l = 0; l < p.depth; ++l) {
     const LayerBuf& L = p.L[l];
@@ -202,6 +223,7 @@ extern "C" int koa_feat_forward(const koa_feat_desc_t* d, const void* const* par
     {
       koa_epilogue_t ep{};
       ep.out = x_mid; ep.out_fp32 = 1; ep.bias = pr.layer(l, P_OUT_B); ep.residual_f32 = x_in;
+      drop.set(ep, site_attn_out(l));
       KOA_TRY(linear(at(ws, L.attn_out), at(ws, L.w_out), p.M, D, D, &ep, st));
     }
     KOA_TRY(koa_k_layernorm_fwd(x_mid, pr.layer(l, P_LN1_W), pr.layer(l, P_LN1_B), at(ws, L.ln1), nullptr, atf(ws, L.st1),
@@ -209,11 +231,13 @@ extern "C" int koa_feat_forward(const koa_feat_desc_t* d, const void* const* par
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, L.g); ep.bias = pr.layer(l, P_FF0_B); ep.act = KOA_ACT_GELU; ep.pre_out_bf16 = at(ws, L.h_pre);
+      drop.set(ep, site_ff_act(l));
       KOA_TRY(linear(at(ws, L.ln1), at(ws, L.w_ff0), p.M, mlp, D, &ep, st));
     }
     {
       koa_epilogue_t ep{};
       ep.out = x_next; ep.out_fp32 = 1; ep.bias = pr.layer(l, P_FF3_B); ep.residual_f32 = x_mid;
+      drop.set(ep, site_ff_out(l));
       KOA_TRY(linear(at(ws, L.g), at(ws, L.w_ff3), p.M, D, mlp, &ep, st));
     }
   }
@@ -229,6 +253,7 @@ extern "C" int koa_feat_forward(const koa_feat_desc_t* d, const void* const* par
     koa_epilogue_t ep{};
     ep.out = at(ws, p.hh); ep.out_fp32 = 1; ep.bias = pr.head(H_1_B); ep.act = KOA_ACT_GELU;
     ep.pre_out_bf16 = at(ws, p.hh_pre);
+    drop.set(ep, kSiteHead);
     KOA_TRY(linear(at(ws, p.cls_ln), at(ws, p.w_h1), p.B, mlp, D, &ep, st));
     KOA_TRY(koa_k_linear_small_fwd(atf(ws, p.hh), pr.head(H_4_W), pr.head(H_4_B), logits_out, nullptr, p.B, p.classes, mlp,
                                    mlp, KOA_ACT_NONE, st));
@@ -248,6 +273,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
   const int D = p.D, mlp = p.mlp;
   const long long M = p.M;
   const float scale = 1.0f / sqrtf((float)D);
+  const Drop drop(d);
 
   float* dx = atf(ws, p.dxa);
   float* dx_other = atf(ws, p.dxb);
@@ -259,6 +285,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
     KOA_TRY(koa_k_linear_small_bwd(d_logits, nullptr, atf(ws, p.hh), pr.head(H_4_W), atf(ws, p.d_scr), atf(ws, p.d_hh),
                                    gr.head(H_4_W), gr.head(H_4_B), p.B, p.classes, mlp, mlp, mlp, KOA_ACT_NONE, 0, st));
     const long long tot = (long long)p.B * mlp;
+    if (drop.mlp) KOA_TRY(koa_k_dropout_apply(atf(ws, p.d_hh), nullptr, nullptr, drop.seed, kSiteHead, tot, drop.p_mlp, st));
     gelu_bwd_rows_kernel<<<koa_cdiv(tot, 256), 256, 0, st>>>(atf(ws, p.d_hh), (const bf16*)at(ws, p.hh_pre),
                                                              (bf16*)at(ws, p.d_hpre), tot);
     KOA_LAUNCH_CHECK();
@@ -277,11 +304,18 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
   for (int l = p.depth - 1; l >= 0; --l) {
     const LayerBuf& L = p.L[l];
     // ---- x_next = ff3(g) + b3 + x_mid ------------------------------------------------------------
-    KOA_TRY(koa_k_col_sum(dx, 0, gr.layer(l, P_FF3_B), M, D, D, st));
+    // p.dx_bf16 = bf16 copy of dx: the gradient w.r.t. (ff3(g) + b3) once the dropout mask of that branch is applied
+    if (drop.mlp) {
+      KOA_TRY(koa_k_dropout_apply(nullptr, dx, at(ws, p.dx_bf16), drop.seed, site_ff_out(l), M * D, drop.p_mlp, st));
+      KOA_TRY(koa_k_col_sum(at(ws, p.dx_bf16), 1, gr.layer(l, P_FF3_B), M, D, D, st));
+    } else {
+      KOA_TRY(koa_k_col_sum(dx, 0, gr.layer(l, P_FF3_B), M, D, D, st));
+    }
     KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.g), gr.layer(l, P_FF3_W), (int)M, D, mlp, st));
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, p.dh); ep.act = KOA_ACT_GELU_GRAD; ep.aux_bf16 = at(ws, L.h_pre);
+      drop.set(ep, site_ff_act(l));
       KOA_TRY(linear(at(ws, p.dx_bf16), at(ws, L.w_ff3_t), M, mlp, D, &ep, st));
     }
     KOA_TRY(koa_k_col_sum(at(ws, p.dh), 1, gr.layer(l, P_FF0_B), M, mlp, mlp, st));
@@ -295,7 +329,12 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
                                 atf(ws, L.st1) + M, dx, dx_other, at(ws, p.dx_bf16), gr.layer(l, P_LN1_W),
                                 gr.layer(l, P_LN1_B), (int)M, D, D, D, st));
     // ---- x_mid = to_out(attn) + bo + x_in ----------------------------------------------------------
-    KOA_TRY(koa_k_col_sum(dx_other, 0, gr.layer(l, P_OUT_B), M, D, D, st));
+    if (drop.mlp) {
+      KOA_TRY(koa_k_dropout_apply(nullptr, dx_other, at(ws, p.dx_bf16), drop.seed, site_attn_out(l), M * D, drop.p_mlp, st));
+      KOA_TRY(koa_k_col_sum(at(ws, p.dx_bf16), 1, gr.layer(l, P_OUT_B), M, D, D, st));
+    } else {
+      KOA_TRY(koa_k_col_sum(dx_other, 0, gr.layer(l, P_OUT_B), M, D, D, st));
+    }
     KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.attn_out), gr.layer(l, P_OUT_W), (int)M, D, D, st));
     {
       koa_epilogue_t ep{};
@@ -315,6 +354,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
                                 gr.layer(l, P_LN0_B), (int)M, D, D, D, st));
   }
   // ---- token assembly + patch embedding ---------------------------------------------------------------
+  if (drop.emb) KOA_TRY(koa_k_dropout_apply(dx, nullptr, nullptr, drop.seed, kSiteEmb, M * D, drop.p_emb, st));
   float* dcls = p.n_cls ? gr.at(0) : nullptr;
   KOA_TRY(koa_k_token_assemble_bwd(dx, gr.at(1), dcls, at(ws, p.d_emb), p.B, p.n, p.n_cls, D, st));
   KOA_TRY(koa_k_col_sum(at(ws, p.d_emb), 1, gr.at(3), p.Mp, D, D, st));

@@ -102,7 +102,7 @@ extern "C" int koa_debug_set_wgrad_desc(unsigned int lbo, unsigned int sbo, unsi
   return 0;
 }
 
-static EpiParams to_epi(const koa_epilogue_t* e) {
+static EpiParams to_epi(const koa_epilogue_t* e, int n) {
   EpiParams p;
   p.out = e->out;
   p.ldo = e->ldo;
@@ -120,6 +120,9 @@ static EpiParams to_epi(const koa_epilogue_t* e) {
   p.stat_y = (const bf16*)e->stat_y;
   p.stat_mean = e->stat_mean;
   p.stat_invstd = e->stat_invstd;
+  p.drop_on = e->drop_p > 0.0f ? 1 : 0;
+  p.drop_cols = n;
+  p.drop = make_drop_spec(e->drop_seed, e->drop_site, e->drop_p);
   return p;
 }
 
@@ -131,6 +134,7 @@ static int check_epi(const koa_epilogue_t* ep, int n) {
   KOA_REQUIRE((ep->col_sum == nullptr) == (ep->col_sumsq == nullptr), "col_sum and col_sumsq go together");
   KOA_REQUIRE(ep->col_sum == nullptr || n <= kMaxStatCols, "column statistics support N <= %d (got %d)", kMaxStatCols, n);
   KOA_REQUIRE(ep->col_sum == nullptr || !ep->out_fp32, "column statistics need a bf16 output");
+  KOA_REQUIRE(ep->drop_p >= 0.0f && ep->drop_p < 1.0f, "dropout probability %f out of range", (double)ep->drop_p);
   KOA_REQUIRE(ep->stat_y == nullptr || (ep->col_sum != nullptr && ep->stat_mean != nullptr && ep->stat_invstd != nullptr),
               "stat_y needs col_sum/col_sumsq and stat_mean/stat_invstd");
   return 0;
@@ -140,7 +144,7 @@ static int check_epi(const koa_epilogue_t* ep, int n) {
 // instantiation; everything else (bias, activations, fp32 residual stream) takes the full one.
 static bool conv_epilogue(const EpiParams& ep) {
   return !ep.out_fp32 && ep.act == ACT_NONE && ep.bias == nullptr && ep.pre_out == nullptr && ep.res_f32 == nullptr &&
-         ep.out_bf16_copy == nullptr;
+         ep.out_bf16_copy == nullptr && !ep.drop_on;
 }
 
 template <int BN, int STAGES, bool IM2COL, bool CONV>
@@ -197,7 +201,7 @@ int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa
   rc = koa_tmap_2d_bf16(&ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)k * 2, 64, 128);
   if (rc) return rc;
   ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
-  return dispatch_kmajor<false>(ta, b, m, n, k, g, to_epi(ep), st);
+  return dispatch_kmajor<false>(ta, b, m, n, k, g, to_epi(ep, n), st);
 }
 
 int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_in, int cin, int cout, int filt_r,
@@ -215,7 +219,7 @@ int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_
   rc = koa_tmap_im2col_bf16(&ta, x, n_img, h, w_in, cin, filt_r, filt_s, stride, pad, 128);
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64, 0};
-  return dispatch_kmajor<true>(ta, w, (int)m, cout, filt_r * filt_s * cin, g, to_epi(ep), st);
+  return dispatch_kmajor<true>(ta, w, (int)m, cout, filt_r * filt_s * cin, g, to_epi(ep, cout), st);
 }
 
 template <int BN, int STAGES, bool IM2COL>
@@ -297,7 +301,7 @@ int koa_conv_grouped_launch(const void* x, const void* w, int n_img, int h, int 
   rc = koa_tmap_2d_bf16(&tb, w, 576, (uint64_t)c, 576 * 2, 64, 64);
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, 1, 3, 1, 1};
-  return launch_kmajor<64, 6, true>(ta, tb, (int)m, c, 576, g, to_epi(ep), st);
+  return launch_kmajor<64, 6, true>(ta, tb, (int)m, c, 576, g, to_epi(ep, c), st);
 }
 
 // dw[C][9][64] += per-chunk dense weight gradient of the grouped convolution.

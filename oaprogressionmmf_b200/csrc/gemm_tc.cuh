@@ -38,6 +38,9 @@ struct EpiParams {
   const bf16* stat_y;     // BatchNorm backward: forward conv output y [M, ldo]; xhat = (y - mean) * invstd
   const float* stat_mean;
   const float* stat_invstd;
+  int drop_on;            // dropout (applied after the activation, before the residual add); element index of the
+  int drop_cols;          // mask = row * drop_cols + column
+  DropSpec drop;
 };
 
 constexpr int kGemmThreads = 192;     // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
@@ -250,6 +253,15 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint64_t* release
       tile_to_row_bf16(h, stage, t_y, lm);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(h[j]);
+    }
+    if (ep.drop_on) {
+      const unsigned long long quad0 = ((unsigned long long)(row0 + lane) * (unsigned long long)ep.drop_cols + n) >> 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s[4];
+        drop_scales4(ep.drop, quad0 + j, s);
+        v[4 * j] *= s[0]; v[4 * j + 1] *= s[1]; v[4 * j + 2] *= s[2]; v[4 * j + 3] *= s[3];
+      }
     }
     if (ep.res_f32 != nullptr) {
 #pragma unroll

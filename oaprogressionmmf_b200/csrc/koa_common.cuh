@@ -242,6 +242,45 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// ------------------------------- dropout RNG --------------------------------
+// Counter-based Philox4x32-10: the keep/drop decision of element `idx` of dropout site `site` is a pure function of
+// (seed, site, idx), so backward regenerates the forward mask instead of storing it. One call yields the decisions of
+// the four consecutive elements 4*(idx/4) .. +3.
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                       uint32_t c3, uint32_t (&out)[4]) {
+  for (int r = 0; r < 10; ++r) {  // constant trip count: fully unrolled by nvcc
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+struct DropSpec {
+  uint32_t k0, k1;     // seed
+  uint32_t site;       // which dropout layer inside the engine call
+  uint32_t threshold;  // drop when the 32-bit draw < threshold (threshold = p * 2^32)
+  float keep_scale;    // 1 / (1 - p)
+};
+__host__ __device__ __forceinline__ DropSpec make_drop_spec(unsigned long long seed, uint32_t site, float p) {
+  DropSpec d;
+  d.k0 = (uint32_t)seed; d.k1 = (uint32_t)(seed >> 32); d.site = site;
+  const double t = (double)p * 4294967296.0;
+  d.threshold = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  d.keep_scale = 1.0f / (1.0f - p);
+  return d;
+}
+// scale factors (0 or 1/(1-p)) of the four elements 4*quad .. 4*quad+3
+__host__ __device__ __forceinline__ void drop_scales4(const DropSpec& d, unsigned long long quad, float (&s)[4]) {
+  uint32_t r[4];
+  philox4x32_10(d.k0, d.k1, (uint32_t)quad, (uint32_t)(quad >> 32), d.site, 0x6b6f61u, r);
+  for (int i = 0; i < 4; ++i) s[i] = r[i] < d.threshold ? 0.0f : d.keep_scale;
+}
+
 // Reduce v[0..31] across the 32 lanes of a warp so that lane L ends with the column-L total in v[0].
 __device__ __forceinline__ void warp_transpose_reduce32(float (&v)[32], int lane) {
 #pragma unroll

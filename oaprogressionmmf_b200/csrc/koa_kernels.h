@@ -65,6 +65,12 @@ int koa_k_linear_small_fwd(const float* x, const float* w, const float* b, float
 int koa_k_linear_small_bwd(const float* dy, const float* pre, const float* x, const float* w, float* dpre_scratch,
                            float* dx, float* dw, float* db, int m, int n, int k, long long x_row_stride,
                            long long dx_row_stride, int act, int accumulate_dx, cudaStream_t st);
+// ---- dropout (counter-based Philox masks, koa_common.cuh) -------------------------------------------------
+// mask (0 or 1/(1-p)) of (seed, site) over n elements, element index = flat index
+int koa_k_dropout_mask(unsigned long long seed, unsigned int site, long long n, float p, float* out, cudaStream_t st);
+// x *= mask in place (fp32) and/or out_bf16 = bf16(x * mask); n % 4 == 0
+int koa_k_dropout_apply(float* x_inplace, const float* x, void* out_bf16, unsigned long long seed, unsigned int site,
+                        long long n, float p, cudaStream_t st);
 int koa_k_focal_loss(const float* logits, const long long* target, float* loss, float* dlogits, int batch, int classes,
                      float gamma, cudaStream_t st);
 
@@ -85,3 +91,8 @@ int koa_k_stem_conv_fwd(const float* img, const float* wfold, void* y, float* su
 // dwfold [49][64] accumulated with atomics (caller zeroes); then expanded to dw [64][3][7][7]
 int koa_k_stem_wgrad(const float* img, const void* dy, float* dwfold, int n, int h, int w, cudaStream_t st);
 int koa_k_stem_unfold_dw(const float* dwfold, float* dw, cudaStream_t st);
+// tensor-core form: im2col operand A [n*ho*wo][64] bf16 (K = 49 padded to 64), weights Wb [64][64] bf16,
+// folded gradient dWb [64][64] fp32 -> dw [64][3][7][7] +=
+int koa_k_stem_im2col(const float* img, void* a, int n, int h, int w, cudaStream_t st);
+int koa_k_stem_pack_wb(const float* w, void* wb, cudaStream_t st);
+int koa_k_stem_unfold_dwb(const float* dwb, float* dw, cudaStream_t st);

@@ -52,3 +52,8 @@ extern "C" int koa_maxpool_bwd(const void* dout, const void* idx, void* dx, int 
 extern "C" int koa_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, void* stream) {
   return koa_k_col_stats(y, sum, sumsq, rows, c, ST);
 }
+extern "C" int koa_dropout_mask(unsigned long long seed, unsigned int site, long long rows, int cols, float p, float* out,
+                                void* stream) {
+  KOA_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "dropout mask needs cols %% 4 == 0");
+  return koa_k_dropout_mask(seed, site, rows * cols, p, out, ST);
+}

@@ -67,14 +67,15 @@ class Transformer(nn.Module):
 
 class _FeaTFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mod: "FeaT", tokens: torch.Tensor, compute_head: bool, need_bw: bool, *params):
+    def forward(ctx, mod: "FeaT", tokens: torch.Tensor, compute_head: bool, need_bw: bool, seed: int, *params):
         lib = _lib.load()
         b, n_p, dim = tokens.shape
         tr = mod.transformer
         desc = _lib.FeatDesc(batch=b, n_patches=n_p, dim=dim, depth=tr.depth, heads=tr.heads, mlp_dim=tr.mlp_dim,
                              num_classes=mod.num_classes, with_cls=1 if mod.with_cls else 0,
                              compute_head=1 if compute_head else 0, training=1 if mod.training else 0,
-                             need_backward=1 if need_bw else 0, emb_dropout=0.0, mlp_dropout=0.0)
+                             need_backward=1 if need_bw else 0, emb_dropout=float(mod._p_emb),
+                             mlp_dropout=float(mod._p_mlp), seed=seed)
         nbytes = lib.koa_feat_workspace_bytes(C.byref(desc))
         if nbytes == 0:
             _lib.check(-1, "koa_feat_workspace_bytes")
@@ -126,7 +127,7 @@ class _FeaTFunction(torch.autograd.Function):
                    "koa_feat_backward")
         ctx.ws = None
         out_grads = [g for g, p in zip(grads, params) if p is not None]
-        return (None, d_tokens, None, None, *out_grads)
+        return (None, d_tokens, None, None, None, *out_grads)
 
 
 class FeaT(nn.Module):
@@ -172,14 +173,16 @@ class FeaT(nn.Module):
         return p
 
     def run(self, features: torch.Tensor, compute_head: bool = True):
+        # nn.Dropout inside FeaT (emb_dropout, mlp_dropout) runs inside the engine with counter-based Philox masks;
+        # the seed of this call comes from torch's CPU generator, so torch.manual_seed makes a run reproducible
+        seed = 0
         if self.training and (self._p_emb or self._p_mlp):
-            raise NotImplementedError(
-                "dropout inside FeaT is not implemented in the CUDA engine yet; use emb_dropout = mlp_dropout = 0 "
-                "for training (eval mode is unaffected)")
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+        self.last_dropout_seed = seed
         params = self._param_list()
         live = [p for p in params if p is not None]
         need_bw = torch.is_grad_enabled() and (features.requires_grad or any(p.requires_grad for p in live))
-        out = _FeaTFunction.apply(self, features, compute_head, need_bw, *live)
+        out = _FeaTFunction.apply(self, features, compute_head, need_bw, seed, *live)
         logits, states, attns = out[0], out[1], list(out[2:])
         return logits[:, None, :], states, attns
 

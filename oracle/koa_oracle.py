@@ -305,8 +305,13 @@ def fe_forward(sd: StateDict, prefix: str, arch: str, x: Tensor, training: bool,
     def conv(inp, key, **kw):  # conv output is stored in bf16 by the CUDA path
         return tap(key[:-len(".weight")] + ".y", _ra(F.conv2d(inp, _rw(sd[key], e), **kw), e))
 
-    # the stem runs in fp32 on the fp32 input/weights; only its output is stored in bf16
-    x = tap(f"{prefix}.0.y", _ra(F.conv2d(x, sd[f"{prefix}.0.weight"], stride=2, padding=3), e))
+    if e:
+        # CUDA path: the three identical input channels are folded into the weights (sum over dim 1), image and
+        # folded weights are rounded to bf16 (operands of the stem's tensor-core GEMM), the output is stored in bf16
+        wf = _rw(sd[f"{prefix}.0.weight"].sum(dim=1, keepdim=True), e)
+        x = tap(f"{prefix}.0.y", _ra(F.conv2d(_ra(x[:, :1], e), wf, stride=2, padding=3), e))
+    else:
+        x = tap(f"{prefix}.0.y", F.conv2d(x, sd[f"{prefix}.0.weight"], stride=2, padding=3))
     x = tap(f"{prefix}.stem", _ra(F.relu(_bn(sd, f"{prefix}.1", x, training)), e))
     x = tap(f"{prefix}.pool", F.max_pool2d(x, kernel_size=3, stride=2, padding=1))
     for b in fe_block_plan(arch):
@@ -333,11 +338,20 @@ def _layernorm(sd: StateDict, p: str, x: Tensor) -> Tensor:
     return F.layer_norm(x, (x.shape[-1],), sd[f"{p}.weight"], sd[f"{p}.bias"], 1e-5)
 
 
-def _dropout(x: Tensor, p: float, training: bool) -> Tensor:
+def _dropout(x: Tensor, p: float, training: bool, mask: Tensor | None = None) -> Tensor:
+    """nn.Dropout. ``mask`` (scale factors 0 or 1/(1-p), same shape as x) replaces torch's random stream so that a
+    test can feed the oracle the very mask the CUDA path drew (koa_dropout_mask)."""
+    if mask is not None:
+        return x * mask.reshape(x.shape)
     return F.dropout(x, p, training) if p else x
 
 
-def attention_forward(sd: StateDict, p: str, x: Tensor, heads: int, dropout: float, training: bool) -> Tuple[Tensor, Tensor]:
+def _mask(masks, key):
+    return None if masks is None else masks.get(key)
+
+
+def attention_forward(sd: StateDict, p: str, x: Tensor, heads: int, dropout: float, training: bool,
+                      mask: Tensor | None = None) -> Tuple[Tensor, Tensor]:
     """``Attention.forward`` (_core_trf.py:167-182): bias-free qkv, feature index = (qkv, head, d),
     scale = model_dim ** -0.5 (NOT head_dim), softmax over keys, output projection with bias."""
     b, n, dim = x.shape
@@ -347,36 +361,37 @@ def attention_forward(sd: StateDict, p: str, x: Tensor, heads: int, dropout: flo
     attn = torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * dim ** -0.5, dim=-1)
     out = torch.matmul(attn, v).permute(0, 2, 1, 3).reshape(b, n, dim)
     out = F.linear(out, sd[f"{p}.to_out.0.weight"], sd[f"{p}.to_out.0.bias"])
-    return _dropout(out, dropout, training), attn
+    return _dropout(out, dropout, training, mask), attn
 
 
 def transformer_forward(sd: StateDict, p: str, x: Tensor, depth: int, heads: int, dropout: float,
-                        training: bool) -> Tensor:
+                        training: bool, masks: Dict[str, Tensor] | None = None) -> Tensor:
     """``Transformer.forward`` (_core_trf.py:195-205): pre-norm residual blocks, no final norm;
     ``FeedForward`` (:141-153) = Linear, exact GELU, Dropout, Linear, Dropout."""
     for d in range(depth):
-        o, _ = attention_forward(sd, f"{p}.attn_{d}", _layernorm(sd, f"{p}.prenorm_0_{d}", x), heads, dropout, training)
+        o, _ = attention_forward(sd, f"{p}.attn_{d}", _layernorm(sd, f"{p}.prenorm_0_{d}", x), heads, dropout, training,
+                                 _mask(masks, f"attn_out_{d}"))
         x = o + x
         h = _layernorm(sd, f"{p}.prenorm_1_{d}", x)
         h = F.gelu(F.linear(h, sd[f"{p}.ff_{d}.net.0.weight"], sd[f"{p}.ff_{d}.net.0.bias"]))
-        h = _dropout(h, dropout, training)
+        h = _dropout(h, dropout, training, _mask(masks, f"ff_act_{d}"))
         h = F.linear(h, sd[f"{p}.ff_{d}.net.3.weight"], sd[f"{p}.ff_{d}.net.3.bias"])
-        x = _dropout(h, dropout, training) + x
+        x = _dropout(h, dropout, training, _mask(masks, f"ff_out_{d}")) + x
     return x
 
 
 def feat_forward(sd: StateDict, p: str, tokens: Tensor, depth: int, heads: int, emb_dropout: float,
-                 mlp_dropout: float, training: bool) -> Tuple[Tensor, Tensor]:
+                 mlp_dropout: float, training: bool, masks: Dict[str, Tensor] | None = None) -> Tuple[Tensor, Tensor]:
     """``FeaT.forward`` (_core_trf.py:118-138) → (head output (B,1,C), token states (B,n,D))."""
     x = F.linear(tokens, sd[f"{p}.patch_to_embedding.weight"], sd[f"{p}.patch_to_embedding.bias"])
     if f"{p}.cls_token" in sd:
         x = torch.cat((sd[f"{p}.cls_token"].expand(x.shape[0], -1, -1), x), dim=1)
     x = x + sd[f"{p}.pos_embedding"]
-    x = _dropout(x, emb_dropout, training)
-    states = transformer_forward(sd, f"{p}.transformer", x, depth, heads, mlp_dropout, training)
+    x = _dropout(x, emb_dropout, training, _mask(masks, "emb"))
+    states = transformer_forward(sd, f"{p}.transformer", x, depth, heads, mlp_dropout, training, masks)
     h = _layernorm(sd, f"{p}.mlp_head0.0", states[:, 0])
     h = F.gelu(F.linear(h, sd[f"{p}.mlp_head0.1.weight"], sd[f"{p}.mlp_head0.1.bias"]))
-    h = _dropout(h, mlp_dropout, training)
+    h = _dropout(h, mlp_dropout, training, _mask(masks, "head"))
     out = F.linear(h, sd[f"{p}.mlp_head0.4.weight"], sd[f"{p}.mlp_head0.4.bias"])
     return out[:, None, :], states
 
