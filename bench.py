@@ -109,11 +109,11 @@ def dist_info():
 # --------------------------------------------------------------------------------------------------
 # reference arm: the reference's algorithm (oracle port, fp32 eager torch) on the host cores
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_step(workload, knees, steps, warmup, threads):
+def cpu_reference_step(workload, knees, steps, warmup, threads, dropout=0.1):
     from oracle import koa_oracle as ko
 
     torch.set_num_threads(threads)
-    cfg = ko.make_config(workload)
+    cfg = ko.make_config(workload, dropout=dropout)
     spec = ko.model_param_spec(workload, cfg)
     sd = ko.make_state_dict(spec, 778)
     inputs, target = ko.make_inputs(workload, cfg, knees, 779)
@@ -133,7 +133,7 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     knees = args.cpu_knees
-    times = cpu_reference_step(args.workload, knees, max(1, args.steps), max(0, min(args.warmup, 1)), threads)
+    times = cpu_reference_step(args.workload, knees, max(1, args.steps), max(0, min(args.warmup, 1)), threads, args.dropout)
     ms = 1e3 * sum(times) / len(times)
     value = knees / (ms / 1e3)
     sample = (f"{len(times)} timed steps (after {max(0, min(args.warmup, 1))} warm-up) of zero_grad+forward+FocalLoss+backward on "
@@ -142,7 +142,7 @@ def run_reference(args):
                 warmup=max(0, min(args.warmup, 1)), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic",
                 config=dict(workload=args.workload, description=WORKLOAD_DESC.get(args.workload, args.workload),
-                            knees_per_step=knees, device="host CPU"),
+                            knees_per_step=knees, device="host CPU", dropout=args.dropout),
                 cpu_baseline=dict(value=value, unit="knees/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit="knees/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -169,7 +169,7 @@ def run_ours(args):
     lib = _lib.load()
 
     torch.manual_seed(778)
-    cfg = model_config(args.workload)
+    cfg = model_config(args.workload, dropout=args.dropout)
     model = dict_models[args.workload](to_attr(cfg), None).to(dev)
     model.train()
     # per-sequence transformer heads never receive gradients (dead compute in the reference): exclude them
@@ -276,7 +276,7 @@ def run_ours(args):
     cpu = None
     if ws == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        times = cpu_reference_step(args.workload, args.cpu_knees, 1, 0, threads)
+        times = cpu_reference_step(args.workload, args.cpu_knees, 1, 0, threads, args.dropout)
         cpu = dict(value=args.cpu_knees / times[0], unit="knees/s", cores=threads, kind="port",
                    sample=f"1 step (no warm-up) of forward+FocalLoss+backward on {args.cpu_knees} knee(s) of the same "
                           f"workload with the fp32 eager PyTorch restatement of the reference (oracle port), {times[0]:.1f} s")
@@ -286,7 +286,7 @@ def run_ours(args):
                             knees_per_gpu=B, global_batch=B * ws, parallelism=f"dp{ws} (knee-wise, one process per GPU)",
                             params=n_params, step="zero_grad + forward + FocalLoss + backward" +
                             (" + NCCL gradient all-reduce (DDP buckets overlapped with backward)" if ws > 1 else ""),
-                            dropout=0.0, bn="train mode (batch statistics per GPU)",
+                            dropout=args.dropout, bn="train mode (batch statistics per GPU)",
                             l2="working set per step (tens of GB of activations) exceeds the 126 MB L2; two input batches alternate"),
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit="knees/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
@@ -304,6 +304,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="XR1MR3C1CnnTrf", choices=sorted(FLOPS_FWD_BWD))
     ap.add_argument("--batch", type=int, default=16, help="knees per GPU (runner.sh:342 trains the full model at 16)")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="fe.*.dropout / agg.emb_dropout / agg.mlp_dropout (authors' recipe: 0.1, runner.sh:352 + conf/model/*.yaml)")
     ap.add_argument("--cpu-knees", type=int, default=1, help="knees in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-dump", default=None, help="write the per-shape tcgen05 kernel timing table to this file")

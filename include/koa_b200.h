@@ -11,8 +11,10 @@
  *   - all pointers are device pointers owned by the caller (PyTorch caching allocator in the host
  *     mirror); `stream` is a cudaStream_t passed as void*. Nothing is allocated behind the caller's
  *     back except per-process immutable state (kernel attributes, driver entry points).
- *   - activations are NHWC bf16 ("pixel-major": a 1x1 convolution is a plain GEMM), parameters
- *     arrive as fp32 master copies in PyTorch layout and are packed to bf16 by koa_pack_*.
+ *   - activations are NHWC 16-bit ("pixel-major": a 1x1 convolution is a plain GEMM): the CNN's forward
+ *     activations and packed weights are fp16, every gradient and the transformer's operands are bf16; the
+ *     per-operator GEMM / conv entry points take the operand formats as flags (default bf16). Parameters
+ *     arrive as fp32 master copies in PyTorch layout and are packed inside the engines.
  *   - the library is sm_100a only and has no CPU path; loading it without a B200 works (symbol
  *     checks), calling compute entry points without one fails with KOA_ERR_CUDA.
  */
@@ -68,6 +70,9 @@ typedef struct koa_epilogue {
   const void* stat_y;        /* BatchNorm backward form of the statistics: when non-NULL, col_sumsq receives */
   const float* stat_mean;    /* sum(out * xhat) with xhat = (stat_y - stat_mean) * stat_invstd (stat_y: bf16 */
   const float* stat_invstd;  /* [M, ldo], the forward conv output), i.e. col_sum / col_sumsq = dbeta / dgamma */
+  int a_f16, b_f16;          /* operand format: 0 = bf16, 1 = fp16; must be equal (one format per tcgen05 kind::f16 MMA) */
+  int out_f16;               /* out / pre_out_bf16 hold fp16 instead of bf16 */
+  int act_f16;               /* gate_bf16 / stat_y (forward activations) hold fp16 instead of bf16 */
   float drop_p;              /* > 0: dropout after the activation, before the residual add: value *= mask / (1 - p), */
   unsigned int drop_site;    /* mask = koa_dropout_mask(drop_seed, drop_site, M, N, drop_p) (counter-based Philox, */
   unsigned long long drop_seed; /* regenerated in backward instead of stored) */
@@ -86,13 +91,14 @@ int koa_gemm_bf16(const void* a, const void* b, int m, int n, int k, const koa_e
 int koa_conv_fprop_bf16(const void* x, const void* w, int n_img, int h, int w_in, int cin, int cout, int filt_r,
                         int filt_s, int stride, int pad, const koa_epilogue_t* ep, void* stream);
 
-/* dw[Cout,Cin] += dy[P,Cout]^T . x[P,Cin] (fp32 accumulate with atomics; caller zeroes dw).
+/* dw[Cout,Cin] += dy[P,Cout]^T . x[P,Cin] (fp32 accumulate with atomics; caller zeroes dw). Both operands bf16, or
+ * both fp16 with x_f16 != 0 (tcgen05 kind::f16 takes one 16-bit format per instruction).
  * Weight gradient of nn.Linear and of 1x1 stride-1 convolutions (autograd of the call sites above). */
-int koa_gemm_wgrad_bf16(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, void* stream);
+int koa_gemm_wgrad_bf16(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, int x_f16, void* stream);
 
 /* dw[Cout,R,S,Cin] += conv weight gradient for dy[N,Ho,Wo,Cout], x[N,H,W,Cin]. */
 int koa_conv_wgrad_bf16(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int cin, int cout,
-                        int filt_r, int filt_s, int stride, int pad, void* stream);
+                        int filt_r, int filt_s, int stride, int pad, int x_f16, void* stream);
 
 /* Test/debug knob: MN-major shared-memory descriptor strides used by the wgrad kernels. */
 int koa_debug_set_wgrad_desc(unsigned int lbo_bytes, unsigned int sbo_bytes, unsigned int k_adv_bytes);
@@ -175,7 +181,8 @@ int koa_attention_bwd(const void* qkv, const float* probs, const void* dout, voi
                       int head_dim, float scale, void* stream);
 /* (B,1,R,C,S) -> [B*S][R*C]: einops "b ch r c s -> (b s) ch r c" (koafusion/models/_xrNmrMcP.py:209-210). */
 int koa_stem_pack(const float* vol, float* img, int batch, int rc, int slices, void* stream);
-/* nn.MaxPool2d(3, 2, 1) on NHWC bf16 (koafusion/models/_torchvision.py:174); idx keeps the winning tap. */
+/* nn.MaxPool2d(3, 2, 1) on NHWC (koafusion/models/_torchvision.py:174); idx keeps the winning tap. Forward: fp16
+ * activations in and out; backward: bf16 gradients in and out. */
 int koa_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, void* stream);
 int koa_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, void* stream);
 /* Dropout scale factors (0 or 1/(1-p)) of site `site` as an fp32 [rows][cols] tensor: exactly the mask the engines

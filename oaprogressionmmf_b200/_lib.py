@@ -37,6 +37,10 @@ class Epilogue(C.Structure):
         ("stat_y", C.c_void_p),
         ("stat_mean", C.c_void_p),
         ("stat_invstd", C.c_void_p),
+        ("a_f16", C.c_int),
+        ("b_f16", C.c_int),
+        ("out_f16", C.c_int),
+        ("act_f16", C.c_int),
         ("drop_p", C.c_float),
         ("drop_site", C.c_uint),
         ("drop_seed", C.c_ulonglong),
@@ -102,8 +106,8 @@ SIGNATURES = {
     "koa_profile_dump": (_I, [C.c_char_p]),
     "koa_gemm_bf16": (_I, [_P, _P, _I, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_conv_fprop_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(Epilogue), _P]),
-    "koa_gemm_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _P]),
-    "koa_conv_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "koa_gemm_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "koa_conv_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "koa_fe_workspace_bytes": (C.c_size_t, [C.POINTER(FeDesc)]),
     "koa_fe_out_shape": (_I, [C.POINTER(FeDesc), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "koa_fe_num_units": (_I, [C.POINTER(FeDesc)]),

@@ -32,6 +32,26 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
   return q;
 }
+// forward activations of the CNN are fp16 (gradients stay bf16): 8-element vectors of that format
+__device__ __forceinline__ void unpack8h(const uint4& q, float (&f)[8]) {
+  float2 t;
+  t = unpack_f16x2(q.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_f16x2(q.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_f16x2(q.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_f16x2(q.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8h(const float (&f)[8]) {
+  uint4 q;
+  q.x = pack_f16x2(f[0], f[1]); q.y = pack_f16x2(f[2], f[3]);
+  q.z = pack_f16x2(f[4], f[5]); q.w = pack_f16x2(f[6], f[7]);
+  return q;
+}
+// mask[u] = (activation u > 0), read from the raw 16-bit patterns
+__device__ __forceinline__ void pos8(const uint4& q, bool (&m)[8]) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { m[2 * u] = pos16(w[u] & 0xffffu); m[2 * u + 1] = pos16(w[u] >> 16); }
+}
 __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p);
   const float4 b = *reinterpret_cast<const float4*>(p + 4);
@@ -99,17 +119,18 @@ __global__ void pack_fe_weights_kernel(const __grid_constant__ PackJobTable tab)
     }
     const KoaPackJob& jb = tab.job[lo];
     long long t = i - tab.begin[lo];
-    bf16* fwd = reinterpret_cast<bf16*>(jb.fwd);
-    bf16* dg = reinterpret_cast<bf16*>(jb.dgrad);
+    __half* fwd = reinterpret_cast<__half*>(jb.fwd);
+    bf16* dg = reinterpret_cast<bf16*>(jb.dgrad);  // pairs with bf16 gradients
     if (jb.cg == 0) {
       const int fr = jb.k, fs = jb.k, cin = jb.cin, cout = jb.cout;
-      const bf16 v = __float2bfloat16_rn(jb.src[t]);
+      const float vsrc = jb.src[t];
+      const __half v = __float2half_rn(vsrc);
       const int s = (int)(t % fs); t /= fs;
       const int r = (int)(t % fr); t /= fr;
       const int ci = (int)(t % cin); t /= cin;
       const int co = (int)t;
       fwd[(((long long)co * fr + r) * fs + s) * cin + ci] = v;
-      if (dg != nullptr) dg[(((long long)ci * fr + (fr - 1 - r)) * fs + (fs - 1 - s)) * cout + co] = v;
+      if (dg != nullptr) dg[(((long long)ci * fr + (fr - 1 - r)) * fs + (fs - 1 - s)) * cout + co] = __float2bfloat16_rn(vsrc);
     } else {
       const int cg = jb.cg;
       const long long idx = t;
@@ -122,7 +143,7 @@ __global__ void pack_fe_weights_kernel(const __grid_constant__ PackJobTable tab)
         vf = jb.src[((long long)row * cg + (other % cg)) * 9 + tap];
         if (dg != nullptr) vd = jb.src[((long long)other * cg + (row % cg)) * 9 + (8 - tap)];
       }
-      fwd[idx] = __float2bfloat16_rn(vf);
+      fwd[idx] = __float2half_rn(vf);
       if (dg != nullptr) dg[idx] = __float2bfloat16_rn(vd);
     }
   }
@@ -254,25 +275,26 @@ __global__ void col_stats_kernel(const bf16* __restrict__ y, float* __restrict__
 // out = [relu]( y*scale + shift  +  (res | y2*scale2 + shift2) )
 __global__ void bn_act_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                               const bf16* __restrict__ res, const bf16* __restrict__ y2, const float* __restrict__ scale2,
-                              const float* __restrict__ shift2, bf16* __restrict__ out, long long rows, int c, int relu) {
+                              const float* __restrict__ shift2, bf16* __restrict__ out, bf16* __restrict__ out_bf,
+                              long long rows, int c, int relu) {
   const int cg = c / 8;
   const long long total = rows * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % cg);
     float f[8], sc[8], sh[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
+    unpack8h(*reinterpret_cast<const uint4*>(y + i * 8), f);
     load8f(scale + g * 8, sc);
     load8f(shift + g * 8, sh);
 #pragma unroll
     for (int u = 0; u < 8; ++u) f[u] = f[u] * sc[u] + sh[u];
     if (res != nullptr) {
       float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(res + i * 8), r);
+      unpack8h(*reinterpret_cast<const uint4*>(res + i * 8), r);
 #pragma unroll
       for (int u = 0; u < 8; ++u) f[u] += r[u];
     } else if (y2 != nullptr) {
       float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(y2 + i * 8), r);
+      unpack8h(*reinterpret_cast<const uint4*>(y2 + i * 8), r);
       load8f(scale2 + g * 8, sc);
       load8f(shift2 + g * 8, sh);
 #pragma unroll
@@ -282,7 +304,8 @@ __global__ void bn_act_kernel(const bf16* __restrict__ y, const float* __restric
 #pragma unroll
       for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.0f);
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8h(f);
+    if (out_bf != nullptr) *reinterpret_cast<uint4*>(out_bf + i * 8) = pack8(f);
   }
 }
 
@@ -326,16 +349,16 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
         float dz[8], yy[8];
         unpack8(qd[j], dz);
         if (has_act) {
-          float m[8];
-          unpack8(qm[j], m);
+          bool m[8];
+          pos8(qm[j], m);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) dz[u] = m[u] > 0.0f ? dz[u] : 0.0f;
+          for (int u = 0; u < 8; ++u) dz[u] = m[u] ? dz[u] : 0.0f;
         }
-        unpack8(qy[j], yy);
+        unpack8h(qy[j], yy);
 #pragma unroll
         for (int u = 0; u < 8; ++u) { a[u] += dz[u]; b[u] += dz[u] * (yy[u] - mu[u]) * is[u]; }
         if (has_y2) {
-          unpack8(qz[j], yy);
+          unpack8h(qz[j], yy);
 #pragma unroll
           for (int u = 0; u < 8; ++u) b2[u] += dz[u] * (yy[u] - mu2[u]) * is2[u];
         }
@@ -403,18 +426,18 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* _
     float dz[8], yy[8], a[8], b[8], cc[8], o[8];
     unpack8(*reinterpret_cast<const uint4*>(dout + i * 8), dz);
     if (act != nullptr) {
-      float m[8];
-      unpack8(*reinterpret_cast<const uint4*>(act + i * 8), m);
+      bool m[8];
+      pos8(*reinterpret_cast<const uint4*>(act + i * 8), m);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) dz[u] = m[u] > 0.0f ? dz[u] : 0.0f;
+      for (int u = 0; u < 8; ++u) dz[u] = m[u] ? dz[u] : 0.0f;
     }
-    unpack8(*reinterpret_cast<const uint4*>(y + i * 8), yy);
+    unpack8h(*reinterpret_cast<const uint4*>(y + i * 8), yy);
     load8f(k0 + g * 8, a); load8f(k1 + g * 8, b); load8f(k2 + g * 8, cc);
 #pragma unroll
     for (int u = 0; u < 8; ++u) o[u] = a[u] * dz[u] - b[u] - cc[u] * yy[u];
     *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
     if (y2 != nullptr) {
-      unpack8(*reinterpret_cast<const uint4*>(y2 + i * 8), yy);
+      unpack8h(*reinterpret_cast<const uint4*>(y2 + i * 8), yy);
       load8f(k0b + g * 8, a); load8f(k1b + g * 8, b); load8f(k2b + g * 8, cc);
 #pragma unroll
       for (int u = 0; u < 8; ++u) o[u] = a[u] * dz[u] - b[u] - cc[u] * yy[u];
@@ -427,7 +450,8 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* _
 // Pooling
 // ------------------------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 max pool, first maximum in scan order wins (as ATen); idx = r*3+s of the winner.
-__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, uint8_t* __restrict__ idx,
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, bf16* __restrict__ out_bf,
+                                   uint8_t* __restrict__ idx,
                                    int n, int h, int w, int c, int ho, int wo) {
   const int cg = c / 8;
   const long long total = (long long)n * ho * wo * cg;
@@ -449,7 +473,7 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
         const int iw = ow * 2 - 1 + s;
         if (iw < 0 || iw >= w) continue;
         float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(x + (((long long)ni * h + ih) * w + iw) * c + g * 8), f);
+        unpack8h(*reinterpret_cast<const uint4*>(x + (((long long)ni * h + ih) * w + iw) * c + g * 8), f);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           if (first || f[u] > best[u]) { best[u] = f[u]; bi[u] = r * 3 + s; }
@@ -457,7 +481,8 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
         first = false;
       }
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(best);
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8h(best);
+    if (out_bf != nullptr) *reinterpret_cast<uint4*>(out_bf + i * 8) = pack8(best);
     uint2 packed;
     packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
     packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
@@ -513,7 +538,7 @@ __global__ void gap_fwd_kernel(const bf16* __restrict__ x, float* __restrict__ f
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int p = 0; p < hw; ++p) {
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + (ni * hw + p) * c + g * 8), f);
+      unpack8h(*reinterpret_cast<const uint4*>(x + (ni * hw + p) * c + g * 8), f);
 #pragma unroll
       for (int u = 0; u < 8; ++u) acc[u] += f[u];
     }
@@ -537,10 +562,10 @@ __global__ void gap_bwd_kernel(const float* __restrict__ dfeat, const bf16* __re
 #pragma unroll
     for (int u = 0; u < 8; ++u) f[u] *= inv;
     if (gate != nullptr) {
-      float m[8];
-      unpack8(*reinterpret_cast<const uint4*>(gate + i * 8), m);
+      bool m[8];
+      pos8(*reinterpret_cast<const uint4*>(gate + i * 8), m);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) f[u] = m[u] > 0.0f ? f[u] : 0.0f;
+      for (int u = 0; u < 8; ++u) f[u] = m[u] ? f[u] : 0.0f;
     }
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(f);
   }
@@ -583,10 +608,10 @@ __global__ void scatter_add2_kernel(const bf16* __restrict__ src, const bf16* __
     unpack8(*reinterpret_cast<const uint4*>(p), a);
     unpack8(*reinterpret_cast<const uint4*>(src + i * 8), b);
     if (gate != nullptr) {
-      float m[8];
-      unpack8(*reinterpret_cast<const uint4*>(gate + o), m);
+      bool m[8];
+      pos8(*reinterpret_cast<const uint4*>(gate + o), m);
 #pragma unroll
-      for (int u = 0; u < 8; ++u) b[u] = m[u] > 0.0f ? b[u] : 0.0f;
+      for (int u = 0; u < 8; ++u) b[u] = m[u] ? b[u] : 0.0f;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) a[u] += b[u];
@@ -959,10 +984,11 @@ int koa_k_col_stats(const void* y, float* sum, float* sumsq, long long rows, int
   return 0;
 }
 int koa_k_bn_act(const void* y, const float* scale, const float* shift, const void* res, const void* y2,
-                 const float* scale2, const float* shift2, void* out, long long rows, int c, int relu, cudaStream_t st) {
+                 const float* scale2, const float* shift2, void* out, void* out_bf16, long long rows, int c, int relu,
+                 cudaStream_t st) {
   KOA_REQ_C8(c);
   bn_act_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
-                                                               (const bf16*)y2, scale2, shift2, (bf16*)out, rows, c, relu);
+                                                               (const bf16*)y2, scale2, shift2, (bf16*)out, (bf16*)out_bf16, rows, c, relu);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -997,11 +1023,11 @@ int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const f
   KOA_LAUNCH_CHECK();
   return 0;
 }
-int koa_k_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, cudaStream_t st) {
+int koa_k_maxpool_fwd(const void* x, void* out, void* out_bf16, void* idx, int n, int h, int w, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), kThreads, 0, st>>>((const bf16*)x, (bf16*)out,
-                                                                                      (uint8_t*)idx, n, h, w, c, ho, wo);
+  maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), kThreads, 0, st>>>(
+      (const bf16*)x, (bf16*)out, (bf16*)out_bf16, (uint8_t*)idx, n, h, w, c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
 }

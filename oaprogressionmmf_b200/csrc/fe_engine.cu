@@ -37,15 +37,16 @@ struct Unit {
 struct Block {
   int kind;  // 0 bottleneck, 1 basic
   int u1, u2, u3, ud;
-  size_t a1, a2, out;
-  size_t in;  // activation feeding the block
+  size_t a1, a2, out;              // fp16 ReLU outputs (operands of the next forward GEMM, gates, mask sources)
+  size_t a1_bf, a2_bf, out_bf;     // bf16 copies, kept only when backward will run: operands of the weight gradients
+  size_t in, in_bf;                // activation feeding the block
   int stride;
 };
 struct Plan {
   int n_img, h, w, out_c, out_h, out_w;
   std::vector<Unit> units;
   std::vector<Block> blocks;
-  size_t img, wstem, dwstem, a_stem, a0, p0, idx0;
+  size_t img, wstem, dwstem, a_stem, a0, p0, p0_bf, idx0;
   size_t fstat_begin, fstat_end;   // contiguous fp32 regions zeroed at the start of forward / backward
   size_t bstat_begin, bstat_end;
   size_t g[2], t[5];               // backward scratch (block gradients ping-pong + temporaries)
@@ -141,28 +142,36 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
   const Unit& us = p.units[stem];
   p.a_stem = ws.take((size_t)us.rows_out * 64 * 2);  // im2col operand of the stem GEMM (kept for its weight gradient)
   p.a0 = ws.take((size_t)us.rows_out * 64 * 2);
+  const bool bw = d->need_backward != 0;
   p.p0 = ws.take((size_t)n * ph * pw * 64 * 2);
+  p.p0_bf = bw ? ws.take((size_t)n * ph * pw * 64 * 2) : 0;
   p.idx0 = ws.take((size_t)n * ph * pw * 64);
-  size_t prev = p.p0;
+  size_t prev = p.p0, prev_bf = p.p0_bf;
   size_t max_act = (size_t)us.rows_out * 64;
   for (Block& b : p.blocks) {
     const Unit& u1 = p.units[b.u1];
     const Unit& u2 = p.units[b.u2];
     b.in = prev;
+    b.in_bf = prev_bf;
     b.a1 = ws.take((size_t)u1.rows_out * u1.cout * 2);
+    b.a1_bf = bw ? ws.take((size_t)u1.rows_out * u1.cout * 2) : 0;
     if (b.kind == 0) {
       b.a2 = ws.take((size_t)u2.rows_out * u2.cout * 2);
+      b.a2_bf = bw ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
       const Unit& u3 = p.units[b.u3];
       b.out = ws.take((size_t)u3.rows_out * u3.cout * 2);
+      b.out_bf = bw ? ws.take((size_t)u3.rows_out * u3.cout * 2) : 0;
       max_act = std::max(max_act, (size_t)u3.rows_out * u3.cout);
     } else {
-      b.a2 = 0;
+      b.a2 = 0; b.a2_bf = 0;
       b.out = ws.take((size_t)u2.rows_out * u2.cout * 2);
+      b.out_bf = bw ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
     }
     max_act = std::max(max_act, (size_t)u1.rows_in * u1.cin);
     max_act = std::max(max_act, (size_t)u1.rows_in * u1.cout);  // zero-inserted / pre-stride tensors
     max_act = std::max(max_act, (size_t)u2.rows_in * u2.cout);
     prev = b.out;
+    prev_bf = b.out_bf;
   }
   p.fstat_begin = ws.off;
   for (Unit& u : p.units) u.fstat = ws.take((size_t)2 * u.cout * 4);
@@ -221,6 +230,7 @@ int conv_forward(const Plan& p, const Unit& u, const void* x, void* ws, int trai
   koa_epilogue_t ep{};
   ep.out = at(ws, u.y);
   ep.ldo = u.cout;
+  ep.a_f16 = ep.b_f16 = ep.out_f16 = 1;  // forward activations and weights of the CNN are fp16
   if (training) {
     ep.col_sum = bn_slot(ws, u, S_SUM);
     ep.col_sumsq = bn_slot(ws, u, S_SUMSQ);
@@ -238,9 +248,9 @@ int bn_finalize(const Unit& u, const ParamView& pv, void* ws, int training, cuda
 }
 
 // a = relu(bn(y))
-int bn_relu(const Unit& u, void* ws, size_t a_off, cudaStream_t st) {
+int bn_relu(const Unit& u, void* ws, size_t a_off, size_t a_bf_off, cudaStream_t st) {
   return koa_k_bn_act(at(ws, u.y), bn_slot(ws, u, S_SCALE), bn_slot(ws, u, S_SHIFT), nullptr, nullptr, nullptr, nullptr,
-                      at(ws, a_off), u.rows_out, u.cout, 1, st);
+                      at(ws, a_off), a_bf_off ? at(ws, a_bf_off) : nullptr, u.rows_out, u.cout, 1, st);
 }
 
 }  // namespace
@@ -266,7 +276,8 @@ extern "C" int koa_fe_num_units(const koa_fe_desc_t* d) {
 }
 
 // what: 0 raw conv output y of unit `index`; 1 block output of block `index`; 2 a1 of block; 3 a2 of block;
-// 4 stem activation a0; 5 pooled p0; 7 max-pool argmax bytes; 6 BN coefficients (scale, shift, mean, invstd, k0, k1, k2) of unit `index`.
+// 4 stem activation a0; 5 pooled p0; 7 max-pool argmax bytes; 8/9/10 bf16 copies of block out / a1 / a2; 11 bf16 pooled;
+// 6 BN coefficients (scale, shift, mean, invstd, k0, k1, k2) of unit `index`.
 extern "C" int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, size_t* offset, size_t* bytes) {
   Plan p;
   KOA_TRY(build_plan(d, p));
@@ -288,6 +299,18 @@ extern "C" int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, 
     if (what == 3) { *offset = b.a2; *bytes = (size_t)u2.rows_out * u2.cout * 2; }
     return 0;
   }
+  if (what >= 8 && what <= 10) {  // bf16 copies of block out / a1 / a2 (only with need_backward)
+    KOA_REQUIRE(index >= 0 && index < (int)p.blocks.size(), "block index out of range");
+    const Block& b = p.blocks[index];
+    const Unit& last = p.units[b.kind == 0 ? b.u3 : b.u2];
+    const Unit& u1 = p.units[b.u1];
+    const Unit& u2 = p.units[b.u2];
+    if (what == 8) { *offset = b.out_bf; *bytes = (size_t)last.rows_out * last.cout * 2; }
+    if (what == 9) { *offset = b.a1_bf; *bytes = (size_t)u1.rows_out * u1.cout * 2; }
+    if (what == 10) { *offset = b.a2_bf; *bytes = (size_t)u2.rows_out * u2.cout * 2; }
+    return 0;
+  }
+  if (what == 11) { *offset = p.p0_bf; *bytes = (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64 * 2; return 0; }
   if (what == 4) { *offset = p.a0; *bytes = (size_t)p.units[0].rows_out * 64 * 2; return 0; }
   if (what == 5) { *offset = p.p0; *bytes = (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64 * 2; return 0; }
   if (what == 7) { *offset = p.idx0; *bytes = (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64; return 0; }
@@ -317,11 +340,12 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
   }
   // stem as a tensor-core GEMM: [pixels, 64 (49 taps of the folded grey channel)] x [64, 64]^T
   KOA_TRY(koa_k_stem_pack_wb(pv.w(us), at(ws, p.wstem), st));
-  KOA_TRY(koa_k_stem_im2col(img, at(ws, p.a_stem), p.n_img, d->h, d->w, st));
+  KOA_TRY(koa_k_stem_im2col(img, at(ws, p.a_stem), p.n_img, d->h, d->w, 1, st));
   {
     koa_epilogue_t ep{};
     ep.out = at(ws, us.y);
     ep.ldo = 64;
+    ep.a_f16 = ep.b_f16 = ep.out_f16 = 1;
     if (training) {
       ep.col_sum = bn_slot(ws, us, S_SUM);
       ep.col_sumsq = bn_slot(ws, us, S_SUMSQ);
@@ -329,8 +353,9 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
     KOA_TRY(koa_gemm_launch(at(ws, p.a_stem), at(ws, p.wstem), (int)us.rows_out, 64, 64, &ep, st));
   }
   KOA_TRY(bn_finalize(us, pv, ws, training, st));
-  KOA_TRY(bn_relu(us, ws, p.a0, st));
-  KOA_TRY(koa_k_maxpool_fwd(at(ws, p.a0), at(ws, p.p0), at(ws, p.idx0), p.n_img, us.hout, us.wout, 64, st));
+  KOA_TRY(bn_relu(us, ws, p.a0, 0, st));
+  KOA_TRY(koa_k_maxpool_fwd(at(ws, p.a0), at(ws, p.p0), p.p0_bf ? at(ws, p.p0_bf) : nullptr, at(ws, p.idx0), p.n_img, us.hout,
+                            us.wout, 64, st));
 
   // ---- residual blocks --------------------------------------------------------------------------
   for (const Block& b : p.blocks) {
@@ -339,13 +364,13 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
     const void* x = at(ws, b.in);
     KOA_TRY(conv_forward(p, u1, x, ws, training, st));
     KOA_TRY(bn_finalize(u1, pv, ws, training, st));
-    KOA_TRY(bn_relu(u1, ws, b.a1, st));
+    KOA_TRY(bn_relu(u1, ws, b.a1, b.a1_bf, st));
     KOA_TRY(conv_forward(p, u2, at(ws, b.a1), ws, training, st));
     KOA_TRY(bn_finalize(u2, pv, ws, training, st));
     const Unit* last = &u2;
     if (b.kind == 0) {
       const Unit& u3 = p.units[b.u3];
-      KOA_TRY(bn_relu(u2, ws, b.a2, st));
+      KOA_TRY(bn_relu(u2, ws, b.a2, b.a2_bf, st));
       KOA_TRY(conv_forward(p, u3, at(ws, b.a2), ws, training, st));
       KOA_TRY(bn_finalize(u3, pv, ws, training, st));
       last = &u3;
@@ -356,10 +381,10 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
       KOA_TRY(bn_finalize(ud, pv, ws, training, st));
       KOA_TRY(koa_k_bn_act(at(ws, last->y), bn_slot(ws, *last, S_SCALE), bn_slot(ws, *last, S_SHIFT), nullptr,
                            at(ws, ud.y), bn_slot(ws, ud, S_SCALE), bn_slot(ws, ud, S_SHIFT), at(ws, b.out),
-                           last->rows_out, last->cout, 1, st));
+                           b.out_bf ? at(ws, b.out_bf) : nullptr, last->rows_out, last->cout, 1, st));
     } else {
       KOA_TRY(koa_k_bn_act(at(ws, last->y), bn_slot(ws, *last, S_SCALE), bn_slot(ws, *last, S_SHIFT), x, nullptr, nullptr,
-                           nullptr, at(ws, b.out), last->rows_out, last->cout, 1, st));
+                           nullptr, at(ws, b.out), b.out_bf ? at(ws, b.out_bf) : nullptr, last->rows_out, last->cout, 1, st));
     }
   }
   // ---- head: global average pool (with_gap) or the raw NHWC map as tokens -------------------------
@@ -398,20 +423,20 @@ int bn_backward(const Unit& u, const Unit* u_b, const ParamView& pv, void* const
                             u.rows_out, u.cout, st);
 }
 
-// dW of one unit into the fp32 gradient tensor (PyTorch layout [Cout][Cin/g][k][k]).
+// dW of one unit into the fp32 gradient tensor (PyTorch layout [Cout][Cin/g][k][k]). `x`: bf16 copy of the unit's input.
 int conv_wgrad(const Plan& p, const Unit& u, const void* x, const void* dy, void* const* grads, void* ws, cudaStream_t st) {
   float* gw = (float*)grads[u.idx * 3 + 0];
   if (gw == nullptr) return 0;
-  if (u.k == 1 && u.stride == 1) return koa_gemm_wgrad_launch(dy, x, gw, (int)u.rows_out, u.cout, u.cin, st);
-  if (u.k == 1) return koa_conv_wgrad_launch(dy, x, gw, p.n_img, u.hin, u.win, u.cin, u.cout, 1, 1, u.stride, 0, st);
+  if (u.k == 1 && u.stride == 1) return koa_gemm_wgrad_launch(dy, x, gw, (int)u.rows_out, u.cout, u.cin, 0, st);
+  if (u.k == 1) return koa_conv_wgrad_launch(dy, x, gw, p.n_img, u.hin, u.win, u.cin, u.cout, 1, 1, u.stride, 0, 0, st);
   float* scratch = (float*)at(ws, u.dw_scratch);
   if (u.groups > 1) {
     KOA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)u.cout * 9 * 64 * 4, st));
-    KOA_TRY(koa_conv_grouped_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.stride, st));
+    KOA_TRY(koa_conv_grouped_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.stride, 0, st));
     return koa_k_unpack_grouped_dw(scratch, gw, u.cout, u.cin / u.groups, st);
   }
   KOA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)u.cout * u.k * u.k * u.cin * 4, st));
-  KOA_TRY(koa_conv_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, st));
+  KOA_TRY(koa_conv_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, 0, st));
   return koa_k_unpack_conv_dw(scratch, gw, u.cout, u.cin, u.k, u.k, st);
 }
 
@@ -419,6 +444,9 @@ int conv_wgrad(const Plan& p, const Unit& u, const void* x, const void* dy, void
 // tmp: scratch for the zero-inserted dy of stride-2 3x3 convolutions.
 int conv_dgrad(const Plan& p, const Unit& u, const void* dy, void* ws, koa_epilogue_t* ep, void* tmp, cudaStream_t st) {
   ep->ldo = u.cin;
+  ep->a_f16 = ep->b_f16 = 0;  // dy and the data-gradient form of the weights: bf16
+  ep->out_f16 = 0;            // dx: bf16 gradient
+  ep->act_f16 = 1;            // gate / stat_y are fp16 forward activations
   if (u.k == 1) {
     // 1x1: dx[rows_out, cin] = dy[rows_out, cout] . W[cout, cin]; B operand = W^T stored [cin][cout]
     return koa_gemm_launch(dy, at(ws, u.w_dgrad), (int)u.rows_out, u.cin, u.cout, ep, st);
@@ -496,27 +524,27 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     KOA_TRY(bn_backward(last, ud, pv, grads, ws, g_out, nullptr, dy_last, ud ? dy_down : nullptr, training, g_stats_done, st));
     void* d_a1 = at(ws, p.t[3]);
     if (u3) {
-      KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2), dy_last, grads, ws, st));
+      KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2_bf), dy_last, grads, ws, st));
       void* d_a2 = at(ws, p.t[2]);
       koa_epilogue_t ep{};
       ep.out = d_a2;
       gate_and_stats(ep, ws, b.a2, &u2, fuse);  // dz2 = dgrad * (a2 > 0)
       KOA_TRY(conv_dgrad(p, *u3, dy_last, ws, &ep, nullptr, st));
       KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, nullptr, d_a2, nullptr, training, fuse, st));  // in place -> dy2
-      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1), d_a2, grads, ws, st));
+      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf), d_a2, grads, ws, st));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
       gate_and_stats(ep2, ws, b.a1, &u1, fuse);
       KOA_TRY(conv_dgrad(p, u2, d_a2, ws, &ep2, at(ws, p.t[4]), st));
     } else {
-      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1), dy_last, grads, ws, st));
+      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf), dy_last, grads, ws, st));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
       gate_and_stats(ep2, ws, b.a1, &u1, fuse);
       KOA_TRY(conv_dgrad(p, u2, dy_last, ws, &ep2, at(ws, p.t[4]), st));
     }
     KOA_TRY(bn_backward(u1, nullptr, pv, grads, ws, d_a1, nullptr, d_a1, nullptr, training, fuse, st));  // in place -> dy1
-    KOA_TRY(conv_wgrad(p, u1, x, d_a1, grads, ws, st));
+    KOA_TRY(conv_wgrad(p, u1, at(ws, b.in_bf), d_a1, grads, ws, st));
     // G of the previous block = (dgrad(conv1) + identity path) * (x > 0); x is that block's output (or the pooled
     // stem activation, where the gate is a no-op for the gradient that survives the stem's own ReLU mask).
     const Block* prev = bi > 0 ? &p.blocks[bi - 1] : nullptr;
@@ -530,7 +558,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       gate_and_stats(ep, ws, b.in, prev_last, fuse_prev);
       KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
     } else {
-      KOA_TRY(conv_wgrad(p, *ud, x, dy_down, grads, ws, st));
+      KOA_TRY(conv_wgrad(p, *ud, at(ws, b.in_bf), dy_down, grads, ws, st));
       if (ud->stride == 1) {
         koa_epilogue_t ep{};
         ep.out = g_in;
@@ -560,7 +588,11 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
   KOA_TRY(koa_k_maxpool_bwd(at(ws, p.g[cur]), at(ws, p.idx0), d_a0, p.n_img, us.hout, us.wout, 64, st));
   KOA_TRY(bn_backward(us, nullptr, pv, grads, ws, d_a0, at(ws, p.a0), d_a0, nullptr, training, false, st));
   if (grads[0] != nullptr) {
-    KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64, st));
+    // the im2col operand is rebuilt in bf16 (the forward GEMM consumed it in fp16): it pairs with the bf16 dy
+    const float* img = d->slices > 0 ? (const float*)at(ws, p.img) : d->input_for_backward;
+    KOA_REQUIRE(img != nullptr, "stem weight gradient needs the input image (input_for_backward)");
+    KOA_TRY(koa_k_stem_im2col(img, at(ws, p.a_stem), p.n_img, d->h, d->w, 0, st));
+    KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64, 0, st));
     KOA_TRY(koa_k_stem_unfold_dwb((const float*)at(ws, p.dwstem), (float*)grads[0], st));
   }
   return 0;

@@ -290,7 +290,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
                                                              (bf16*)at(ws, p.d_hpre), tot);
     KOA_LAUNCH_CHECK();
     KOA_TRY(koa_k_col_sum(at(ws, p.d_hpre), 1, gr.head(H_1_B), p.B, mlp, mlp, st));
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.d_hpre), at(ws, p.cls_ln), gr.head(H_1_W), p.B, mlp, D, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.d_hpre), at(ws, p.cls_ln), gr.head(H_1_W), p.B, mlp, D, 0, st));
     koa_epilogue_t ep{};
     ep.out = at(ws, p.d_clsln); ep.out_fp32 = 1;
     KOA_TRY(linear(at(ws, p.d_hpre), at(ws, p.w_h1_t), p.B, D, mlp, &ep, st));
@@ -311,7 +311,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
     } else {
       KOA_TRY(koa_k_col_sum(dx, 0, gr.layer(l, P_FF3_B), M, D, D, st));
     }
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.g), gr.layer(l, P_FF3_W), (int)M, D, mlp, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.g), gr.layer(l, P_FF3_W), (int)M, D, mlp, 0, st));
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, p.dh); ep.act = KOA_ACT_GELU_GRAD; ep.aux_bf16 = at(ws, L.h_pre);
@@ -319,7 +319,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
       KOA_TRY(linear(at(ws, p.dx_bf16), at(ws, L.w_ff3_t), M, mlp, D, &ep, st));
     }
     KOA_TRY(koa_k_col_sum(at(ws, p.dh), 1, gr.layer(l, P_FF0_B), M, mlp, mlp, st));
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dh), at(ws, L.ln1), gr.layer(l, P_FF0_W), (int)M, mlp, D, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dh), at(ws, L.ln1), gr.layer(l, P_FF0_W), (int)M, mlp, D, 0, st));
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, p.d_ln); ep.out_fp32 = 1;
@@ -335,7 +335,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
     } else {
       KOA_TRY(koa_k_col_sum(dx_other, 0, gr.layer(l, P_OUT_B), M, D, D, st));
     }
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.attn_out), gr.layer(l, P_OUT_W), (int)M, D, D, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.attn_out), gr.layer(l, P_OUT_W), (int)M, D, D, 0, st));
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, p.dattn);
@@ -343,7 +343,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
     }
     KOA_TRY(koa_k_attention_bwd(at(ws, L.qkv), atf(ws, L.probs), at(ws, p.dattn), at(ws, p.dqkv), p.B, p.n, p.heads,
                                 D / p.heads, scale, st));
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dqkv), at(ws, L.ln0), gr.layer(l, P_QKV_W), (int)M, 3 * D, D, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dqkv), at(ws, L.ln0), gr.layer(l, P_QKV_W), (int)M, 3 * D, D, 0, st));
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, p.d_ln); ep.out_fp32 = 1;
@@ -358,7 +358,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
   float* dcls = p.n_cls ? gr.at(0) : nullptr;
   KOA_TRY(koa_k_token_assemble_bwd(dx, gr.at(1), dcls, at(ws, p.d_emb), p.B, p.n, p.n_cls, D, st));
   KOA_TRY(koa_k_col_sum(at(ws, p.d_emb), 1, gr.at(3), p.Mp, D, D, st));
-  KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.d_emb), at(ws, p.tok_bf16), gr.at(2), (int)p.Mp, D, D, st));
+  KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.d_emb), at(ws, p.tok_bf16), gr.at(2), (int)p.Mp, D, D, 0, st));
   if (d_tokens != nullptr) {
     koa_epilogue_t ep{};
     ep.out = d_tokens; ep.out_fp32 = 1;

@@ -120,6 +120,7 @@ static EpiParams to_epi(const koa_epilogue_t* e, int n) {
   p.stat_y = (const bf16*)e->stat_y;
   p.stat_mean = e->stat_mean;
   p.stat_invstd = e->stat_invstd;
+  p.a_f16 = e->a_f16; p.b_f16 = e->b_f16; p.out_f16 = e->out_f16; p.act_f16 = e->act_f16;
   p.drop_on = e->drop_p > 0.0f ? 1 : 0;
   p.drop_cols = n;
   p.drop = make_drop_spec(e->drop_seed, e->drop_site, e->drop_p);
@@ -134,6 +135,7 @@ static int check_epi(const koa_epilogue_t* ep, int n) {
   KOA_REQUIRE((ep->col_sum == nullptr) == (ep->col_sumsq == nullptr), "col_sum and col_sumsq go together");
   KOA_REQUIRE(ep->col_sum == nullptr || n <= kMaxStatCols, "column statistics support N <= %d (got %d)", kMaxStatCols, n);
   KOA_REQUIRE(ep->col_sum == nullptr || !ep->out_fp32, "column statistics need a bf16 output");
+  KOA_REQUIRE((ep->a_f16 != 0) == (ep->b_f16 != 0), "tcgen05 kind::f16 needs both operands in the same 16-bit format");
   KOA_REQUIRE(ep->drop_p >= 0.0f && ep->drop_p < 1.0f, "dropout probability %f out of range", (double)ep->drop_p);
   KOA_REQUIRE(ep->stat_y == nullptr || (ep->col_sum != nullptr && ep->stat_mean != nullptr && ep->stat_invstd != nullptr),
               "stat_y needs col_sum/col_sumsq and stat_mean/stat_invstd");
@@ -224,7 +226,7 @@ int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_
 
 template <int BN, int STAGES, bool IM2COL>
 static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, int cin, int pixels, int taps,
-                        const ConvGeom& g, float* dw, cudaStream_t st) {
+                        const ConvGeom& g, float* dw, int x_f16, cudaStream_t st) {
   constexpr size_t smem = wgrad_smem_bytes<BN, STAGES>();
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -248,13 +250,13 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
     const double n_eff = g.grouped ? 64.0 : (double)cin;
     ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps, cout, cin * taps, pixels, IM2COL ? 1 : 0);
     gemm_wgrad_kernel<BN, STAGES, IM2COL>
-        <<<grid, kGemmThreads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc);
+        <<<grid, kGemmThreads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16);
   }
   KOA_LAUNCH_CHECK();
   return 0;
 }
 
-int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, cudaStream_t st) {
+int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, int x_f16, cudaStream_t st) {
   KOA_REQUIRE(pixels > 0 && cout > 0 && cin > 0, "empty wgrad");
   KOA_REQUIRE(cout % 8 == 0 && cin % 64 == 0, "wgrad needs Cout %% 8 == 0 and Cin %% 64 == 0 (got %d, %d)", cout, cin);
   CUtensorMap ta, tb;
@@ -263,12 +265,12 @@ int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, 
   rc = koa_tmap_2d_bf16(&tb, x, (uint64_t)cin, (uint64_t)pixels, (uint64_t)cin * 2, 64, 64);
   if (rc) return rc;
   ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
-  if (cin % 128 == 0) return launch_wgrad<128, 6, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
-  return launch_wgrad<64, 6, false>(ta, tb, cout, cin, pixels, 1, g, dw, st);
+  if (cin % 128 == 0) return launch_wgrad<128, 3, false>(ta, tb, cout, cin, pixels, 1, g, dw, x_f16, st);
+  return launch_wgrad<64, 3, false>(ta, tb, cout, cin, pixels, 1, g, dw, x_f16, st);
 }
 
 int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int cin, int cout,
-                          int filt_r, int filt_s, int stride, int pad, cudaStream_t st) {
+                          int filt_r, int filt_s, int stride, int pad, int x_f16, cudaStream_t st) {
   KOA_REQUIRE(cout % 8 == 0 && cin % 64 == 0, "wgrad needs Cout %% 8 == 0 and Cin %% 64 == 0 (got %d, %d)", cout, cin);
   const int hout = (h + 2 * pad - filt_r) / stride + 1;
   const int wout = (w_in + 2 * pad - filt_s) / stride + 1;
@@ -281,8 +283,8 @@ int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, i
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64, 0};
   const int taps = filt_r * filt_s;
-  if (cin % 128 == 0) return launch_wgrad<128, 6, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
-  return launch_wgrad<64, 6, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, st);
+  if (cin % 128 == 0) return launch_wgrad<128, 3, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, x_f16, st);
+  return launch_wgrad<64, 3, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, x_f16, st);
 }
 
 // Grouped 3x3 convolution (ResNeXt, koafusion/models/_torchvision.py:110,327-328) as a block-diagonal dense
@@ -306,7 +308,7 @@ int koa_conv_grouped_launch(const void* x, const void* w, int n_img, int h, int 
 
 // dw[C][9][64] += per-chunk dense weight gradient of the grouped convolution.
 int koa_conv_grouped_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int c,
-                                  int stride, cudaStream_t st) {
+                                  int stride, int x_f16, cudaStream_t st) {
   KOA_REQUIRE(c % 64 == 0, "grouped conv needs C %% 64 == 0 (got %d)", c);
   const int hout = (h + 2 - 3) / stride + 1, wout = (w_in + 2 - 3) / stride + 1;
   const long long pixels = (long long)n_img * hout * wout;
@@ -317,7 +319,7 @@ int koa_conv_grouped_wgrad_launch(const void* dy, const void* x, float* dw, int 
   rc = koa_tmap_im2col_bf16(&tb, x, n_img, h, w_in, c, 3, 3, stride, 1, 64);
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, 1, 3, c / 64, 1};
-  return launch_wgrad<64, 6, true>(ta, tb, c, c, (int)pixels, 9, g, dw, st);
+  return launch_wgrad<64, 3, true>(ta, tb, c, c, (int)pixels, 9, g, dw, x_f16, st);
 }
 
 // ------------------------------------ C ABI ----------------------------------------------------
@@ -330,11 +332,11 @@ extern "C" int koa_conv_fprop_bf16(const void* x, const void* w, int n_img, int 
                                    void* stream) {
   return koa_conv_fprop_launch(x, w, n_img, h, w_in, cin, cout, filt_r, filt_s, stride, pad, ep, (cudaStream_t)stream);
 }
-extern "C" int koa_gemm_wgrad_bf16(const void* dy, const void* x, float* dw, int pixels, int cout, int cin,
+extern "C" int koa_gemm_wgrad_bf16(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, int x_f16,
                                    void* stream) {
-  return koa_gemm_wgrad_launch(dy, x, dw, pixels, cout, cin, (cudaStream_t)stream);
+  return koa_gemm_wgrad_launch(dy, x, dw, pixels, cout, cin, x_f16, (cudaStream_t)stream);
 }
 extern "C" int koa_conv_wgrad_bf16(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int cin,
-                                   int cout, int filt_r, int filt_s, int stride, int pad, void* stream) {
-  return koa_conv_wgrad_launch(dy, x, dw, n_img, h, w_in, cin, cout, filt_r, filt_s, stride, pad, (cudaStream_t)stream);
+                                   int cout, int filt_r, int filt_s, int stride, int pad, int x_f16, void* stream) {
+  return koa_conv_wgrad_launch(dy, x, dw, n_img, h, w_in, cin, cout, filt_r, filt_s, stride, pad, x_f16, (cudaStream_t)stream);
 }

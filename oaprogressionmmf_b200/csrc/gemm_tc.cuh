@@ -38,6 +38,9 @@ struct EpiParams {
   const bf16* stat_y;     // BatchNorm backward: forward conv output y [M, ldo]; xhat = (y - mean) * invstd
   const float* stat_mean;
   const float* stat_invstd;
+  int a_f16, b_f16;       // operand format (0 = bf16, 1 = fp16); the launcher enforces a_f16 == b_f16
+  int out_f16;            // out / pre_out (16-bit outputs) are fp16 instead of bf16
+  int act_f16;            // gate and stat_y (forward activations) are fp16 instead of bf16
   int drop_on;            // dropout (applied after the activation, before the residual add); element index of the
   int drop_cols;          // mask = row * drop_cols + column
   DropSpec drop;
@@ -147,11 +150,11 @@ __device__ __forceinline__ void unpack_row_bf16(float (&f)[32], const uint4 (&q)
     a = unpack_bf16x2(q[p].w); f[p * 8 + 6] = a.x; f[p * 8 + 7] = a.y;
   }
 }
-__device__ __forceinline__ void pack_row_bf16(uint4 (&q)[4], const float (&v)[32]) {
+__device__ __forceinline__ void pack_row_16(uint4 (&q)[4], const float (&v)[32], bool f16) {
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    q[p].x = pack_bf16x2(v[p * 8 + 0], v[p * 8 + 1]); q[p].y = pack_bf16x2(v[p * 8 + 2], v[p * 8 + 3]);
-    q[p].z = pack_bf16x2(v[p * 8 + 4], v[p * 8 + 5]); q[p].w = pack_bf16x2(v[p * 8 + 6], v[p * 8 + 7]);
+    q[p].x = pack16x2(v[p * 8 + 0], v[p * 8 + 1], f16); q[p].y = pack16x2(v[p * 8 + 2], v[p * 8 + 3], f16);
+    q[p].z = pack16x2(v[p * 8 + 4], v[p * 8 + 5], f16); q[p].w = pack16x2(v[p * 8 + 6], v[p * 8 + 7], f16);
   }
 }
 // staged coalesced tile -> this thread's row as 32 floats (whole warp; syncs on both sides)
@@ -178,10 +181,10 @@ __device__ __forceinline__ void stage_flush(uint32_t stage, uint8_t* gbase, long
   __syncwarp();
 }
 
-__device__ __forceinline__ void store_row_bf16(const float (&v)[32], uint32_t stage, bf16* g, long long ld, int rows_valid,
-                                               const LaneMap& lm) {
+__device__ __forceinline__ void store_row_16(const float (&v)[32], uint32_t stage, bf16* g, long long ld, int rows_valid,
+                                             const LaneMap& lm, bool f16) {
   uint4 q[4];
-  pack_row_bf16(q, v);
+  pack_row_16(q, v, f16);
   row_sts(stage, q, lm);
   stage_flush(stage, reinterpret_cast<uint8_t*>(g), ld * 2, rows_valid, lm);
 }
@@ -241,7 +244,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint64_t* release
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     }
-    if (ep.pre_out != nullptr) store_row_bf16(v, stage, ep.pre_out + tile_off, ep.ldo, rows_valid, lm);
+    if (ep.pre_out != nullptr) store_row_16(v, stage, ep.pre_out + tile_off, ep.ldo, rows_valid, lm, ep.out_f16 != 0);
     if (ep.act == ACT_RELU) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -294,21 +297,27 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint64_t* release
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += a[j];
     }
-    if (has_gate) {
-      float g[32];
-      unpack_row_bf16(g, qg);
+    if (has_gate) {  // format-agnostic: the sign / zero test reads the 16-bit patterns directly
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = g[j] > 0.0f ? v[j] : 0.0f;
+      for (int p = 0; p < 4; ++p) {
+        const uint32_t w[4] = {qg[p].x, qg[p].y, qg[p].z, qg[p].w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[p * 8 + 2 * u] = pos16(w[u] & 0xffffu) ? v[p * 8 + 2 * u] : 0.0f;
+          v[p * 8 + 2 * u + 1] = pos16(w[u] >> 16) ? v[p * 8 + 2 * u + 1] : 0.0f;
+        }
+      }
     }
   }
   if (!CONV && ep.out_fp32) {
     store_row_f32(v, stage, reinterpret_cast<float*>(ep.out) + tile_off, ep.ldo, rows_valid, lm);
-    if (ep.out_bf16_copy != nullptr) store_row_bf16(v, stage, ep.out_bf16_copy + tile_off, ep.ldo, rows_valid, lm);
+    if (ep.out_bf16_copy != nullptr) store_row_16(v, stage, ep.out_bf16_copy + tile_off, ep.ldo, rows_valid, lm, false);
     return;
   }
   // bf16 output: stage, (statistics from the staged, i.e. rounded, values), coalesced write-back
+  const bool of16 = ep.out_f16 != 0, af16 = ep.act_f16 != 0;
   uint4 q[4];
-  pack_row_bf16(q, v);
+  pack_row_16(q, v, of16);
   if (stats && lane >= rows_valid) {  // rows past M contribute exact zeros to the statistics
 #pragma unroll
     for (int p = 0; p < 4; ++p) q[p] = make_uint4(0, 0, 0, 0);
@@ -345,17 +354,16 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint64_t* release
         wy[i] = lds32(base + kStageBytesPerWarp + (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4));
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float x0 = __uint_as_float(w[i] << 16), x1 = __uint_as_float(w[i] & 0xffff0000u);
-        const float y0 = __uint_as_float(wy[i] << 16), y1 = __uint_as_float(wy[i] & 0xffff0000u);
-        sa[i & 1] += x0; sb[i & 1] += x1;
-        qa[i & 1] = fmaf(x0, (y0 - mu0) * is0, qa[i & 1]); qb[i & 1] = fmaf(x1, (y1 - mu1) * is1, qb[i & 1]);
+        const float2 x = unpack16x2(w[i], of16), y = unpack16x2(wy[i], af16);
+        sa[i & 1] += x.x; sb[i & 1] += x.y;
+        qa[i & 1] = fmaf(x.x, (y.x - mu0) * is0, qa[i & 1]); qb[i & 1] = fmaf(x.y, (y.y - mu1) * is1, qb[i & 1]);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float x0 = __uint_as_float(w[i] << 16), x1 = __uint_as_float(w[i] & 0xffff0000u);
-        sa[i & 1] += x0; sb[i & 1] += x1;
-        qa[i & 1] = fmaf(x0, x0, qa[i & 1]); qb[i & 1] = fmaf(x1, x1, qb[i & 1]);
+        const float2 x = unpack16x2(w[i], of16);
+        sa[i & 1] += x.x; sb[i & 1] += x.y;
+        qa[i & 1] = fmaf(x.x, x.x, qa[i & 1]); qb[i & 1] = fmaf(x.y, x.y, qb[i & 1]);
       }
     }
     float s0 = sa[0] + sa[1], s1 = sb[0] + sb[1], q0 = qa[0] + qa[1], q1 = qb[0] + qb[1];
@@ -468,7 +476,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      const uint32_t idesc = umma_idesc_16(BM, BN, 0, 0, ep.a_f16, ep.b_f16);
       uint32_t it = 0, lt = 0;  // k-block counter, local tile counter
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const uint32_t acc = lt % ACC;
@@ -580,7 +588,8 @@ constexpr size_t wgrad_smem_bytes() {
 template <int BN, int STAGES, bool B_IM2COL>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int cout, int cin,
-                  int pixels, int taps, ConvGeom g, float* __restrict__ dw, int kb_per_split, WgradDesc wd) {
+                  int pixels, int taps, ConvGeom g, float* __restrict__ dw, int kb_per_split, WgradDesc wd, int a_f16,
+                  int b_f16) {
   // g.grouped: dw is [C][taps][64] (per-64-channel-chunk dense blocks); tile n_t pairs input chunk n_t with
   // output chunk n_t only (BN must be 64; the upper 64 accumulator rows are discarded).
   constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -662,7 +671,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 1, 1);
+      const uint32_t idesc = umma_idesc_16(BM, BN, 1, 1, a_f16, b_f16);
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t phase = (i / STAGES) & 1;

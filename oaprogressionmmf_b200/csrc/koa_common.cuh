@@ -7,6 +7,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -214,6 +215,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_ma
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// Same with the operand format as an argument: a_format / b_format 0 = fp16, 1 = bf16. On B200 a kind::f16 MMA whose
+// operands differ in format faults (illegal instruction), so callers pass a_f16 == b_f16.
+__host__ __device__ constexpr uint32_t umma_idesc_16(int m, int n, int a_mn_major, int b_mn_major, int a_f16, int b_f16) {
+  return (1u << 4) | ((a_f16 ? 0u : 1u) << 7) | ((b_f16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 // ------------------------------- misc math ----------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -225,6 +232,23 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   bf162 b = *reinterpret_cast<bf162*>(&v);
   return __bfloat1622float2(b);
 }
+// 16-bit storage formats of the path: forward activations / weights of the CNN are fp16 (11-bit significand), gradients
+// and the transformer operands bf16 (fp32 range). `f16` selects the format of a packed pair.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  __half2 h = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(h);
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, bool f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack16x2(uint32_t v, bool f16) { return f16 ? unpack_f16x2(v) : unpack_bf16x2(v); }
+// x > 0 for either format straight from the bits (sign clear and magnitude non-zero)
+__device__ __forceinline__ bool pos16(uint32_t bits16) { return (bits16 & 0x8000u) == 0u && (bits16 & 0x7fffu) != 0u; }
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));

@@ -10,10 +10,11 @@ int koa_num_sms();
 int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep, cudaStream_t st);
 int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_in, int cin, int cout, int filt_r,
                           int filt_s, int stride, int pad, const koa_epilogue_t* ep, cudaStream_t st);
-int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, cudaStream_t st);
+int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, int x_f16,
+                          cudaStream_t st);
 int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int cin, int cout,
-                          int filt_r, int filt_s, int stride, int pad, cudaStream_t st);
+                          int filt_r, int filt_s, int stride, int pad, int x_f16, cudaStream_t st);
 int koa_conv_grouped_launch(const void* x, const void* w, int n_img, int h, int w_in, int c, int stride,
                             const koa_epilogue_t* ep, cudaStream_t st);
 int koa_conv_grouped_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, int h, int w_in, int c,
-                                  int stride, cudaStream_t st);
+                                  int stride, int x_f16, cudaStream_t st);

@@ -28,8 +28,11 @@ int koa_k_bn_finalize(const float* sum, const float* sumsq, const float* gamma, 
                       float* run_var, float* scale, float* shift, float* mean, float* invstd, int c, double count,
                       int training, cudaStream_t st);
 int koa_k_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, cudaStream_t st);
+// y / res / y2 / out: fp16 forward activations; out_bf16 (optional): bf16 copy of out (the weight-gradient GEMMs of
+// the backward pass pair it with bf16 gradients: tcgen05 kind::f16 wants both operands in one format)
 int koa_k_bn_act(const void* y, const float* scale, const float* shift, const void* res, const void* y2,
-                 const float* scale2, const float* shift2, void* out, long long rows, int c, int relu, cudaStream_t st);
+                 const float* scale2, const float* shift2, void* out, void* out_bf16, long long rows, int c, int relu,
+                 cudaStream_t st);
 int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
                         const void* y2, const float* mean2, const float* invstd2, float* sum_dz, float* sum_dzx,
                         float* sum_dzx2, long long rows, int c, cudaStream_t st);
@@ -41,7 +44,7 @@ int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const f
                        void* dy2, long long rows, int c, cudaStream_t st);
 
 // ---- pooling / resampling -------------------------------------------------------------------------
-int koa_k_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, cudaStream_t st);
+int koa_k_maxpool_fwd(const void* x, void* out, void* out_bf16, void* idx, int n, int h, int w, int c, cudaStream_t st);
 int koa_k_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, cudaStream_t st);
 int koa_k_gap_fwd(const void* x, float* feat, int n, int hw, int c, cudaStream_t st);
 int koa_k_gap_bwd(const float* dfeat, const void* gate, void* dx, int n, int hw, int c, cudaStream_t st);
@@ -93,6 +96,6 @@ int koa_k_stem_wgrad(const float* img, const void* dy, float* dwfold, int n, int
 int koa_k_stem_unfold_dw(const float* dwfold, float* dw, cudaStream_t st);
 // tensor-core form: im2col operand A [n*ho*wo][64] bf16 (K = 49 padded to 64), weights Wb [64][64] bf16,
 // folded gradient dWb [64][64] fp32 -> dw [64][3][7][7] +=
-int koa_k_stem_im2col(const float* img, void* a, int n, int h, int w, cudaStream_t st);
+int koa_k_stem_im2col(const float* img, void* a, int n, int h, int w, int f16, cudaStream_t st);
 int koa_k_stem_pack_wb(const float* w, void* wb, cudaStream_t st);
 int koa_k_stem_unfold_dwb(const float* dwb, float* dw, cudaStream_t st);

@@ -44,7 +44,7 @@ extern "C" int koa_stem_pack(const float* vol, float* img, int batch, int rc, in
   return koa_k_stem_pack(vol, img, batch, rc, slices, ST);
 }
 extern "C" int koa_maxpool_fwd(const void* x, void* out, void* idx, int n, int h, int w, int c, void* stream) {
-  return koa_k_maxpool_fwd(x, out, idx, n, h, w, c, ST);
+  return koa_k_maxpool_fwd(x, out, nullptr, idx, n, h, w, c, ST);
 }
 extern "C" int koa_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, void* stream) {
   return koa_k_maxpool_bwd(dout, idx, dx, n, h, w, c, ST);

@@ -50,9 +50,10 @@ __global__ void stem_unfold_dw_kernel(const float* __restrict__ dwfold, float* _
   dw[i] += dwfold[tap * 64 + co];
 }
 
-// Tensor-core form of the stem: img fp32 [n][h][w] -> A bf16 [n*ho*wo][64], column k = r*7 + s holds
+// Tensor-core form of the stem: img fp32 [n][h][w] -> A fp16 [n*ho*wo][64], column k = r*7 + s holds
 // img[2*oh - 3 + r][2*ow - 3 + s] (zero outside the image and for the 15 padding columns k >= 49). The convolution
 // is then the plain GEMM A . Wb^T with Wb[64 co][64 k] (koa_k_stem_pack_wb), its weight gradient dy^T . A.
+template <bool F16>
 __global__ void stem_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ a, long long total, int h, int w,
                                    int ho, int wo) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -70,20 +71,20 @@ __global__ void stem_im2col_kernel(const float* __restrict__ img, bf16* __restri
       const int iy = oh * 2 - 3 + r, ix = ow * 2 - 3 + s;
       f[u] = (k < 49 && iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(src + (long long)iy * w + ix) : 0.0f;
     }
-    uint4 q;
-    q.x = pack_bf16x2(f[0], f[1]); q.y = pack_bf16x2(f[2], f[3]); q.z = pack_bf16x2(f[4], f[5]); q.w = pack_bf16x2(f[6], f[7]);
+    uint4 q;  // fp16 as the forward GEMM operand, bf16 when rebuilt for the weight gradient (pairs with bf16 dy)
+    q.x = pack16x2(f[0], f[1], F16); q.y = pack16x2(f[2], f[3], F16); q.z = pack16x2(f[4], f[5], F16); q.w = pack16x2(f[6], f[7], F16);
     *reinterpret_cast<uint4*>(a + i * 8) = q;
   }
 }
 
-// W[64][3][7][7] fp32 -> Wb[64 co][64 k] bf16 = sum over the three identical input channels, zero for k >= 49
+// W[64][3][7][7] fp32 -> Wb[64 co][64 k] fp16 = sum over the three identical input channels, zero for k >= 49
 __global__ void stem_pack_wb_kernel(const float* __restrict__ w, bf16* __restrict__ wb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 64) return;
   const int co = i / 64, k = i % 64;
   float v = 0.0f;
   if (k < 49) v = w[(co * 3 + 0) * 49 + k] + w[(co * 3 + 1) * 49 + k] + w[(co * 3 + 2) * 49 + k];
-  wb[i] = __float2bfloat16_rn(v);
+  reinterpret_cast<__half*>(wb)[i] = __float2half_rn(v);
 }
 
 // dWb[64 co][64 k] fp32 -> dW[64][3][7][7] += (the folded gradient reaches each of the three channels)
@@ -246,12 +247,13 @@ int koa_k_stem_unfold_dw(const float* dwfold, float* dw, cudaStream_t st) {
   KOA_LAUNCH_CHECK();
   return 0;
 }
-int koa_k_stem_im2col(const float* img, void* a, int n, int h, int w, cudaStream_t st) {
+int koa_k_stem_im2col(const float* img, void* a, int n, int h, int w, int f16, cudaStream_t st) {
   const int ho = (h + 6 - 7) / 2 + 1, wo = (w + 6 - 7) / 2 + 1;
   const long long total = (long long)n * ho * wo * 8;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  stem_im2col_kernel<<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
+  if (f16) stem_im2col_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
+  else stem_im2col_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
 }

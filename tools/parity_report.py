@@ -44,7 +44,7 @@ def rel(a, b):
 
 
 def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False, emulate=False):
-    print(f"== FE {arch} B={n_b} S={slices} {size}x{size} train={train} xr={xr} emulate_bf16={emulate}", flush=True)
+    print(f"== FE {arch} B={n_b} S={slices} {size}x{size} train={train} xr={xr} emulate_16bit={emulate}", flush=True)
     dev = "cuda"
     spec = ko.fe_param_spec(arch, "_fe")
     sd = ko.make_state_dict(spec, 11, device=dev, res_gain=RES_GAIN)
@@ -67,7 +67,7 @@ def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False, emulate=Fal
     for v in params.values():
         v.requires_grad_(True)
     taps = {}
-    ref = ko.fe_forward(sd, "_fe", arch, imgs, train, True, taps, emulate_bf16=emulate).flatten(1)
+    ref = ko.fe_forward(sd, "_fe", arch, imgs, train, True, taps, emulate_16bit=emulate).flatten(1)
     got = tok.reshape(-1, tok.shape[-1])
     print(f"features rel={rel(got, ref):.3e}  |ref|={ref.norm():.3f} finite={bool(torch.isfinite(got).all())}")
     # intermediates
@@ -83,12 +83,12 @@ def section_fe(arch, n_b=2, slices=3, size=64, train=True, xr=False, emulate=Fal
     if ws is not None:
         off, nb = C.c_size_t(), C.c_size_t()
         _lib.check(lib.koa_fe_debug_offset(C.byref(desc), 4, 0, C.byref(off), C.byref(nb)), "dbg")
-        a0 = ws[off.value:off.value + nb.value].view(torch.bfloat16)
+        a0 = ws[off.value:off.value + nb.value].view(torch.float16)
         r0 = taps["_fe.stem"].permute(0, 2, 3, 1).reshape(-1)
         print(f"  stem act rel={rel(a0.float(), r0):.3e}")
         for bi, b in enumerate(ko.fe_block_plan(arch)):
             _lib.check(lib.koa_fe_debug_offset(C.byref(desc), 1, bi, C.byref(off), C.byref(nb)), "dbg")
-            out = ws[off.value:off.value + nb.value].view(torch.bfloat16)
+            out = ws[off.value:off.value + nb.value].view(torch.float16)
             r = taps[f"_fe.{b['layer']}.{b['index']}"].permute(0, 2, 3, 1).reshape(-1)
             print(f"  block {b['layer']}.{b['index']} out rel={rel(out.float(), r):.3e}")
     # backward
@@ -124,7 +124,7 @@ def _ws_view(lib, desc, ws, what, index, dtype):
 
 
 def _nhwc_bf16(t):
-    return t.detach().permute(0, 2, 3, 1).contiguous().bfloat16().reshape(-1)
+    return t.detach().permute(0, 2, 3, 1).contiguous().half().reshape(-1)
 
 
 def section_fe_teacher(arch, n_b=2, slices=3, size=64, xr=False):
@@ -156,7 +156,7 @@ def section_fe_teacher(arch, n_b=2, slices=3, size=64, xr=False):
     for v in params.values():
         v.requires_grad_(True)
     taps = {}
-    ref = ko.fe_forward(sd, "_fe", arch, imgs, True, True, taps, emulate_bf16=True).flatten(1)
+    ref = ko.fe_forward(sd, "_fe", arch, imgs, True, True, taps, emulate_16bit=True).flatten(1)
     # unit order of the engine: stem, then per block conv1, conv2, [conv3], [downsample]
     ykeys = ["_fe.0.y"]
     for b in ko.fe_block_plan(arch):
@@ -169,7 +169,7 @@ def section_fe_teacher(arch, n_b=2, slices=3, size=64, xr=False):
     worst_fwd = 0.0
     for ui, key in enumerate(ykeys):
         y = taps[key]
-        dst = _ws_view(lib, desc, ws, 0, ui, torch.bfloat16)
+        dst = _ws_view(lib, desc, ws, 0, ui, torch.float16)
         src = _nhwc_bf16(y)
         worst_fwd = max(worst_fwd, rel(dst.float(), src.float()))
         dst.copy_(src)
@@ -180,16 +180,16 @@ def section_fe_teacher(arch, n_b=2, slices=3, size=64, xr=False):
         coef[2].copy_(mean)
         coef[3].copy_(torch.rsqrt(var + 1e-5))
     print(f"  forward raw conv outputs before overwrite: worst rel={worst_fwd:.3e}")
-    _ws_view(lib, desc, ws, 4, 0, torch.bfloat16).copy_(_nhwc_bf16(taps["_fe.stem"]))
+    _ws_view(lib, desc, ws, 4, 0, torch.float16).copy_(_nhwc_bf16(taps["_fe.stem"]))
     for bi, b in enumerate(ko.fe_block_plan(arch)):
         p = f"_fe.{b['layer']}.{b['index']}"
-        _ws_view(lib, desc, ws, 1, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[p]))
-        _ws_view(lib, desc, ws, 2, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[f"{p}.a1"]))
+        _ws_view(lib, desc, ws, 1, bi, torch.float16).copy_(_nhwc_bf16(taps[p]))
+        _ws_view(lib, desc, ws, 2, bi, torch.float16).copy_(_nhwc_bf16(taps[f"{p}.a1"]))
         if b["kind"] == "bottleneck":
-            _ws_view(lib, desc, ws, 3, bi, torch.bfloat16).copy_(_nhwc_bf16(taps[f"{p}.a2"]))
+            _ws_view(lib, desc, ws, 3, bi, torch.float16).copy_(_nhwc_bf16(taps[f"{p}.a2"]))
     # pooled activation + argmax from the overwritten stem activation
-    a0 = _ws_view(lib, desc, ws, 4, 0, torch.bfloat16)
-    p0 = _ws_view(lib, desc, ws, 5, 0, torch.bfloat16)
+    a0 = _ws_view(lib, desc, ws, 4, 0, torch.float16)
+    p0 = _ws_view(lib, desc, ws, 5, 0, torch.float16)
     idx0 = _ws_view(lib, desc, ws, 7, 0, torch.uint8)
     hs = (size + 6 - 7) // 2 + 1
     _lib.check(lib.koa_maxpool_fwd(a0.data_ptr(), p0.data_ptr(), idx0.data_ptr(), imgs.shape[0], hs, hs, 64,
@@ -231,7 +231,7 @@ def section_floor(arch, n_b=2, slices=3, size=64, train=True):
         for v in params.values():
             v.requires_grad_(True)
         taps = {}
-        f = ko.fe_forward(sd, "_fe", arch, imgs, train, True, taps, emulate_bf16=emu).flatten(1)
+        f = ko.fe_forward(sd, "_fe", arch, imgs, train, True, taps, emulate_16bit=emu).flatten(1)
         if gy is None:
             gy = torch.randn(f.shape, generator=g).to(dev)
         (f * gy).sum().backward()
