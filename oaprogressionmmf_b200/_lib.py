@@ -143,12 +143,13 @@ def ptr_table(tensors):
 
 def zeros_like_flat(tensors):
     """Zero-initialised gradient buffers for ``tensors`` (None entries stay None) carved out of ONE flat
-    allocation: a single memset instead of one fill kernel per parameter."""
+    allocation: a single memset instead of one fill kernel per parameter, and one contiguous buffer per engine call
+    for the data-parallel gradient all-reduce (dataparallel.sync_flat). Returns (views, flat)."""
     import torch
 
     live = [t for t in tensors if t is not None]
     if not live:
-        return [None] * len(tensors)
+        return [None] * len(tensors), None
     sizes = [(t.numel() + 63) // 64 * 64 for t in live]  # 256-byte aligned slices
     flat = torch.zeros(sum(sizes), dtype=torch.float32, device=live[0].device)
     out, off, it = [], 0, iter(sizes)
@@ -159,7 +160,7 @@ def zeros_like_flat(tensors):
         n = next(it)
         out.append(flat[off:off + t.numel()].view(t.shape))
         off += n
-    return out
+    return out, flat
 
 
 _lib = None

@@ -238,7 +238,11 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
   const int tiles = (g.grouped ? 1 : koa_cdiv(cout, BM)) * koa_cdiv(cin, BN) * taps;
   const int num_kb = koa_cdiv(pixels, BK);
   // Split the pixel (reduction) range so that the grid covers the machine a few times over.
-  int splits = koa_cdiv(4 * koa_num_sms(), tiles);
+  static const int waves = [] {
+    const char* e = getenv("KOA_WGRAD_WAVES");
+    return e ? atoi(e) : 4;
+  }();
+  int splits = koa_cdiv(waves * koa_num_sms(), tiles);
   if (splits > num_kb) splits = num_kb;
   if (splits < 1) splits = 1;
   int kb_per_split = koa_cdiv(num_kb, splits);

@@ -15,7 +15,7 @@ from typing import List
 import torch
 from torch import nn
 
-from .. import _lib
+from .. import _lib, dataparallel
 
 _BLOCKS = {
     "resnet18": ("basic", (2, 2, 2, 2), 1, 64),
@@ -153,12 +153,13 @@ class _FEFunction(torch.autograd.Function):
         lib = _lib.load()
         enc = ctx.enc
         params = enc._trainable()
-        grads = _lib.zeros_like_flat([p if p.requires_grad else None for p in params])
+        grads, flat = _lib.zeros_like_flat([p if p.requires_grad else None for p in params])
         gtable = _lib.ptr_table(grads)
         dfeat = dfeat.contiguous().float()
         _lib.check(lib.koa_fe_backward(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(), dfeat.data_ptr(),
                                        _lib.current_stream()), "koa_fe_backward")
         ctx.ws = None
+        dataparallel.sync_flat(flat, [p for p in params if p.requires_grad])  # no-op outside a data-parallel run
         return (None, None, None, None, None, None, None, *grads)
 
 

@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 from torch import nn
 
-from .. import _lib
+from .. import _lib, dataparallel
 
 
 class FeedForward(nn.Module):
@@ -115,7 +115,7 @@ class _FeaTFunction(torch.autograd.Function):
         if not ctx.desc.compute_head:
             live[-n_head:] = [None] * n_head
             d_logits = None
-        gfull = _lib.zeros_like_flat(live)
+        gfull, flat = _lib.zeros_like_flat(live)
         grads = [g if (g is not None and p.requires_grad) else None for g, p in zip(gfull, params)]
         gtable = _lib.ptr_table(gfull)
         d_tokens = torch.empty(ctx.token_shape, dtype=torch.float32, device=ctx.ws.device) if ctx.tokens_need_grad else None
@@ -126,6 +126,7 @@ class _FeaTFunction(torch.autograd.Function):
                                          None if d_tokens is None else d_tokens.data_ptr(), _lib.current_stream()),
                    "koa_feat_backward")
         ctx.ws = None
+        dataparallel.sync_flat(flat, [p for g, p in zip(grads, params) if g is not None])
         out_grads = [g for g, p in zip(grads, params) if p is not None]
         return (None, d_tokens, None, None, None, *out_grads)
 
