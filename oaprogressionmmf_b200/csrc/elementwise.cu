@@ -309,6 +309,63 @@ __global__ void bn_act_kernel(const bf16* __restrict__ y, const float* __restric
   }
 }
 
+// Same, for the common case that the thread stride is a multiple of the channel-group count (C a power of two <= 2048:
+// every thread stays on ONE channel group): the per-channel coefficients live in registers for the whole kernel and each
+// iteration issues the loads of two elements before the first use.
+__global__ void __launch_bounds__(256)
+bn_act_fixed_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const bf16* __restrict__ res, const bf16* __restrict__ y2, const float* __restrict__ scale2,
+                    const float* __restrict__ shift2, bf16* __restrict__ out, bf16* __restrict__ out_bf, long long rows,
+                    int c, int relu) {
+  const int cg = c / 8;
+  const long long total = rows * cg;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = (int)(i0 % cg);
+  float sc[8], sh[8], sc2[8], sh2[8];
+  load8f(scale + g * 8, sc);
+  load8f(shift + g * 8, sh);
+  const bool has_res = res != nullptr, has_y2 = y2 != nullptr;
+  if (has_y2) { load8f(scale2 + g * 8, sc2); load8f(shift2 + g * 8, sh2); }
+  for (long long i = i0; i < total; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool two = j < total;
+    uint4 qa = *reinterpret_cast<const uint4*>(y + i * 8), qb = make_uint4(0, 0, 0, 0), ra, rb = make_uint4(0, 0, 0, 0);
+    if (two) qb = *reinterpret_cast<const uint4*>(y + j * 8);
+    const bf16* second = has_res ? res : y2;
+    if (has_res || has_y2) {
+      ra = *reinterpret_cast<const uint4*>(second + i * 8);
+      if (two) rb = *reinterpret_cast<const uint4*>(second + j * 8);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (e == 1 && !two) break;
+      float f[8];
+      unpack8h(e == 0 ? qa : qb, f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) f[u] = f[u] * sc[u] + sh[u];
+      if (has_res) {
+        float r[8];
+        unpack8h(e == 0 ? ra : rb, r);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] += r[u];
+      } else if (has_y2) {
+        float r[8];
+        unpack8h(e == 0 ? ra : rb, r);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] += r[u] * sc2[u] + sh2[u];
+      }
+      if (relu) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.0f);
+      }
+      const long long o = e == 0 ? i : j;
+      *reinterpret_cast<uint4*>(out + o * 8) = pack8h(f);
+      if (out_bf != nullptr) *reinterpret_cast<uint4*>(out_bf + o * 8) = pack8(f);
+    }
+  }
+}
+
 // Backward reduction: dz = dout * (act > 0) [if act != NULL]; accumulates per channel
 //   sum_dz, sum_dz_xhat (xhat from y/mean/invstd) and optionally sum_dz_xhat2 for a second BN
 //   (the downsample branch that shares dz).
@@ -442,6 +499,62 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* _
 #pragma unroll
       for (int u = 0; u < 8; ++u) o[u] = a[u] * dz[u] - b[u] - cc[u] * yy[u];
       *reinterpret_cast<uint4*>(dy2 + i * 8) = pack8(o);
+    }
+  }
+}
+
+// Fixed-channel-group variant (see bn_act_fixed_kernel): coefficients in registers, two elements in flight.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_fixed_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ act, const bf16* __restrict__ y,
+                          const float* __restrict__ k0, const float* __restrict__ k1, const float* __restrict__ k2,
+                          bf16* __restrict__ dy, const bf16* __restrict__ y2, const float* __restrict__ k0b,
+                          const float* __restrict__ k1b, const float* __restrict__ k2b, bf16* __restrict__ dy2,
+                          long long rows, int c) {
+  const int cg = c / 8;
+  const long long total = rows * cg;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = (int)(i0 % cg);
+  float a[8], b[8], cc[8], a2[8], b2[8], c2[8];
+  load8f(k0 + g * 8, a); load8f(k1 + g * 8, b); load8f(k2 + g * 8, cc);
+  const bool has_act = act != nullptr, has_y2 = y2 != nullptr;
+  if (has_y2) { load8f(k0b + g * 8, a2); load8f(k1b + g * 8, b2); load8f(k2b + g * 8, c2); }
+  for (long long i = i0; i < total; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool two = j < total;
+    uint4 qd[2], qy[2], qm[2], qz[2];
+    qd[0] = *reinterpret_cast<const uint4*>(dout + i * 8);
+    qy[0] = *reinterpret_cast<const uint4*>(y + i * 8);
+    if (has_act) qm[0] = *reinterpret_cast<const uint4*>(act + i * 8);
+    if (has_y2) qz[0] = *reinterpret_cast<const uint4*>(y2 + i * 8);
+    if (two) {
+      qd[1] = *reinterpret_cast<const uint4*>(dout + j * 8);
+      qy[1] = *reinterpret_cast<const uint4*>(y + j * 8);
+      if (has_act) qm[1] = *reinterpret_cast<const uint4*>(act + j * 8);
+      if (has_y2) qz[1] = *reinterpret_cast<const uint4*>(y2 + j * 8);
+    }
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (e == 1 && !two) break;
+      const long long o8 = (e == 0 ? i : j) * 8;
+      float dz[8], yy[8], o[8];
+      unpack8(qd[e], dz);
+      if (has_act) {
+        bool m[8];
+        pos8(qm[e], m);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dz[u] = m[u] ? dz[u] : 0.0f;
+      }
+      unpack8h(qy[e], yy);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = a[u] * dz[u] - b[u] - cc[u] * yy[u];
+      *reinterpret_cast<uint4*>(dy + o8) = pack8(o);
+      if (has_y2) {
+        unpack8h(qz[e], yy);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) o[u] = a2[u] * dz[u] - b2[u] - c2[u] * yy[u];
+        *reinterpret_cast<uint4*>(dy2 + o8) = pack8(o);
+      }
     }
   }
 }
@@ -987,8 +1100,14 @@ int koa_k_bn_act(const void* y, const float* scale, const float* shift, const vo
                  const float* scale2, const float* shift2, void* out, void* out_bf16, long long rows, int c, int relu,
                  cudaStream_t st) {
   KOA_REQ_C8(c);
-  bn_act_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
-                                                               (const bf16*)y2, scale2, shift2, (bf16*)out, (bf16*)out_bf16, rows, c, relu);
+  if (kThreads % (c / 8) == 0)
+    bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
+                                                                           (const bf16*)y2, scale2, shift2, (bf16*)out,
+                                                                           (bf16*)out_bf16, rows, c, relu);
+  else
+    bn_act_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
+                                                                 (const bf16*)y2, scale2, shift2, (bf16*)out,
+                                                                 (bf16*)out_bf16, rows, c, relu);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1017,9 +1136,14 @@ int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const f
                        const float* k2, void* dy, const void* y2, const float* k0b, const float* k1b, const float* k2b,
                        void* dy2, long long rows, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
-  bn_bwd_apply_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)dout, (const bf16*)act, (const bf16*)y,
-                                                                     k0, k1, k2, (bf16*)dy, (const bf16*)y2, k0b, k1b,
-                                                                     k2b, (bf16*)dy2, rows, c);
+  if (kThreads % (c / 8) == 0)
+    bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
+        (const bf16*)dout, (const bf16*)act, (const bf16*)y, k0, k1, k2, (bf16*)dy, (const bf16*)y2, k0b, k1b, k2b,
+        (bf16*)dy2, rows, c);
+  else
+    bn_bwd_apply_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)dout, (const bf16*)act, (const bf16*)y,
+                                                                       k0, k1, k2, (bf16*)dy, (const bf16*)y2, k0b, k1b,
+                                                                       k2b, (bf16*)dy2, rows, c);
   KOA_LAUNCH_CHECK();
   return 0;
 }
