@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../include/koa_b200.h"
+#include "gemm_conv.cuh"
 #include "gemm_tc.cuh"
 #include "koa_internal.h"
 #include "koa_tma.h"
@@ -149,6 +150,11 @@ static bool conv_epilogue(const EpiParams& ep) {
          ep.out_bf16_copy == nullptr && !ep.drop_on;
 }
 
+static int prof_flavor(bool im2col, const EpiParams& ep) {
+  return (im2col ? 1 : 0) | (ep.col_sum ? 2 : 0) | (ep.add_bf16 ? 4 : 0) | (ep.gate_bf16 ? 8 : 0) | (ep.res_f32 ? 16 : 0) |
+         (ep.out_fp32 ? 32 : 0) | (ep.act ? 64 : 0) | (ep.stat_y ? 128 : 0);
+}
+
 template <int BN, int STAGES, bool IM2COL, bool CONV>
 static int launch_kmajor_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
                            const EpiParams& ep, cudaStream_t st) {
@@ -164,19 +170,86 @@ static int launch_kmajor_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, 
   KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
   const unsigned grid = (unsigned)(tiles < koa_num_sms() ? tiles : koa_num_sms());  // persistent: one CTA per SM
   {
-    const int flavor = (IM2COL ? 1 : 0) | (ep.col_sum ? 2 : 0) | (ep.add_bf16 ? 4 : 0) | (ep.gate_bf16 ? 8 : 0) |
-                       (ep.res_f32 ? 16 : 0) | (ep.out_fp32 ? 32 : 0) | (ep.act ? 64 : 0) | (ep.stat_y ? 128 : 0);
-    ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, flavor);
+    ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep));
     gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV><<<grid, kKmajorThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
   }
   KOA_LAUNCH_CHECK();
   return 0;
 }
 
+// Convolution flavour: 16 epilogue warps, one n-tile per CTA (gemm_conv.cuh). grid = a multiple of the n-tile count.
+template <int BN, int STAGES, bool IM2COL, int MODE, bool OF16, bool AF16>
+static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
+                         const EpiParams& ep, cudaStream_t st) {
+  constexpr size_t smem = conv_smem_bytes<BN, STAGES, MODE>();
+  static_assert(smem <= 232448, "shared memory budget of one CTA per SM");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_conv_kernel<BN, STAGES, IM2COL, MODE, OF16, AF16>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  });
+  KOA_CHECK_CUDA(attr_err);
+  const int n_tiles = koa_cdiv(n, BN);
+  const long long tiles = (long long)koa_cdiv(m, BM) * n_tiles;
+  KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
+  const long long cap = tiles < koa_num_sms() ? tiles : koa_num_sms();
+  const unsigned grid = (unsigned)(cap / n_tiles * n_tiles);
+  // MODE 1 moves its epilogue operands and its output with the TMA unit: [M, N] views with row pitch ldo
+  CUtensorMap t_out = ta, t_add = ta, t_gate = ta, t_y = ta;
+  if (MODE == 1) {
+    const uint64_t pitch = (uint64_t)ep.ldo * 2;
+    int rc = koa_tmap_2d_sw64(&t_out, ep.out, (uint64_t)n, (uint64_t)m, pitch);
+    if (rc) return rc;
+    t_add = t_gate = t_y = t_out;
+    if (ep.add_bf16 && (rc = koa_tmap_2d_sw64(&t_add, ep.add_bf16, (uint64_t)n, (uint64_t)m, pitch))) return rc;
+    if (ep.gate_bf16 && (rc = koa_tmap_2d_sw64(&t_gate, ep.gate_bf16, (uint64_t)n, (uint64_t)m, pitch))) return rc;
+    if (ep.stat_y && (rc = koa_tmap_2d_sw64(&t_y, ep.stat_y, (uint64_t)n, (uint64_t)m, pitch))) return rc;
+  }
+  {
+    ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep));
+    gemm_conv_kernel<BN, STAGES, IM2COL, MODE, OF16, AF16>
+        <<<grid, kConvThreads, smem, st>>>(ta, tb, t_out, t_add, t_gate, t_y, m, n, k, g, ep);
+  }
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+
+static int conv_mode1_enabled() {
+  static const int v = [] {
+    const char* e = getenv("KOA_CONV_MODE1");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+
+static int conv_max_ntiles() {
+  static const int v = [] {
+    const char* e = getenv("KOA_CONV_MAX_NT");
+    return e ? atoi(e) : 8;
+  }();
+  return v;
+}
+
 template <int BN, int STAGES, bool IM2COL>
 static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
                          const EpiParams& ep, cudaStream_t st) {
-  if (conv_epilogue(ep)) return launch_kmajor_t<BN, STAGES, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
+  if (conv_epilogue(ep)) {
+    const int n_tiles = koa_cdiv(n, BN);
+    const bool mode1 = ep.add_bf16 != nullptr || ep.gate_bf16 != nullptr || ep.stat_y != nullptr;
+    constexpr int ST0 = BN == 128 ? 5 : 6, ST1 = BN == 128 ? 4 : 5;
+    if (n_tiles <= conv_max_ntiles() && n_tiles <= koa_num_sms()) {
+      if (!mode1) {
+        if (ep.out_f16) return launch_conv_t<BN, ST0, IM2COL, 0, true, false>(ta, tb, m, n, k, g, ep, st);
+        return launch_conv_t<BN, ST0, IM2COL, 0, false, false>(ta, tb, m, n, k, g, ep, st);
+      }
+      if (!ep.out_f16 && conv_mode1_enabled()) {
+        if (ep.act_f16) return launch_conv_t<BN, ST1, IM2COL, 1, false, true>(ta, tb, m, n, k, g, ep, st);
+        return launch_conv_t<BN, ST1, IM2COL, 1, false, false>(ta, tb, m, n, k, g, ep, st);
+      }
+    }
+    return launch_kmajor_t<BN, STAGES, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
+  }
   return launch_kmajor_t<BN, STAGES, IM2COL, false>(ta, tb, m, n, k, g, ep, st);
 }
 

@@ -50,8 +50,20 @@ static void resolve_entry_points() {
   cudaDriverGetVersion(&s_driver_version);
 }
 
+static int tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                         uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle);
+
 int koa_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                      uint32_t box_inner, uint32_t box_outer) {
+  return tmap_2d_16bit(out, base, inner, outer, pitch_bytes, box_inner, box_outer, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int koa_tmap_2d_sw64(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes) {
+  return tmap_2d_16bit(out, base, inner, outer, pitch_bytes, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+static int tmap_2d_16bit(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                         uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle) {
   std::call_once(s_once, resolve_entry_points);
   KOA_REQUIRE(s_encode_tiled != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   KOA_REQUIRE(((uintptr_t)base & 15) == 0, "TMA base address must be 16-byte aligned");
@@ -62,7 +74,7 @@ int koa_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = s_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     koa_set_error("cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu pitch=%llu box=%ux%u", (int)r,

@@ -14,3 +14,7 @@ int koa_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 // A load fetches `pixels` consecutive output pixels x 64 channels for one filter tap.
 int koa_tmap_im2col_bf16(CUtensorMap* out, const void* base, int n_img, int h, int w, int c, int filt_r, int filt_s,
                          int stride, int pad, uint32_t pixels);
+
+// 2-D row-major 16-bit matrix viewed in {32 columns x 32 rows} boxes with the 64-byte swizzle: the staging-tile layout of
+// the convolution epilogue (gemm_conv.cuh), used for its operand loads and its output store.
+int koa_tmap_2d_sw64(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes);
