@@ -178,23 +178,24 @@ static int launch_kmajor_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, 
 }
 
 // Convolution flavour: 16 epilogue warps, one n-tile per CTA (gemm_conv.cuh). grid = a multiple of the n-tile count.
-template <int BN, int STAGES, bool IM2COL, int MODE, bool OF16, bool AF16>
+// CTA2: CTA pairs (cluster of 2, tcgen05 cta_group::2) on 256-row tiles; `tb` then has a box of BN / 2 rows.
+template <int BN, int STAGES, bool IM2COL, int MODE, bool OF16, bool AF16, bool CTA2>
 static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
                          const EpiParams& ep, cudaStream_t st) {
-  constexpr size_t smem = conv_smem_bytes<BN, STAGES, MODE>();
+  constexpr size_t smem = conv_smem_bytes<BN, STAGES, MODE, CTA2>();
   static_assert(smem <= 232448, "shared memory budget of one CTA per SM");
+  auto kern = gemm_conv_kernel<BN, STAGES, IM2COL, MODE, OF16, AF16, CTA2>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_conv_kernel<BN, STAGES, IM2COL, MODE, OF16, AF16>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  });
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   KOA_CHECK_CUDA(attr_err);
   const int n_tiles = koa_cdiv(n, BN);
-  const long long tiles = (long long)koa_cdiv(m, BM) * n_tiles;
+  const long long tiles = (long long)koa_cdiv(m, CTA2 ? 2 * BM : BM) * n_tiles;
   KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
-  const long long cap = tiles < koa_num_sms() ? tiles : koa_num_sms();
-  const unsigned grid = (unsigned)(cap / n_tiles * n_tiles);
+  const long long units_max = CTA2 ? koa_num_sms() / 2 : koa_num_sms();
+  const long long cap = tiles < units_max ? tiles : units_max;
+  const unsigned units = (unsigned)(cap / n_tiles * n_tiles);
+  KOA_REQUIRE(units > 0, "more n-tiles than SMs");
   // MODE 1 moves its epilogue operands and its output with the TMA unit: [M, N] views with row pitch ldo
   CUtensorMap t_out = ta, t_add = ta, t_gate = ta, t_y = ta;
   if (MODE == 1) {
@@ -207,28 +208,52 @@ static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
     if (ep.stat_y && (rc = koa_tmap_2d_sw64(&t_y, ep.stat_y, (uint64_t)n, (uint64_t)m, pitch))) return rc;
   }
   {
-    ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep));
-    gemm_conv_kernel<BN, STAGES, IM2COL, MODE, OF16, AF16>
-        <<<grid, kConvThreads, smem, st>>>(ta, tb, t_out, t_add, t_gate, t_y, m, n, k, g, ep);
+    ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep) | (CTA2 ? 256 : 0));
+    if (CTA2) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * units, 1, 1);
+      cfg.blockDim = dim3(kConvThreads, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t_out, t_add, t_gate, t_y, m, n, k, g, ep));
+    } else {
+      kern<<<units, kConvThreads, smem, st>>>(ta, tb, t_out, t_add, t_gate, t_y, m, n, k, g, ep);
+    }
   }
   KOA_LAUNCH_CHECK();
   return 0;
 }
 
-static int conv_mode1_enabled() {
-  static const int v = [] {
-    const char* e = getenv("KOA_CONV_MODE1");
-    return e ? atoi(e) : 1;
-  }();
-  return v;
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
+static int conv_mode1_enabled() { static const int v = env_int("KOA_CONV_MODE1", 1); return v; }
+static int conv_max_ntiles() { static const int v = env_int("KOA_CONV_MAX_NT", 16); return v; }
+// CTA pairs for the compute-bound layers: K at least this (0 disables)
+static int conv_cta2_min_k() { static const int v = env_int("KOA_CONV_CTA2_MINK", 512); return v; }
 
-static int conv_max_ntiles() {
-  static const int v = [] {
-    const char* e = getenv("KOA_CONV_MAX_NT");
-    return e ? atoi(e) : 8;
-  }();
-  return v;
+// mode / format dispatch of the convolution flavour; returns 1 when no instantiation matches (caller falls back)
+template <int BN, int ST0, int ST1, bool IM2COL, bool CTA2>
+static int launch_conv_fmt(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
+                           const EpiParams& ep, cudaStream_t st) {
+  const bool mode1 = ep.add_bf16 != nullptr || ep.gate_bf16 != nullptr || ep.stat_y != nullptr;
+  if (!mode1) {
+    if (ep.out_f16) return launch_conv_t<BN, ST0, IM2COL, 0, true, false, CTA2>(ta, tb, m, n, k, g, ep, st);
+    return launch_conv_t<BN, ST0, IM2COL, 0, false, false, CTA2>(ta, tb, m, n, k, g, ep, st);
+  }
+  if (!ep.out_f16 && conv_mode1_enabled()) {
+    if (ep.act_f16) return launch_conv_t<BN, ST1, IM2COL, 1, false, true, CTA2>(ta, tb, m, n, k, g, ep, st);
+    return launch_conv_t<BN, ST1, IM2COL, 1, false, false, CTA2>(ta, tb, m, n, k, g, ep, st);
+  }
+  return 1;
 }
 
 template <int BN, int STAGES, bool IM2COL>
@@ -236,17 +261,9 @@ static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
                          const EpiParams& ep, cudaStream_t st) {
   if (conv_epilogue(ep)) {
     const int n_tiles = koa_cdiv(n, BN);
-    const bool mode1 = ep.add_bf16 != nullptr || ep.gate_bf16 != nullptr || ep.stat_y != nullptr;
-    constexpr int ST0 = BN == 128 ? 5 : 6, ST1 = BN == 128 ? 4 : 5;
     if (n_tiles <= conv_max_ntiles() && n_tiles <= koa_num_sms()) {
-      if (!mode1) {
-        if (ep.out_f16) return launch_conv_t<BN, ST0, IM2COL, 0, true, false>(ta, tb, m, n, k, g, ep, st);
-        return launch_conv_t<BN, ST0, IM2COL, 0, false, false>(ta, tb, m, n, k, g, ep, st);
-      }
-      if (!ep.out_f16 && conv_mode1_enabled()) {
-        if (ep.act_f16) return launch_conv_t<BN, ST1, IM2COL, 1, false, true>(ta, tb, m, n, k, g, ep, st);
-        return launch_conv_t<BN, ST1, IM2COL, 1, false, false>(ta, tb, m, n, k, g, ep, st);
-      }
+      const int rc = launch_conv_fmt<BN, (BN == 128 ? 5 : 6), (BN == 128 ? 4 : 5), IM2COL, false>(ta, tb, m, n, k, g, ep, st);
+      if (rc != 1) return rc;
     }
     return launch_kmajor_t<BN, STAGES, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
   }
@@ -256,12 +273,25 @@ static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
 template <bool IM2COL>
 static int dispatch_kmajor(const CUtensorMap& ta, const void* b, int m, int n, int k, const ConvGeom& g,
                            const EpiParams& ep, cudaStream_t st) {
-  const int num_kb = koa_cdiv(k, BK);
   const bool bn128 = (n % 128 == 0);
   CUtensorMap tb;
-  int rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, bn128 ? 128 : 64);
+  int rc;
+  // compute-bound convolution layers: CTA pairs on 256 x BN tiles, each CTA stages BN / 2 rows of B
+  if (bn128 && !g.grouped && conv_epilogue(ep) && conv_cta2_min_k() > 0 && k >= conv_cta2_min_k() && koa_num_sms() >= 2) {
+    if (n % 256 == 0 && n / 256 <= koa_num_sms() / 2) {
+      rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, 128);
+      if (rc) return rc;
+      rc = launch_conv_fmt<256, 5, 4, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
+      if (rc != 1) return rc;
+    } else if (n / 128 <= koa_num_sms() / 2) {
+      rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, 64);
+      if (rc) return rc;
+      rc = launch_conv_fmt<128, 6, 5, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
+      if (rc != 1) return rc;
+    }
+  }
+  rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, bn128 ? 128 : 64);
   if (rc) return rc;
-  (void)num_kb;
   // persistent kernel, one CTA per SM: a deep smem ring lets the TMA producer run ahead across tiles
   if (bn128) return launch_kmajor<128, 5, IM2COL>(ta, tb, m, n, k, g, ep, st);
   return launch_kmajor<64, 6, IM2COL>(ta, tb, m, n, k, g, ep, st);

@@ -4,8 +4,9 @@
 //
 // Same TMA -> smem ring -> tcgen05.mma -> double-buffered TMEM pipeline as gemm_kmajor_kernel (gemm_tc.cuh), but
 //   * 16 epilogue warps (4 per TMEM lane quarter): with BN = 128 every warp owns one fixed 32-column chunk of every
-//     tile, with BN = 64 the warps split into two sets that take alternate tiles (both accumulator stages drain at
-//     the same time). Four warps per scheduler hide the tcgen05.ld / LDS / LDG latencies that two could not.
+//     tile (two chunks with BN = 256), with BN = 64 the warps split into two sets that take alternate tiles (both
+//     accumulator stages drain at the same time). Four warps per scheduler hide the tcgen05.ld / LDS / LDG latencies
+//     that two could not.
 //   * a CTA keeps ONE n-tile for its whole life (tile = (m, n_t) with n_t = blockIdx % n_tiles): the columns of a
 //     warp never change, so the BatchNorm statistics live in four registers per lane for the whole kernel: no
 //     shared-memory accumulation, no per-tile barrier; one exchange through shared memory + one global atomic per
@@ -13,6 +14,12 @@
 //   * formats are template parameters (no per-element format selects), the statistics use packed fp32x2 math
 //     (FADD2 / FFMA2), the ReLU gate is one HSET2 + AND per element pair on the packed output,
 //     sum(dz * xhat) is accumulated as sum(dz * y) and corrected once per CTA: invstd * (sum(dz*y) - mean * sum(dz)).
+//   * MODE 1 (backward) moves its epilogue operands and its output with the TMA unit ([32 x 32] boxes in the 64-byte
+//     swizzle, which IS the staging layout): no operand registers, no address arithmetic, no row predicates.
+//   * CTA2: the compute-bound layers run as CTA pairs (cluster of 2 along M, tcgen05.mma.cta_group::2, M = 256): each
+//     CTA stages its own 128 A rows and HALF of the B tile, the pair's tensor cores read both halves, so the
+//     shared-memory fill per FLOP drops from (128 + BN) to (128 + BN / 2) rows per k-block. Only the rank-0 CTA
+//     issues MMAs; its commits arrive on the barriers of both CTAs; both CTAs' TMA loads complete on rank 0's barrier.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -20,14 +27,15 @@ namespace koa {
 
 constexpr int kConvEpiWarps = 16;
 constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;  // TMA warp, MMA warp, 16 epilogue warps
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;         // shared::cluster address of the same offset in CTA rank 0 of a pair
 
 // MODE 0: forward (statistics optional). MODE 1: backward (addend / gate / BatchNorm-backward statistics).
-template <int BN, int STAGES, int MODE>
+template <int BN, int STAGES, int MODE, bool CTA2>
 constexpr size_t conv_smem_bytes() {
   // MODE 0: one staging buffer per epilogue warp + the end-of-kernel statistics exchange; MODE 1: three staging
   // buffers per warp (addend -> output, gate, y), the statistics exchange re-uses them
-  return 1024 /*align slack*/ + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 +
-         kConvEpiWarps * 8 /*operand mbarriers*/ + (MODE == 0 ? kConvEpiWarps * 64 * sizeof(float) : 0) + 1024 +
+  return 1024 /*align slack*/ + (size_t)STAGES * (BM * BK * 2 + (CTA2 ? BN / 2 : BN) * BK * 2) + (2 * STAGES + 4) * 8 + 16 +
+         kConvEpiWarps * 8 /*operand mbarriers*/ + (MODE == 0 ? kConvEpiWarps * 128 * sizeof(float) : 0) + 1024 +
          (size_t)kConvEpiWarps * (MODE == 0 ? 1 : 3) * kStageBytesPerWarp;
 }
 
@@ -55,18 +63,87 @@ __device__ __forceinline__ uint32_t gt0_mask(uint32_t v) {
   return __hgt2_mask(*reinterpret_cast<bf162*>(&v), bf162(__ushort_as_bfloat16(0), __ushort_as_bfloat16(0)));
 }
 
-template <int BN, int STAGES, bool A_IM2COL, int MODE, bool OF16, bool AF16>
+// ---- CTA-pair (cta_group::2) plumbing ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far complete) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// TMA loads of a CTA pair: the bytes complete on CTA rank 0's barrier
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c, int32_t w,
+                                                    int32_t h, int32_t n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w),
+      "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+
+template <int BN, int STAGES, bool A_IM2COL, int MODE, bool OF16, bool AF16, bool CTA2>
 __global__ void __launch_bounds__(kConvThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
                  const __grid_constant__ CUtensorMap tmGate, const __grid_constant__ CUtensorMap tmY, int M, int N, int K,
                  ConvGeom g, EpiParams ep) {
+  static_assert(BN == 64 || BN == 128 || BN == 256, "tile widths");
+  static_assert(BN != 256 || CTA2, "BN = 256 needs the CTA pair (shared-memory budget)");
+  constexpr uint32_t B_ROWS = CTA2 ? BN / 2 : BN;    // B rows staged by this CTA
   constexpr uint32_t A_BYTES = BM * BK * 2;
-  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
   constexpr int ACC = 2;
   constexpr int NSTG = MODE == 0 ? 1 : 3;            // staging buffers per epilogue warp
-  constexpr int kDrainWarps = BN == 128 ? 16 : 8;    // warps that read one accumulator stage
+  constexpr int CH = BN == 256 ? 2 : 1;              // 32-column chunks per epilogue warp and tile
+  constexpr int kDrainWarps = BN == 64 ? 8 : 16;     // warps (of one CTA) that read one accumulator stage
   constexpr int kEpiThreads = kConvEpiWarps * 32;
+  constexpr int BMT = CTA2 ? 2 * BM : BM;            // rows of the tile of a CTA (pair)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
@@ -81,22 +158,26 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* s_fin0 = reinterpret_cast<float*>(op_bar + kConvEpiWarps);
   // staging buffers: 1024-byte aligned (the 64-byte TMA swizzle pattern is a function of the address bits 4..8)
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(
-      ((uintptr_t)(s_fin0 + (MODE == 0 ? kConvEpiWarps * 64 : 0)) + 1023) & ~(uintptr_t)1023);
-  // end-of-kernel statistics exchange [16 warps][16 lanes][4]; MODE 1 re-uses the first staging buffer of each warp
+      ((uintptr_t)(s_fin0 + (MODE == 0 ? kConvEpiWarps * 128 : 0)) + 1023) & ~(uintptr_t)1023);
+  // end-of-kernel statistics exchange [16 warps][CH][16 lanes][4]; MODE 1 re-uses the first staging buffer of each warp
   float* s_fin = MODE == 0 ? s_fin0 : reinterpret_cast<float*>(s_stage);
-  constexpr int kFinStride = MODE == 0 ? 64 : NSTG * kStageBytesPerWarp / 4;  // floats between two warps' slots
+  constexpr int kFinStride = MODE == 0 ? 128 : NSTG * kStageBytesPerWarp / 4;  // floats between two warps' slots
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const int n_tiles = (N + BN - 1) / BN;
-  const int m_tiles = (M + BM - 1) / BM;
+  const int m_tiles = (M + BMT - 1) / BMT;
   const int num_kb = (K + BK - 1) / BK;
-  // this CTA: n-tile n_t, m-tiles m_start, m_start + m_step, ... (CTAs that run together share their A rows in L2)
-  const int n_t = blockIdx.x % n_tiles;
-  const int m_start = blockIdx.x / n_tiles;
-  const int m_step = gridDim.x / n_tiles;
+  // this CTA (pair): n-tile n_t, m-tiles m_start, m_start + m_step, ... (CTAs that run together share their A rows in L2)
+  const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_t = unit % n_tiles;
+  const int m_start = unit / n_tiles;
+  const int m_step = n_units / n_tiles;
   const int my_tiles = m_start < m_tiles ? (m_tiles - m_start + m_step - 1) / m_step : 0;
   const int n0 = n_t * BN;
+  const int m_off = (int)rank * BM;  // rows of this CTA inside the pair's tile
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -112,15 +193,19 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
     for (int a = 0; a < ACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], kDrainWarps);
+      mbar_init(&tmem_empty_bar[a], kDrainWarps * (CTA2 ? 2 : 1));  // pair: rank 0 collects both CTAs' epilogue warps
     }
 #pragma unroll
     for (int w = 0; w < kConvEpiWarps; ++w) mbar_init(&op_bar[w], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, ACC * BN);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc2(tmem_slot, ACC * BN);
+    else tmem_alloc(tmem_slot, ACC * BN);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -128,7 +213,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       uint32_t it = 0;
       for (int lt = 0; lt < my_tiles; ++lt) {
-        const int m0 = (m_start + lt * m_step) * BM;
+        const int m0 = (m_start + lt * m_step) * BMT + m_off;
         int pw = 0, ph = 0, pn = 0;
         if (A_IM2COL) {
           const int hw = g.hout * g.wout;
@@ -143,24 +228,33 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % STAGES;
           const uint32_t phase = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], phase ^ 1, 0x900 + s);
-          mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          // pair: rank 0 announces the bytes of both CTAs; the peer's loads complete on rank 0's barrier
+          if (!CTA2) mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          else if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_BYTES + B_BYTES));
+          int ca = kb * BK;
+          uint16_t fs = 0, fr = 0;
           if (A_IM2COL) {
             const int tap = kb / g.cin_blocks;
             const int cb = kb - tap * g.cin_blocks;
-            const int fr = tap / g.filt_s;
-            const int fs = tap - fr * g.filt_s;
-            const int c0 = g.grouped ? n_t * 64 : cb * 64;
-            tma_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], c0, pw, ph, pn, (uint16_t)fs, (uint16_t)fr);
-          } else {
-            tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+            fr = (uint16_t)(tap / g.filt_s);
+            fs = (uint16_t)(tap - fr * g.filt_s);
+            ca = g.grouped ? n_t * 64 : cb * 64;
           }
-          tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+          if (!CTA2) {
+            if (A_IM2COL) tma_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], ca, pw, ph, pn, fs, fr);
+            else tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], ca, m0);
+            tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+          } else {
+            if (A_IM2COL) tma2_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], ca, pw, ph, pn, fs, fr);
+            else tma2_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], ca, m0);
+            tma2_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0 + (int)(rank * B_ROWS));
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_16(BM, BN, 0, 0, ep.a_f16, ep.b_f16);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_16(BMT, BN, 0, 0, ep.a_f16, ep.b_f16);
       uint32_t it = 0;
       for (int lt = 0; lt < my_tiles; ++lt) {
         const uint32_t acc = lt & 1;
@@ -176,22 +270,24 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * B_BYTES), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          umma_commit(&empty_bar[s]);
+          for (int k = 0; k < BK / 16; ++k) {
+            if (CTA2) umma2_bf16_ss(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else umma_bf16_ss(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          if (CTA2) umma2_commit_both(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if (CTA2) umma2_commit_both(&tmem_full_bar[acc]);
+        else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
     const int e = warp - 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int cg = e >> 2;
-    const int c0 = BN == 128 ? cg * 32 : (cg & 1) * 32;
-    const int lt_first = BN == 128 ? 0 : (cg >> 1);
-    constexpr int lt_step = BN == 128 ? 1 : 2;
-    const int n = n0 + c0;
-    const bool col_ok = n < N;
+    const int c0 = BN == 64 ? (cg & 1) * 32 : cg * 32;  // first chunk of this warp (BN = 256: second chunk at + 128)
+    const int lt_first = BN == 64 ? (cg >> 1) : 0;
+    constexpr int lt_step = BN == 64 ? 2 : 1;
     // MODE 0: `stage` = the output staging buffer. MODE 1: stage = addend, then output; stage_g = gate; stage_y = y.
     const uint32_t stage = smem_u32(s_stage) + e * (NSTG * kStageBytesPerWarp);
     const uint32_t stage_g = stage + (NSTG > 1 ? 1 : 0) * kStageBytesPerWarp;
@@ -205,158 +301,182 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // statistics lane mapping: lane = (h, p): column pair (2p, 2p + 1) of the chunk over the 16 rows 2i + h
     const int h = lane >> 4, p = lane & 15;
     const uint32_t st_base = (uint32_t)(h * 64 + (p & 3) * 4);
-    float2 s_a = make_float2(0.f, 0.f), s_b = make_float2(0.f, 0.f);  // two chains: sum over even / odd steps
-    float2 q_a = make_float2(0.f, 0.f), q_b = make_float2(0.f, 0.f);
+    float2 s_a[CH], s_b[CH], q_a[CH], q_b[CH];  // two chains per chunk: sums over even / odd steps
+#pragma unroll
+    for (int j = 0; j < CH; ++j) s_a[j] = s_b[j] = q_a[j] = q_b[j] = make_float2(0.f, 0.f);
 
     for (int lt = lt_first; lt < my_tiles; lt += lt_step) {
-      const int m0 = (m_start + lt * m_step) * BM;
+      const int m0 = (m_start + lt * m_step) * BMT + m_off;
       const uint32_t acc = lt & 1;
       const uint32_t acc_phase = (lt >> 1) & 1;
       const int row0 = m0 + q * 32;
       const int rows_valid = max(0, min(32, M - row0));
-      if (MODE == 1 && col_ok && lane == 0) {
-        // The TMA unit fetches the operand tiles of this chunk ([32 rows][32 columns], 64-byte swizzle = the staging
-        // layout; rows past M arrive as zeros) while the accumulator is still being computed. The previous tile's
-        // output store must have finished reading the buffer the addend lands in.
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (op_bytes != 0) {
-          mbar_arrive_expect_tx(&op_bar[e], op_bytes);
-          if (has_add) tma_load_2d(s_stage + (stage - smem_u32(s_stage)), &tmAdd, &op_bar[e], n, row0);
-          if (has_gate) tma_load_2d(s_stage + (stage_g - smem_u32(s_stage)), &tmGate, &op_bar[e], n, row0);
-          if (bwd) tma_load_2d(s_stage + (stage_y - smem_u32(s_stage)), &tmY, &op_bar[e], n, row0);
-        }
-      }
-      mbar_wait(&tmem_full_bar[acc], acc_phase, 0xc00 + acc);
-      tc_fence_after();
-      uint32_t r[32];
-      if (col_ok) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c0, r);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);  // accumulator handed back before any global traffic
-      if (!col_ok) continue;
-
-      if (MODE == 1 && op_bytes != 0) {
-        mbar_wait(&op_bar[e], op_phase, 0xd00 + e);
-        op_phase ^= 1;
-      }
-      if (has_add) {
-        uint4 qa[4];
-        row_lds(qa, stage, lm);
+      bool waited = false;
 #pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          const uint32_t w[4] = {qa[pc].x, qa[pc].y, qa[pc].z, qa[pc].w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 a = unpack_bf16x2(w[u]);
-            r[pc * 8 + 2 * u] = __float_as_uint(__uint_as_float(r[pc * 8 + 2 * u]) + a.x);
-            r[pc * 8 + 2 * u + 1] = __float_as_uint(__uint_as_float(r[pc * 8 + 2 * u + 1]) + a.y);
+      for (int j = 0; j < CH; ++j) {
+        const int cj = c0 + j * 128;
+        const int n = n0 + cj;
+        const bool col_ok = n < N;
+        const bool last = j == CH - 1;
+        if (MODE == 1 && col_ok && lane == 0) {
+          // The TMA unit fetches the operand tiles of this chunk ([32 rows][32 columns], 64-byte swizzle = the staging
+          // layout; rows past M arrive as zeros) while the accumulator is still being computed. The previous
+          // output store must have finished reading the buffer the addend lands in.
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (op_bytes != 0) {
+            mbar_arrive_expect_tx(&op_bar[e], op_bytes);
+            if (has_add) tma_load_2d(s_stage + (stage - smem_u32(s_stage)), &tmAdd, &op_bar[e], n, row0);
+            if (has_gate) tma_load_2d(s_stage + (stage_g - smem_u32(s_stage)), &tmGate, &op_bar[e], n, row0);
+            if (bwd) tma_load_2d(s_stage + (stage_y - smem_u32(s_stage)), &tmY, &op_bar[e], n, row0);
           }
         }
-      }
-      uint4 qv[4];
+        if (!waited) {
+          mbar_wait(&tmem_full_bar[acc], acc_phase, 0xc00 + acc);
+          tc_fence_after();
+          waited = true;
+        }
+        uint32_t r[32];
+        if (col_ok) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)cj, r);
+          tmem_ld_wait();
+        }
+        if (last) {  // accumulator handed back before the global traffic of the last chunk
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CTA2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
+        }
+        if (!col_ok) continue;
+
+        if (MODE == 1 && op_bytes != 0) {
+          mbar_wait(&op_bar[e], op_phase, 0xd00 + e);
+          op_phase ^= 1;
+        }
+        if (has_add) {
+          uint4 qa[4];
+          row_lds(qa, stage, lm);
 #pragma unroll
-      for (int pc = 0; pc < 4; ++pc) {
-        qv[pc].x = pack16<OF16>(__uint_as_float(r[pc * 8 + 0]), __uint_as_float(r[pc * 8 + 1]));
-        qv[pc].y = pack16<OF16>(__uint_as_float(r[pc * 8 + 2]), __uint_as_float(r[pc * 8 + 3]));
-        qv[pc].z = pack16<OF16>(__uint_as_float(r[pc * 8 + 4]), __uint_as_float(r[pc * 8 + 5]));
-        qv[pc].w = pack16<OF16>(__uint_as_float(r[pc * 8 + 6]), __uint_as_float(r[pc * 8 + 7]));
-      }
-      if (has_gate) {  // ReLU backward: zero where the forward activation is not positive
-        uint4 qg[4];
-        row_lds(qg, stage_g, lm);
+          for (int pc = 0; pc < 4; ++pc) {
+            const uint32_t w[4] = {qa[pc].x, qa[pc].y, qa[pc].z, qa[pc].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 a = unpack_bf16x2(w[u]);
+              r[pc * 8 + 2 * u] = __float_as_uint(__uint_as_float(r[pc * 8 + 2 * u]) + a.x);
+              r[pc * 8 + 2 * u + 1] = __float_as_uint(__uint_as_float(r[pc * 8 + 2 * u + 1]) + a.y);
+            }
+          }
+        }
+        uint4 qv[4];
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) {
-          qv[pc].x &= gt0_mask<AF16>(qg[pc].x); qv[pc].y &= gt0_mask<AF16>(qg[pc].y);
-          qv[pc].z &= gt0_mask<AF16>(qg[pc].z); qv[pc].w &= gt0_mask<AF16>(qg[pc].w);
+          qv[pc].x = pack16<OF16>(__uint_as_float(r[pc * 8 + 0]), __uint_as_float(r[pc * 8 + 1]));
+          qv[pc].y = pack16<OF16>(__uint_as_float(r[pc * 8 + 2]), __uint_as_float(r[pc * 8 + 3]));
+          qv[pc].z = pack16<OF16>(__uint_as_float(r[pc * 8 + 4]), __uint_as_float(r[pc * 8 + 5]));
+          qv[pc].w = pack16<OF16>(__uint_as_float(r[pc * 8 + 6]), __uint_as_float(r[pc * 8 + 7]));
         }
-      }
-      if (rows_valid < 32 && lane >= rows_valid) {  // rows past M contribute exact zeros to the statistics
+        if (has_gate) {  // ReLU backward: zero where the forward activation is not positive
+          uint4 qg[4];
+          row_lds(qg, stage_g, lm);
 #pragma unroll
-        for (int pc = 0; pc < 4; ++pc) qv[pc] = make_uint4(0, 0, 0, 0);
-      }
-      if (has_add) __syncwarp();  // every lane has read its addend row: the buffer becomes the output buffer
-      row_sts(stage, qv, lm);
-      if (MODE == 1) {
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
-        __syncwarp();
-        if (lane == 0) {  // rows past M / columns past N are clipped by the TMA unit
-          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                           reinterpret_cast<uint64_t>(&tmOut)),
-                       "r"(n), "r"(row0), "r"(stage)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          for (int pc = 0; pc < 4; ++pc) {
+            qv[pc].x &= gt0_mask<AF16>(qg[pc].x); qv[pc].y &= gt0_mask<AF16>(qg[pc].y);
+            qv[pc].z &= gt0_mask<AF16>(qg[pc].z); qv[pc].w &= gt0_mask<AF16>(qg[pc].w);
+          }
         }
-      } else {
-        __syncwarp();
-      }
-      if (stats) {
-        // row 2i + h, 4 bytes at column pair p: piece p >> 2 (swizzled by ((2i + h) >> 1) & 3 = i & 3), word p & 3
-        uint32_t w[16];
+        if (rows_valid < 32 && lane >= rows_valid) {  // rows past M contribute exact zeros to the statistics
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = lds32(stage + st_base + (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4));
-        if (bwd) {
-          uint32_t wy[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            wy[i] = lds32(stage_y + st_base + (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4));
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float2 x0 = unpack16<OF16>(w[i]), x1 = unpack16<OF16>(w[i + 1]);
-            s_a = add2(s_a, x0); s_b = add2(s_b, x1);
-            q_a = fma2(x0, unpack16<AF16>(wy[i]), q_a); q_b = fma2(x1, unpack16<AF16>(wy[i + 1]), q_b);
+          for (int pc = 0; pc < 4; ++pc) qv[pc] = make_uint4(0, 0, 0, 0);
+        }
+        if (has_add) __syncwarp();  // every lane has read its addend row: the buffer becomes the output buffer
+        row_sts(stage, qv, lm);
+        if (MODE == 1) {
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) {  // rows past M / columns past N are clipped by the TMA unit
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmOut)),
+                         "r"(n), "r"(row0), "r"(stage)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         } else {
+          __syncwarp();
+        }
+        if (stats) {
+          // row 2i + h, 4 bytes at column pair p: piece p >> 2 (swizzled by ((2i + h) >> 1) & 3 = i & 3), word p & 3
+          uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float2 x0 = unpack16<OF16>(w[i]), x1 = unpack16<OF16>(w[i + 1]);
-            s_a = add2(s_a, x0); s_b = add2(s_b, x1);
-            q_a = fma2(x0, x0, q_a); q_b = fma2(x1, x1, q_b);
+          for (int i = 0; i < 16; ++i)
+            w[i] = lds32(stage + st_base + (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4));
+          if (bwd) {
+            uint32_t wy[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              wy[i] = lds32(stage_y + st_base + (uint32_t)(i * 128) + ((uint32_t)((p >> 2) ^ (i & 3)) << 4));
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float2 x0 = unpack16<OF16>(w[i]), x1 = unpack16<OF16>(w[i + 1]);
+              s_a[j] = add2(s_a[j], x0); s_b[j] = add2(s_b[j], x1);
+              q_a[j] = fma2(x0, unpack16<AF16>(wy[i]), q_a[j]); q_b[j] = fma2(x1, unpack16<AF16>(wy[i + 1]), q_b[j]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float2 x0 = unpack16<OF16>(w[i]), x1 = unpack16<OF16>(w[i + 1]);
+              s_a[j] = add2(s_a[j], x0); s_b[j] = add2(s_b[j], x1);
+              q_a[j] = fma2(x0, x0, q_a[j]); q_b[j] = fma2(x1, x1, q_b[j]);
+            }
           }
         }
-      }
-      if (MODE == 0) {
-        // coalesced write-back: 8 rows x 64 contiguous bytes per instruction
-        uint4 o[4];
+        if (MODE == 0) {
+          // coalesced write-back: 8 rows x 64 contiguous bytes per instruction
+          uint4 o[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = lds128(stage + lm.co_off + i * 512);
-        __syncwarp();  // every lane has read the staging buffer: the next tile may overwrite it
-        uint8_t* gp = reinterpret_cast<uint8_t*>(ep.out) + ((long long)row0 * ep.ldo + n) * 2 +
-                      lm.co_row * (long long)ep.ldo * 2 + lm.co_byte;
+          for (int i = 0; i < 4; ++i) o[i] = lds128(stage + lm.co_off + i * 512);
+          __syncwarp();  // every lane has read the staging buffer: the next chunk may overwrite it
+          uint8_t* gp = reinterpret_cast<uint8_t*>(ep.out) + ((long long)row0 * ep.ldo + n) * 2 +
+                        lm.co_row * (long long)ep.ldo * 2 + lm.co_byte;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i * 8 + lm.co_row < rows_valid) stg128(gp + (long long)i * 8 * ep.ldo * 2, o[i]);
-      } else {
-        __syncwarp();  // every lane has read the staging buffers: the next tile's operand loads may overwrite them
+          for (int i = 0; i < 4; ++i)
+            if (i * 8 + lm.co_row < rows_valid) stg128(gp + (long long)i * 8 * ep.ldo * 2, o[i]);
+        } else {
+          __syncwarp();  // every lane has read the staging buffers: the next operand loads may overwrite them
+        }
       }
     }
     if (MODE == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // output stores complete
     __syncwarp();
 
     if (stats) {
-      float2 s = add2(s_a, s_b), qq = add2(q_a, q_b);
-      s.x += __shfl_xor_sync(0xffffffffu, s.x, 16); s.y += __shfl_xor_sync(0xffffffffu, s.y, 16);
-      qq.x += __shfl_xor_sync(0xffffffffu, qq.x, 16); qq.y += __shfl_xor_sync(0xffffffffu, qq.y, 16);
-      if (bwd && col_ok) {  // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)); linear, so per-CTA partials are fine
-        const float2 mu = __ldg(reinterpret_cast<const float2*>(ep.stat_mean + n + 2 * p));
-        const float2 is = __ldg(reinterpret_cast<const float2*>(ep.stat_invstd + n + 2 * p));
-        qq.x = is.x * (qq.x - mu.x * s.x);
-        qq.y = is.y * (qq.y - mu.y * s.y);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int n = n0 + c0 + j * 128;
+        float2 s = add2(s_a[j], s_b[j]), qq = add2(q_a[j], q_b[j]);
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, 16); s.y += __shfl_xor_sync(0xffffffffu, s.y, 16);
+        qq.x += __shfl_xor_sync(0xffffffffu, qq.x, 16); qq.y += __shfl_xor_sync(0xffffffffu, qq.y, 16);
+        if (bwd && n < N) {  // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)); linear: per-CTA partials are fine
+          const float2 mu = __ldg(reinterpret_cast<const float2*>(ep.stat_mean + n + 2 * p));
+          const float2 is = __ldg(reinterpret_cast<const float2*>(ep.stat_invstd + n + 2 * p));
+          qq.x = is.x * (qq.x - mu.x * s.x);
+          qq.y = is.y * (qq.y - mu.y * s.y);
+        }
+        if (h == 0) *reinterpret_cast<float4*>(s_fin + e * kFinStride + j * 64 + p * 4) = make_float4(s.x, qq.x, s.y, qq.y);
       }
-      if (h == 0) *reinterpret_cast<float4*>(s_fin + e * kFinStride + p * 4) = make_float4(s.x, qq.x, s.y, qq.y);
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       const int c = e * 32 + lane;  // column of the CTA's n-tile handled by this thread
       if (c < BN && n0 + c < N) {
         const int chunk = c >> 5, within = c & 31;
+        const int jj = chunk >> 2;  // BN = 256: chunks 4..7 are the second chunk of their warps
         float ts = 0.f, tq = 0.f;
 #pragma unroll
         for (int w = 0; w < kConvEpiWarps; ++w) {
           const int w_cg = w >> 2;
-          const int w_chunk = BN == 128 ? w_cg : (w_cg & 1);
-          if (w_chunk == chunk) {
-            const float2 v = *reinterpret_cast<const float2*>(s_fin + w * kFinStride + (within >> 1) * 4 + (within & 1) * 2);
+          const int w_chunk = BN == 64 ? (w_cg & 1) : w_cg;
+          if (w_chunk == (chunk & 3)) {
+            const float2 v =
+                *reinterpret_cast<const float2*>(s_fin + w * kFinStride + jj * 64 + (within >> 1) * 4 + (within & 1) * 2);
             ts += v.x; tq += v.y;
           }
         }
@@ -367,7 +487,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ACC * BN);
+  if (CTA2) cluster_sync_all();  // the peer may still arrive on this CTA's barriers / read its B half until it is done
+  if (warp == 1) {
+    if (CTA2) tmem_dealloc2(tmem_base, ACC * BN);
+    else tmem_dealloc(tmem_base, ACC * BN);
+  }
 }
 
 }  // namespace koa

@@ -195,7 +195,8 @@ def test_gemm_column_statistics_many_tiles(cuda, m, n, k):
 
 
 @pytest.mark.parametrize("m,n,k", [(333, 256, 64), (40000, 64, 256), (6, 1024, 256), (128 * 148 * 2 + 77, 128, 64),
-                                   (5000, 512, 128), (96, 96, 64), (2500, 2048, 512)])
+                                   (5000, 512, 128), (96, 96, 64), (2500, 2048, 512), (3000, 128, 1024), (1000, 768, 512),
+                                   (257, 256, 576), (128 * 74 * 4 + 300, 256, 512)])
 @pytest.mark.parametrize("act_f16", [0, 1])
 def test_gemm_conv_backward_epilogue(cuda, m, n, k, act_f16):
     """Data-gradient epilogue of a residual block (fe_engine.cu: G = (dgrad + G_b) * (x > 0) with the fused
@@ -239,7 +240,8 @@ def test_gemm_conv_backward_epilogue(cuda, m, n, k, act_f16):
     assert _lib.debug_flag() == 0
 
 
-@pytest.mark.parametrize("m,n,k", [(333, 256, 64), (40000, 64, 64), (6, 1024, 256), (128 * 148 * 2 + 77, 128, 64), (96, 96, 128)])
+@pytest.mark.parametrize("m,n,k", [(333, 256, 64), (40000, 64, 64), (6, 1024, 256), (128 * 148 * 2 + 77, 128, 64), (96, 96, 128),
+                                   (3000, 128, 1024), (1000, 768, 512), (257, 256, 576), (128 * 74 * 4 + 300, 512, 512)])
 def test_gemm_conv_forward_epilogue_fp16(cuda, m, n, k):
     """Forward convolution flavour as the extractor runs it (fe_engine.cu conv_forward): fp16 operands and output with
     the BatchNorm batch statistics (sum, sum of squares) of the stored values."""
