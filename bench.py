@@ -235,18 +235,21 @@ def run_ours(args):
         tgt = tgt_h.to(dev, non_blocking=True)
         return float(step(ins, tgt).item())
 
-    for i in range(min(2, args.warmup)):
-        e2e_step(i)
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        last_loss = e2e_step(i)
-    ev1.record()
-    barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if ws > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = ws * B * args.steps / (float(t.item()) / 1e3)
+    if args.skip_e2e:  # profiler runs only (ncu replays every launch): the line then carries no end-to-end number
+        last_loss, e2e_value = float(loss.item()), None
+    else:
+        for i in range(min(2, args.warmup)):
+            e2e_step(i)
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            last_loss = e2e_step(i)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if ws > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = ws * B * args.steps / (float(t.item()) / 1e3)
 
     if rank != 0:
         if ws > 1:
@@ -260,8 +263,17 @@ def run_ours(args):
     k_ms, k_flops, k_n = prof[0], prof[1], prof[2]
     w_ms, w_flops, w_n = prof[3], prof[4], prof[5]
     achieved = (k_flops / (k_ms / 1e3)) / 1e12 if k_ms > 0 else 0.0
-    roofline = dict(bound="tensor", kernel="gemm_kmajor_kernel (tcgen05 GEMM / im2col implicit-GEMM conv, fwd + dgrad)",
-                    achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], traffic=None,
+    # DRAM bytes per launch of the same kernel family from the committed ncu capture of this command (profiles/)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if args.workload == "XR1MR3C1CnnTrf" and B == 16 and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r01_traffic.json (ncu dram__bytes_read+write.sum per launch, same workload)"
+    roofline = dict(bound="tensor", kernel="gemm_conv_kernel + gemm_kmajor_kernel (tcgen05 GEMM / im2col implicit-GEMM conv, fwd + dgrad)",
+                    achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], traffic=traffic,
+                    traffic_source=traffic_src,
+                    dram_gbs=(traffic / (k_ms / max(1.0, k_n) * 1e-3) / 1e9) if traffic and k_ms > 0 else None,
                     peak_source=peaks["source"], avg_launch_ms=k_ms / max(1.0, k_n), launches_timed=int(k_n),
                     share_of_step=k_ms / ms_total,
                     wgrad=dict(kernel="gemm_wgrad_kernel (tcgen05 MN-major split-K)",
@@ -306,6 +318,7 @@ def main():
                     help="fe.*.dropout / agg.emb_dropout / agg.mlp_dropout (authors' recipe: 0.1, runner.sh:352 + conf/model/*.yaml)")
     ap.add_argument("--cpu-knees", type=int, default=1, help="knees in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiler runs: skip the end-to-end pass")
     ap.add_argument("--profile-dump", default=None, help="write the per-shape tcgen05 kernel timing table to this file")
     args = ap.parse_args()
     if args.impl == "reference":

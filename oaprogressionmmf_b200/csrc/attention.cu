@@ -15,7 +15,7 @@ using namespace koa;
 
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 32;  // one CTA per SM (K, V and dS fill the shared memory): 32 warps hide the FMA / LDS latency
 constexpr int kMaxN = 128;
 
 __device__ __forceinline__ float dot8(const uint4& a, const uint4& b) {

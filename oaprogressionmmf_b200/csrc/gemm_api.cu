@@ -278,15 +278,11 @@ static int dispatch_kmajor(const CUtensorMap& ta, const void* b, int m, int n, i
   int rc;
   // compute-bound convolution layers: CTA pairs on 256 x BN tiles, each CTA stages BN / 2 rows of B
   if (bn128 && !g.grouped && conv_epilogue(ep) && conv_cta2_min_k() > 0 && k >= conv_cta2_min_k() && koa_num_sms() >= 2) {
+    // (pairs on 256 x 128 tiles, N = 128, measured slower than single CTAs: 430 vs 480 TFLOP/s at K = 512)
     if (n % 256 == 0 && n / 256 <= koa_num_sms() / 2) {
       rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, 128);
       if (rc) return rc;
       rc = launch_conv_fmt<256, 5, 4, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
-      if (rc != 1) return rc;
-    } else if (n / 128 <= koa_num_sms() / 2) {
-      rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, 64);
-      if (rc) return rc;
-      rc = launch_conv_fmt<128, 6, 5, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
       if (rc != 1) return rc;
     }
   }
