@@ -309,6 +309,63 @@ __global__ void bn_act_kernel(const bf16* __restrict__ y, const float* __restric
   }
 }
 
+// Coefficients of channels g*8 .. g*8+7 straight from the raw sums (the arithmetic of bn_finalize_kernel); `writer`
+// threads (one per channel group in the grid) also publish them and update the running statistics.
+__device__ __forceinline__ void bn_fwd_coef8(const KoaBnFwdFin& f, int g, double count, int training, bool writer,
+                                             float (&sc)[8], float (&sh)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = g * 8 + u;
+    float mean, var;
+    if (training) {
+      const double m = (double)f.sum[i] / count;
+      double v = (double)f.sumsq[i] / count - m * m;
+      if (v < 0.0) v = 0.0;
+      mean = (float)m;
+      var = (float)v;
+      if (writer) {
+        const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+        f.run_mean[i] = (1.0f - 0.1f) * f.run_mean[i] + 0.1f * mean;
+        f.run_var[i] = (1.0f - 0.1f) * f.run_var[i] + 0.1f * (float)unbiased;
+      }
+    } else {
+      mean = f.run_mean[i];
+      var = f.run_var[i];
+    }
+    const float invstd = rsqrtf(var + 1e-5f);
+    sc[u] = f.gamma[i] * invstd;
+    sh[u] = f.beta[i] - mean * sc[u];
+    if (writer) {
+      f.scale[i] = sc[u]; f.shift[i] = sh[u]; f.mean[i] = mean; f.invstd[i] = invstd;
+    }
+  }
+}
+__device__ __forceinline__ void bn_bwd_coef8(const KoaBnBwdFin& f, const float* sum_dz, int g, double count, int training,
+                                             bool writer, float (&k0)[8], float (&k1)[8], float (&k2)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int i = g * 8 + u;
+    const float gm = f.gamma[i], is = f.invstd[i], mu = f.mean[i];
+    const float sdz = sum_dz[i], sdzx = f.sum_dzx[i];
+    const float s = gm * is;
+    k0[u] = s;
+    if (training) {
+      const float a = (float)((double)sdz / count);
+      const float b = (float)((double)sdzx / count);
+      k2[u] = s * b * is;
+      k1[u] = s * a - s * b * is * mu;
+    } else {
+      k1[u] = 0.0f;
+      k2[u] = 0.0f;
+    }
+    if (writer) {
+      if (f.dgamma != nullptr) f.dgamma[i] += sdzx;
+      if (f.dbeta != nullptr) f.dbeta[i] += sdz;
+      f.k0[i] = k0[u]; f.k1[i] = k1[u]; f.k2[i] = k2[u];
+    }
+  }
+}
+
 // Same, for the common case that the thread stride is a multiple of the channel-group count (C a power of two <= 2048:
 // every thread stays on ONE channel group): the per-channel coefficients live in registers for the whole kernel and each
 // iteration issues the loads of two elements before the first use.
@@ -316,17 +373,21 @@ __global__ void __launch_bounds__(256)
 bn_act_fixed_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     const bf16* __restrict__ res, const bf16* __restrict__ y2, const float* __restrict__ scale2,
                     const float* __restrict__ shift2, bf16* __restrict__ out, bf16* __restrict__ out_bf, long long rows,
-                    int c, int relu) {
+                    int c, int relu, KoaBnFwdFin fa, KoaBnFwdFin fb, double count, int training) {
   const int cg = c / 8;
   const long long total = rows * cg;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int g = (int)(i0 % cg);
   float sc[8], sh[8], sc2[8], sh2[8];
-  load8f(scale + g * 8, sc);
-  load8f(shift + g * 8, sh);
   const bool has_res = res != nullptr, has_y2 = y2 != nullptr;
-  if (has_y2) { load8f(scale2 + g * 8, sc2); load8f(shift2 + g * 8, sh2); }
+  const bool writer = i0 < cg;  // exactly one thread per channel group
+  if (fa.gamma != nullptr) bn_fwd_coef8(fa, g, count, training, writer, sc, sh);
+  else { load8f(scale + g * 8, sc); load8f(shift + g * 8, sh); }
+  if (has_y2) {
+    if (fb.gamma != nullptr) bn_fwd_coef8(fb, g, count, training, writer, sc2, sh2);
+    else { load8f(scale2 + g * 8, sc2); load8f(shift2 + g * 8, sh2); }
+  }
   for (long long i = i0; i < total; i += 2 * stride) {
     const long long j = i + stride;
     const bool two = j < total;
@@ -509,16 +570,21 @@ bn_bwd_apply_fixed_kernel(const bf16* __restrict__ dout, const bf16* __restrict_
                           const float* __restrict__ k0, const float* __restrict__ k1, const float* __restrict__ k2,
                           bf16* __restrict__ dy, const bf16* __restrict__ y2, const float* __restrict__ k0b,
                           const float* __restrict__ k1b, const float* __restrict__ k2b, bf16* __restrict__ dy2,
-                          long long rows, int c) {
+                          long long rows, int c, KoaBnBwdFin fa, KoaBnBwdFin fb, double count, int training) {
   const int cg = c / 8;
   const long long total = rows * cg;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int g = (int)(i0 % cg);
   float a[8], b[8], cc[8], a2[8], b2[8], c2[8];
-  load8f(k0 + g * 8, a); load8f(k1 + g * 8, b); load8f(k2 + g * 8, cc);
   const bool has_act = act != nullptr, has_y2 = y2 != nullptr;
-  if (has_y2) { load8f(k0b + g * 8, a2); load8f(k1b + g * 8, b2); load8f(k2b + g * 8, c2); }
+  const bool writer = i0 < cg;  // exactly one thread per channel group
+  if (fa.gamma != nullptr) bn_bwd_coef8(fa, fa.sum_dz, g, count, training, writer, a, b, cc);
+  else { load8f(k0 + g * 8, a); load8f(k1 + g * 8, b); load8f(k2 + g * 8, cc); }
+  if (has_y2) {
+    if (fb.gamma != nullptr) bn_bwd_coef8(fb, fb.sum_dz, g, count, training, writer, a2, b2, c2);
+    else { load8f(k0b + g * 8, a2); load8f(k1b + g * 8, b2); load8f(k2b + g * 8, c2); }
+  }
   for (long long i = i0; i < total; i += 2 * stride) {
     const long long j = i + stride;
     const bool two = j < total;
@@ -1103,11 +1169,34 @@ int koa_k_bn_act(const void* y, const float* scale, const float* shift, const vo
   if (kThreads % (c / 8) == 0)
     bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
                                                                            (const bf16*)y2, scale2, shift2, (bf16*)out,
-                                                                           (bf16*)out_bf16, rows, c, relu);
+                                                                           (bf16*)out_bf16, rows, c, relu, KoaBnFwdFin{},
+                                                                           KoaBnFwdFin{}, 1.0, 0);
   else
     bn_act_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
                                                                  (const bf16*)y2, scale2, shift2, (bf16*)out,
                                                                  (bf16*)out_bf16, rows, c, relu);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_bn_fused_ok(int c) { return c % 8 == 0 && c / 8 <= kThreads && kThreads % (c / 8) == 0; }
+int koa_k_bn_act_fin(const void* y, const KoaBnFwdFin* a, const void* res, const void* y2, const KoaBnFwdFin* b, void* out,
+                     void* out_bf16, long long rows, int c, int relu, double count, int training, cudaStream_t st) {
+  KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm apply needs C/8 | %d (C=%d)", kThreads, c);
+  KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
+  bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
+      (const bf16*)y, nullptr, nullptr, (const bf16*)res, (const bf16*)y2, nullptr, nullptr, (bf16*)out, (bf16*)out_bf16, rows,
+      c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_bn_bwd_apply_fin(const void* dout, const void* act, const void* y, const KoaBnBwdFin* a, void* dy, const void* y2,
+                           const KoaBnBwdFin* b, void* dy2, long long rows, int c, double count, int training,
+                           cudaStream_t st) {
+  KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm backward needs C/8 | %d (C=%d)", kThreads, c);
+  KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
+  bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
+      (const bf16*)dout, (const bf16*)act, (const bf16*)y, nullptr, nullptr, nullptr, (bf16*)dy, (const bf16*)y2, nullptr,
+      nullptr, nullptr, (bf16*)dy2, rows, c, *a, b ? *b : KoaBnBwdFin{}, count, training);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1139,7 +1228,7 @@ int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const f
   if (kThreads % (c / 8) == 0)
     bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
         (const bf16*)dout, (const bf16*)act, (const bf16*)y, k0, k1, k2, (bf16*)dy, (const bf16*)y2, k0b, k1b, k2b,
-        (bf16*)dy2, rows, c);
+        (bf16*)dy2, rows, c, KoaBnBwdFin{}, KoaBnBwdFin{}, 1.0, 0);
   else
     bn_bwd_apply_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)dout, (const bf16*)act, (const bf16*)y,
                                                                        k0, k1, k2, (bf16*)dy, (const bf16*)y2, k0b, k1b,

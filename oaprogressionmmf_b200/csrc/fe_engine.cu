@@ -247,10 +247,27 @@ int bn_finalize(const Unit& u, const ParamView& pv, void* ws, int training, cuda
                            bn_slot(ws, u, S_INVSTD), u.cout, (double)u.rows_out, training, st);
 }
 
-// a = relu(bn(y))
-int bn_relu(const Unit& u, void* ws, size_t a_off, size_t a_bf_off, cudaStream_t st) {
-  return koa_k_bn_act(at(ws, u.y), bn_slot(ws, u, S_SCALE), bn_slot(ws, u, S_SHIFT), nullptr, nullptr, nullptr, nullptr,
-                      at(ws, a_off), a_bf_off ? at(ws, a_bf_off) : nullptr, u.rows_out, u.cout, 1, st);
+KoaBnFwdFin fwd_fin(const Unit& u, const ParamView& pv, void* ws) {
+  return KoaBnFwdFin{bn_slot(ws, u, S_SUM), bn_slot(ws, u, S_SUMSQ), pv.gamma(u), pv.beta(u), pv.run_mean(u), pv.run_var(u),
+                     bn_slot(ws, u, S_SCALE), bn_slot(ws, u, S_SHIFT), bn_slot(ws, u, S_MEAN), bn_slot(ws, u, S_INVSTD)};
+}
+
+// out = relu(bn(y) [+ res | + bn_d(y_d)]) with the BatchNorm coefficients derived inside the apply kernel (one launch
+// per BatchNorm instead of finalize + apply) whenever the channel count allows it.
+int bn_apply(const Unit& u, const Unit* ud, const ParamView& pv, void* ws, const void* res, void* out, void* out_bf,
+             int training, cudaStream_t st) {
+  if (koa_k_bn_fused_ok(u.cout)) {
+    const KoaBnFwdFin fa = fwd_fin(u, pv, ws);
+    KoaBnFwdFin fb{};
+    if (ud) fb = fwd_fin(*ud, pv, ws);
+    return koa_k_bn_act_fin(at(ws, u.y), &fa, res, ud ? at(ws, ud->y) : nullptr, ud ? &fb : nullptr, out, out_bf, u.rows_out,
+                            u.cout, 1, (double)u.rows_out, training, st);
+  }
+  KOA_TRY(bn_finalize(u, pv, ws, training, st));
+  if (ud) KOA_TRY(bn_finalize(*ud, pv, ws, training, st));
+  return koa_k_bn_act(at(ws, u.y), bn_slot(ws, u, S_SCALE), bn_slot(ws, u, S_SHIFT), res, ud ? at(ws, ud->y) : nullptr,
+                      ud ? bn_slot(ws, *ud, S_SCALE) : nullptr, ud ? bn_slot(ws, *ud, S_SHIFT) : nullptr, out, out_bf,
+                      u.rows_out, u.cout, 1, st);
 }
 
 }  // namespace
@@ -352,8 +369,7 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
     }
     KOA_TRY(koa_gemm_launch(at(ws, p.a_stem), at(ws, p.wstem), (int)us.rows_out, 64, 64, &ep, st));
   }
-  KOA_TRY(bn_finalize(us, pv, ws, training, st));
-  KOA_TRY(bn_relu(us, ws, p.a0, 0, st));
+  KOA_TRY(bn_apply(us, nullptr, pv, ws, nullptr, at(ws, p.a0), nullptr, training, st));
   KOA_TRY(koa_k_maxpool_fwd(at(ws, p.a0), at(ws, p.p0), p.p0_bf ? at(ws, p.p0_bf) : nullptr, at(ws, p.idx0), p.n_img, us.hout,
                             us.wout, 64, st));
 
@@ -363,28 +379,22 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
     const Unit& u2 = p.units[b.u2];
     const void* x = at(ws, b.in);
     KOA_TRY(conv_forward(p, u1, x, ws, training, st));
-    KOA_TRY(bn_finalize(u1, pv, ws, training, st));
-    KOA_TRY(bn_relu(u1, ws, b.a1, b.a1_bf, st));
+    KOA_TRY(bn_apply(u1, nullptr, pv, ws, nullptr, at(ws, b.a1), b.a1_bf ? at(ws, b.a1_bf) : nullptr, training, st));
     KOA_TRY(conv_forward(p, u2, at(ws, b.a1), ws, training, st));
-    KOA_TRY(bn_finalize(u2, pv, ws, training, st));
     const Unit* last = &u2;
     if (b.kind == 0) {
       const Unit& u3 = p.units[b.u3];
-      KOA_TRY(bn_relu(u2, ws, b.a2, b.a2_bf, st));
+      KOA_TRY(bn_apply(u2, nullptr, pv, ws, nullptr, at(ws, b.a2), b.a2_bf ? at(ws, b.a2_bf) : nullptr, training, st));
       KOA_TRY(conv_forward(p, u3, at(ws, b.a2), ws, training, st));
-      KOA_TRY(bn_finalize(u3, pv, ws, training, st));
       last = &u3;
     }
+    void* out_bf = b.out_bf ? at(ws, b.out_bf) : nullptr;
     if (b.ud >= 0) {
       const Unit& ud = p.units[b.ud];
       KOA_TRY(conv_forward(p, ud, x, ws, training, st));
-      KOA_TRY(bn_finalize(ud, pv, ws, training, st));
-      KOA_TRY(koa_k_bn_act(at(ws, last->y), bn_slot(ws, *last, S_SCALE), bn_slot(ws, *last, S_SHIFT), nullptr,
-                           at(ws, ud.y), bn_slot(ws, ud, S_SCALE), bn_slot(ws, ud, S_SHIFT), at(ws, b.out),
-                           b.out_bf ? at(ws, b.out_bf) : nullptr, last->rows_out, last->cout, 1, st));
+      KOA_TRY(bn_apply(*last, &ud, pv, ws, nullptr, at(ws, b.out), out_bf, training, st));
     } else {
-      KOA_TRY(koa_k_bn_act(at(ws, last->y), bn_slot(ws, *last, S_SCALE), bn_slot(ws, *last, S_SHIFT), x, nullptr, nullptr,
-                           nullptr, at(ws, b.out), b.out_bf ? at(ws, b.out_bf) : nullptr, last->rows_out, last->cout, 1, st));
+      KOA_TRY(bn_apply(*last, nullptr, pv, ws, x, at(ws, b.out), out_bf, training, st));
     }
   }
   // ---- head: global average pool (with_gap) or the raw NHWC map as tokens -------------------------
@@ -407,6 +417,18 @@ int bn_backward(const Unit& u, const Unit* u_b, const ParamView& pv, void* const
                                 u_b ? at(ws, u_b->y) : nullptr, u_b ? bn_slot(ws, *u_b, S_MEAN) : nullptr,
                                 u_b ? bn_slot(ws, *u_b, S_INVSTD) : nullptr, bn_slot(ws, u, S_SDZ), bn_slot(ws, u, S_SDZX),
                                 u_b ? bn_slot(ws, *u_b, S_SDZX) : nullptr, u.rows_out, u.cout, st));
+  if (koa_k_bn_fused_ok(u.cout)) {  // finalize (dgamma / dbeta + coefficients) inside the apply kernel
+    const KoaBnBwdFin fa{bn_slot(ws, u, S_SDZ), bn_slot(ws, u, S_SDZX), pv.gamma(u), bn_slot(ws, u, S_MEAN),
+                         bn_slot(ws, u, S_INVSTD), (float*)grads[u.idx * 3 + 1], (float*)grads[u.idx * 3 + 2],
+                         bn_slot(ws, u, S_K0), bn_slot(ws, u, S_K1), bn_slot(ws, u, S_K2)};
+    KoaBnBwdFin fb{};
+    if (u_b)
+      fb = KoaBnBwdFin{bn_slot(ws, u, S_SDZ), bn_slot(ws, *u_b, S_SDZX), pv.gamma(*u_b), bn_slot(ws, *u_b, S_MEAN),
+                       bn_slot(ws, *u_b, S_INVSTD), (float*)grads[u_b->idx * 3 + 1], (float*)grads[u_b->idx * 3 + 2],
+                       bn_slot(ws, *u_b, S_K0), bn_slot(ws, *u_b, S_K1), bn_slot(ws, *u_b, S_K2)};
+    return koa_k_bn_bwd_apply_fin(dout, act_mask, at(ws, u.y), &fa, dy, u_b ? at(ws, u_b->y) : nullptr, u_b ? &fb : nullptr,
+                                  dy_b, u.rows_out, u.cout, (double)u.rows_out, training, st);
+  }
   KOA_TRY(koa_k_bn_bwd_finalize(bn_slot(ws, u, S_SDZ), bn_slot(ws, u, S_SDZX), pv.gamma(u), bn_slot(ws, u, S_MEAN),
                                 bn_slot(ws, u, S_INVSTD), (float*)grads[u.idx * 3 + 1], (float*)grads[u.idx * 3 + 2],
                                 bn_slot(ws, u, S_K0), bn_slot(ws, u, S_K1), bn_slot(ws, u, S_K2), u.cout,

@@ -33,6 +33,26 @@ int koa_k_col_stats(const void* y, float* sum, float* sumsq, long long rows, int
 int koa_k_bn_act(const void* y, const float* scale, const float* shift, const void* res, const void* y2,
                  const float* scale2, const float* shift2, void* out, void* out_bf16, long long rows, int c, int relu,
                  cudaStream_t st);
+// Finalize-in-consumer forms (one launch instead of finalize + apply; C/8 must divide 256, see koa_k_bn_fused_ok):
+// the apply kernels derive their per-channel coefficients from the raw sums themselves; the threads that own each
+// channel group first also write what later kernels read (mean, invstd, scale, shift / k0..k2), update the running
+// statistics (forward, training) and accumulate dgamma / dbeta (backward).
+struct KoaBnFwdFin {
+  const float* sum; const float* sumsq; const float* gamma; const float* beta;
+  float* run_mean; float* run_var; float* scale; float* shift; float* mean; float* invstd;
+};
+struct KoaBnBwdFin {
+  const float* sum_dz; const float* sum_dzx; const float* gamma; const float* mean; const float* invstd;
+  float* dgamma; float* dbeta; float* k0; float* k1; float* k2;
+};
+int koa_k_bn_fused_ok(int c);
+// out = act(bn_a(y) [+ res | + bn_b(y2)]); b may be NULL
+int koa_k_bn_act_fin(const void* y, const KoaBnFwdFin* a, const void* res, const void* y2, const KoaBnFwdFin* b, void* out,
+                     void* out_bf16, long long rows, int c, int relu, double count, int training, cudaStream_t st);
+// dy = BatchNorm-backward of a (and dy2 of b, sharing dz = dout * (act > 0)); b may be NULL
+int koa_k_bn_bwd_apply_fin(const void* dout, const void* act, const void* y, const KoaBnBwdFin* a, void* dy, const void* y2,
+                           const KoaBnBwdFin* b, void* dy2, long long rows, int c, double count, int training,
+                           cudaStream_t st);
 int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const float* mean, const float* invstd,
                         const void* y2, const float* mean2, const float* invstd2, float* sum_dz, float* sum_dzx,
                         float* sum_dzx2, long long rows, int c, cudaStream_t st);
