@@ -309,32 +309,35 @@ __global__ void bn_act_kernel(const bf16* __restrict__ y, const float* __restric
   }
 }
 
-// Coefficients of channels g*8 .. g*8+7 straight from the raw sums (the arithmetic of bn_finalize_kernel); `writer`
-// threads (one per channel group in the grid) also publish them and update the running statistics.
+// Coefficients of channels g*8 .. g*8+7 straight from the raw sums. fp32 arithmetic (the sums are fp32 atomics; fp64 here
+// buys nothing and costs 5 % of the step when 600 k threads each do it); `writer` threads (one per channel group in the
+// grid) also publish them and update the running statistics.
 __device__ __forceinline__ void bn_fwd_coef8(const KoaBnFwdFin& f, int g, double count, int training, bool writer,
                                              float (&sc)[8], float (&sh)[8]) {
+  const float inv_n = (float)(1.0 / count);
+  const float unbias = count > 1.0 ? (float)(count / (count - 1.0)) : 1.0f;
+  float su[8], sq[8], ga[8], be[8];
+  load8f(f.gamma + g * 8, ga); load8f(f.beta + g * 8, be);
+  if (training) { load8f(f.sum + g * 8, su); load8f(f.sumsq + g * 8, sq); }
+  else { load8f(f.run_mean + g * 8, su); load8f(f.run_var + g * 8, sq); }
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     const int i = g * 8 + u;
     float mean, var;
     if (training) {
-      const double m = (double)f.sum[i] / count;
-      double v = (double)f.sumsq[i] / count - m * m;
-      if (v < 0.0) v = 0.0;
-      mean = (float)m;
-      var = (float)v;
+      mean = su[u] * inv_n;
+      var = fmaxf(fmaf(-mean, mean, sq[u] * inv_n), 0.0f);
       if (writer) {
-        const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
         f.run_mean[i] = (1.0f - 0.1f) * f.run_mean[i] + 0.1f * mean;
-        f.run_var[i] = (1.0f - 0.1f) * f.run_var[i] + 0.1f * (float)unbiased;
+        f.run_var[i] = (1.0f - 0.1f) * f.run_var[i] + 0.1f * (var * unbias);
       }
     } else {
-      mean = f.run_mean[i];
-      var = f.run_var[i];
+      mean = su[u];
+      var = sq[u];
     }
     const float invstd = rsqrtf(var + 1e-5f);
-    sc[u] = f.gamma[i] * invstd;
-    sh[u] = f.beta[i] - mean * sc[u];
+    sc[u] = ga[u] * invstd;
+    sh[u] = be[u] - mean * sc[u];
     if (writer) {
       f.scale[i] = sc[u]; f.shift[i] = sh[u]; f.mean[i] = mean; f.invstd[i] = invstd;
     }
@@ -342,25 +345,27 @@ __device__ __forceinline__ void bn_fwd_coef8(const KoaBnFwdFin& f, int g, double
 }
 __device__ __forceinline__ void bn_bwd_coef8(const KoaBnBwdFin& f, const float* sum_dz, int g, double count, int training,
                                              bool writer, float (&k0)[8], float (&k1)[8], float (&k2)[8]) {
+  const float inv_n = (float)(1.0 / count);
+  float ga[8], is[8], mu[8], sdz[8], sdzx[8];
+  load8f(f.gamma + g * 8, ga); load8f(f.invstd + g * 8, is); load8f(f.mean + g * 8, mu);
+  load8f(sum_dz + g * 8, sdz); load8f(f.sum_dzx + g * 8, sdzx);
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
     const int i = g * 8 + u;
-    const float gm = f.gamma[i], is = f.invstd[i], mu = f.mean[i];
-    const float sdz = sum_dz[i], sdzx = f.sum_dzx[i];
-    const float s = gm * is;
+    const float s = ga[u] * is[u];
     k0[u] = s;
     if (training) {
-      const float a = (float)((double)sdz / count);
-      const float b = (float)((double)sdzx / count);
-      k2[u] = s * b * is;
-      k1[u] = s * a - s * b * is * mu;
+      const float a = sdz[u] * inv_n;
+      const float b = sdzx[u] * inv_n;
+      k2[u] = s * b * is[u];
+      k1[u] = s * a - s * b * is[u] * mu[u];
     } else {
       k1[u] = 0.0f;
       k2[u] = 0.0f;
     }
     if (writer) {
-      if (f.dgamma != nullptr) f.dgamma[i] += sdzx;
-      if (f.dbeta != nullptr) f.dbeta[i] += sdz;
+      if (f.dgamma != nullptr) f.dgamma[i] += sdzx[u];
+      if (f.dbeta != nullptr) f.dbeta[i] += sdz[u];
       f.k0[i] = k0[u]; f.k1[i] = k1[u]; f.k2[i] = k2[u];
     }
   }
