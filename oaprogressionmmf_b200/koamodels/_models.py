@@ -53,6 +53,50 @@ def _apply_drop2d(drop, tokens):
     return drop(tokens.reshape(b * s, c, 1, 1)).reshape(b, s, c)
 
 
+_BRANCH_STREAMS = {}
+_BRANCH_STREAMS_ON = [None]  # None: follow the environment (KOA_BRANCH_STREAMS, default on)
+
+
+def set_branch_streams(on):
+    """Run the modality branches of the fusion models on their own CUDA streams (default) or one after the other on
+    the current stream (``False``; what a per-kernel timing pass wants). ``None`` restores the environment default."""
+    _BRANCH_STREAMS_ON[0] = on
+
+
+def _branch_streams_on():
+    import os
+
+    if _BRANCH_STREAMS_ON[0] is not None:
+        return bool(_BRANCH_STREAMS_ON[0])
+    return os.environ.get("KOA_BRANCH_STREAMS", "1") != "0"
+
+
+def _run_branches(fns):
+    """Run the independent modality branches (extractor [+ per-sequence transformer]) of a fusion model, each on its
+    own CUDA stream: their kernels are launched back to back by one host thread, but the small ones (transformer
+    GEMMs at a few hundred rows, layer-4 convolutions, pooling) no longer leave SMs idle while the next branch waits.
+    Autograd replays each branch's backward on the branch's stream. The reference computes the branches one after
+    the other on one stream (``_xrNmrMcP.py:209-236``); the results are the same."""
+    if len(fns) < 2 or not _branch_streams_on() or not torch.cuda.is_available():
+        return [f() for f in fns]
+    main = torch.cuda.current_stream()
+    key = (main.device.index, len(fns))
+    if key not in _BRANCH_STREAMS:
+        _BRANCH_STREAMS[key] = [torch.cuda.Stream(device=main.device) for _ in fns]
+        # parameters shared by runs with and without branch streams keep their AccumulateGrad node: intentional
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    outs = []
+    for f, st in zip(fns, _BRANCH_STREAMS[key]):
+        st.wait_stream(main)
+        with torch.cuda.stream(st):
+            outs.append(f())
+    for o, st in zip(outs, _BRANCH_STREAMS[key]):
+        main.wait_stream(st)
+        o.record_stream(main)  # consumed on the main stream: keep the allocator from recycling it early
+    return outs
+
+
 def _scaled(shape, scale):
     return [round(s * d) for s, d in zip(shape, scale)]
 
@@ -272,9 +316,9 @@ class XR1MR2C1CnnTrf(_XRMRBase):
         self._finish(path_weights)
 
     def forward(self, input0, input1, input2, input3):
-        t0 = self._xr_tokens(input0)
-        _, s1, _ = self._agg_1.run(self._mr_tokens(1, input1), compute_head=False)
-        _, s2, _ = self._agg_2.run(self._mr_tokens(2, input2), compute_head=False)
+        s1, s2, t0 = _run_branches([lambda: self._agg_1.run(self._mr_tokens(1, input1), compute_head=False)[1],
+                                    lambda: self._agg_2.run(self._mr_tokens(2, input2), compute_head=False)[1],
+                                    lambda: self._xr_tokens(input0)])
         t3 = self._fe3(input3)
         out, _, _ = self._agg_final.run(torch.cat([t0, s1, s2, t3], dim=1), compute_head=True)
         return _output(self.config, out.flatten(1))
@@ -321,10 +365,12 @@ class XR1MR3C1CnnTrf(_XRMRBase):
         self._finish(path_weights)
 
     def forward(self, input0, input1, input2, input3, input4):
-        parts = [self._xr_tokens(input0)]
-        for i, vol in enumerate((input1, input2, input3), start=1):
-            parts.append(getattr(self, f"_agg_{i}").run(self._mr_tokens(i, vol), compute_head=False)[1])
-        parts.append(self._fe4(input4))
+        def mr(i, vol):
+            return lambda: getattr(self, f"_agg_{i}").run(self._mr_tokens(i, vol), compute_head=False)[1]
+
+        # the largest branch (DESS, 64 slices) first: the others fill in around it
+        s1, s2, s3, t0 = _run_branches([mr(1, input1), mr(2, input2), mr(3, input3), lambda: self._xr_tokens(input0)])
+        parts = [t0, s1, s2, s3, self._fe4(input4)]
         out, _, _ = self._agg_final.run(torch.cat(parts, dim=1), compute_head=True)
         return _output(self.config, out.flatten(1))
 

@@ -924,3 +924,40 @@ def test_full_size_model_step_properties(cuda):
         if p.grad is not None:
             assert torch.isfinite(p.grad).all(), k
     assert int(model._fe1[1].num_batches_tracked) == 1
+
+
+def test_branch_streams_do_not_change_the_results(cuda, golden_dir):
+    """The fusion models run their modality branches on concurrent CUDA streams (koamodels/_models.py::_run_branches);
+    the reference runs them one after the other (_xrNmrMcP.py:209-236). Eval logits are bit-identical either way, a
+    train step gives the same loss and gradients up to the run-to-run noise of the statistics atomics."""
+    from oaprogressionmmf_b200.koamodels import set_branch_streams
+    from oaprogressionmmf_b200.losses import FocalLoss
+
+    case = [c for c in GOLDEN if c.startswith("XR1MR3C1CnnTrf")][0]
+    gold, cfg, model, inputs, target = _golden_case(case, golden_dir, cuda, pos_scale=0.02)
+    try:
+        res = {}
+        for on in (False, True):
+            set_branch_streams(on)
+            model.eval()
+            with torch.no_grad():
+                lg = model(*inputs)["main"].clone()
+            res[on] = lg
+        assert torch.equal(res[False], res[True])
+        # train mode on concurrent streams: finite, gradients everywhere the serial run has them, several repeats
+        # (a missing cross-stream dependency shows up as NaN / garbage, not as a small deviation)
+        set_branch_streams(True)
+        model.train()
+        for _ in range(3):
+            model.zero_grad(set_to_none=True)
+            loss = FocalLoss(gamma=2)(model(*inputs)["main"], target)
+            loss.backward()
+            torch.cuda.synchronize()
+            assert bool(torch.isfinite(loss))
+            assert abs(float(loss) - gold["train_loss"]) < 0.4 * max(gold["train_loss"], 0.1)
+            for k, p in model.named_parameters():
+                if gold["grads"][k] is not None:
+                    assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+    finally:
+        set_branch_streams(None)
+    assert _lib.debug_flag() == 0
