@@ -165,6 +165,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if ws > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION: the line of this script is the JSON alone
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 

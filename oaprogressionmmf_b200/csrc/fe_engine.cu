@@ -9,6 +9,8 @@
 // Activations are NHWC bf16; everything needed by backward stays in the caller-provided workspace whose
 // layout is a pure function of the descriptor (koa_fe_workspace_bytes / koa_fe_debug_offset).
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/koa_b200.h"
@@ -503,6 +505,89 @@ bool fuse_bn_bwd_stats() {
   return v != 0;
 }
 
+// ---- weight gradients on a side stream ------------------------------------------------------------------------------
+// Nothing downstream in the backward chain reads a weight gradient, so the wgrad GEMMs (compute-bound, 17 % of a step)
+// CAN run on a second stream next to the BatchNorm-backward passes (HBM-bound) of the main chain. OFF by default
+// (KOA_WGRAD_STREAM=1 enables it): measured on B200 it is neutral when the modality branches already run on concurrent
+// streams (165.0 vs 164.3 knees/s) and a loss with serial branches (123.8 vs 107.1 ms per step: the wgrad CTAs and the
+// persistent data-gradient CTAs evict each other's shared memory residency instead of overlapping). Dependencies: a wgrad
+// starts after its dy is ready (event on the main stream) and the main chain waits for it before it overwrites the dy
+// scratch buffer the wgrad reads (one event per scratch buffer).
+struct WgradSide {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ready = nullptr, all_done = nullptr;
+  cudaEvent_t done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool pending[5] = {false, false, false, false, false};
+  cudaStream_t main = nullptr;
+  bool on = false;
+
+  // the main chain is about to overwrite scratch buffer k
+  int before_write(int k) {
+    if (on && pending[k]) {
+      KOA_CHECK_CUDA(cudaStreamWaitEvent(main, done[k], 0));
+      pending[k] = false;
+    }
+    return 0;
+  }
+  // stream for a wgrad whose operands the main chain has just produced
+  int begin(cudaStream_t* out) {
+    *out = main;
+    if (!on) return 0;
+    KOA_CHECK_CUDA(cudaEventRecord(ready, main));
+    KOA_CHECK_CUDA(cudaStreamWaitEvent(side, ready, 0));
+    *out = side;
+    return 0;
+  }
+  // the wgrad just launched reads scratch buffer k
+  int reads(int k) {
+    if (!on) return 0;
+    KOA_CHECK_CUDA(cudaEventRecord(done[k], side));
+    pending[k] = true;
+    return 0;
+  }
+  int join() {
+    if (!on) return 0;
+    KOA_CHECK_CUDA(cudaEventRecord(all_done, side));
+    KOA_CHECK_CUDA(cudaStreamWaitEvent(main, all_done, 0));
+    for (bool& p : pending) p = false;
+    return 0;
+  }
+};
+
+bool wgrad_side_enabled() {
+  static const int v = [] {
+    const char* e = getenv("KOA_WGRAD_STREAM");
+    return e == nullptr ? 0 : atoi(e);
+  }();
+  return v != 0;
+}
+
+// one side stream (+ events) per calling stream, created on first use and kept for the life of the process
+int get_wgrad_side(cudaStream_t main, WgradSide* out) {
+  static std::mutex mu;
+  static std::map<cudaStream_t, WgradSide> pool;
+  *out = WgradSide{};
+  out->main = main;
+  if (!wgrad_side_enabled()) return 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(main, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return 0;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = pool.find(main);
+  if (it == pool.end()) {
+    WgradSide w;
+    w.main = main;
+    KOA_CHECK_CUDA(cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking));
+    KOA_CHECK_CUDA(cudaEventCreateWithFlags(&w.ready, cudaEventDisableTiming));
+    KOA_CHECK_CUDA(cudaEventCreateWithFlags(&w.all_done, cudaEventDisableTiming));
+    for (auto& e : w.done) KOA_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    it = pool.emplace(main, w).first;
+  }
+  *out = it->second;
+  out->on = true;
+  for (bool& p : out->pending) p = false;
+  return 0;
+}
+
 }  // namespace
 
 // Backward. The gradient handed from block to block is G_b = dL/d(pre-ReLU residual sum of block b), i.e. the
@@ -523,6 +608,9 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
   const int hw = p.out_h * p.out_w;
   const bool fuse = fuse_bn_bwd_stats();
   KOA_CHECK_CUDA(cudaMemsetAsync(at(ws, p.bstat_begin), 0, p.bstat_end - p.bstat_begin, st));
+  WgradSide side;
+  KOA_TRY(get_wgrad_side(st, &side));
+  cudaStream_t sw = st;  // stream of the next weight-gradient GEMM
   int cur = 0;  // p.g[cur] holds G of the current block
   {
     const Block& lb = p.blocks.back();
@@ -543,30 +631,43 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     void* x = at(ws, b.in);
     void* dy_last = at(ws, p.t[0]);
     void* dy_down = at(ws, p.t[1]);
+    KOA_TRY(side.before_write(0));
+    KOA_TRY(side.before_write(1));
     KOA_TRY(bn_backward(last, ud, pv, grads, ws, g_out, nullptr, dy_last, ud ? dy_down : nullptr, training, g_stats_done, st));
     void* d_a1 = at(ws, p.t[3]);
     if (u3) {
-      KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2_bf), dy_last, grads, ws, st));
+      KOA_TRY(side.begin(&sw));
+      KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2_bf), dy_last, grads, ws, sw));
+      KOA_TRY(side.reads(0));
       void* d_a2 = at(ws, p.t[2]);
       koa_epilogue_t ep{};
       ep.out = d_a2;
       gate_and_stats(ep, ws, b.a2, &u2, fuse);  // dz2 = dgrad * (a2 > 0)
+      KOA_TRY(side.before_write(2));
       KOA_TRY(conv_dgrad(p, *u3, dy_last, ws, &ep, nullptr, st));
       KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, nullptr, d_a2, nullptr, training, fuse, st));  // in place -> dy2
-      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf), d_a2, grads, ws, st));
+      KOA_TRY(side.begin(&sw));
+      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf), d_a2, grads, ws, sw));
+      KOA_TRY(side.reads(2));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
       gate_and_stats(ep2, ws, b.a1, &u1, fuse);
+      KOA_TRY(side.before_write(3));
       KOA_TRY(conv_dgrad(p, u2, d_a2, ws, &ep2, at(ws, p.t[4]), st));
     } else {
-      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf), dy_last, grads, ws, st));
+      KOA_TRY(side.begin(&sw));
+      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf), dy_last, grads, ws, sw));
+      KOA_TRY(side.reads(0));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
       gate_and_stats(ep2, ws, b.a1, &u1, fuse);
+      KOA_TRY(side.before_write(3));
       KOA_TRY(conv_dgrad(p, u2, dy_last, ws, &ep2, at(ws, p.t[4]), st));
     }
     KOA_TRY(bn_backward(u1, nullptr, pv, grads, ws, d_a1, nullptr, d_a1, nullptr, training, fuse, st));  // in place -> dy1
-    KOA_TRY(conv_wgrad(p, u1, at(ws, b.in_bf), d_a1, grads, ws, st));
+    KOA_TRY(side.begin(&sw));
+    KOA_TRY(conv_wgrad(p, u1, at(ws, b.in_bf), d_a1, grads, ws, sw));
+    KOA_TRY(side.reads(3));
     // G of the previous block = (dgrad(conv1) + identity path) * (x > 0); x is that block's output (or the pooled
     // stem activation, where the gate is a no-op for the gradient that survives the stem's own ReLU mask).
     const Block* prev = bi > 0 ? &p.blocks[bi - 1] : nullptr;
@@ -580,7 +681,9 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       gate_and_stats(ep, ws, b.in, prev_last, fuse_prev);
       KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
     } else {
-      KOA_TRY(conv_wgrad(p, *ud, at(ws, b.in_bf), dy_down, grads, ws, st));
+      KOA_TRY(side.begin(&sw));
+      KOA_TRY(conv_wgrad(p, *ud, at(ws, b.in_bf), dy_down, grads, ws, sw));
+      KOA_TRY(side.reads(1));
       if (ud->stride == 1) {
         koa_epilogue_t ep{};
         ep.out = g_in;
@@ -597,6 +700,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
         KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
         koa_epilogue_t ep2{};
         ep2.out = at(ws, p.t[2]);
+        KOA_TRY(side.before_write(2));
         KOA_TRY(conv_dgrad(p, *ud, dy_down, ws, &ep2, nullptr, st));
         KOA_TRY(koa_k_scatter_add2(at(ws, p.t[2]), x, g_in, p.n_img, ud->hin, ud->win, ud->cin, ud->hout, ud->wout, st));
       }
@@ -607,6 +711,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
   // ---- stem -----------------------------------------------------------------------------------------
   const Unit& us = p.units[0];
   void* d_a0 = at(ws, p.t[0]);
+  KOA_TRY(side.before_write(0));
   KOA_TRY(koa_k_maxpool_bwd(at(ws, p.g[cur]), at(ws, p.idx0), d_a0, p.n_img, us.hout, us.wout, 64, st));
   KOA_TRY(bn_backward(us, nullptr, pv, grads, ws, d_a0, at(ws, p.a0), d_a0, nullptr, training, false, st));
   if (grads[0] != nullptr) {
@@ -617,5 +722,6 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64, 0, st));
     KOA_TRY(koa_k_stem_unfold_dwb((const float*)at(ws, p.dwstem), (float*)grads[0], st));
   }
+  KOA_TRY(side.join());  // every weight gradient is complete in the order of the caller's stream
   return 0;
 }
