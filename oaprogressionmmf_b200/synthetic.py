@@ -99,5 +99,37 @@ class SyntheticKneeLoader:
         return b
 
 
+class DevicePrefetcher:
+    """Host batches -> device batches with the copy of batch i+1 issued on a copy stream while step i computes (what
+    the reference's ``DataLoader(pin_memory=True)`` + ``.to(device, non_blocking=True)`` loop amounts to,
+    ``koafusion/run/train_prog_fus.py:136-140``). Every batch is copied from pinned host memory, none is reused."""
+
+    def __init__(self, loader, device):
+        self.loader = iter(loader)
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.next = None
+        self._issue()
+
+    def _issue(self):
+        ins_h, tgt_h = next(self.loader)
+        with torch.cuda.stream(self.copy_stream):
+            ins = [t.to(self.device, non_blocking=True) for t in ins_h]
+            tgt = tgt_h.to(self.device, non_blocking=True)
+        self.next = (ins, tgt)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.copy_stream)
+        ins, tgt = self.next
+        for t in ins + [tgt]:
+            t.record_stream(cur)  # allocated on the copy stream, consumed on the compute stream
+        self._issue()
+        return ins, tgt
+
+
 def input_bytes(ins: Sequence[torch.Tensor], target: torch.Tensor) -> int:
     return sum(t.numel() * t.element_size() for t in ins) + target.numel() * target.element_size()
