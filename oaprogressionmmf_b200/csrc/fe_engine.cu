@@ -25,6 +25,22 @@
   } while (0)
 
 namespace {
+// KOA_WGRAD_XCVT=1: the weight gradients read the fp16 forward activations and convert them to bf16 in shared memory
+// (gemm_wgrad_kernel XCVT); the forward pass then writes no bf16 copies (2 of the 6 bytes per element of the
+// BatchNorm-apply pass, a quarter of the activation workspace). Measured on B200 the step time is the same (165.4 vs
+// 165.8 knees/s): the conversion doubles the shared-memory traffic of a kernel whose 128 x 128 tiles are already
+// shared-memory bound (494 -> 425 TFLOP/s), which costs what the smaller BatchNorm-apply pass saves. Default: keep the
+// copies; turn the conversion on when the 25 % of workspace matter (larger batches).
+bool wgrad_converts_x() {
+  static const int v = [] {
+    const char* e = getenv("KOA_WGRAD_XCVT");
+    return e == nullptr ? 0 : atoi(e);
+  }();
+  return v != 0;
+}
+}  // namespace
+
+namespace {
 
 struct Unit {
   int cin, cout, k, stride, pad, groups;
@@ -145,8 +161,11 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
   p.a_stem = ws.take((size_t)us.rows_out * 64 * 2);  // im2col operand of the stem GEMM (kept for its weight gradient)
   p.a0 = ws.take((size_t)us.rows_out * 64 * 2);
   const bool bw = d->need_backward != 0;
+  // bf16 copies of the activations (operands of the weight gradients) only when the weight-gradient kernels do not
+  // convert the fp16 activations themselves (KOA_WGRAD_XCVT=0)
+  const bool bwc = bw && !wgrad_converts_x();
   p.p0 = ws.take((size_t)n * ph * pw * 64 * 2);
-  p.p0_bf = bw ? ws.take((size_t)n * ph * pw * 64 * 2) : 0;
+  p.p0_bf = bwc ? ws.take((size_t)n * ph * pw * 64 * 2) : 0;
   p.idx0 = ws.take((size_t)n * ph * pw * 64);
   size_t prev = p.p0, prev_bf = p.p0_bf;
   size_t max_act = (size_t)us.rows_out * 64;
@@ -156,18 +175,18 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
     b.in = prev;
     b.in_bf = prev_bf;
     b.a1 = ws.take((size_t)u1.rows_out * u1.cout * 2);
-    b.a1_bf = bw ? ws.take((size_t)u1.rows_out * u1.cout * 2) : 0;
+    b.a1_bf = bwc ? ws.take((size_t)u1.rows_out * u1.cout * 2) : 0;
     if (b.kind == 0) {
       b.a2 = ws.take((size_t)u2.rows_out * u2.cout * 2);
-      b.a2_bf = bw ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
+      b.a2_bf = bwc ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
       const Unit& u3 = p.units[b.u3];
       b.out = ws.take((size_t)u3.rows_out * u3.cout * 2);
-      b.out_bf = bw ? ws.take((size_t)u3.rows_out * u3.cout * 2) : 0;
+      b.out_bf = bwc ? ws.take((size_t)u3.rows_out * u3.cout * 2) : 0;
       max_act = std::max(max_act, (size_t)u3.rows_out * u3.cout);
     } else {
       b.a2 = 0; b.a2_bf = 0;
       b.out = ws.take((size_t)u2.rows_out * u2.cout * 2);
-      b.out_bf = bw ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
+      b.out_bf = bwc ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
     }
     max_act = std::max(max_act, (size_t)u1.rows_in * u1.cin);
     max_act = std::max(max_act, (size_t)u1.rows_in * u1.cout);  // zero-inserted / pre-stride tensors
@@ -324,12 +343,12 @@ extern "C" int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, 
     const Unit& last = p.units[b.kind == 0 ? b.u3 : b.u2];
     const Unit& u1 = p.units[b.u1];
     const Unit& u2 = p.units[b.u2];
-    if (what == 8) { *offset = b.out_bf; *bytes = (size_t)last.rows_out * last.cout * 2; }
-    if (what == 9) { *offset = b.a1_bf; *bytes = (size_t)u1.rows_out * u1.cout * 2; }
-    if (what == 10) { *offset = b.a2_bf; *bytes = (size_t)u2.rows_out * u2.cout * 2; }
+    if (what == 8) { *offset = b.out_bf; *bytes = b.out_bf ? (size_t)last.rows_out * last.cout * 2 : 0; }
+    if (what == 9) { *offset = b.a1_bf; *bytes = b.a1_bf ? (size_t)u1.rows_out * u1.cout * 2 : 0; }
+    if (what == 10) { *offset = b.a2_bf; *bytes = b.a2_bf ? (size_t)u2.rows_out * u2.cout * 2 : 0; }
     return 0;
   }
-  if (what == 11) { *offset = p.p0_bf; *bytes = (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64 * 2; return 0; }
+  if (what == 11) { *offset = p.p0_bf; *bytes = !p.p0_bf ? 0 : (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64 * 2; return 0; }
   if (what == 4) { *offset = p.a0; *bytes = (size_t)p.units[0].rows_out * 64 * 2; return 0; }
   if (what == 5) { *offset = p.p0; *bytes = (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64 * 2; return 0; }
   if (what == 7) { *offset = p.idx0; *bytes = (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64; return 0; }
@@ -451,16 +470,17 @@ int bn_backward(const Unit& u, const Unit* u_b, const ParamView& pv, void* const
 int conv_wgrad(const Plan& p, const Unit& u, const void* x, const void* dy, void* const* grads, void* ws, cudaStream_t st) {
   float* gw = (float*)grads[u.idx * 3 + 0];
   if (gw == nullptr) return 0;
-  if (u.k == 1 && u.stride == 1) return koa_gemm_wgrad_launch(dy, x, gw, (int)u.rows_out, u.cout, u.cin, 0, st);
-  if (u.k == 1) return koa_conv_wgrad_launch(dy, x, gw, p.n_img, u.hin, u.win, u.cin, u.cout, 1, 1, u.stride, 0, 0, st);
+  const int xf = wgrad_converts_x() ? 2 : 0;  // 2: x is the fp16 activation, converted inside the kernel
+  if (u.k == 1 && u.stride == 1) return koa_gemm_wgrad_launch(dy, x, gw, (int)u.rows_out, u.cout, u.cin, xf, st);
+  if (u.k == 1) return koa_conv_wgrad_launch(dy, x, gw, p.n_img, u.hin, u.win, u.cin, u.cout, 1, 1, u.stride, 0, xf, st);
   float* scratch = (float*)at(ws, u.dw_scratch);
   if (u.groups > 1) {
     KOA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)u.cout * 9 * 64 * 4, st));
-    KOA_TRY(koa_conv_grouped_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.stride, 0, st));
+    KOA_TRY(koa_conv_grouped_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.stride, xf, st));
     return koa_k_unpack_grouped_dw(scratch, gw, u.cout, u.cin / u.groups, st);
   }
   KOA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)u.cout * u.k * u.k * u.cin * 4, st));
-  KOA_TRY(koa_conv_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, 0, st));
+  KOA_TRY(koa_conv_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, xf, st));
   return koa_k_unpack_conv_dw(scratch, gw, u.cout, u.cin, u.k, u.k, st);
 }
 
@@ -637,7 +657,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     void* d_a1 = at(ws, p.t[3]);
     if (u3) {
       KOA_TRY(side.begin(&sw));
-      KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2_bf), dy_last, grads, ws, sw));
+      KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2_bf ? b.a2_bf : b.a2), dy_last, grads, ws, sw));
       KOA_TRY(side.reads(0));
       void* d_a2 = at(ws, p.t[2]);
       koa_epilogue_t ep{};
@@ -647,7 +667,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       KOA_TRY(conv_dgrad(p, *u3, dy_last, ws, &ep, nullptr, st));
       KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, nullptr, d_a2, nullptr, training, fuse, st));  // in place -> dy2
       KOA_TRY(side.begin(&sw));
-      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf), d_a2, grads, ws, sw));
+      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf ? b.a1_bf : b.a1), d_a2, grads, ws, sw));
       KOA_TRY(side.reads(2));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
@@ -656,7 +676,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       KOA_TRY(conv_dgrad(p, u2, d_a2, ws, &ep2, at(ws, p.t[4]), st));
     } else {
       KOA_TRY(side.begin(&sw));
-      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf), dy_last, grads, ws, sw));
+      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf ? b.a1_bf : b.a1), dy_last, grads, ws, sw));
       KOA_TRY(side.reads(0));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
@@ -666,7 +686,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     }
     KOA_TRY(bn_backward(u1, nullptr, pv, grads, ws, d_a1, nullptr, d_a1, nullptr, training, fuse, st));  // in place -> dy1
     KOA_TRY(side.begin(&sw));
-    KOA_TRY(conv_wgrad(p, u1, at(ws, b.in_bf), d_a1, grads, ws, sw));
+    KOA_TRY(conv_wgrad(p, u1, at(ws, b.in_bf ? b.in_bf : b.in), d_a1, grads, ws, sw));
     KOA_TRY(side.reads(3));
     // G of the previous block = (dgrad(conv1) + identity path) * (x > 0); x is that block's output (or the pooled
     // stem activation, where the gate is a no-op for the gradient that survives the stem's own ReLU mask).
@@ -682,7 +702,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
     } else {
       KOA_TRY(side.begin(&sw));
-      KOA_TRY(conv_wgrad(p, *ud, at(ws, b.in_bf), dy_down, grads, ws, sw));
+      KOA_TRY(conv_wgrad(p, *ud, at(ws, b.in_bf ? b.in_bf : b.in), dy_down, grads, ws, sw));
       KOA_TRY(side.reads(1));
       if (ud->stride == 1) {
         koa_epilogue_t ep{};

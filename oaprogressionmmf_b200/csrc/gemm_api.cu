@@ -323,14 +323,16 @@ int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_
   return dispatch_kmajor<true>(ta, w, (int)m, cout, filt_r * filt_s * cin, g, to_epi(ep, cout), st);
 }
 
-template <int BN, int STAGES, bool IM2COL>
+// x_f16: 0 = dY and X bf16; 1 = both fp16; 2 = dY bf16, X fp16 converted to bf16 inside the kernel (XCVT)
+template <int BN, int STAGES, bool IM2COL, bool XCVT = false>
 static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, int cin, int pixels, int taps,
                         const ConvGeom& g, float* dw, int x_f16, cudaStream_t st) {
+  if (!XCVT && x_f16 == 2) return launch_wgrad<BN, STAGES, IM2COL, true>(ta, tb, cout, cin, pixels, taps, g, dw, 0, st);
   constexpr size_t smem = wgrad_smem_bytes<BN, STAGES>();
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_wgrad_kernel<BN, STAGES, IM2COL>,
+    attr_err = cudaFuncSetAttribute(gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   });
   KOA_CHECK_CUDA(attr_err);
@@ -352,8 +354,8 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
     // grouped: only the diagonal 64x64 blocks are algorithmic work
     const double n_eff = g.grouped ? 64.0 : (double)cin;
     ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps, cout, cin * taps, pixels, IM2COL ? 1 : 0);
-    gemm_wgrad_kernel<BN, STAGES, IM2COL>
-        <<<grid, kGemmThreads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16);
+    gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT><<<grid, XCVT ? kWgradCvtThreads : kGemmThreads, smem, st>>>(
+        ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16);
   }
   KOA_LAUNCH_CHECK();
   return 0;

@@ -582,11 +582,22 @@ struct WgradDesc {
 
 template <int BN, int STAGES>
 constexpr size_t wgrad_smem_bytes() {
-  return 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16;
+  return 1024 + (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (3 * STAGES + 1) * 8 + 16;
 }
 
-template <int BN, int STAGES, bool B_IM2COL>
-__global__ void __launch_bounds__(kGemmThreads)
+constexpr int kWgradCvtWarps = 8;  // XCVT: warps 2..9 convert the activation tile (fp16 -> bf16) in shared memory
+constexpr int kWgradCvtThreads = 64 + 32 * kWgradCvtWarps;
+
+__device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t v) {
+  const float2 f = unpack_f16x2(v);
+  return pack_bf16x2(f.x, f.y);
+}
+
+// XCVT: the activation operand X arrives in fp16 (the forward storage format) and is rewritten as bf16 in shared memory
+// between the TMA load and the MMA (one tcgen05 kind::f16 MMA takes ONE 16-bit format and dY is bf16): the forward pass
+// does not have to write a second, bf16 copy of every activation for the weight gradients.
+template <int BN, int STAGES, bool B_IM2COL, bool XCVT>
+__global__ void __launch_bounds__(XCVT ? kWgradCvtThreads : kGemmThreads)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int cout, int cin,
                   int pixels, int taps, ConvGeom g, float* __restrict__ dw, int kb_per_split, WgradDesc wd, int a_f16,
                   int b_f16) {
@@ -603,7 +614,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* xf_bar = tmem_full_bar + 1;  // [STAGES] XCVT: the converted tile is visible to the tensor core
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xf_bar + STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -628,6 +640,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&xf_bar[s], kWgradCvtWarps);
     }
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
@@ -675,7 +688,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t phase = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], phase, 0x500 + s);
+        mbar_wait(XCVT ? &xf_bar[s] : &full_bar[s], phase, 0x500 + s);
         tc_fence_after();
         const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_BYTES), wd.lbo, wd.sbo);
         const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * B_BYTES), wd.lbo, wd.sbo);
@@ -689,6 +702,32 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       umma_commit(tmem_full_bar);
     }
   } else {
+    if (XCVT) {
+      // fp16 -> bf16 in place, 16 bytes per thread and step; the swizzled layout is untouched (element-wise)
+      const int t = threadIdx.x - 64;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(&full_bar[s], phase, 0x800 + s);
+        const uint32_t tile = smem_u32(sB + s * B_BYTES);
+        constexpr int kVec = B_BYTES / 16;
+        constexpr int kPer = kVec / (kWgradCvtWarps * 32);
+        static_assert(kVec % (kWgradCvtWarps * 32) == 0, "tile divides over the converting threads");
+        uint4 v[kPer];
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) v[j] = lds128(tile + (uint32_t)(t + j * kWgradCvtWarps * 32) * 16);
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+          v[j].x = f16x2_to_bf16x2(v[j].x); v[j].y = f16x2_to_bf16x2(v[j].y);
+          v[j].z = f16x2_to_bf16x2(v[j].z); v[j].w = f16x2_to_bf16x2(v[j].w);
+          sts128(tile + (uint32_t)(t + j * kWgradCvtWarps * 32) * 16, v[j]);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xf_bar[s]);
+      }
+      if (warp >= 6) goto done;  // warps 6..9 only convert
+    }
     const int q = warp & 3;
     mbar_wait(tmem_full_bar, 0, 0x600);
     tc_fence_after();
@@ -715,6 +754,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   }
+done:
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BN);

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <mutex>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "koa_common.cuh"
@@ -123,6 +124,9 @@ int koa_num_sms() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    // experiments: persistent GEMM grids smaller than the machine leave SMs to the kernels of concurrent streams
+    const char* e = getenv("KOA_NUM_SMS");
+    if (e != nullptr && atoi(e) > 0 && atoi(e) < n) n = atoi(e);
   }
   return n;
 }

@@ -290,6 +290,14 @@ def test_conv_fprop_and_wgrad(cuda, n_img, h, w, cin, cout, k, stride, pad):
     _lib.check(lib.koa_conv_wgrad_bf16(dy_nhwc.data_ptr(), x_nhwc.data_ptr(), dw.data_ptr(), n_img, h, w, cin, cout, k, k,
                                        stride, pad, 0, _stream()), "conv wgrad")
     assert rel(dw, gw.permute(0, 2, 3, 1)) < 1e-4
+    # the same from the fp16 activation, converted to bf16 inside the kernel (x_f16 = 2; im2col operand)
+    dw.zero_()
+    x16 = (x_nhwc.float() * 1.37).half().contiguous()  # generic fp16 values: the kernel rounds them to bf16
+    (gw16,) = torch.autograd.grad(F.conv2d(x16.bfloat16().float().permute(0, 3, 1, 2), wf, stride=stride, padding=pad), wf,
+                                  dy.float())
+    _lib.check(lib.koa_conv_wgrad_bf16(dy_nhwc.data_ptr(), x16.data_ptr(), dw.data_ptr(), n_img, h, w, cin, cout, k, k,
+                                       stride, pad, 2, _stream()), "conv wgrad xcvt")
+    assert rel(dw, gw16.permute(0, 2, 3, 1)) < 1e-4
     # the CNN's forward formats: fp16 activations / weights in, fp16 out
     xh, wh = x.float().half(), wt.float().half()
     ref_h = F.conv2d(xh.float(), wh.float(), stride=stride, padding=pad)
@@ -316,6 +324,13 @@ def test_gemm_wgrad(cuda, pixels, cout, cin):
     dw.zero_()
     _lib.check(lib.koa_gemm_wgrad_bf16(dyh.data_ptr(), xh.data_ptr(), dw.data_ptr(), pixels, cout, cin, 1, _stream()), "wgrad")
     assert rel(dw, dyh.float().t() @ xh.float()) < 1e-4
+    # x_f16 = 2: bf16 dy with the fp16 forward activation, converted to bf16 in shared memory inside the kernel (what the
+    # extractor backward runs): equals the product with the bf16-rounded activation
+    xh = (_randn(pixels, cin, seed=23) * 1.7).half().contiguous()
+    dw.zero_()
+    _lib.check(lib.koa_gemm_wgrad_bf16(dy.data_ptr(), xh.data_ptr(), dw.data_ptr(), pixels, cout, cin, 2, _stream()), "wgrad")
+    assert rel(dw, dy.float().t() @ xh.bfloat16().float()) < 1e-4
+    assert _lib.debug_flag() == 0
 
 
 @pytest.mark.parametrize("rows,d", [(7, 2048), (1472, 2048), (33, 256)])
@@ -561,6 +576,14 @@ def _ws_view(lib, desc, ws, what, index, dtype):
     return ws[off.value:off.value + nb.value].view(dtype)
 
 
+def _set_bf16_copy(lib, desc, ws, what, index, values):
+    """bf16 copies of the activations exist only with KOA_WGRAD_XCVT=0 (otherwise the weight-gradient kernels convert
+    the fp16 activations themselves and the selector reports 0 bytes)."""
+    v = _ws_view(lib, desc, ws, what, index, torch.bfloat16)
+    if v.numel():
+        v.copy_(values)
+
+
 def _nhwc_f16(t):
     return t.detach().permute(0, 2, 3, 1).contiguous().half().reshape(-1)
 
@@ -610,12 +633,12 @@ def test_fe_backward_teacher_forced(cuda, arch, xr, b, s, size):
         p = f"_fe.{blk['layer']}.{blk['index']}"
         # fp16 activations (gates / next-layer operands) and their bf16 copies (weight-gradient operands)
         _ws_view(lib, desc, ws, 1, bi, torch.float16).copy_(_nhwc_f16(taps[p]))
-        _ws_view(lib, desc, ws, 8, bi, torch.bfloat16).copy_(_nhwc_f16(taps[p]).bfloat16())
+        _set_bf16_copy(lib, desc, ws, 8, bi, _nhwc_f16(taps[p]).bfloat16())
         _ws_view(lib, desc, ws, 2, bi, torch.float16).copy_(_nhwc_f16(taps[f"{p}.a1"]))
-        _ws_view(lib, desc, ws, 9, bi, torch.bfloat16).copy_(_nhwc_f16(taps[f"{p}.a1"]).bfloat16())
+        _set_bf16_copy(lib, desc, ws, 9, bi, _nhwc_f16(taps[f"{p}.a1"]).bfloat16())
         if blk["kind"] == "bottleneck":
             _ws_view(lib, desc, ws, 3, bi, torch.float16).copy_(_nhwc_f16(taps[f"{p}.a2"]))
-            _ws_view(lib, desc, ws, 10, bi, torch.bfloat16).copy_(_nhwc_f16(taps[f"{p}.a2"]).bfloat16())
+            _set_bf16_copy(lib, desc, ws, 10, bi, _nhwc_f16(taps[f"{p}.a2"]).bfloat16())
     a0 = _ws_view(lib, desc, ws, 4, 0, torch.float16)
     p0 = _ws_view(lib, desc, ws, 5, 0, torch.float16)
     idx0 = _ws_view(lib, desc, ws, 7, 0, torch.uint8)
@@ -623,7 +646,7 @@ def test_fe_backward_teacher_forced(cuda, arch, xr, b, s, size):
     _lib.check(lib.koa_maxpool_fwd(a0.data_ptr(), p0.data_ptr(), idx0.data_ptr(), imgs.shape[0], hs, hs, 64, _stream()),
                "maxpool")
     assert torch.equal(p0.float(), _nhwc_f16(taps["_fe.pool"]).float())
-    _ws_view(lib, desc, ws, 11, 0, torch.bfloat16).copy_(p0.bfloat16())
+    _set_bf16_copy(lib, desc, ws, 11, 0, p0.bfloat16())
     gy = _randn(*ref.shape, seed=7)
     (tok.reshape(-1, tok.shape[-1]) * gy).sum().backward()
     (ref * gy).sum().backward()
