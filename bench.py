@@ -51,6 +51,49 @@ def measured_peaks():
     return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback of B200_PROFILING.md")
 
 
+def split_by_bound(path, peaks, ms_total):
+    """The GEMM family launch by launch (per-shape records of koa_profile_dump): a launch is tensor-bound when its
+    algorithmic intensity 2MNK / bytes exceeds the measured ridge (peak TFLOP/s / peak GB/s), HBM-bound otherwise.
+    Algorithmic bytes of a fprop / dgrad launch: operands once (a 3x3 im2col operand counts its input once, not nine
+    times), output once, 2 B per element of every fused epilogue operand; of a weight-gradient launch: dY and X once,
+    dW as fp32."""
+    ridge = peaks["tflops"] * 1e12 / (peaks["hbm"] * 1e9)
+    acc = {"tensor": [0.0, 0.0, 0.0, 0], "hbm": [0.0, 0.0, 0.0, 0]}  # ms, flops, bytes, launches
+    try:
+        rows = [l.split() for l in open(path) if not l.startswith("#")]
+    except OSError:
+        return None
+    for r in rows:
+        cls, tag, m, n, k, cnt = (int(v) for v in r[:6])
+        ms = float(r[6])
+        tag &= 255
+        if cls == 0:
+            taps = 9 if (tag & 1) and k % 9 == 0 else 1
+            by = 2.0 * (m * k / taps + n * k + m * n)
+            for bit in (4, 8, 128):
+                if tag & bit:
+                    by += 2.0 * m * n
+            if tag & 16:
+                by += 4.0 * m * n
+            if tag & 32:
+                by += 2.0 * m * n
+        else:
+            taps = 9 if (tag & 1) and n % 9 == 0 else 1
+            by = 2.0 * k * (m + n / taps) + 4.0 * m * n
+        fl = 2.0 * m * n * k
+        a = acc["tensor" if fl / by > ridge else "hbm"]
+        a[0] += ms; a[1] += fl * cnt; a[2] += by * cnt; a[3] += cnt
+    out = {"ridge_flop_per_byte": ridge}
+    t, h = acc["tensor"], acc["hbm"]
+    if t[0] > 0:
+        out["tensor"] = dict(launches=t[3], share_of_step=t[0] / ms_total, achieved=t[1] / (t[0] * 1e-3) / 1e12,
+                             peak=peaks["tflops"], unit="TFLOP/s", frac=t[1] / (t[0] * 1e-3) / 1e12 / peaks["tflops"])
+    if h[0] > 0:
+        out["hbm"] = dict(launches=h[3], share_of_step=h[0] / ms_total, achieved=h[2] / (h[0] * 1e-3) / 1e9,
+                          peak=peaks["hbm"], unit="GB/s (algorithmic bytes)", frac=h[2] / (h[0] * 1e-3) / 1e9 / peaks["hbm"])
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -242,8 +285,9 @@ def run_ours(args):
     barrier()
     ms_serial_total = ev0.elapsed_time(ev1)
     prof = (C.c_double * 6)()
-    if args.profile_dump and rank == 0:
-        lib.koa_profile_dump(args.profile_dump.encode())
+    dump_path = args.profile_dump or os.path.join("/tmp", f"koa_shapes_{os.getpid()}.txt")
+    if rank == 0:
+        lib.koa_profile_dump(dump_path.encode())
     lib.koa_profile_read(prof)
     lib.koa_profile_enable(0)
     set_branch_streams(None)
@@ -308,6 +352,7 @@ def run_ours(args):
                                           "`value` is measured with the branches on concurrent streams"),
                     whole_step=dict(achieved=value / ws * flops_knee / 1e12, frac=value / ws * flops_knee / 1e12 / peaks["tflops"],
                                     note="algorithmic FLOPs of the whole step / step time, per GPU"))
+    roofline["by_bound"] = split_by_bound(dump_path, peaks, ms_serial_total)
     cpu = None
     if ws == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
