@@ -12,12 +12,14 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// Grid-stride kernels: two CTAs per SM saturate HBM (measured: the BatchNorm passes run at the same 5.1-5.4 TB/s with
-// 296 as with 2368 CTAs) and leave the rest of the SM to the kernels of the concurrent branch streams (+3 % on the step).
+// Grid-stride kernels: a few CTAs per SM saturate HBM and leave the rest of the SM to the kernels of the concurrent
+// branch streams (+3 % on the step against 16 CTAs per SM). Four per SM by default; the BatchNorm-backward kernels keep
+// 6-8 16-byte loads in flight per thread and run at the same 5.2 TB/s with two (kDeepGrid).
+constexpr int kDeepGrid = 148 * 2;
 inline int grid_for(long long work_items, int threads = kThreads, int max_blocks = 148 * 16) {
   static const int env_cap = [] {
     const char* e = getenv("KOA_EW_MAX_BLOCKS");
-    return e ? atoi(e) : 148 * 2;
+    return e ? atoi(e) : 148 * 4;
   }();
   if (env_cap > 0 && max_blocks > env_cap) max_blocks = env_cap;
   long long b = (work_items + threads - 1) / threads;
@@ -1213,7 +1215,7 @@ int koa_k_bn_bwd_apply_fin(const void* dout, const void* act, const void* y, con
                            cudaStream_t st) {
   KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm backward needs C/8 | %d (C=%d)", kThreads, c);
   KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
-  bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
+  bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid), kThreads, 0, st>>>(
       (const bf16*)dout, (const bf16*)act, (const bf16*)y, nullptr, nullptr, nullptr, (bf16*)dy, (const bf16*)y2, nullptr,
       nullptr, nullptr, (bf16*)dy2, rows, c, *a, b ? *b : KoaBnBwdFin{}, count, training);
   KOA_LAUNCH_CHECK();
@@ -1226,7 +1228,7 @@ int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const 
   if (rc) return rc;
   const int threads = reduce_threads(c);
   const int lanes = threads / (c / 8);
-  bn_bwd_reduce_kernel<<<grid_for(rows, lanes, 148 * 8), threads, 3 * c * sizeof(float), st>>>(
+  bn_bwd_reduce_kernel<<<grid_for(rows, lanes, kDeepGrid), threads, 3 * c * sizeof(float), st>>>(
       (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean, invstd, (const bf16*)y2, mean2, invstd2, sum_dz,
       sum_dzx, sum_dzx2, rows, c);
   KOA_LAUNCH_CHECK();
@@ -1245,7 +1247,7 @@ int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const f
                        void* dy2, long long rows, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
   if (kThreads % (c / 8) == 0)
-    bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
+    bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid), kThreads, 0, st>>>(
         (const bf16*)dout, (const bf16*)act, (const bf16*)y, k0, k1, k2, (bf16*)dy, (const bf16*)y2, k0b, k1b, k2b,
         (bf16*)dy2, rows, c, KoaBnBwdFin{}, KoaBnBwdFin{}, 1.0, 0);
   else
