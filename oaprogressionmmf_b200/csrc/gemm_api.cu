@@ -198,10 +198,14 @@ static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
   KOA_REQUIRE(units > 0, "more n-tiles than SMs");
   // MODE 1 moves its epilogue operands and its output with the TMA unit: [M, N] views with row pitch ldo
   CUtensorMap t_out = ta, t_add = ta, t_gate = ta, t_y = ta;
-  if (MODE == 1) {
+  {
     const uint64_t pitch = (uint64_t)ep.ldo * 2;
     int rc = koa_tmap_2d_sw64(&t_out, ep.out, (uint64_t)n, (uint64_t)m, pitch);
     if (rc) return rc;
+  }
+  if (MODE == 1) {
+    const uint64_t pitch = (uint64_t)ep.ldo * 2;
+    int rc;
     t_add = t_gate = t_y = t_out;
     if (ep.add_bf16 && (rc = koa_tmap_2d_sw64(&t_add, ep.add_bf16, (uint64_t)n, (uint64_t)m, pitch))) return rc;
     if (ep.gate_bf16 && (rc = koa_tmap_2d_sw64(&t_gate, ep.gate_bf16, (uint64_t)n, (uint64_t)m, pitch))) return rc;

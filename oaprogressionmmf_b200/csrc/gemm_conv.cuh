@@ -144,6 +144,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int kDrainWarps = BN == 64 ? 8 : 16;     // warps (of one CTA) that read one accumulator stage
   constexpr int kEpiThreads = kConvEpiWarps * 32;
   constexpr int BMT = CTA2 ? 2 * BM : BM;            // rows of the tile of a CTA (pair)
+#ifdef KOA_CONV_FWD_STG
+  constexpr bool TMA_OUT = false;                    // MODE 0 output through LDS + STG.128 (first version)
+#else
+  constexpr bool TMA_OUT = true;                     // MODE 0 output through TMA stores as well
+#endif
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (base & 1023u)) & 1023u);
@@ -184,6 +189,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     if (MODE == 1) {
       tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmAdd); tma_prefetch_desc(&tmGate); tma_prefetch_desc(&tmY);
+    } else if (TMA_OUT) {
+      tma_prefetch_desc(&tmOut);
     }
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
@@ -318,6 +325,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n = n0 + cj;
         const bool col_ok = n < N;
         const bool last = j == CH - 1;
+        if (MODE == 0 && TMA_OUT && col_ok && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (MODE == 1 && col_ok && lane == 0) {
           // The TMA unit fetches the operand tiles of this chunk ([32 rows][32 columns], 64-byte swizzle = the staging
           // layout; rows past M arrive as zeros) while the accumulator is still being computed. The previous
@@ -330,6 +338,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (bwd) tma_load_2d(s_stage + (stage_y - smem_u32(s_stage)), &tmY, &op_bar[e], n, row0);
           }
         }
+        // (lane 0 has waited for the previous TMA store to finish reading the staging buffer: no lane may write it earlier)
+        if (MODE == 1 || TMA_OUT) __syncwarp();
         if (!waited) {
           mbar_wait(&tmem_full_bar[acc], acc_phase, 0xc00 + acc);
           tc_fence_after();
@@ -391,7 +401,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (has_add) __syncwarp();  // every lane has read its addend row: the buffer becomes the output buffer
         row_sts(stage, qv, lm);
-        if (MODE == 1) {
+        if (MODE == 1 || TMA_OUT) {
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
           __syncwarp();
           if (lane == 0) {  // rows past M / columns past N are clipped by the TMA unit
@@ -430,7 +440,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        if (MODE == 0) {
+        if (MODE == 0 && !TMA_OUT) {
           // coalesced write-back: 8 rows x 64 contiguous bytes per instruction
           uint4 o[4];
 #pragma unroll
@@ -446,7 +456,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-    if (MODE == 1 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // output stores complete
+    if ((MODE == 1 || TMA_OUT) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
     __syncwarp();
 
     if (stats) {
