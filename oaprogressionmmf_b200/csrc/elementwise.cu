@@ -16,12 +16,16 @@ constexpr int kThreads = 256;
 // branch streams (+3 % on the step against 16 CTAs per SM). Four per SM by default; the BatchNorm-backward kernels keep
 // 6-8 16-byte loads in flight per thread and run at the same 5.2 TB/s with two (kDeepGrid).
 constexpr int kDeepGrid = 148 * 2;
+// One element per thread and iteration with index arithmetic in front of every access (pooling, packing, resampling):
+// latency-bound, these keep the full grid (they ran 30-60 % slower with the cap).
+constexpr int kWideGrid = -148 * 16;
 inline int grid_for(long long work_items, int threads = kThreads, int max_blocks = 148 * 16) {
   static const int env_cap = [] {
     const char* e = getenv("KOA_EW_MAX_BLOCKS");
     return e ? atoi(e) : 148 * 4;
   }();
-  if (env_cap > 0 && max_blocks > env_cap) max_blocks = env_cap;
+  if (max_blocks < 0) max_blocks = -max_blocks;  // exempt from the cap
+  else if (env_cap > 0 && max_blocks > env_cap) max_blocks = env_cap;
   long long b = (work_items + threads - 1) / threads;
   if (b < 1) b = 1;
   if (b > max_blocks) b = max_blocks;
@@ -1107,13 +1111,13 @@ __global__ void focal_loss_kernel(const float* __restrict__ logits, const long l
 
 int koa_k_pack_conv_w(const float* src, void* dst, int cout, int cin, int fr, int fs, int dgrad_form, cudaStream_t st) {
   const long long total = (long long)cout * cin * fr * fs;
-  pack_conv_w_kernel<<<grid_for(total), kThreads, 0, st>>>(src, (bf16*)dst, cout, cin, fr, fs, dgrad_form);
+  pack_conv_w_kernel<<<grid_for(total, kThreads, kWideGrid), kThreads, 0, st>>>(src, (bf16*)dst, cout, cin, fr, fs, dgrad_form);
   KOA_LAUNCH_CHECK();
   return 0;
 }
 int koa_k_pack_grouped_w(const float* src, void* dst, int c, int cg, int dgrad_form, cudaStream_t st) {
   KOA_REQUIRE(c % 64 == 0 && cg >= 1 && 64 % cg == 0, "grouped conv packing needs C %% 64 == 0 and Cg | 64 (C=%d Cg=%d)", c, cg);
-  pack_grouped_w_kernel<<<grid_for((long long)c * 9 * 64), kThreads, 0, st>>>(src, (bf16*)dst, c, cg, dgrad_form);
+  pack_grouped_w_kernel<<<grid_for((long long)c * 9 * 64, kThreads, kWideGrid), kThreads, 0, st>>>(src, (bf16*)dst, c, cg, dgrad_form);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1133,17 +1137,17 @@ int koa_k_pack_fe_weights(const KoaPackJob* jobs, int n_jobs, cudaStream_t st) {
     }
   }
   tab.begin[n_jobs] = acc;
-  pack_fe_weights_kernel<<<grid_for(acc, kThreads, 148 * 8), kThreads, 0, st>>>(tab);
+  pack_fe_weights_kernel<<<grid_for(acc, kThreads, kWideGrid), kThreads, 0, st>>>(tab);
   KOA_LAUNCH_CHECK();
   return 0;
 }
 int koa_k_unpack_grouped_dw(const float* dense, float* grad, int c, int cg, cudaStream_t st) {
-  unpack_grouped_dw_kernel<<<grid_for((long long)c * cg * 9), kThreads, 0, st>>>(dense, grad, c, cg);
+  unpack_grouped_dw_kernel<<<grid_for((long long)c * cg * 9, kThreads, kWideGrid), kThreads, 0, st>>>(dense, grad, c, cg);
   KOA_LAUNCH_CHECK();
   return 0;
 }
 int koa_k_unpack_conv_dw(const float* src, float* dst, int cout, int cin, int fr, int fs, cudaStream_t st) {
-  unpack_conv_dw_kernel<<<grid_for((long long)cout * cin * fr * fs), kThreads, 0, st>>>(src, dst, cout, cin, fr, fs);
+  unpack_conv_dw_kernel<<<grid_for((long long)cout * cin * fr * fs, kThreads, kWideGrid), kThreads, 0, st>>>(src, dst, cout, cin, fr, fs);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1260,7 +1264,7 @@ int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const f
 int koa_k_maxpool_fwd(const void* x, void* out, void* out_bf16, void* idx, int n, int h, int w, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), kThreads, 0, st>>>(
+  maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8), kThreads, kWideGrid), kThreads, 0, st>>>(
       (const bf16*)x, (bf16*)out, (bf16*)out_bf16, (uint8_t*)idx, n, h, w, c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
@@ -1268,7 +1272,7 @@ int koa_k_maxpool_fwd(const void* x, void* out, void* out_bf16, void* idx, int n
 int koa_k_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx,
+  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), kThreads, kWideGrid), kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx,
                                                                                     (bf16*)dx, n, h, w, c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
@@ -1281,13 +1285,13 @@ int koa_k_gap_fwd(const void* x, float* feat, int n, int hw, int c, cudaStream_t
 }
 int koa_k_gap_bwd(const float* dfeat, const void* gate, void* dx, int n, int hw, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
-  gap_bwd_kernel<<<grid_for((long long)n * hw * (c / 8)), kThreads, 0, st>>>(dfeat, (const bf16*)gate, (bf16*)dx, n, hw, c);
+  gap_bwd_kernel<<<grid_for((long long)n * hw * (c / 8), kThreads, kWideGrid), kThreads, 0, st>>>(dfeat, (const bf16*)gate, (bf16*)dx, n, hw, c);
   KOA_LAUNCH_CHECK();
   return 0;
 }
 int koa_k_zero_insert2(const void* src, void* dst, int n, int h, int w, int c, int ho, int wo, cudaStream_t st) {
   KOA_REQ_C8(c);
-  zero_insert2_kernel<<<grid_for((long long)n * h * w * (c / 8)), kThreads, 0, st>>>((const bf16*)src, (bf16*)dst, n, h, w,
+  zero_insert2_kernel<<<grid_for((long long)n * h * w * (c / 8), kThreads, kWideGrid), kThreads, 0, st>>>((const bf16*)src, (bf16*)dst, n, h, w,
                                                                                      c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
@@ -1295,7 +1299,7 @@ int koa_k_zero_insert2(const void* src, void* dst, int n, int h, int w, int c, i
 int koa_k_scatter_add2(const void* src, const void* gate, void* dx, int n, int h, int w, int c, int ho, int wo,
                        cudaStream_t st) {
   KOA_REQ_C8(c);
-  scatter_add2_kernel<<<grid_for((long long)n * ho * wo * (c / 8)), kThreads, 0, st>>>((const bf16*)src, (const bf16*)gate,
+  scatter_add2_kernel<<<grid_for((long long)n * ho * wo * (c / 8), kThreads, kWideGrid), kThreads, 0, st>>>((const bf16*)src, (const bf16*)gate,
                                                                                        (bf16*)dx, n, h, w, c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;

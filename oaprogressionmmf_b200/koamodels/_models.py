@@ -368,7 +368,7 @@ class XR1MR3C1CnnTrf(_XRMRBase):
         def mr(i, vol):
             return lambda: getattr(self, f"_agg_{i}").run(self._mr_tokens(i, vol), compute_head=False)[1]
 
-        # the largest branch (DESS, 64 slices) first: the others fill in around it
+        # the largest branch (DESS, 64 slices) first (the launch order was measured not to matter: 177-178 knees/s either way)
         s1, s2, s3, t0 = _run_branches([mr(1, input1), mr(2, input2), mr(3, input3), lambda: self._xr_tokens(input0)])
         parts = [t0, s1, s2, s3, self._fe4(input4)]
         out, _, _ = self._agg_final.run(torch.cat(parts, dim=1), compute_head=True)
