@@ -328,41 +328,67 @@ int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_
 }
 
 // x_f16: 0 = dY and X bf16; 1 = both fp16; 2 = dY bf16, X fp16 converted to bf16 inside the kernel (XCVT)
-template <int BN, int STAGES, bool IM2COL, bool XCVT = false>
+// CTA2: CTA pairs on 256 x BN tiles (the tensor map of X then has boxes of 64 columns as always; each CTA loads BN / 2)
+template <int BN, int STAGES, bool IM2COL, bool XCVT = false, bool CTA2 = false>
 static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, int cin, int pixels, int taps,
                         const ConvGeom& g, float* dw, int x_f16, cudaStream_t st) {
-  if (!XCVT && x_f16 == 2) return launch_wgrad<BN, STAGES, IM2COL, true>(ta, tb, cout, cin, pixels, taps, g, dw, 0, st);
-  constexpr size_t smem = wgrad_smem_bytes<BN, STAGES>();
+  if (!XCVT && !CTA2 && x_f16 == 2) return launch_wgrad<BN, STAGES, IM2COL, true, false>(ta, tb, cout, cin, pixels, taps, g, dw, 0, st);
+  constexpr size_t smem = wgrad_smem_bytes<CTA2 ? BN / 2 : BN, STAGES>();
+  auto kern = gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT, CTA2>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  });
+  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
   KOA_CHECK_CUDA(attr_err);
-  const int tiles = (g.grouped ? 1 : koa_cdiv(cout, BM)) * koa_cdiv(cin, BN) * taps;
+  const int tiles = (g.grouped ? 1 : koa_cdiv(cout, CTA2 ? 2 * BM : BM)) * koa_cdiv(cin, BN) * taps;
   const int num_kb = koa_cdiv(pixels, BK);
   // Split the pixel (reduction) range so that the grid covers the machine a few times over.
   static const int waves = [] {
     const char* e = getenv("KOA_WGRAD_WAVES");
     return e ? atoi(e) : 4;
   }();
-  int splits = koa_cdiv(waves * koa_num_sms(), tiles);
+  int splits = koa_cdiv(waves * koa_num_sms(), tiles * (CTA2 ? 2 : 1));
   if (splits > num_kb) splits = num_kb;
   if (splits < 1) splits = 1;
   int kb_per_split = koa_cdiv(num_kb, splits);
   if (kb_per_split < 4 && num_kb >= 4) kb_per_split = 4;
   splits = koa_cdiv(num_kb, kb_per_split);
-  dim3 grid((unsigned)tiles, (unsigned)splits);
+  dim3 grid((unsigned)tiles * (CTA2 ? 2 : 1), (unsigned)splits);
+  const unsigned threads = XCVT ? kWgradCvtThreads : kGemmThreads;
   {
     // grouped: only the diagonal 64x64 blocks are algorithmic work
     const double n_eff = g.grouped ? 64.0 : (double)cin;
-    ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps, cout, cin * taps, pixels, IM2COL ? 1 : 0);
-    gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT><<<grid, XCVT ? kWgradCvtThreads : kGemmThreads, smem, st>>>(
-        ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16);
+    ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps, cout, cin * taps, pixels,
+                   (IM2COL ? 1 : 0) | (CTA2 ? 256 : 0));
+    if (CTA2) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(threads, 1, 1);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16));
+    } else {
+      kern<<<grid, threads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16);
+    }
   }
   KOA_LAUNCH_CHECK();
   return 0;
+}
+
+// CTA pairs for weight gradients. KOA_WGRAD_CTA2: 0 never, 1 (default) where measured faster on B200, 2 wherever the
+// shape allows (Cout and Cin multiples of 256). Measured (tools/prof_wgrad.py): 3x3 with 256 channels 79.9 -> 68.6 us;
+// 3x3 with 512 channels 80.9 -> 85.0 us; 1x1 layers 50 -> 61 us and the transformer Linears 34-46 -> 39-69 us: with
+// half as many, twice as large tiles the split-K count doubles and the kernel becomes bound by its fp32 atomics.
+static bool wgrad_cta2(int cout, int cin, int x_f16, bool conv3x3) {
+  static const int mode = env_int("KOA_WGRAD_CTA2", 1);
+  if (mode == 0 || x_f16 == 2 || koa_num_sms() < 2 || cout % 256 != 0 || cin % 256 != 0) return false;
+  return mode >= 2 || (conv3x3 && cout == 256 && cin == 256);
 }
 
 int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, int x_f16, cudaStream_t st) {
@@ -374,6 +400,7 @@ int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, 
   rc = koa_tmap_2d_bf16(&tb, x, (uint64_t)cin, (uint64_t)pixels, (uint64_t)cin * 2, 64, 64);
   if (rc) return rc;
   ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
+  if (wgrad_cta2(cout, cin, x_f16, false)) return launch_wgrad<256, 3, false, false, true>(ta, tb, cout, cin, pixels, 1, g, dw, x_f16, st);
   if (cin % 128 == 0) return launch_wgrad<128, 3, false>(ta, tb, cout, cin, pixels, 1, g, dw, x_f16, st);
   return launch_wgrad<64, 3, false>(ta, tb, cout, cin, pixels, 1, g, dw, x_f16, st);
 }
@@ -392,6 +419,7 @@ int koa_conv_wgrad_launch(const void* dy, const void* x, float* dw, int n_img, i
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, pad, filt_s, cin / 64, 0};
   const int taps = filt_r * filt_s;
+  if (wgrad_cta2(cout, cin, x_f16, taps == 9)) return launch_wgrad<256, 3, true, false, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, x_f16, st);
   if (cin % 128 == 0) return launch_wgrad<128, 3, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, x_f16, st);
   return launch_wgrad<64, 3, true>(ta, tb, cout, cin, (int)pixels, taps, g, dw, x_f16, st);
 }

@@ -596,15 +596,20 @@ __device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t v) {
 // XCVT: the activation operand X arrives in fp16 (the forward storage format) and is rewritten as bf16 in shared memory
 // between the TMA load and the MMA (one tcgen05 kind::f16 MMA takes ONE 16-bit format and dY is bf16): the forward pass
 // does not have to write a second, bf16 copy of every activation for the weight gradients.
-template <int BN, int STAGES, bool B_IM2COL, bool XCVT>
+// CTA2: CTA pairs (cluster of 2 along Cout, tcgen05 cta_group::2, M = 256): each CTA stages its own 128 dY columns and
+// HALF of the BN activation columns, like the convolution kernel's pairs (gemm_conv.cuh); rank 0 issues the MMAs.
+template <int BN, int STAGES, bool B_IM2COL, bool XCVT, bool CTA2 = false>
 __global__ void __launch_bounds__(XCVT ? kWgradCvtThreads : kGemmThreads)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int cout, int cin,
                   int pixels, int taps, ConvGeom g, float* __restrict__ dw, int kb_per_split, WgradDesc wd, int a_f16,
                   int b_f16) {
   // g.grouped: dw is [C][taps][64] (per-64-channel-chunk dense blocks); tile n_t pairs input chunk n_t with
   // output chunk n_t only (BN must be 64; the upper 64 accumulator rows are discarded).
+  static_assert(!(CTA2 && XCVT), "the in-kernel conversion is not combined with CTA pairs");
+  constexpr int BN_LOCAL = CTA2 ? BN / 2 : BN;  // activation columns staged by this CTA
+  constexpr int BMT = CTA2 ? 2 * BM : BM;       // Cout rows of the tile of a CTA (pair)
   constexpr uint32_t A_BYTES = BM * BK * 2;
-  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t B_BYTES = BN_LOCAL * BK * 2;
   constexpr uint32_t BOX_BYTES = 64 * BK * 2;  // one {64 channels x 64 pixels} TMA box
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -619,14 +624,16 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const int n_tiles = (cin + BN - 1) / BN;
-  const int m_tiles = g.grouped ? 1 : (cout + BM - 1) / BM;
-  int t = blockIdx.x;
+  const int m_tiles = g.grouped ? 1 : (cout + BMT - 1) / BMT;
+  int t = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_t = t % n_tiles; t /= n_tiles;
   const int m_t = t % m_tiles; t /= m_tiles;
   const int tap = t;
-  const int m0 = g.grouped ? n_t * 64 : m_t * BM;
-  const int n0 = n_t * BN;
+  const int m0 = g.grouped ? n_t * 64 : m_t * BMT + (int)rank * BM;  // first Cout row of this CTA
+  const int n0 = n_t * BN + (int)rank * BN_LOCAL;                     // first activation column staged by this CTA
+  const int n0_tile = n_t * BN;
   const int num_kb_total = (pixels + BK - 1) / BK;
   const int kb_begin = blockIdx.y * kb_per_split;
   const int kb_end = min(num_kb_total, kb_begin + kb_per_split);
@@ -645,9 +652,13 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     mbar_init(tmem_full_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) {
+    if (CTA2) tmem_alloc2(tmem_slot, BN);
+    else tmem_alloc(tmem_slot, BN);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -661,30 +672,41 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int s = i % STAGES;
         const uint32_t phase = (i / STAGES) & 1;
         mbar_wait(&empty_bar[s], phase ^ 1, 0x400 + s);
-        mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        // pair: rank 0 announces the bytes of both CTAs; the peer's loads complete on rank 0's barrier
+        if (!CTA2) mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+        else if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_BYTES + B_BYTES));
         const int p0 = kb * BK;
 #pragma unroll
-        for (int j = 0; j < BM / 64; ++j)
-          tma_load_2d(sA + s * A_BYTES + j * BOX_BYTES, &tmA, &full_bar[s], m0 + j * 64, p0);
+        for (int j = 0; j < BM / 64; ++j) {
+          if (CTA2) tma2_load_2d(sA + s * A_BYTES + j * BOX_BYTES, &tmA, &full_bar[s], m0 + j * 64, p0);
+          else tma_load_2d(sA + s * A_BYTES + j * BOX_BYTES, &tmA, &full_bar[s], m0 + j * 64, p0);
+        }
         if (B_IM2COL) {
           const int pn = p0 / hw;
           const int rem = p0 - pn * hw;
           const int oh = rem / g.wout;
           const int ow = rem - oh * g.wout;
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_im2col_4d(sB + s * B_BYTES + j * BOX_BYTES, &tmB, &full_bar[s], n0 + j * 64,
-                               ow * g.stride - g.pad, oh * g.stride - g.pad, pn, (uint16_t)fs, (uint16_t)fr);
+          for (int j = 0; j < BN_LOCAL / 64; ++j) {
+            if (CTA2)
+              tma2_load_im2col_4d(sB + s * B_BYTES + j * BOX_BYTES, &tmB, &full_bar[s], n0 + j * 64,
+                                  ow * g.stride - g.pad, oh * g.stride - g.pad, pn, (uint16_t)fs, (uint16_t)fr);
+            else
+              tma_load_im2col_4d(sB + s * B_BYTES + j * BOX_BYTES, &tmB, &full_bar[s], n0 + j * 64,
+                                 ow * g.stride - g.pad, oh * g.stride - g.pad, pn, (uint16_t)fs, (uint16_t)fr);
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(sB + s * B_BYTES + j * BOX_BYTES, &tmB, &full_bar[s], n0 + j * 64, p0);
+          for (int j = 0; j < BN_LOCAL / 64; ++j) {
+            if (CTA2) tma2_load_2d(sB + s * B_BYTES + j * BOX_BYTES, &tmB, &full_bar[s], n0 + j * 64, p0);
+            else tma_load_2d(sB + s * B_BYTES + j * BOX_BYTES, &tmB, &full_bar[s], n0 + j * 64, p0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_16(BM, BN, 1, 1, a_f16, b_f16);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_16(BMT, BN, 1, 1, a_f16, b_f16);
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t phase = (i / STAGES) & 1;
@@ -695,11 +717,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           const uint64_t adv = (uint64_t)((k * wd.k_adv) >> 4);
-          umma_bf16_ss(tmem_base, adesc + adv, bdesc + adv, idesc, (i | k) != 0);
+          if (CTA2) umma2_bf16_ss(tmem_base, adesc + adv, bdesc + adv, idesc, (i | k) != 0);
+          else umma_bf16_ss(tmem_base, adesc + adv, bdesc + adv, idesc, (i | k) != 0);
         }
-        umma_commit(&empty_bar[s]);
+        if (CTA2) umma2_commit_both(&empty_bar[s]);
+        else umma_commit(&empty_bar[s]);
       }
-      umma_commit(tmem_full_bar);
+      if (CTA2) umma2_commit_both(tmem_full_bar);
+      else umma_commit(tmem_full_bar);
     }
   } else {
     if (XCVT) {
@@ -734,11 +759,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = m0 + q * 32 + lane;  // output channel
     const bool row_ok = g.grouped ? (q * 32 + lane) < 64 : row < cout;
     const int ldw = g.grouped ? 64 : cin;
-    const int col0 = g.grouped ? 0 : n0;
+    const int col0 = g.grouped ? 0 : n0_tile;
     float* dst_row = dw + ((long long)row * taps + tap) * ldw;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= cin) break;
+      if (n0_tile + c0 >= cin) break;
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
@@ -757,7 +782,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 done:
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (CTA2) cluster_sync_all();  // the peer's MMAs read this CTA's tiles and arrive on its barriers until it is done
+  if (warp == 1) {
+    if (CTA2) tmem_dealloc2(tmem_base, BN);
+    else tmem_dealloc(tmem_base, BN);
+  }
 }
 
 }  // namespace koa
