@@ -4,8 +4,10 @@
 // One CTA computes a 128 x BN fp32 accumulator tile held in TMEM:
 //   warp 0     : TMA producer (tiled 2-D loads, or im2col-mode loads of an NHWC tensor)
 //   warp 1     : TMEM allocation + single-thread tcgen05.mma issue
-//   warps 2..5 : epilogue (tcgen05.ld -> registers -> fused epilogue -> global)
-// Operands are bf16 staged in 128-byte-swizzled shared memory, STAGES deep.
+//   warps 2..  : epilogue (tcgen05.ld -> registers -> fused epilogue -> global): 8 warps in gemm_kmajor_kernel (general
+//                epilogue: transformer Linears), 4 in gemm_wgrad_kernel; the convolution flavour with 16 epilogue warps,
+//                TMA epilogue I/O and CTA pairs is gemm_conv.cuh
+// Operands are 16-bit (bf16 or fp16) staged in 128-byte-swizzled shared memory, STAGES deep.
 #pragma once
 #include "koa_common.cuh"
 
