@@ -124,24 +124,33 @@ struct PackJobTable {
 };
 __global__ void pack_fe_weights_kernel(const __grid_constant__ PackJobTable tab) {
   const long long total = tab.begin[tab.n];
+  int lo = 0;
+  long long lo_begin = 0, lo_end = 0;  // [begin, end) of the job found last: the index only grows, most steps stay inside
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int lo = 0, hi = tab.n - 1;
-    while (lo < hi) {  // last job whose begin <= i
-      const int mid = (lo + hi + 1) >> 1;
-      if (tab.begin[mid] <= i) lo = mid; else hi = mid - 1;
+    if (i >= lo_end) {
+      int hi = tab.n - 1;
+      while (lo < hi) {  // last job whose begin <= i
+        const int mid = (lo + hi + 1) >> 1;
+        if (tab.begin[mid] <= i) lo = mid; else hi = mid - 1;
+      }
+      lo_begin = tab.begin[lo];
+      lo_end = tab.begin[lo + 1];
     }
     const KoaPackJob& jb = tab.job[lo];
-    long long t = i - tab.begin[lo];
+    long long t = i - lo_begin;
     __half* fwd = reinterpret_cast<__half*>(jb.fwd);
     bf16* dg = reinterpret_cast<bf16*>(jb.dgrad);  // pairs with bf16 gradients
     if (jb.cg == 0) {
       const int fr = jb.k, fs = jb.k, cin = jb.cin, cout = jb.cout;
       const float vsrc = jb.src[t];
       const __half v = __float2half_rn(vsrc);
-      const int s = (int)(t % fs); t /= fs;
-      const int r = (int)(t % fr); t /= fr;
-      const int ci = (int)(t % cin); t /= cin;
-      const int co = (int)t;
+      int s = 0, r = 0;
+      if (fr != 1) {  // 1x1 convolutions (half of the parameters): the forward form is a plain cast
+        s = (int)(t % fs); t /= fs;
+        r = (int)(t % fr); t /= fr;
+      }
+      const int ci = (int)((unsigned)t % (unsigned)cin);
+      const int co = (int)((unsigned)t / (unsigned)cin);
       fwd[(((long long)co * fr + r) * fs + s) * cin + ci] = v;
       if (dg != nullptr) dg[(((long long)ci * fr + (fr - 1 - r)) * fs + (fs - 1 - s)) * cout + co] = __float2bfloat16_rn(vsrc);
     } else {
@@ -716,15 +725,16 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dout, const uint8_t*
         if (s < 0 || s > 2) continue;
         const long long o = (((long long)ni * ho + oh) * wo + ow) * cg + g;
         const uint2 packed = *reinterpret_cast<const uint2*>(idx + o * 8);
+        uint4 q = *reinterpret_cast<const uint4*>(dout + o * 8);
+        // the eight winner bytes against this position at once; byte masks widened to the bf16 pairs of the gradient
+        const uint32_t me4 = (uint32_t)(r * 3 + s) * 0x01010101u;
+        const uint32_t ex = __vcmpeq4(packed.x, me4), ey = __vcmpeq4(packed.y, me4);
+        q.x &= __byte_perm(ex, 0, 0x1100); q.y &= __byte_perm(ex, 0, 0x3322);
+        q.z &= __byte_perm(ey, 0, 0x1100); q.w &= __byte_perm(ey, 0, 0x3322);
         float d[8];
-        unpack8(*reinterpret_cast<const uint4*>(dout + o * 8), d);
-        const int me = r * 3 + s;
+        unpack8(q, d);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t word = u < 4 ? packed.x : packed.y;
-          const int sel = (word >> ((u & 3) * 8)) & 0xff;
-          if (sel == me) acc[u] += d[u];
-        }
+        for (int u = 0; u < 8; ++u) acc[u] += d[u];
       }
     }
     *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);

@@ -735,11 +735,10 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
   KOA_TRY(koa_k_maxpool_bwd(at(ws, p.g[cur]), at(ws, p.idx0), d_a0, p.n_img, us.hout, us.wout, 64, st));
   KOA_TRY(bn_backward(us, nullptr, pv, grads, ws, d_a0, at(ws, p.a0), d_a0, nullptr, training, false, st));
   if (grads[0] != nullptr) {
-    // the im2col operand is rebuilt in bf16 (the forward GEMM consumed it in fp16): it pairs with the bf16 dy
-    const float* img = d->slices > 0 ? (const float*)at(ws, p.img) : d->input_for_backward;
-    KOA_REQUIRE(img != nullptr, "stem weight gradient needs the input image (input_for_backward)");
-    KOA_TRY(koa_k_stem_im2col(img, at(ws, p.a_stem), p.n_img, d->h, d->w, 0, st));
-    KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64, 0, st));
+    // the forward pass kept its fp16 im2col operand; the weight-gradient kernel converts it to bf16 in shared memory
+    // (x_f16 = 2) to pair it with the bf16 dy. This GEMM is HBM-bound (64 x 64 outputs over millions of pixels), so the
+    // conversion is free and the second im2col pass (1 ms per step) is gone.
+    KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64, 2, st));
     KOA_TRY(koa_k_stem_unfold_dwb((const float*)at(ws, p.dwstem), (float*)grads[0], st));
   }
   KOA_TRY(side.join());  // every weight gradient is complete in the order of the caller's stream

@@ -344,7 +344,7 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
   // Split the pixel (reduction) range so that the grid covers the machine a few times over.
   static const int waves = [] {
     const char* e = getenv("KOA_WGRAD_WAVES");
-    return e ? atoi(e) : 4;
+    return e ? atoi(e) : 2;  // measured on the full step: 2 waves 103.3 ms, 4 waves 103.7 ms, 6 waves 105.2 ms (serial pass)
   }();
   int splits = koa_cdiv(waves * koa_num_sms(), tiles * (CTA2 ? 2 : 1));
   if (splits > num_kb) splits = num_kb;
