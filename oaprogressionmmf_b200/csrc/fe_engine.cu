@@ -25,18 +25,20 @@
   } while (0)
 
 namespace {
-// KOA_WGRAD_XCVT=1: the weight gradients read the fp16 forward activations and convert them to bf16 in shared memory
-// (gemm_wgrad_kernel XCVT); the forward pass then writes no bf16 copies (2 of the 6 bytes per element of the
-// BatchNorm-apply pass, a quarter of the activation workspace). Measured on B200 the step time is the same (165.4 vs
-// 165.8 knees/s): the conversion doubles the shared-memory traffic of a kernel whose 128 x 128 tiles are already
-// shared-memory bound (494 -> 425 TFLOP/s), which costs what the smaller BatchNorm-apply pass saves. Default: keep the
-// copies; turn the conversion on when the 25 % of workspace matter (larger batches).
-bool wgrad_converts_x() {
+// Operands of the weight gradients. dY is bf16 and one tcgen05 MMA takes one 16-bit format, so the fp16 forward
+// activations either get a bf16 copy (written by the BatchNorm-apply pass: 2 of its 6-8 bytes per element) or are
+// converted to bf16 in shared memory by the weight-gradient kernel (gemm_wgrad_kernel XCVT, x_f16 = 2), which doubles the
+// shared-memory traffic of a kernel whose 128 x 128 tiles are already shared-memory bound (494 -> 425 TFLOP/s).
+// KOA_WGRAD_XCVT: 0 = copies everywhere; 1 = no copies (-25 % workspace, same step time as 0); 2 (default) = no copies
+// where the consuming weight gradient is HBM-bound anyway and the conversion is free: the pooled stem output and the
+// outputs of the bottleneck blocks with at most 512 channels (layer1 / layer2: consumed by 1x1 convolutions with
+// 50-170 FLOP per byte), copies for the rest.
+int wgrad_xcvt_mode() {
   static const int v = [] {
     const char* e = getenv("KOA_WGRAD_XCVT");
-    return e == nullptr ? 0 : atoi(e);
+    return e == nullptr ? 2 : atoi(e);
   }();
-  return v != 0;
+  return v;
 }
 }  // namespace
 
@@ -161,11 +163,12 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
   p.a_stem = ws.take((size_t)us.rows_out * 64 * 2);  // im2col operand of the stem GEMM (kept for its weight gradient)
   p.a0 = ws.take((size_t)us.rows_out * 64 * 2);
   const bool bw = d->need_backward != 0;
-  // bf16 copies of the activations (operands of the weight gradients) only when the weight-gradient kernels do not
-  // convert the fp16 activations themselves (KOA_WGRAD_XCVT=0)
-  const bool bwc = bw && !wgrad_converts_x();
+  // bf16 copies of the activations (operands of the weight gradients): see wgrad_xcvt_mode()
+  const int xm = wgrad_xcvt_mode();
+  const bool bwc = bw && xm != 1;                 // copies of the narrow a1 / a2 tensors
+  const bool bwc_p0 = bwc && !(xm == 2 && bottleneck);
   p.p0 = ws.take((size_t)n * ph * pw * 64 * 2);
-  p.p0_bf = bwc ? ws.take((size_t)n * ph * pw * 64 * 2) : 0;
+  p.p0_bf = bwc_p0 ? ws.take((size_t)n * ph * pw * 64 * 2) : 0;
   p.idx0 = ws.take((size_t)n * ph * pw * 64);
   size_t prev = p.p0, prev_bf = p.p0_bf;
   size_t max_act = (size_t)us.rows_out * 64;
@@ -181,7 +184,8 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
       b.a2_bf = bwc ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
       const Unit& u3 = p.units[b.u3];
       b.out = ws.take((size_t)u3.rows_out * u3.cout * 2);
-      b.out_bf = bwc ? ws.take((size_t)u3.rows_out * u3.cout * 2) : 0;
+      const bool wide_hbm_bound = xm == 2 && u3.cout <= 512;  // consumers: 1x1 conv1 / downsample of the next block
+      b.out_bf = (bwc && !wide_hbm_bound) ? ws.take((size_t)u3.rows_out * u3.cout * 2) : 0;
       max_act = std::max(max_act, (size_t)u3.rows_out * u3.cout);
     } else {
       b.a2 = 0; b.a2_bf = 0;
@@ -467,10 +471,13 @@ int bn_backward(const Unit& u, const Unit* u_b, const ParamView& pv, void* const
 }
 
 // dW of one unit into the fp32 gradient tensor (PyTorch layout [Cout][Cin/g][k][k]). `x`: bf16 copy of the unit's input.
-int conv_wgrad(const Plan& p, const Unit& u, const void* x, const void* dy, void* const* grads, void* ws, cudaStream_t st) {
+// `x_bf`: offset of the bf16 copy of the unit's input (0 = none: the fp16 activation at `x_f16` is converted in-kernel).
+int conv_wgrad(const Plan& p, const Unit& u, size_t x_bf, size_t x_f16, const void* dy, void* const* grads, void* ws,
+               cudaStream_t st) {
   float* gw = (float*)grads[u.idx * 3 + 0];
   if (gw == nullptr) return 0;
-  const int xf = wgrad_converts_x() ? 2 : 0;  // 2: x is the fp16 activation, converted inside the kernel
+  const void* x = at(ws, x_bf ? x_bf : x_f16);
+  const int xf = x_bf ? 0 : 2;  // 2: x is the fp16 activation, converted inside the kernel
   if (u.k == 1 && u.stride == 1) return koa_gemm_wgrad_launch(dy, x, gw, (int)u.rows_out, u.cout, u.cin, xf, st);
   if (u.k == 1) return koa_conv_wgrad_launch(dy, x, gw, p.n_img, u.hin, u.win, u.cin, u.cout, 1, 1, u.stride, 0, xf, st);
   float* scratch = (float*)at(ws, u.dw_scratch);
@@ -657,7 +664,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     void* d_a1 = at(ws, p.t[3]);
     if (u3) {
       KOA_TRY(side.begin(&sw));
-      KOA_TRY(conv_wgrad(p, *u3, at(ws, b.a2_bf ? b.a2_bf : b.a2), dy_last, grads, ws, sw));
+      KOA_TRY(conv_wgrad(p, *u3, b.a2_bf, b.a2, dy_last, grads, ws, sw));
       KOA_TRY(side.reads(0));
       void* d_a2 = at(ws, p.t[2]);
       koa_epilogue_t ep{};
@@ -667,7 +674,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       KOA_TRY(conv_dgrad(p, *u3, dy_last, ws, &ep, nullptr, st));
       KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, nullptr, d_a2, nullptr, training, fuse, st));  // in place -> dy2
       KOA_TRY(side.begin(&sw));
-      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf ? b.a1_bf : b.a1), d_a2, grads, ws, sw));
+      KOA_TRY(conv_wgrad(p, u2, b.a1_bf, b.a1, d_a2, grads, ws, sw));
       KOA_TRY(side.reads(2));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
@@ -676,7 +683,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       KOA_TRY(conv_dgrad(p, u2, d_a2, ws, &ep2, at(ws, p.t[4]), st));
     } else {
       KOA_TRY(side.begin(&sw));
-      KOA_TRY(conv_wgrad(p, u2, at(ws, b.a1_bf ? b.a1_bf : b.a1), dy_last, grads, ws, sw));
+      KOA_TRY(conv_wgrad(p, u2, b.a1_bf, b.a1, dy_last, grads, ws, sw));
       KOA_TRY(side.reads(0));
       koa_epilogue_t ep2{};
       ep2.out = d_a1;
@@ -686,7 +693,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     }
     KOA_TRY(bn_backward(u1, nullptr, pv, grads, ws, d_a1, nullptr, d_a1, nullptr, training, fuse, st));  // in place -> dy1
     KOA_TRY(side.begin(&sw));
-    KOA_TRY(conv_wgrad(p, u1, at(ws, b.in_bf ? b.in_bf : b.in), d_a1, grads, ws, sw));
+    KOA_TRY(conv_wgrad(p, u1, b.in_bf, b.in, d_a1, grads, ws, sw));
     KOA_TRY(side.reads(3));
     // G of the previous block = (dgrad(conv1) + identity path) * (x > 0); x is that block's output (or the pooled
     // stem activation, where the gate is a no-op for the gradient that survives the stem's own ReLU mask).
@@ -702,7 +709,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
     } else {
       KOA_TRY(side.begin(&sw));
-      KOA_TRY(conv_wgrad(p, *ud, at(ws, b.in_bf ? b.in_bf : b.in), dy_down, grads, ws, sw));
+      KOA_TRY(conv_wgrad(p, *ud, b.in_bf, b.in, dy_down, grads, ws, sw));
       KOA_TRY(side.reads(1));
       if (ud->stride == 1) {
         koa_epilogue_t ep{};
