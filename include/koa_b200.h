@@ -194,6 +194,56 @@ int koa_dropout_mask(unsigned long long seed, unsigned int site, long long rows,
 /* per-channel sum / sum of squares of a bf16 [rows][c] tensor (stand-alone BatchNorm statistics). */
 int koa_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, void* stream);
 
+/* ---- either side of the path: optimiser step, input resampling, predictions --------- */
+/* One tensor of an Adam step: fp32 parameter, its gradient and the two moment buffers (device pointers). */
+typedef struct koa_adam_tensor {
+  float* param;
+  const float* grad;         /* NULL: the parameter is skipped, as torch.optim skips `p.grad is None` */
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long numel;
+} koa_adam_tensor_t;
+
+typedef struct koa_adam_hyper {
+  double lr, beta1, beta2, eps, weight_decay;
+  double grad_scale;         /* gradients are multiplied by this first; 0 means 1 */
+  int step;                  /* 1 for the first update (bias corrections 1 - beta^step) */
+  int decoupled_weight_decay; /* 0: Adam (weight_decay * param added to the gradient), 1: AdamW */
+} koa_adam_hyper_t;
+
+/* torch.optim.Adam / AdamW (amsgrad=False, maximize=False) on `n_tensors` tensors: the optimiser the reference builds
+ * from dict_optimizers (koafusion/various/_optimizers.py:49-54, koafusion/run/train_prog_fus.py:88-91) and steps after
+ * every backward (train_prog_fus.py:166). `tensors` is a HOST array of descriptors holding device pointers; the library
+ * passes them to the kernel 64 at a time as launch parameters (no device-side table, no copy). 28 bytes of HBM traffic
+ * per parameter element. */
+int koa_adam_step(const koa_adam_tensor_t* tensors, int n_tensors, const koa_adam_hyper_t* h, void* stream);
+
+enum { KOA_DT_F32 = 0, KOA_DT_U8 = 1, KOA_DT_U16 = 2, KOA_DT_I16 = 3 };
+
+/* out[b] = scale[b] * interpolate(in[b]) + shift[b] for `batch` volumes of in_dims[3] -> out_dims[3] elements (last
+ * dimension innermost; 2-D images pass a leading 1): torch.nn.functional.interpolate(mode="linear" / "bilinear" /
+ * "trilinear", align_corners=False, recompute_scale_factor=True) as PTInterpolate applies it to every modality right
+ * before the model (koafusion/preproc/_pt.py:175-200, koafusion/run/train_prog_fus.py:111-116,143-146). For the factors
+ * of the recipes (0.5 / 1.0 on even sizes) this is a 2x2(x2) box mean. The input may be fp32 or the integer type the
+ * volumes have on disk (KOA_DT_*); scale / shift (fp32 [batch], both or neither) fold an affine intensity map in front
+ * of the model into the same pass (the interpolation is linear, so the two commute). */
+int koa_resample_linear(const void* in, int in_dtype, float* out, int batch, const int* in_dims, const int* out_dims,
+                        const float* scale, const float* shift, void* stream);
+
+/* Per-volume coefficients of PTToUnitRange followed by PTNormalize(mean, std) (koafusion/preproc/_pt.py:75-124;
+ * koafusion/datasets/_data_provider.py:297-334): z = ((x - min) / (max - min) - mean) / std = x * scale + shift with the
+ * minimum / maximum taken over each of the `batch` volumes of n_per elements. workspace: 2 * batch unsigned ints;
+ * minmax (optional): fp32 [batch][2]. */
+int koa_unit_range_affine(const void* in, int in_dtype, int batch, long long n_per, float mean, float stdev,
+                          unsigned int* workspace, float* scale, float* shift, float* minmax, void* stream);
+
+/* proba = softmax(logits, dim=1), pred = argmax(logits, dim=1) for logits [batch][classes]
+ * (koafusion/run/eval_prog_fus.py:300-304). proba / pred may be NULL. */
+int koa_predict(const float* logits, float* proba, long long* pred, int batch, int classes, void* stream);
+/* Fold ensemble of the reference: out = softmax(mean over folds of proba[folds][batch][classes]), pred = argmax(out)
+ * (koafusion/run/eval_prog_fus.py:330-336; the softmax is applied to the averaged probabilities, as the reference does). */
+int koa_ensemble_proba(const float* proba, float* out, long long* pred, int folds, int batch, int classes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

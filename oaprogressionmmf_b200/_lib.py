@@ -84,7 +84,35 @@ class FeatDesc(C.Structure):
     ]
 
 
+class AdamTensor(C.Structure):
+    """Mirror of ``koa_adam_tensor_t``."""
+
+    _fields_ = [
+        ("param", C.c_void_p),
+        ("grad", C.c_void_p),
+        ("exp_avg", C.c_void_p),
+        ("exp_avg_sq", C.c_void_p),
+        ("numel", C.c_longlong),
+    ]
+
+
+class AdamHyper(C.Structure):
+    """Mirror of ``koa_adam_hyper_t``."""
+
+    _fields_ = [
+        ("lr", C.c_double),
+        ("beta1", C.c_double),
+        ("beta2", C.c_double),
+        ("eps", C.c_double),
+        ("weight_decay", C.c_double),
+        ("grad_scale", C.c_double),
+        ("step", C.c_int),
+        ("decoupled_weight_decay", C.c_int),
+    ]
+
+
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2, 3
+DT_F32, DT_U8, DT_U16, DT_I16 = 0, 1, 2, 3
 ARCH_IDS = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnext50_32x4d": 3}
 
 _P = C.c_void_p
@@ -131,6 +159,11 @@ SIGNATURES = {
     "koa_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "koa_col_stats": (_I, [_P, _P, _P, C.c_longlong, _I, _P]),
     "koa_dropout_mask": (_I, [C.c_ulonglong, C.c_uint, C.c_longlong, _I, _F, _P, _P]),
+    "koa_adam_step": (_I, [_P, _I, C.POINTER(AdamHyper), _P]),
+    "koa_resample_linear": (_I, [_P, _I, _P, _I, C.POINTER(_I), C.POINTER(_I), _P, _P, _P]),
+    "koa_unit_range_affine": (_I, [_P, _I, _I, C.c_longlong, _F, _F, _P, _P, _P, _P, _P]),
+    "koa_predict": (_I, [_P, _P, _P, _I, _I, _P]),
+    "koa_ensemble_proba": (_I, [_P, _P, _P, _I, _I, _I, _P]),
 }
 
 
@@ -188,6 +221,19 @@ def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().koa_last_error()
         raise KoaError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def require_cuda(t, what: str) -> None:
+    """The product has no CPU path: a host tensor is an error, never a silent fallback."""
+    if not t.is_cuda:
+        raise KoaError(f"{what} needs a CUDA tensor: this path has no CPU fallback")
+
+
+def on_device(device):
+    """Context manager making ``device`` the current CUDA device for the launches of a C call."""
+    import torch
+
+    return torch.cuda.device(device)
 
 
 def debug_flag() -> int:

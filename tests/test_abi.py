@@ -64,6 +64,9 @@ def test_struct_mirrors_match_header_field_order():
     assert fields("koa_epilogue") == [f[0] for f in _lib.Epilogue._fields_]
     assert fields("koa_fe_desc") == [f[0] for f in _lib.FeDesc._fields_]
     assert fields("koa_feat_desc") == [f[0] for f in _lib.FeatDesc._fields_]
+    assert fields("koa_adam_tensor") == [f[0] for f in _lib.AdamTensor._fields_]
+    assert fields("koa_adam_hyper") == [f[0] for f in _lib.AdamHyper._fields_]
+    assert ctypes.sizeof(_lib.AdamTensor) == 40 and ctypes.sizeof(_lib.AdamHyper) == 56
 
 
 def test_product_never_imports_the_oracle():
