@@ -194,6 +194,39 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+def measure_full_step(step, model, dev_batches, steps, knees, peaks):
+    """zero_grad + forward + FocalLoss + backward + Adam (koa_adam_step) on device-resident batches: knees/s of the full
+    training step, and the optimiser update on its own against the HBM roofline (28 B per parameter element: parameter
+    and both moments read and written, gradient read)."""
+    from oaprogressionmmf_b200.optim import Adam
+
+    opt = Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for i in range(2):
+        step(*dev_batches[i % 2])
+        opt.step()
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(steps):
+        step(*dev_batches[i % 2])
+        marks[i][0].record()
+        opt.step()
+        marks[i][1].record()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    adam_ms = sum(a.elapsed_time(b) for a, b in marks)
+    n_live = sum(p.numel() for g in opt.param_groups for p in g["params"] if p.grad is not None)
+    adam_ms /= steps
+    gbs = 28.0 * n_live / (adam_ms * 1e-3) / 1e9 if adam_ms > 0 else None
+    return dict(value=knees / (ms * 1e-3), unit="knees/s", ms_per_step=ms,
+                step="zero_grad + forward + FocalLoss + backward + Adam(lr 1e-4, weight_decay 1e-4)",
+                adam=dict(kernel="adam_kernel (multi-tensor, 64 tensors per launch)", ms=adam_ms, elements=n_live,
+                          bound="hbm", achieved=gbs, peak=peaks["hbm"], unit="GB/s (28 B per element)",
+                          frac=gbs / peaks["hbm"] if gbs else None))
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -361,6 +394,15 @@ def run_ours(args):
         cpu = dict(value=args.cpu_knees / times[0], unit="knees/s", cores=threads, kind="port",
                    sample=f"1 step (no warm-up) of forward+FocalLoss+backward on {args.cpu_knees} knee(s) of the same "
                           f"workload with the fp32 eager PyTorch restatement of the reference (oracle port), {times[0]:.1f} s")
+    # ---- full training step: the same step followed by the optimiser update of the reference's training
+    # configuration (Adam, lr 1e-4, weight decay 1e-4: conf/prog_fus.yaml:47-48) through koa_adam_step. Reported next to
+    # `value`, never instead of it; single GPU only and last, so that nothing above depends on it.
+    full_step = None
+    if ws == 1 and not args.skip_e2e and not args.no_full_step:
+        try:
+            full_step = measure_full_step(step, model, dev_batches, args.steps, B, peaks)
+        except Exception as e:  # noqa: BLE001
+            full_step = dict(error=f"{type(e).__name__}: {e}"[:300])
     line = dict(metric=METRIC, value=value, unit="knees/s", n_gpus=ws, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=args.workload, description=WORKLOAD_DESC.get(args.workload, args.workload),
@@ -374,7 +416,7 @@ def run_ours(args):
                             l2="working set per step (tens of GB of activations) exceeds the 126 MB L2; two input batches alternate"),
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit="knees/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
-                gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag)
+                gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag, full_step=full_step)
     print(json.dumps(line), flush=True)
     if ws > 1:
         dist.destroy_process_group()
@@ -393,6 +435,7 @@ def main():
     ap.add_argument("--cpu-knees", type=int, default=1, help="knees in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiler runs: skip the end-to-end pass")
+    ap.add_argument("--no-full-step", action="store_true", help="skip the forward+backward+Adam measurement")
     ap.add_argument("--profile-dump", default=None, help="write the per-shape tcgen05 kernel timing table to this file")
     args = ap.parse_args()
     if args.impl == "reference":
