@@ -354,6 +354,9 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
   splits = koa_cdiv(num_kb, kb_per_split);
   dim3 grid((unsigned)tiles * (CTA2 ? 2 : 1), (unsigned)splits);
   const unsigned threads = XCVT ? kWgradCvtThreads : kGemmThreads;
+  // experiment (default off, not yet measured): split-K partial sums leave through cp.reduce.async.bulk, one 256 / 512-byte
+  // reduction per output row instead of 16-byte red instructions (gemm_tc.cuh)
+  static const int bulk_red = env_int("KOA_WGRAD_BULK_RED", 0);
   {
     // grouped: only the diagonal 64x64 blocks are algorithmic work
     const double n_eff = g.grouped ? 64.0 : (double)cin;
@@ -372,9 +375,9 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16));
+      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16, 0));
     } else {
-      kern<<<grid, threads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16);
+      kern<<<grid, threads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16, bulk_red);
     }
   }
   KOA_LAUNCH_CHECK();
