@@ -237,6 +237,26 @@ int koa_resample_linear(const void* in, int in_dtype, float* out, int batch, con
 int koa_unit_range_affine(const void* in, int in_dtype, int batch, long long n_per, float mean, float stdev,
                           unsigned int* workspace, float* scale, float* shift, float* minmax, void* stream);
 
+/* One volume of a training batch: where its crop starts in the stored volume and the state of the random transforms. */
+typedef struct koa_augment {
+  int off0, off1, off2;      /* first voxel of the crop (RandomCrop / CenterCrop, koafusion/preproc/_np_nd.py:62-140) */
+  int rotate;                /* 1: in-slice rotation by theta (PTRotate3DInSlice / PTRotate2D, _pt.py:257-358) */
+  float cos_t, sin_t;
+  float inv_gamma;           /* 0: no gamma correction; else u -> u^(1/gamma) (PTGammaCorrection, _pt.py:203-232) */
+  float lo, range;           /* minimum and max - min of the crop: written by the call, the caller leaves them alone */
+  float reserved;
+} koa_augment_t;
+
+/* The per-sample transform chain of the training loader (koafusion/datasets/_data_provider.py:297-334) followed by the
+ * on-GPU downscale, on the volumes as stored: crop -> PTToUnitRange (min / max of the crop) -> rotation about the slice
+ * axis (F.affine_grid + F.grid_sample, bilinear, zero padding, align_corners=False) -> gamma -> PTNormalize(mean, std)
+ * -> PTInterpolate to out_dims. in: `batch` volumes of src_dims[3] elements (rows, columns, slices; slices innermost; a
+ * 2-D image has 1 slice); params: DEVICE array [batch]; workspace: 2 * batch unsigned ints. The validation / test
+ * chain is the same call with rotate = 0, inv_gamma = 0 and the centre-crop offsets. */
+int koa_augment_resample(const void* in, int in_dtype, float* out, koa_augment_t* params, int batch, const int* src_dims,
+                         const int* crop_dims, const int* out_dims, float mean, float stdev, unsigned int* workspace,
+                         void* stream);
+
 /* proba = softmax(logits, dim=1), pred = argmax(logits, dim=1) for logits [batch][classes]
  * (koafusion/run/eval_prog_fus.py:300-304). proba / pred may be NULL. */
 int koa_predict(const float* logits, float* proba, long long* pred, int batch, int classes, void* stream);

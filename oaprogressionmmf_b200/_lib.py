@@ -111,6 +111,23 @@ class AdamHyper(C.Structure):
     ]
 
 
+class Augment(C.Structure):
+    """Mirror of ``koa_augment_t``."""
+
+    _fields_ = [
+        ("off0", C.c_int),
+        ("off1", C.c_int),
+        ("off2", C.c_int),
+        ("rotate", C.c_int),
+        ("cos_t", C.c_float),
+        ("sin_t", C.c_float),
+        ("inv_gamma", C.c_float),
+        ("lo", C.c_float),
+        ("range", C.c_float),
+        ("reserved", C.c_float),
+    ]
+
+
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2, 3
 DT_F32, DT_U8, DT_U16, DT_I16 = 0, 1, 2, 3
 ARCH_IDS = {"resnet18": 0, "resnet34": 1, "resnet50": 2, "resnext50_32x4d": 3}
@@ -162,6 +179,7 @@ SIGNATURES = {
     "koa_adam_step": (_I, [_P, _I, C.POINTER(AdamHyper), _P]),
     "koa_resample_linear": (_I, [_P, _I, _P, _I, C.POINTER(_I), C.POINTER(_I), _P, _P, _P]),
     "koa_unit_range_affine": (_I, [_P, _I, _I, C.c_longlong, _F, _F, _P, _P, _P, _P, _P]),
+    "koa_augment_resample": (_I, [_P, _I, _P, _P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _F, _F, _P, _P]),
     "koa_predict": (_I, [_P, _P, _P, _I, _I, _P]),
     "koa_ensemble_proba": (_I, [_P, _P, _P, _I, _I, _I, _P]),
 }

@@ -8,6 +8,7 @@
 
 #include "koa_common.cuh"
 #include "koa_internal.h"
+#include "step_arith.cuh"
 
 namespace {
 
@@ -100,46 +101,20 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
 // linear resampling of (B, D0, D1, D2) volumes, D2 innermost (F.interpolate, align_corners=False, scales recomputed
 // from the sizes) with an optional per-volume affine map (unit range + z-score) folded in
 // ======================================================================================================
-template <typename T> __device__ __forceinline__ float ld_f(const T* p) { return (float)__ldg(p); }
+using koa_arith::Dims3;
+using koa_arith::ld_f;
 
-struct Tap { int i0, step; float l0, l1; };
-__device__ __forceinline__ Tap make_tap(int dst, float rscale, int n_in) {
-  // area_pixel_compute_source_index: src = scale * (dst + 0.5) - 0.5, clamped at 0 (linear modes)
-  float src = rscale * ((float)dst + 0.5f) - 0.5f;
-  if (src < 0.f) src = 0.f;
-  Tap t;
-  t.i0 = (int)src;
-  if (t.i0 > n_in - 1) t.i0 = n_in - 1;
-  t.step = t.i0 < n_in - 1 ? 1 : 0;
-  t.l1 = src - (float)t.i0;
-  t.l0 = 1.f - t.l1;
-  return t;
-}
-
+// the per-element arithmetic lives in step_arith.cuh (shared with the CPU check of tests/host_emul)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) resample_linear_kernel(const T* __restrict__ in, float* __restrict__ out,
-                                                                    long long total, int d0i, int d1i, int d2i, int d0o,
-                                                                    int d1o, int d2o, float rs0, float rs1, float rs2,
-                                                                    const float* __restrict__ scale,
+                                                                    long long total, Dims3 di, Dims3 dout, float rs0,
+                                                                    float rs1, float rs2, const float* __restrict__ scale,
                                                                     const float* __restrict__ shift) {
-  const long long in_per = (long long)d0i * d1i * d2i;
+  const long long in_per = (long long)di.d0 * di.d1 * di.d2;
   for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    long long t = i;
-    const int x2 = (int)(t % d2o); t /= d2o;
-    const int x1 = (int)(t % d1o); t /= d1o;
-    const int x0 = (int)(t % d0o);
-    const long long b = t / d0o;
-    const Tap a = make_tap(x0, rs0, d0i), h = make_tap(x1, rs1, d1i), w = make_tap(x2, rs2, d2i);
-    const T* p00 = in + b * in_per + ((long long)a.i0 * d1i + h.i0) * d2i + w.i0;
-    const T* p01 = p00 + (long long)h.step * d2i;
-    const T* p10 = p00 + (long long)a.step * d1i * d2i;
-    const T* p11 = p10 + (long long)h.step * d2i;
-    // nesting of upsample_trilinear3d: depth outermost, width innermost
-    const float v00 = w.l0 * ld_f(p00) + w.l1 * ld_f(p00 + w.step);
-    const float v01 = w.l0 * ld_f(p01) + w.l1 * ld_f(p01 + w.step);
-    const float v10 = w.l0 * ld_f(p10) + w.l1 * ld_f(p10 + w.step);
-    const float v11 = w.l0 * ld_f(p11) + w.l1 * ld_f(p11 + w.step);
-    float val = a.l0 * (h.l0 * v00 + h.l1 * v01) + a.l1 * (h.l0 * v10 + h.l1 * v11);
+    int x0, x1, x2;
+    const long long b = koa_arith::split_index(i, dout, x0, x1, x2);
+    float val = koa_arith::resample_element<T>(in + b * in_per, di, x0, x1, x2, rs0, rs1, rs2);
     if (scale != nullptr) val = fmaf(val, __ldg(scale + b), __ldg(shift + b));
     out[i] = val;
   }
@@ -259,6 +234,68 @@ __global__ void ensemble_kernel(const float* __restrict__ proba, float* __restri
   if (pred != nullptr) pred[b] = arg;
 }
 
+// ======================================================================================================
+// training-time augmentation fused with the resampling: crop -> unit range -> in-slice rotation (bilinear, zero
+// padding) -> gamma -> z-score -> linear resampling, one pass over the stored integers
+// ======================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads) augment_resample_kernel(const T* __restrict__ in, float* __restrict__ out,
+                                                                     const koa_augment_t* __restrict__ params,
+                                                                     long long total, Dims3 src, Dims3 crop, Dims3 dout,
+                                                                     float rs0, float rs1, float rs2, float mean,
+                                                                     float stdev) {
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    int x0, x1, x2;
+    const long long b = koa_arith::split_index(i, dout, x0, x1, x2);
+    const koa_augment_t a = params[b];
+    out[i] = koa_arith::augment_element<T>(koa_arith::crop_origin(in, b, a, src), a, src, crop, x0, x1, x2, rs0, rs1, rs2,
+                                           mean, stdev);
+  }
+}
+
+// minimum / maximum over the crop of every stored volume (strided), into the ordered-integer workspace
+template <typename T>
+__global__ void __launch_bounds__(kThreads) crop_minmax_kernel(const T* __restrict__ in,
+                                                                const koa_augment_t* __restrict__ params, int s0, int s1,
+                                                                int s2, int d0, int d1, int d2, unsigned* __restrict__ mm) {
+  const long long st_r = (long long)s1 * s2, st_c = s2;
+  const koa_augment_t a = params[blockIdx.y];
+  const T* vol = koa_arith::crop_origin(in, (long long)blockIdx.y, a, Dims3{s0, s1, s2});
+  const long long n = (long long)d0 * d1 * d2;
+  float lo = INFINITY, hi = -INFINITY;
+  for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+    long long t = i;
+    const int s = (int)(t % d2); t /= d2;
+    const int c = (int)(t % d1);
+    const int r = (int)(t / d1);
+    const float f = ld_f(vol + r * st_r + c * st_c + s);
+    lo = fminf(lo, f); hi = fmaxf(hi, f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float s_lo[kThreads / 32], s_hi[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < kThreads / 32; ++k) { lo = fminf(lo, s_lo[k]); hi = fmaxf(hi, s_hi[k]); }
+    if (lo <= hi) {
+      atomicMin(mm + 2 * blockIdx.y, ordered_u32(lo));
+      atomicMax(mm + 2 * blockIdx.y + 1, ordered_u32(hi));
+    }
+  }
+}
+
+__global__ void crop_minmax_finish_kernel(const unsigned* __restrict__ mm, koa_augment_t* params, int batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch) return;
+  const float lo = from_ordered_u32(mm[2 * i]), hi = from_ordered_u32(mm[2 * i + 1]);
+  params[i].lo = lo;
+  params[i].range = hi - lo;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename T>
@@ -267,7 +304,8 @@ int launch_resample(const void* in, float* out, long long total, const int* di, 
   // the scale PyTorch derives when recompute_scale_factor=True: input size / output size, in float
   const float rs0 = (float)di[0] / (float)dout[0], rs1 = (float)di[1] / (float)dout[1], rs2 = (float)di[2] / (float)dout[2];
   resample_linear_kernel<T><<<capped_grid((total + kThreads - 1) / kThreads, 16), kThreads, 0, st>>>(
-      static_cast<const T*>(in), out, total, di[0], di[1], di[2], dout[0], dout[1], dout[2], rs0, rs1, rs2, scale, shift);
+      static_cast<const T*>(in), out, total, Dims3{di[0], di[1], di[2]}, Dims3{dout[0], dout[1], dout[2]}, rs0, rs1, rs2, scale,
+      shift);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -283,6 +321,30 @@ int launch_minmax(const void* in, int batch, long long n_per, unsigned* mm, cuda
   if (per < 1) per = 1;
   dim3 grid((unsigned)per, (unsigned)batch);
   minmax_kernel<T><<<grid, kThreads, 0, st>>>(static_cast<const T*>(in), n_per, vec_ok, mm);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+int launch_augment(const void* in, float* out, const koa_augment_t* params, int batch, const int* src, const int* crop,
+                   const int* dout, float mean, float stdev, unsigned* ws, cudaStream_t st) {
+  minmax_init_kernel<<<koa_cdiv(batch, 128), 128, 0, st>>>(ws, batch);
+  KOA_LAUNCH_CHECK();
+  const long long n = (long long)crop[0] * crop[1] * crop[2];
+  long long per = (n + kThreads * 8 - 1) / (kThreads * 8);  // ~8 elements per thread
+  const long long want = ((long long)koa_num_sms() * 8 + batch - 1) / batch;
+  if (per > want) per = want;
+  if (per < 1) per = 1;
+  crop_minmax_kernel<T><<<dim3((unsigned)per, (unsigned)batch), kThreads, 0, st>>>(static_cast<const T*>(in), params, src[0],
+                                                                                  src[1], src[2], crop[0], crop[1], crop[2], ws);
+  KOA_LAUNCH_CHECK();
+  crop_minmax_finish_kernel<<<koa_cdiv(batch, 128), 128, 0, st>>>(ws, const_cast<koa_augment_t*>(params), batch);
+  KOA_LAUNCH_CHECK();
+  const long long total = (long long)batch * dout[0] * dout[1] * dout[2];
+  const float rs0 = (float)crop[0] / (float)dout[0], rs1 = (float)crop[1] / (float)dout[1], rs2 = (float)crop[2] / (float)dout[2];
+  augment_resample_kernel<T><<<capped_grid((total + kThreads - 1) / kThreads, 16), kThreads, 0, st>>>(
+      static_cast<const T*>(in), out, params, total, Dims3{src[0], src[1], src[2]}, Dims3{crop[0], crop[1], crop[2]},
+      Dims3{dout[0], dout[1], dout[2]}, rs0, rs1, rs2, mean, stdev);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -378,6 +440,22 @@ extern "C" int koa_unit_range_affine(const void* in, int in_dtype, int batch, lo
   unit_range_affine_kernel<<<koa_cdiv(batch, 128), 128, 0, ST>>>(workspace, mean, stdev, scale, shift, minmax, batch);
   KOA_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int koa_augment_resample(const void* in, int in_dtype, float* out, koa_augment_t* params, int batch,
+                                    const int* src_dims, const int* crop_dims, const int* out_dims, float mean, float stdev,
+                                    unsigned int* workspace, void* stream) {
+  KOA_REQUIRE(in && out && params && src_dims && crop_dims && out_dims && workspace && batch > 0, "null / empty argument");
+  KOA_REQUIRE(batch <= 65535, "at most 65535 volumes per call");
+  for (int d = 0; d < 3; ++d)
+    KOA_REQUIRE(crop_dims[d] > 0 && out_dims[d] > 0 && src_dims[d] >= crop_dims[d], "crop larger than the stored volume");
+  switch (in_dtype) {
+    case KOA_DT_F32: return launch_augment<float>(in, out, params, batch, src_dims, crop_dims, out_dims, mean, stdev, workspace, ST);
+    case KOA_DT_U8: return launch_augment<uint8_t>(in, out, params, batch, src_dims, crop_dims, out_dims, mean, stdev, workspace, ST);
+    case KOA_DT_U16: return launch_augment<uint16_t>(in, out, params, batch, src_dims, crop_dims, out_dims, mean, stdev, workspace, ST);
+    case KOA_DT_I16: return launch_augment<int16_t>(in, out, params, batch, src_dims, crop_dims, out_dims, mean, stdev, workspace, ST);
+    default: koa_set_error("koa_augment_resample: unknown input type %d", in_dtype); return KOA_ERR_ARG;
+  }
 }
 
 extern "C" int koa_predict(const float* logits, float* proba, long long* pred, int batch, int classes, void* stream) {

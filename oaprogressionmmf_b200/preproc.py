@@ -12,6 +12,10 @@ CPU workers have already mapped to the unit range and z-scored (``koafusion/prep
   (uint8 / uint16: a quarter / half of the fp32 host->device bytes): per-volume minimum / maximum on the device
   (``koa_unit_range_affine``), then unit range + z-score + resampling in a single pass over the integers.
 
+* ``augment_normalize_downscale`` goes one step further up the loader: the whole per-sample transform chain of
+  ``koafusion/datasets/_data_provider.py:297-334`` (crop, unit range, in-slice rotation, gamma, z-score) and the downscale
+  in one ``koa_augment_resample`` call on the stored integers, so the 24 CPU workers of the reference only read files.
+
 No CPU or PyTorch fallback: CPU tensors raise.
 """
 from __future__ import annotations
@@ -110,3 +114,78 @@ def unit_range_normalize_downscale(x: torch.Tensor, mean: float, std: float, fac
     scale, shift, _ = unit_range_affine(x, mean, std)
     size_out = output_size(x.shape[2:], tuple(factor)) if factor else list(x.shape[2:])
     return _resample(x, size_out, scale, shift)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the per-sample transform chain of the loaders, fused with the downscale
+# ---------------------------------------------------------------------------------------------------------------------
+def crop_offsets(size_in: Sequence[int], size_out: Sequence[int], ratios=None) -> list:
+    """First voxel of the crop: ``RandomCrop`` (``floor(ratio * (in - out))`` per axis, ``ratios`` in [0, 1)) or, without
+    ratios, ``CenterCrop`` (``(in - out) // 2``) — ``koafusion/preproc/_np_nd.py:62-140``."""
+    for d_in, d_out in zip(size_in, size_out):
+        if d_in < d_out:
+            raise ValueError(f"Invalid crop size {list(size_out)!r} for input {list(size_in)!r}")
+    if ratios is None:
+        return [(i - o) // 2 for i, o in zip(size_in, size_out)]
+    return [int(math.floor(r * (i - o))) for r, i, o in zip(ratios, size_in, size_out)]
+
+
+def draw_train_state(rng, size_in, size_out, degree_range=(-15.0, 15.0), rotate_prob=0.5, gamma_range=(0.5, 2.0),
+                     gamma_prob=0.5, with_gamma=True) -> dict:
+    """One sample's random state, drawn as the reference transforms draw theirs (``random.random()`` per crop axis,
+    ``p`` then ``theta`` for the rotation, ``p`` then ``gamma`` for the gamma correction; ``_np_nd.py:103-105``,
+    ``_pt.py:229-232,305-307``). ``rng`` is a ``random.Random``. Sequences without gamma (T2 maps) pass
+    ``with_gamma=False``."""
+    ratios = [rng.random() for _ in size_out]
+    p_rot, theta = rng.random(), rng.uniform(math.radians(degree_range[0]), math.radians(degree_range[1]))
+    state = {"offsets": crop_offsets(size_in, size_out, ratios), "theta": theta if p_rot < rotate_prob else None,
+             "gamma": None}
+    if with_gamma:
+        p_gam, gamma = rng.random(), rng.uniform(*gamma_range)
+        state["gamma"] = gamma if p_gam < gamma_prob else None
+    return state
+
+
+def augment_normalize_downscale(x: torch.Tensor, crop_size: Sequence[int], states: Sequence[dict], mean: float, std: float,
+                                factor=None) -> torch.Tensor:
+    """``PTInterpolate(factor)(PTNormalize(mean, std)(PTGammaCorrection(PTRotate*(PTToUnitRange(crop(x))))))`` for every
+    stored volume ``x[b, 0]`` of a (B, 1, R, C[, S]) batch in its storage type, with the per-sample state of
+    ``draw_train_state`` (``offsets``, ``theta`` or None, ``gamma`` or None). The validation / test chain is the same call
+    with ``{"offsets": crop_offsets(in, out), "theta": None, "gamma": None}``. One ``koa_augment_resample`` call; fp32
+    output of shape (B, 1, *floor(crop * factor))."""
+    _lib.require_cuda(x, "koa_augment_resample")
+    if x.dtype not in _DTYPES:
+        raise _lib.KoaError(f"koa_augment_resample takes float32 / uint8 / uint16 / int16 input, got {x.dtype}")
+    if x.ndim not in (4, 5) or x.shape[1] != 1:
+        raise ValueError(f"expected a (B, 1, R, C[, S]) batch, got {tuple(x.shape)}")
+    spatial = list(x.shape[2:])
+    crop_size = [int(c) for c in crop_size]
+    if len(crop_size) != len(spatial) or len(states) != x.shape[0]:
+        raise ValueError("crop size / state list do not match the batch")
+    size_out = output_size(crop_size, tuple(factor)) if factor else list(crop_size)
+    if any(s < 1 for s in size_out):
+        raise ValueError(f"output size {size_out} is empty")
+    pad = [1] * (3 - len(spatial))           # a 2-D image is a volume with one slice
+    table = (_lib.Augment * len(states))()
+    for t, st in zip(table, states):
+        off = list(st["offsets"]) + [0] * len(pad)
+        for o, c, s in zip(off, crop_size + pad, spatial + pad):
+            if o < 0 or o + c > s:
+                raise ValueError(f"crop {crop_size} at {st['offsets']} leaves the stored volume {spatial}")
+        t.off0, t.off1, t.off2 = off
+        theta = st.get("theta")
+        t.rotate = int(theta is not None)
+        t.cos_t, t.sin_t = (math.cos(theta), math.sin(theta)) if theta is not None else (1.0, 0.0)
+        gamma = st.get("gamma")
+        t.inv_gamma = 1.0 / gamma if gamma is not None else 0.0
+    x = x.contiguous()
+    b = x.shape[0]
+    params = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(x.device)
+    ws = torch.empty(2 * b, dtype=torch.int32, device=x.device)
+    out = torch.empty((b, 1) + tuple(size_out), dtype=torch.float32, device=x.device)
+    dims = [(C.c_int * 3)(*(list(d) + pad)) for d in (spatial, crop_size, size_out)]
+    with _lib.on_device(x.device):
+        _lib.check(_lib.load().koa_augment_resample(x.data_ptr(), _DTYPES[x.dtype], out.data_ptr(), params.data_ptr(), b,
+                                                    dims[0], dims[1], dims[2], float(mean), float(std), ws.data_ptr(),
+                                                    _lib.current_stream()), "koa_augment_resample")
+    return out

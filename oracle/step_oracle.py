@@ -15,6 +15,10 @@ that they are independent of the library kernels the reference happens to call:
                                  align_corners=False, recompute_scale_factor=True)``. Pinned against outputs of the
                                  unmodified reference class (``tests/golden_step/step_rows.json``, ``oracle/make_golden_step.py``).
 * ``unit_range_normalize``     — ``PTToUnitRange`` + ``PTNormalize`` (``koafusion/preproc/_pt.py:75-124``), same fixture.
+* ``augment_chain``            — crop + ``PTToUnitRange`` + ``PTRotate3DInSlice`` / ``PTRotate2D`` + ``PTGammaCorrection`` +
+                                 ``PTNormalize`` (``koafusion/preproc/_np_nd.py:62-140``, ``_pt.py:75-124,203-358``) in the
+                                 order of ``koafusion/datasets/_data_provider.py:297-334``; same fixture (reference
+                                 classes with their random state set explicitly).
 * ``predict`` / ``ensemble``   — ``koafusion/run/eval_prog_fus.py:300-304,330-336``; the fixture holds the output of the
                                  reference's own ``ensemble_eval_foldw`` source, executed unmodified.
 * ``lr_lambda_*``              — ``koafusion/various/_optimizers.py:4-46``, fixture from the reference functions.
@@ -96,6 +100,53 @@ def unit_range_normalize(x, mean, std):
             lo, hi = vol.min(), vol.max()
             out[b, ch] = ((vol - lo) / (hi - lo) - f(mean)) / f(std)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# per-sample transform chain of the training loader
+# ---------------------------------------------------------------------------------------------------------------------
+def rotate_in_slice(vol, theta):
+    """``PTRotate3DInSlice`` / ``PTRotate2D`` with the rotation applied (``koafusion/preproc/_pt.py:257-358``): every slice
+    of a (R, C, S) volume resampled on the grid of ``F.affine_grid([[cos, -sin, 0], [sin, cos, 0]], align_corners=False)``
+    with ``F.grid_sample(mode="bilinear", padding_mode="zeros", align_corners=False)``, written out as index arithmetic."""
+    f = np.float32
+    vol = np.asarray(vol, dtype=f)
+    R, C, _ = vol.shape
+    cs, sn = f(math.cos(theta)), f(math.sin(theta))
+    x = ((f(2) * np.arange(C, dtype=f) + f(1)) / f(C) - f(1))[None, :]
+    y = ((f(2) * np.arange(R, dtype=f) + f(1)) / f(R) - f(1))[:, None]
+    gx, gy = cs * x - sn * y, sn * x + cs * y
+    ix, iy = ((gx + f(1)) * f(C) - f(1)) * f(0.5), ((gy + f(1)) * f(R) - f(1)) * f(0.5)
+    x0, y0 = np.floor(ix).astype(np.int64), np.floor(iy).astype(np.int64)
+    wx1, wy1 = (ix - x0).astype(f), (iy - y0).astype(f)
+    out = np.zeros_like(vol)
+    for dy, wy in ((0, f(1) - wy1), (1, wy1)):
+        for dx, wx in ((0, f(1) - wx1), (1, wx1)):
+            yy, xx = y0 + dy, x0 + dx
+            ok = (yy >= 0) & (yy < R) & (xx >= 0) & (xx < C)
+            tap = vol[np.clip(yy, 0, R - 1), np.clip(xx, 0, C - 1), :] * ok[..., None]
+            out += tap * (wx * wy)[..., None].astype(f)
+    return out.astype(f)
+
+
+def augment_chain(raw, offsets, crop_size, theta, gamma, mean, std, factor):
+    """One sample of the training loader (``koafusion/datasets/_data_provider.py:297-334``) and the on-GPU downscale:
+    crop -> ``PTToUnitRange`` -> rotation (``theta`` or None) -> ``PTGammaCorrection`` (``gamma`` or None) ->
+    ``PTNormalize`` -> ``PTInterpolate``. ``raw``: stored (R, C[, S]) array; returns (1, R', C'[, S']) fp32."""
+    f = np.float32
+    raw = np.asarray(raw)
+    two_d = raw.ndim == 2
+    sel = tuple(slice(o, o + c) for o, c in zip(offsets, crop_size))
+    vol = raw[sel].astype(f)
+    vol = (vol - vol.min()) / (vol.max() - vol.min())
+    if theta is not None:
+        vol = rotate_in_slice(vol[..., None], theta)[..., 0] if two_d else rotate_in_slice(vol, theta)
+    if gamma is not None:
+        vol = np.power(vol, f(1.0 / gamma)).astype(f)
+    vol = ((vol - f(mean)) / f(std)).astype(f)[None, None]
+    if factor:
+        vol = interpolate_linear(vol, factor)
+    return vol[0]
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -67,6 +67,7 @@ def test_struct_mirrors_match_header_field_order():
     assert fields("koa_adam_tensor") == [f[0] for f in _lib.AdamTensor._fields_]
     assert fields("koa_adam_hyper") == [f[0] for f in _lib.AdamHyper._fields_]
     assert ctypes.sizeof(_lib.AdamTensor) == 40 and ctypes.sizeof(_lib.AdamHyper) == 56
+    assert fields("koa_augment") == [f[0] for f in _lib.Augment._fields_] and ctypes.sizeof(_lib.Augment) == 40
 
 
 def test_product_never_imports_the_oracle():

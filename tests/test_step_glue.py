@@ -69,6 +69,21 @@ class HostStandIn:
             _view(minmax, 2 * batch, np.float32)[:] = np.stack([lo, hi], 1).ravel()
         return 0
 
+    def koa_augment_resample(self, src, dtype, out, params, batch, sdims, cdims, odims, mean, std, ws, stream):
+        sdims, cdims, odims = list(sdims), list(cdims), list(odims)
+        x = _view(src, batch * int(np.prod(sdims)), _NP[dtype]).reshape([batch] + sdims)
+        table = C.cast(params, C.POINTER(_lib.Augment * batch)).contents
+        res = []
+        for b, t in enumerate(table):
+            theta = float(np.arctan2(t.sin_t, t.cos_t)) if t.rotate else None
+            gamma = 1.0 / t.inv_gamma if t.inv_gamma != 0 else None
+            factor = [o / c for o, c in zip(odims, cdims)]
+            res.append(so.augment_chain(x[b], [t.off0, t.off1, t.off2], cdims, theta, gamma, mean, std, factor))
+        y = np.stack(res)
+        assert list(y.shape[2:]) == odims
+        _view(out, y.size, np.float32)[:] = y.astype(np.float32).ravel()
+        return 0
+
     def koa_predict(self, logits, proba, pred, b, c, stream):
         p, a = so.predict(_view(logits, b * c, np.float32).reshape(b, c))
         _view(proba, b * c, np.float32)[:] = p.astype(np.float32).ravel()
@@ -184,3 +199,30 @@ def test_evalpath_glue(host):
     assert ens["exam_knee_id"] == ref["exam_knee_id"] and ens["predict"] == ref["predict"]
     np.testing.assert_allclose(ens["predict_proba"], ref["predict_proba"], rtol=1e-6)
     assert set(ens) == set(ref)
+
+
+def test_augment_glue(host):
+    import json
+    import os
+
+    from oracle.make_golden_step import seeded_volume
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = json.load(open(os.path.join(root, "tests", "golden_step", "step_rows.json")))
+    for case in gold["augment"]:
+        x = torch.from_numpy(seeded_volume(case["seed"], tuple(case["stored"]), case["kind"]))
+        batch = torch.stack([x, x])[:, None]     # two knees with different states: the second one is the plain chain
+        states = [{"offsets": case["offsets"], "theta": case["theta"], "gamma": case["gamma"]},
+                  {"offsets": preproc.crop_offsets(case["stored"], case["crop"]), "theta": None, "gamma": None}]
+        y = preproc.augment_normalize_downscale(batch, case["crop"], states, case["mean"], case["std"], case["factor"])
+        ref = np.asarray(case["out"], dtype=np.float32).reshape(case["out_shape"])
+        assert list(y.shape) == [2] + case["out_shape"], case["name"]
+        np.testing.assert_allclose(y[0].numpy(), ref, rtol=1e-4, atol=1e-4, err_msg=case["name"])
+        plain = so.augment_chain(x.numpy(), states[1]["offsets"], case["crop"], None, None, case["mean"], case["std"],
+                                 case["factor"])
+        np.testing.assert_allclose(y[1].numpy(), plain, rtol=1e-5, atol=1e-5, err_msg=case["name"])
+    with pytest.raises(ValueError):
+        preproc.augment_normalize_downscale(batch, case["crop"], [{"offsets": [5, 5, 5], "theta": None, "gamma": None}] * 2,
+                                            0.3, 0.2)
+    with pytest.raises(ValueError):
+        preproc.augment_normalize_downscale(batch, case["crop"], states[:1], 0.3, 0.2)

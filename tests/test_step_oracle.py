@@ -69,6 +69,40 @@ def test_affine_form_of_the_normalisation_commutes_with_resampling(gold):
         np.testing.assert_allclose(out, ref, rtol=1e-5, atol=2e-5, err_msg=case["name"])
 
 
+def test_augment_chain_oracle_matches_reference(gold):
+    """crop -> unit range -> rotation -> gamma -> z-score -> downscale against the reference transform classes run with
+    the same (hand-set) random state; every stage switched on and off, 2-D and 3-D, integer and fp32 storage."""
+    assert {c["name"] for c in gold["augment"]} >= {"dess_all", "tse_rot_only", "t2_gamma_only", "xr_2d", "val_center"}
+    for case in gold["augment"]:
+        x = seeded_volume(case["seed"], tuple(case["stored"]), case["kind"])
+        y = so.augment_chain(x, case["offsets"], case["crop"], case["theta"], case["gamma"], case["mean"], case["std"],
+                             case["factor"])
+        ref = np.asarray(case["out"], dtype=np.float32).reshape(case["out_shape"])
+        np.testing.assert_allclose(y, ref, rtol=1e-5, atol=1e-5, err_msg=case["name"])
+    # offsets as the reference computes them
+    assert preproc.crop_offsets((14, 12, 6), (12, 10, 4), (0.3, 0.9, 0.5)) == gold["augment"][0]["offsets"]
+    assert preproc.crop_offsets((12, 12, 4), (8, 10, 4)) == [2, 1, 0]
+    with pytest.raises(ValueError):
+        preproc.crop_offsets((4, 4), (5, 4))
+
+
+def test_train_state_draws_follow_the_reference_order():
+    """Same consumption of the ``random`` stream as the reference transforms: ratio per crop axis, (p, theta), (p, gamma)."""
+    import math
+    import random
+
+    a, b = random.Random(5), random.Random(5)
+    st = preproc.draw_train_state(a, (20, 20, 8), (16, 16, 8))
+    ratios = [b.random() for _ in range(3)]
+    p_rot, theta = b.random(), b.uniform(math.radians(-15.0), math.radians(15.0))
+    p_gam, gamma = b.random(), b.uniform(0.5, 2.0)
+    assert st["offsets"] == [int(math.floor(r * d)) for r, d in zip(ratios, (4, 4, 0))]
+    assert st["theta"] == (theta if p_rot < 0.5 else None) and st["gamma"] == (gamma if p_gam < 0.5 else None)
+    assert a.random() == b.random()
+    st = preproc.draw_train_state(a, (20, 20, 8), (16, 16, 8), with_gamma=False)
+    assert st["gamma"] is None
+
+
 @pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (False, 1e-4), (True, 1e-2)])
 def test_adam_oracle_matches_torch_optim(decoupled, wd):
     """The reference's optimiser IS torch.optim.Adam (dict_optimizers): five steps on the same gradients."""

@@ -1,5 +1,5 @@
 """GPU parity of the rows next to the hot path through the C ABI: ``koa_adam_step``,
-``koa_resample_linear``, ``koa_unit_range_affine``, ``koa_predict``, ``koa_ensemble_proba``.
+``koa_resample_linear``, ``koa_unit_range_affine``, ``koa_augment_resample``, ``koa_predict``, ``koa_ensemble_proba``.
 
 Checked against (a) the golden vectors made from the unmodified reference (``tests/golden_step/step_rows.json``), (b) the
 numpy oracle on seeded inputs, (c) ``torch.optim.Adam`` / ``AdamW`` — which *are* the reference's optimisers — on the same
@@ -203,6 +203,106 @@ def test_downscaled_input_feeds_the_model(cuda):
     with torch.no_grad():
         a, b = model(x), model(x_ref)
     torch.testing.assert_close(a, b, rtol=0, atol=5e-3)  # plumbing check: the two inputs differ by fp32 round-off
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the loader's transform chain fused with the downscale
+# ---------------------------------------------------------------------------------------------------------------------
+def test_augment_matches_reference_golden(cuda, gold):
+    """Outputs of the unmodified reference transform classes (random state set by hand); two knees per call with different
+    states, the second one the validation chain."""
+    for case in gold["augment"]:
+        x = torch.from_numpy(seeded_volume(case["seed"], tuple(case["stored"]), case["kind"]))
+        batch = torch.stack([x, x])[:, None].to(cuda)
+        states = [{"offsets": case["offsets"], "theta": case["theta"], "gamma": case["gamma"]},
+                  {"offsets": preproc.crop_offsets(case["stored"], case["crop"]), "theta": None, "gamma": None}]
+        y = preproc.augment_normalize_downscale(batch, case["crop"], states, case["mean"], case["std"], case["factor"])
+        assert list(y.shape) == [2] + case["out_shape"], case["name"]
+        ref = torch.tensor(case["out"], dtype=torch.float32).reshape(case["out_shape"])
+        torch.testing.assert_close(y[0].cpu(), ref, rtol=1e-5, atol=5e-5, msg=case["name"])
+        plain = so.augment_chain(x.numpy(), states[1]["offsets"], case["crop"], None, None, case["mean"], case["std"],
+                                 case["factor"])
+        torch.testing.assert_close(y[1].cpu(), torch.from_numpy(plain), rtol=1e-5, atol=5e-5, msg=case["name"])
+
+
+@pytest.mark.parametrize("stored,crop,dtype,factor", [
+    ((40, 36, 10), (32, 33, 7), torch.uint8, (0.5, 0.5, 0.5)),      # odd crop sizes: not a box mean
+    ((50, 44), (41, 37), torch.uint16, (0.5, 0.5)),                 # 2-D
+    ((24, 24, 5), (20, 22, 4), torch.int16, None),                  # signed storage, no downscale
+    ((18, 20, 4), (16, 16, 4), torch.float32, (0.75, 0.4, 1.0)),    # non-dyadic factors
+])
+def test_augment_matches_the_oracle_on_random_states(cuda, stored, crop, dtype, factor):
+    import random
+
+    rng = random.Random(12)
+    g = torch.Generator().manual_seed(13)
+    b = 5
+    if dtype == torch.float32:
+        x = torch.randn((b, 1) + stored, generator=g)
+    else:
+        lo, hi = {torch.uint8: (3, 250), torch.uint16: (100, 4000), torch.int16: (-1500, 2500)}[dtype]
+        x = torch.randint(lo, hi, (b, 1) + stored, generator=g, dtype=torch.int32).to(dtype)
+    states = [preproc.draw_train_state(rng, stored, crop, rotate_prob=0.75, gamma_prob=0.75) for _ in range(b)]
+    states[-1] = {"offsets": preproc.crop_offsets(stored, crop), "theta": 0.26, "gamma": 0.5}    # extreme angle / gamma
+    y = preproc.augment_normalize_downscale(x.to(cuda), crop, states, 0.4, 0.25, factor).cpu()
+    for k, st in enumerate(states):
+        ref = so.augment_chain(x[k, 0].numpy(), st["offsets"], crop, st["theta"], st["gamma"], 0.4, 0.25, factor)
+        torch.testing.assert_close(y[k], torch.from_numpy(ref), rtol=1e-5, atol=5e-5, msg=f"volume {k}: {st}")
+
+
+def _torch_chain(vol, st, crop, mean, std, factor):
+    """The reference chain written with the torch calls the reference makes (F.affine_grid / F.grid_sample /
+    F.interpolate), on the device: the full-size counterpart of the numpy oracle."""
+    sel = tuple(slice(o, o + c) for o, c in zip(st["offsets"], crop))
+    v = vol[sel].float()
+    v = (v - v.min()) / (v.max() - v.min())
+    if st["theta"] is not None:
+        th = torch.tensor(st["theta"])
+        mat = torch.tensor([[torch.cos(th), -torch.sin(th), 0], [torch.sin(th), torch.cos(th), 0]], device=v.device)
+        img = v.permute(2, 0, 1)[:, None] if v.ndim == 3 else v[None, None]          # (S, 1, R, C)
+        grid = F.affine_grid(mat[None].repeat(img.shape[0], 1, 1), img.size(), align_corners=False)
+        img = F.grid_sample(img, grid, align_corners=False)
+        v = img[:, 0].permute(1, 2, 0) if v.ndim == 3 else img[0, 0]
+    if st["gamma"] is not None:
+        v = v ** (1.0 / st["gamma"])
+    v = ((v - mean) / std)[None, None]
+    if factor:
+        v = F.interpolate(v, scale_factor=tuple(factor), mode="trilinear" if v.ndim == 5 else "bilinear",
+                          align_corners=False, recompute_scale_factor=True)
+    return v[0]
+
+
+def test_augment_recipe_sizes(cuda):
+    """Full sizes of the reference recipes: DESS 320x320x128 crops of uint8 volumes at (0.5, 0.5, 0.5), XR 700x700 crops of
+    uint16 images at (0.5, 0.5). Properties that need no oracle — the chain without rotation and gamma is
+    unit_range_normalize_downscale of the crop; rotation by 0 is the identity — and the torch calls of the reference on
+    the same device for the rotated / gamma-corrected samples."""
+    g = torch.Generator().manual_seed(21)
+    stored, crop = (352, 340, 136), (320, 320, 128)
+    dess = torch.randint(0, 256, (3, 1) + stored, dtype=torch.uint8, generator=g).to(cuda)
+    states = [{"offsets": [7, 13, 5], "theta": None, "gamma": None},
+              {"offsets": [32, 20, 8], "theta": 0.0, "gamma": None},
+              {"offsets": [0, 0, 0], "theta": -0.21, "gamma": 1.7}]
+    y = preproc.augment_normalize_downscale(dess, crop, states, 0.257, 0.235, (0.5, 0.5, 0.5))
+    assert y.shape == (3, 1, 160, 160, 64)
+    for k in (0, 1):
+        o = states[k]["offsets"]
+        cut = dess[k:k + 1, :, o[0]:o[0] + 320, o[1]:o[1] + 320, o[2]:o[2] + 128].contiguous()
+        ref = preproc.unit_range_normalize_downscale(cut, 0.257, 0.235, (0.5, 0.5, 0.5))
+        # k = 0: same arithmetic up to the folded affine map; k = 1: the identity grid lands on the voxel centres up to
+        # one ulp of a coordinate ~320 (3e-5 of a unit-range step of at most 1 / 0.235)
+        torch.testing.assert_close(y[k:k + 1], ref, rtol=1e-5, atol=2e-5 if k == 0 else 5e-4)
+    # coordinates ~320 carry an ulp of 3e-5, a unit-range difference between neighbours of up to 1, divided by std
+    torch.testing.assert_close(y[2], _torch_chain(dess[2, 0], states[2], crop, 0.257, 0.235, (0.5, 0.5, 0.5)),
+                               rtol=1e-4, atol=1e-3)
+    xr = torch.randint(0, 4096, (2, 1, 720, 712), dtype=torch.int32, generator=g).to(torch.uint16).to(cuda)
+    states = [{"offsets": [20, 12], "theta": 0.15, "gamma": 0.6}, {"offsets": [3, 0], "theta": None, "gamma": 1.9}]
+    y = preproc.augment_normalize_downscale(xr, (700, 700), states, 0.543, 0.296, (0.5, 0.5))
+    assert y.shape == (2, 1, 350, 350)
+    for k in range(2):
+        ref = _torch_chain(xr[k, 0].to(torch.int32), states[k], (700, 700), 0.543, 0.296, (0.5, 0.5))
+        torch.testing.assert_close(y[k], ref, rtol=1e-4, atol=1e-3)
+    assert torch.isfinite(y).all()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
