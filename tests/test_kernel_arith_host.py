@@ -154,7 +154,7 @@ def test_harness_is_test_only():
         assert b"emul_augment_resample" not in f.read()
 
 
-def test_gpu_tests_of_the_augment_row_dry_run_through_the_harness(emul, gold, monkeypatch):
+def test_gpu_tests_of_the_step_rows_dry_run_on_the_host(emul, gold, monkeypatch):
     """The ``-m gpu`` tests of ``koa_augment_resample`` (golden, oracle on random states, recipe sizes against the torch
     calls of the reference) executed here with the C entry point answered by the host build of the kernel arithmetic:
     their tolerances and their torch-side reference chain are exercised at full size before they ever see a GPU."""
@@ -188,3 +188,15 @@ def test_gpu_tests_of_the_augment_row_dry_run_through_the_harness(emul, gold, mo
     gpu_tests.test_augment_recipe_sizes(cpu)
     gpu_tests.test_interpolate_matches_reference_golden(cpu, gold)
     gpu_tests.test_normalize_downscale_matches_reference_golden(cpu, gold)
+    gpu_tests.test_interpolate_matches_the_oracle(cpu, (3, 1, 21, 18, 7), (0.5, 0.5, 0.5), torch.float32)
+    gpu_tests.test_interpolate_matches_the_oracle(cpu, (2, 2, 30, 31), (0.75, 0.4), torch.float32)
+    gpu_tests.test_interpolate_matches_the_oracle(cpu, (2, 1, 16, 12, 5), (0.5, 0.5, 1.0), torch.int16)
+    gpu_tests.test_recipe_sizes_box_mean_identity_and_minmax(cpu)
+    # the rows without host-compiled arithmetic: the test bodies run against the oracle stand-in (their logic, their
+    # bookkeeping assertions and their tolerances against torch.optim on the same device)
+    from oaprogressionmmf_b200 import optim as koptim
+
+    gpu_tests.test_adam_matches_torch_optim(cpu, koptim.Adam, torch.optim.Adam, 1e-4)
+    gpu_tests.test_adam_matches_torch_optim(cpu, koptim.AdamW, torch.optim.AdamW, 1e-2)
+    gpu_tests.test_adam_matches_the_oracle(cpu)
+    gpu_tests.test_predict_and_ensemble(cpu, gold)
