@@ -93,7 +93,9 @@ int koa_conv_fprop_bf16(const void* x, const void* w, int n_img, int h, int w_in
 
 /* dw[Cout,Cin] += dy[P,Cout]^T . x[P,Cin] (fp32 accumulate with atomics; caller zeroes dw). Both operands bf16, or
  * both fp16 with x_f16 == 1 (tcgen05 kind::f16 takes one 16-bit format per instruction); x_f16 == 2: dy bf16 and x fp16,
- * x is converted to bf16 in shared memory inside the kernel (no bf16 copy of the forward activations in HBM).
+ * x is converted to bf16 in shared memory inside the kernel (no bf16 copy of the forward activations in HBM);
+ * x_f16 == 3 (experiment, unconfirmed on hardware): dy bf16 and x fp16 multiplied as they are, one format field per
+ * operand in the tcgen05 instruction descriptor.
  * Weight gradient of nn.Linear and of 1x1 stride-1 convolutions (autograd of the call sites above). */
 int koa_gemm_wgrad_bf16(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, int x_f16, void* stream);
 

@@ -327,12 +327,16 @@ int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_
   return dispatch_kmajor<true>(ta, w, (int)m, cout, filt_r * filt_s * cin, g, to_epi(ep, cout), st);
 }
 
-// x_f16: 0 = dY and X bf16; 1 = both fp16; 2 = dY bf16, X fp16 converted to bf16 inside the kernel (XCVT)
+// x_f16: 0 = dY and X bf16; 1 = both fp16; 2 = dY bf16, X fp16 converted to bf16 inside the kernel (XCVT);
+// 3 = dY bf16, X fp16, multiplied as they are: the instruction descriptor of tcgen05.mma kind::f16 carries one format
+// field per operand (experiment, KOA_WGRAD_XCVT=3: written without a GPU, to be confirmed on a B200 by
+// tools/try_mixed_wgrad.py before anything relies on it)
 // CTA2: CTA pairs on 256 x BN tiles (the tensor map of X then has boxes of 64 columns as always; each CTA loads BN / 2)
 template <int BN, int STAGES, bool IM2COL, bool XCVT = false, bool CTA2 = false>
 static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, int cin, int pixels, int taps,
                         const ConvGeom& g, float* dw, int x_f16, cudaStream_t st) {
   if (!XCVT && !CTA2 && x_f16 == 2) return launch_wgrad<BN, STAGES, IM2COL, true, false>(ta, tb, cout, cin, pixels, taps, g, dw, 0, st);
+  const int a_f16 = x_f16 == 3 ? 0 : x_f16, b_f16 = x_f16 == 3 ? 1 : x_f16;  // dY, X
   constexpr size_t smem = wgrad_smem_bytes<CTA2 ? BN / 2 : BN, STAGES>();
   auto kern = gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT, CTA2>;
   static std::once_flag once;
@@ -375,9 +379,9 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16, 0));
+      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, a_f16, b_f16, 0));
     } else {
-      kern<<<grid, threads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, x_f16, x_f16, bulk_red);
+      kern<<<grid, threads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, a_f16, b_f16, bulk_red);
     }
   }
   KOA_LAUNCH_CHECK();

@@ -87,6 +87,27 @@ def main():
         report(f"minmax_kernel[{name}]", ms, float(x.numel() * x.element_size()), shape=list(shape))
         del x
 
+    # the training loader's chain fused with the downscale (koa_augment_resample), 16 knees: plain chain, rotation +
+    # gamma on every knee (the worst case: four taps and one powf per stored voxel)
+    import random
+
+    for name, stored, crop, factor, dtype in [("dess_u8", (352, 340, 136), (320, 320, 128), (0.5, 0.5, 0.5), torch.uint8),
+                                              ("xr_u16", (720, 712), (700, 700), (0.5, 0.5), torch.int16)]:
+        x = torch.randint(0, 200, (16, 1) + stored, device=dev, dtype=dtype)
+        rng = random.Random(1)
+        crop_elems = 16
+        for c in crop:
+            crop_elems *= c
+        out_elems = crop_elems
+        for f in factor:
+            out_elems *= f
+        nbytes = 2.0 * crop_elems * x.element_size() + 4.0 * out_elems   # min / max pass + resampling pass + output
+        for label, rp, gp in [("plain", 0.0, 0.0), ("train p=0.5", 0.5, 0.5), ("rotate+gamma", 1.0, 1.0)]:
+            states = [preproc.draw_train_state(rng, stored, crop, rotate_prob=rp, gamma_prob=gp) for _ in range(16)]
+            ms = timed(lambda: preproc.augment_normalize_downscale(x, crop, states, 0.257, 0.235, factor), args.iters)
+            report(f"augment_resample (3 launches)[{name}, {label}]", ms, nbytes, stored=list(stored), crop=list(crop))
+        del x
+
 
 if __name__ == "__main__":
     main()
