@@ -401,6 +401,8 @@ bn_act_fixed_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                     const bf16* __restrict__ res, const bf16* __restrict__ y2, const float* __restrict__ scale2,
                     const float* __restrict__ shift2, bf16* __restrict__ out, bf16* __restrict__ out_bf, long long rows,
                     int c, int relu, KoaBnFwdFin fa, KoaBnFwdFin fb, double count, int training) {
+  griddep_wait();  // KOA_PDL (koa_common.cuh): launched early, the predecessor's data is visible from here
+  griddep_launch_dependents();
   const int cg = c / 8;
   const long long total = rows * cg;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -463,6 +465,8 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
                                      const float* __restrict__ mean2, const float* __restrict__ invstd2,
                                      float* __restrict__ sum_dz, float* __restrict__ sum_dzx,
                                      float* __restrict__ sum_dzx2, long long rows, int c) {
+  griddep_wait();  // KOA_PDL (koa_common.cuh): launched early, the predecessor's data is visible from here
+  griddep_launch_dependents();
   extern __shared__ float sm[];
   const int cg = c / 8;
   const int lanes = blockDim.x / cg;
@@ -605,6 +609,8 @@ bn_bwd_apply_fixed_kernel(const bf16* __restrict__ dout, const bf16* __restrict_
                           bf16* __restrict__ dy, const bf16* __restrict__ y2, const float* __restrict__ k0b,
                           const float* __restrict__ k1b, const float* __restrict__ k2b, bf16* __restrict__ dy2,
                           long long rows, int c, KoaBnBwdFin fa, KoaBnBwdFin fb, double count, int training) {
+  griddep_wait();  // KOA_PDL (koa_common.cuh): launched early, the predecessor's data is visible from here
+  griddep_launch_dependents();
   const int cg = c / 8;
   const long long total = rows * cg;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1218,9 +1224,14 @@ int koa_k_bn_act_fin(const void* y, const KoaBnFwdFin* a, const void* res, const
                      void* out_bf16, long long rows, int c, int relu, double count, int training, cudaStream_t st) {
   KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm apply needs C/8 | %d (C=%d)", kThreads, c);
   KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
-  bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
-      (const bf16*)y, nullptr, nullptr, (const bf16*)res, (const bf16*)y2, nullptr, nullptr, (bf16*)out, (bf16*)out_bf16, rows,
-      c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training);
+  if (koa_pdl_enabled())
+    KOA_CHECK_CUDA(koa_launch_pdl(bn_act_fixed_kernel, dim3(grid_for(rows * (c / 8) / 2)), dim3(kThreads), 0, st, 1u,
+                                  (const bf16*)y, nullptr, nullptr, (const bf16*)res, (const bf16*)y2, nullptr, nullptr,
+                                  (bf16*)out, (bf16*)out_bf16, rows, c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training));
+  else
+    bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
+        (const bf16*)y, nullptr, nullptr, (const bf16*)res, (const bf16*)y2, nullptr, nullptr, (bf16*)out, (bf16*)out_bf16, rows,
+        c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1229,9 +1240,15 @@ int koa_k_bn_bwd_apply_fin(const void* dout, const void* act, const void* y, con
                            cudaStream_t st) {
   KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm backward needs C/8 | %d (C=%d)", kThreads, c);
   KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
-  bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid), kThreads, 0, st>>>(
-      (const bf16*)dout, (const bf16*)act, (const bf16*)y, nullptr, nullptr, nullptr, (bf16*)dy, (const bf16*)y2, nullptr,
-      nullptr, nullptr, (bf16*)dy2, rows, c, *a, b ? *b : KoaBnBwdFin{}, count, training);
+  if (koa_pdl_enabled())
+    KOA_CHECK_CUDA(koa_launch_pdl(bn_bwd_apply_fixed_kernel, dim3(grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid)),
+                                  dim3(kThreads), 0, st, 1u, (const bf16*)dout, (const bf16*)act, (const bf16*)y, nullptr,
+                                  nullptr, nullptr, (bf16*)dy, (const bf16*)y2, nullptr, nullptr, nullptr, (bf16*)dy2, rows, c,
+                                  *a, b ? *b : KoaBnBwdFin{}, count, training));
+  else
+    bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid), kThreads, 0, st>>>(
+        (const bf16*)dout, (const bf16*)act, (const bf16*)y, nullptr, nullptr, nullptr, (bf16*)dy, (const bf16*)y2, nullptr,
+        nullptr, nullptr, (bf16*)dy2, rows, c, *a, b ? *b : KoaBnBwdFin{}, count, training);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1242,9 +1259,14 @@ int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const 
   if (rc) return rc;
   const int threads = reduce_threads(c);
   const int lanes = threads / (c / 8);
-  bn_bwd_reduce_kernel<<<grid_for(rows, lanes, kDeepGrid), threads, 3 * c * sizeof(float), st>>>(
-      (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean, invstd, (const bf16*)y2, mean2, invstd2, sum_dz,
-      sum_dzx, sum_dzx2, rows, c);
+  if (koa_pdl_enabled())
+    KOA_CHECK_CUDA(koa_launch_pdl(bn_bwd_reduce_kernel, dim3(grid_for(rows, lanes, kDeepGrid)), dim3(threads),
+                                  3 * c * sizeof(float), st, 1u, (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean,
+                                  invstd, (const bf16*)y2, mean2, invstd2, sum_dz, sum_dzx, sum_dzx2, rows, c));
+  else
+    bn_bwd_reduce_kernel<<<grid_for(rows, lanes, kDeepGrid), threads, 3 * c * sizeof(float), st>>>(
+        (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean, invstd, (const bf16*)y2, mean2, invstd2, sum_dz,
+        sum_dzx, sum_dzx2, rows, c);
   KOA_LAUNCH_CHECK();
   return 0;
 }

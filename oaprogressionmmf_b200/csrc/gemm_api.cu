@@ -171,7 +171,11 @@ static int launch_kmajor_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, 
   const unsigned grid = (unsigned)(tiles < koa_num_sms() ? tiles : koa_num_sms());  // persistent: one CTA per SM
   {
     ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep));
-    gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV><<<grid, kKmajorThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
+    if (koa_pdl_enabled())
+      KOA_CHECK_CUDA(koa_launch_pdl(gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV>, dim3(grid), dim3(kKmajorThreads), smem, st, 1u,
+                                    ta, tb, m, n, k, g, ep));
+    else
+      gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV><<<grid, kKmajorThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
   }
   KOA_LAUNCH_CHECK();
   return 0;
@@ -213,7 +217,10 @@ static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
   }
   {
     ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep) | (CTA2 ? 256 : 0));
-    if (CTA2) {
+    if (koa_pdl_enabled()) {
+      KOA_CHECK_CUDA(koa_launch_pdl(kern, dim3(CTA2 ? 2 * units : units), dim3(kConvThreads), smem, st, CTA2 ? 2u : 1u, ta, tb,
+                                    t_out, t_add, t_gate, t_y, m, n, k, g, ep));
+    } else if (CTA2) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2 * units, 1, 1);
       cfg.blockDim = dim3(kConvThreads, 1, 1);
@@ -366,7 +373,10 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
     const double n_eff = g.grouped ? 64.0 : (double)cin;
     ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps, cout, cin * taps, pixels,
                    (IM2COL ? 1 : 0) | (CTA2 ? 256 : 0));
-    if (CTA2) {
+    if (koa_pdl_enabled()) {
+      KOA_CHECK_CUDA(koa_launch_pdl(kern, grid, dim3(threads), smem, st, CTA2 ? 2u : 1u, ta, tb, cout, cin, pixels, taps, g, dw,
+                                    kb_per_split, s_wgrad_desc, a_f16, b_f16, CTA2 ? 0 : bulk_red));
+    } else if (CTA2) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = grid;
       cfg.blockDim = dim3(threads, 1, 1);

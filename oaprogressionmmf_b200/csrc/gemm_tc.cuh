@@ -439,6 +439,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                // KOA_PDL (koa_common.cuh): the prologue above overlapped the predecessor's tail
+  griddep_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -663,6 +665,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (CTA2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                // KOA_PDL (koa_common.cuh): the prologue above overlapped the predecessor's tail
+  griddep_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {

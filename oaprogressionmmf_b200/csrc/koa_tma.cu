@@ -130,3 +130,11 @@ int koa_num_sms() {
   }
   return n;
 }
+
+int koa_pdl_enabled() {
+  static const int v = [] {
+    const char* e = getenv("KOA_PDL");
+    return e != nullptr && atoi(e) > 0 ? 1 : 0;
+  }();
+  return v;
+}
