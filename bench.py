@@ -416,7 +416,8 @@ def run_ours(args):
                             l2="working set per step (tens of GB of activations) exceeds the 126 MB L2; two input batches alternate"),
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit="knees/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
-                gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag, full_step=full_step)
+                gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag, full_step=full_step,
+                switches={k: v for k, v in sorted(os.environ.items()) if k.startswith("KOA_")})
     print(json.dumps(line), flush=True)
     if ws > 1:
         dist.destroy_process_group()
