@@ -19,6 +19,16 @@ constexpr int kDeepGrid = 148 * 2;
 // One element per thread and iteration with index arithmetic in front of every access (pooling, packing, resampling):
 // latency-bound, these keep the full grid (they ran 30-60 % slower with the cap).
 constexpr int kWideGrid = -148 * 16;
+// KOA_IDX32=1 (experiment, default off, not yet run on a B200): 32-bit work-item indices in the pooling kernels whenever
+// the item count and one grid stride both stay below 2^31
+inline bool koa_idx32_ok(long long items, int blocks, int threads) {
+  static const int on = [] {
+    const char* e = getenv("KOA_IDX32");
+    return e != nullptr && atoi(e) > 0 ? 1 : 0;
+  }();
+  return on && items < 0x7fffffffLL && (long long)blocks * threads < 0x7fffffffLL;
+}
+
 inline int grid_for(long long work_items, int threads = kThreads, int max_blocks = 148 * 16) {
   static const int env_cap = [] {
     const char* e = getenv("KOA_EW_MAX_BLOCKS");
@@ -669,16 +679,19 @@ bn_bwd_apply_fixed_kernel(const bf16* __restrict__ dout, const bf16* __restrict_
 // Pooling
 // ------------------------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 max pool, first maximum in scan order wins (as ATen); idx = r*3+s of the winner.
+// I: type of the flat work-item index. long long always works; unsigned (KOA_IDX32=1, launcher checks the range) replaces
+// the three 64-bit divisions per item, which make these kernels issue-bound (~400 instructions per 16 bytes), by 32-bit ones.
+template <typename I>
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, bf16* __restrict__ out_bf,
                                    uint8_t* __restrict__ idx,
                                    int n, int h, int w, int c, int ho, int wo) {
   const int cg = c / 8;
-  const long long total = (long long)n * ho * wo * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int g = (int)(t % cg); t /= cg;
-    const int ow = (int)(t % wo); t /= wo;
-    const int oh = (int)(t % ho); t /= ho;
+  const I total = (I)((long long)n * ho * wo * cg);
+  for (I i = (I)(blockIdx.x * (long long)blockDim.x + threadIdx.x); i < total; i += (I)((long long)gridDim.x * blockDim.x)) {
+    I t = i;
+    const int g = (int)(t % (I)cg); t /= (I)cg;
+    const int ow = (int)(t % (I)wo); t /= (I)wo;
+    const int oh = (int)(t % (I)ho); t /= (I)ho;
     const int ni = (int)t;
     float best[8];
     int bi[8];
@@ -700,24 +713,26 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
         first = false;
       }
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8h(best);
-    if (out_bf != nullptr) *reinterpret_cast<uint4*>(out_bf + i * 8) = pack8(best);
+    const long long o8 = (long long)i * 8;
+    *reinterpret_cast<uint4*>(out + o8) = pack8h(best);
+    if (out_bf != nullptr) *reinterpret_cast<uint4*>(out_bf + o8) = pack8(best);
     uint2 packed;
     packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
     packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-    *reinterpret_cast<uint2*>(idx + i * 8) = packed;
+    *reinterpret_cast<uint2*>(idx + o8) = packed;
   }
 }
 
+template <typename I>
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ idx, bf16* __restrict__ dx,
                                    int n, int h, int w, int c, int ho, int wo) {
   const int cg = c / 8;
-  const long long total = (long long)n * h * w * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int g = (int)(t % cg); t /= cg;
-    const int iw = (int)(t % w); t /= w;
-    const int ih = (int)(t % h); t /= h;
+  const I total = (I)((long long)n * h * w * cg);
+  for (I i = (I)(blockIdx.x * (long long)blockDim.x + threadIdx.x); i < total; i += (I)((long long)gridDim.x * blockDim.x)) {
+    I t = i;
+    const int g = (int)(t % (I)cg); t /= (I)cg;
+    const int iw = (int)(t % (I)w); t /= (I)w;
+    const int ih = (int)(t % (I)h); t /= (I)h;
     const int ni = (int)t;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // windows (oh, ow) with 2*oh-1 <= ih <= 2*oh+1
@@ -743,7 +758,7 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dout, const uint8_t*
         for (int u = 0; u < 8; ++u) acc[u] += d[u];
       }
     }
-    *reinterpret_cast<uint4*>(dx + i * 8) = pack8(acc);
+    *reinterpret_cast<uint4*>(dx + (long long)i * 8) = pack8(acc);
   }
 }
 
@@ -1296,16 +1311,26 @@ int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const f
 int koa_k_maxpool_fwd(const void* x, void* out, void* out_bf16, void* idx, int n, int h, int w, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<grid_for((long long)n * ho * wo * (c / 8), kThreads, kWideGrid), kThreads, 0, st>>>(
-      (const bf16*)x, (bf16*)out, (bf16*)out_bf16, (uint8_t*)idx, n, h, w, c, ho, wo);
+  const long long items = (long long)n * ho * wo * (c / 8);
+  const int blocks = grid_for(items, kThreads, kWideGrid);
+  if (koa_idx32_ok(items, blocks, kThreads))
+    maxpool_fwd_kernel<unsigned><<<blocks, kThreads, 0, st>>>((const bf16*)x, (bf16*)out, (bf16*)out_bf16, (uint8_t*)idx, n, h, w, c,
+                                                              ho, wo);
+  else
+    maxpool_fwd_kernel<long long><<<blocks, kThreads, 0, st>>>((const bf16*)x, (bf16*)out, (bf16*)out_bf16, (uint8_t*)idx, n, h, w,
+                                                               c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
 }
 int koa_k_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, int w, int c, cudaStream_t st) {
   KOA_REQ_C8(c);
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8), kThreads, kWideGrid), kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx,
-                                                                                    (bf16*)dx, n, h, w, c, ho, wo);
+  const long long items = (long long)n * h * w * (c / 8);
+  const int blocks = grid_for(items, kThreads, kWideGrid);
+  if (koa_idx32_ok(items, blocks, kThreads))
+    maxpool_bwd_kernel<unsigned><<<blocks, kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx, (bf16*)dx, n, h, w, c, ho, wo);
+  else
+    maxpool_bwd_kernel<long long><<<blocks, kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx, (bf16*)dx, n, h, w, c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
 }

@@ -21,5 +21,7 @@ KOA_WGRAD_BULK_RED=1 run parity_bulkred 600 python -m pytest tests/test_gpu_pari
 KOA_WGRAD_BULK_RED=1 run bench_bulkred 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
 KOA_PDL=1 run parity_pdl 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu
 KOA_PDL=1 run bench_pdl 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
+KOA_IDX32=1 run parity_idx32 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu
+KOA_IDX32=1 run bench_idx32 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
 run step_ops_bench 300 python tools/step_ops_bench.py
 cat gpurun_out/r2_summary.log
