@@ -246,11 +246,13 @@ typedef struct koa_augment {
   float cos_t, sin_t;
   float inv_gamma;           /* 0: no gamma correction; else u -> u^(1/gamma) (PTGammaCorrection, _pt.py:203-232) */
   float lo, range;           /* minimum and max - min of the crop: written by the call, the caller leaves them alone */
-  float reserved;
+  int flip;                  /* RIGHT knees are mirrored to the LEFT orientation before the crop (koafusion/datasets/oai/
+                                _dataset.py:303-316): 0 none, 1 along the columns (COR IW TSE, XR), 2 along the slices
+                                (SAG 3D DESS, SAG T2 map); the crop offsets count in the mirrored volume */
 } koa_augment_t;
 
 /* The per-sample transform chain of the training loader (koafusion/datasets/_data_provider.py:297-334) followed by the
- * on-GPU downscale, on the volumes as stored: crop -> PTToUnitRange (min / max of the crop) -> rotation about the slice
+ * on-GPU downscale, on the volumes as stored: mirror (RIGHT knees) -> crop -> PTToUnitRange (min / max of the crop) -> rotation about the slice
  * axis (F.affine_grid + F.grid_sample, bilinear, zero padding, align_corners=False) -> gamma -> PTNormalize(mean, std)
  * -> PTInterpolate to out_dims. in: `batch` volumes of src_dims[3] elements (rows, columns, slices; slices innermost; a
  * 2-D image has 1 slice); params: DEVICE array [batch]; workspace: 2 * batch unsigned ints. The validation / test

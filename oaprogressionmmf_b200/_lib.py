@@ -124,7 +124,7 @@ class Augment(C.Structure):
         ("inv_gamma", C.c_float),
         ("lo", C.c_float),
         ("range", C.c_float),
-        ("reserved", C.c_float),
+        ("flip", C.c_int),
     ]
 
 

@@ -74,19 +74,34 @@ KOA_HD float resample_element(const T* vol, const Dims3& in, int x0, int x1, int
   return a.l0 * (h.l0 * v00 + h.l1 * v01) + a.l1 * (h.l0 * v10 + h.l1 * v11);
 }
 
-// unit-range value of the crop at (yy, xx, s); zero padding of F.grid_sample outside the crop
+// The crop of volume b as a strided view of the stored batch: p is crop voxel (0, 0, 0), st_* the element strides along
+// rows, columns and slices. A mirrored volume (koa_augment_t::flip, RIGHT knees) is the same view with a negative stride:
+// mirrored column off1 + c is stored column C - 1 - off1 - c.
+template <typename T> struct CropView { const T* p; long long st_r, st_c, st_s; };
 template <typename T>
-KOA_HD float unit_tap(const T* vol, const koa_augment_t& a, int yy, int xx, int s, int R, int C, long long st_r,
-                      long long st_c) {
-  if (yy < 0 || yy >= R || xx < 0 || xx >= C) return 0.f;
-  return div_rn(ld_f(vol + yy * st_r + xx * st_c + s) - a.lo, a.range);
+KOA_HD CropView<T> crop_view(const T* in, long long b, const koa_augment_t& a, const Dims3& src) {
+  const long long st_r = (long long)src.d1 * src.d2, st_c = src.d2;
+  CropView<T> v;
+  v.p = in + b * (long long)src.d0 * st_r + a.off0 * st_r;
+  v.st_r = st_r;
+  if (a.flip == 1) { v.p += (long long)(src.d1 - 1 - a.off1) * st_c; v.st_c = -st_c; }
+  else { v.p += a.off1 * st_c; v.st_c = st_c; }
+  if (a.flip == 2) { v.p += src.d2 - 1 - a.off2; v.st_s = -1; }
+  else { v.p += a.off2; v.st_s = 1; }
+  return v;
 }
 
-// value of the augmented full-resolution crop at (r, c, s), crop coordinates; vol points at the first crop voxel of the
-// stored volume, whose row / column strides are st_r / st_c (slice axis innermost)
+// unit-range value of the crop at (yy, xx, s); zero padding of F.grid_sample outside the crop
 template <typename T>
-KOA_HD float aug_voxel(const T* vol, const koa_augment_t& a, int r, int c, int s, int R, int C, long long st_r,
-                       long long st_c, float mean, float stdev) {
+KOA_HD float unit_tap(const CropView<T>& v, const koa_augment_t& a, int yy, int xx, int s, int R, int C) {
+  if (yy < 0 || yy >= R || xx < 0 || xx >= C) return 0.f;
+  return div_rn(ld_f(v.p + yy * v.st_r + xx * v.st_c + s * v.st_s) - a.lo, a.range);
+}
+
+// value of the augmented full-resolution crop at (r, c, s), crop coordinates
+template <typename T>
+KOA_HD float aug_voxel(const CropView<T>& v, const koa_augment_t& a, int r, int c, int s, int R, int C, float mean,
+                       float stdev) {
   float u;
   if (a.rotate) {
     // F.affine_grid([[cos, -sin, 0], [sin, cos, 0]]) + F.grid_sample on the (S, CH, R, C) view, align_corners=False:
@@ -100,29 +115,19 @@ KOA_HD float aug_voxel(const T* vol, const koa_augment_t& a, int r, int c, int s
     const float fx = floorf(ix), fy = floorf(iy);
     const int x0 = (int)fx, y0 = (int)fy;
     const float wx1 = ix - fx, wy1 = iy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-    u = unit_tap(vol, a, y0, x0, s, R, C, st_r, st_c) * (wx0 * wy0) +
-        unit_tap(vol, a, y0, x0 + 1, s, R, C, st_r, st_c) * (wx1 * wy0) +
-        unit_tap(vol, a, y0 + 1, x0, s, R, C, st_r, st_c) * (wx0 * wy1) +
-        unit_tap(vol, a, y0 + 1, x0 + 1, s, R, C, st_r, st_c) * (wx1 * wy1);
+    u = unit_tap(v, a, y0, x0, s, R, C) * (wx0 * wy0) + unit_tap(v, a, y0, x0 + 1, s, R, C) * (wx1 * wy0) +
+        unit_tap(v, a, y0 + 1, x0, s, R, C) * (wx0 * wy1) + unit_tap(v, a, y0 + 1, x0 + 1, s, R, C) * (wx1 * wy1);
   } else {
-    u = div_rn(ld_f(vol + r * st_r + c * st_c + s) - a.lo, a.range);
+    u = div_rn(ld_f(v.p + r * v.st_r + c * v.st_c + s * v.st_s) - a.lo, a.range);
   }
   if (a.inv_gamma != 0.f) u = powf(u, a.inv_gamma);
   return div_rn(u - mean, stdev);
 }
 
-// first crop voxel of volume b inside the stored batch
+// one output element of mirror -> crop -> unit range -> rotation -> gamma -> z-score -> linear resampling
 template <typename T>
-KOA_HD const T* crop_origin(const T* in, long long b, const koa_augment_t& a, const Dims3& src) {
-  const long long st_r = (long long)src.d1 * src.d2, st_c = src.d2;
-  return in + b * (long long)src.d0 * st_r + a.off0 * st_r + a.off1 * st_c + a.off2;
-}
-
-// one output element of crop -> unit range -> rotation -> gamma -> z-score -> linear resampling
-template <typename T>
-KOA_HD float augment_element(const T* vol, const koa_augment_t& a, const Dims3& src, const Dims3& crop, int x0, int x1,
-                             int x2, float rs0, float rs1, float rs2, float mean, float stdev) {
-  const long long st_r = (long long)src.d1 * src.d2, st_c = src.d2;
+KOA_HD float augment_element(const CropView<T>& v, const koa_augment_t& a, const Dims3& crop, int x0, int x1, int x2,
+                             float rs0, float rs1, float rs2, float mean, float stdev) {
   const Tap ta = make_tap(x0, rs0, crop.d0), th = make_tap(x1, rs1, crop.d1), tw = make_tap(x2, rs2, crop.d2);
   float acc = 0.f;
 #if defined(__CUDA_ARCH__)
@@ -132,7 +137,7 @@ KOA_HD float augment_element(const T* vol, const koa_augment_t& a, const Dims3& 
     const float wgt = ((k & 4) ? ta.l1 : ta.l0) * ((k & 2) ? th.l1 : th.l0) * ((k & 1) ? tw.l1 : tw.l0);
     if (wgt == 0.f) continue;  // factor 1 along an axis, last index of an axis
     const int r = ta.i0 + ((k & 4) ? ta.step : 0), c = th.i0 + ((k & 2) ? th.step : 0), s = tw.i0 + ((k & 1) ? tw.step : 0);
-    acc = fmaf(wgt, aug_voxel<T>(vol, a, r, c, s, crop.d0, crop.d1, st_r, st_c, mean, stdev), acc);
+    acc = fmaf(wgt, aug_voxel<T>(v, a, r, c, s, crop.d0, crop.d1, mean, stdev), acc);
   }
   return acc;
 }

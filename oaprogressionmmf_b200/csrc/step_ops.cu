@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(kThreads) augment_resample_kernel(const T* __r
     int x0, x1, x2;
     const long long b = koa_arith::split_index(i, dout, x0, x1, x2);
     const koa_augment_t a = params[b];
-    out[i] = koa_arith::augment_element<T>(koa_arith::crop_origin(in, b, a, src), a, src, crop, x0, x1, x2, rs0, rs1, rs2,
-                                           mean, stdev);
+    out[i] = koa_arith::augment_element<T>(koa_arith::crop_view(in, b, a, src), a, crop, x0, x1, x2, rs0, rs1, rs2, mean,
+                                           stdev);
   }
 }
 
@@ -258,9 +258,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) crop_minmax_kernel(const T* __restrict__ in,
                                                                 const koa_augment_t* __restrict__ params, int s0, int s1,
                                                                 int s2, int d0, int d1, int d2, unsigned* __restrict__ mm) {
-  const long long st_r = (long long)s1 * s2, st_c = s2;
   const koa_augment_t a = params[blockIdx.y];
-  const T* vol = koa_arith::crop_origin(in, (long long)blockIdx.y, a, Dims3{s0, s1, s2});
+  const koa_arith::CropView<T> v = koa_arith::crop_view(in, (long long)blockIdx.y, a, Dims3{s0, s1, s2});
   const long long n = (long long)d0 * d1 * d2;
   float lo = INFINITY, hi = -INFINITY;
   for (long long i = blockIdx.x * (long long)kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
@@ -268,7 +267,7 @@ __global__ void __launch_bounds__(kThreads) crop_minmax_kernel(const T* __restri
     const int s = (int)(t % d2); t /= d2;
     const int c = (int)(t % d1);
     const int r = (int)(t / d1);
-    const float f = ld_f(vol + r * st_r + c * st_c + s);
+    const float f = ld_f(v.p + r * v.st_r + c * v.st_c + s * v.st_s);
     lo = fminf(lo, f); hi = fmaxf(hi, f);
   }
 #pragma unroll

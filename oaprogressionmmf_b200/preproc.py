@@ -119,6 +119,10 @@ def unit_range_normalize_downscale(x: torch.Tensor, mean: float, std: float, fac
 # ---------------------------------------------------------------------------------------------------------------------
 # the per-sample transform chain of the loaders, fused with the downscale
 # ---------------------------------------------------------------------------------------------------------------------
+# axis mirrored for RIGHT knees, per sequence (koafusion/datasets/oai/_dataset.py:303-316; the value of koa_augment_t::flip)
+FLIP_AXIS = {"sag_3d_dess": 2, "cor_iw_tse": 1, "sag_t2_map": 2, "xr_pa": 1}
+
+
 def crop_offsets(size_in: Sequence[int], size_out: Sequence[int], ratios=None) -> list:
     """First voxel of the crop: ``RandomCrop`` (``floor(ratio * (in - out))`` per axis, ``ratios`` in [0, 1)) or, without
     ratios, ``CenterCrop`` (``(in - out) // 2``) — ``koafusion/preproc/_np_nd.py:62-140``."""
@@ -151,8 +155,10 @@ def augment_normalize_downscale(x: torch.Tensor, crop_size: Sequence[int], state
     """``PTInterpolate(factor)(PTNormalize(mean, std)(PTGammaCorrection(PTRotate*(PTToUnitRange(crop(x))))))`` for every
     stored volume ``x[b, 0]`` of a (B, 1, R, C[, S]) batch in its storage type, with the per-sample state of
     ``draw_train_state`` (``offsets``, ``theta`` or None, ``gamma`` or None). The validation / test chain is the same call
-    with ``{"offsets": crop_offsets(in, out), "theta": None, "gamma": None}``. One ``koa_augment_resample`` call; fp32
-    output of shape (B, 1, *floor(crop * factor))."""
+    with ``{"offsets": crop_offsets(in, out), "theta": None, "gamma": None}``. An optional ``"flip"`` entry mirrors the
+    stored volume first, as the dataset does for RIGHT knees (``koafusion/datasets/oai/_dataset.py:303-316``): ``FLIP_AXIS``
+    of the sequence (columns for COR IW TSE and XR, slices for SAG 3D DESS and SAG T2 map) or None / 0; the offsets count
+    in the mirrored volume. One ``koa_augment_resample`` call; fp32 output of shape (B, 1, *floor(crop * factor))."""
     _lib.require_cuda(x, "koa_augment_resample")
     if x.dtype not in _DTYPES:
         raise _lib.KoaError(f"koa_augment_resample takes float32 / uint8 / uint16 / int16 input, got {x.dtype}")
@@ -178,6 +184,10 @@ def augment_normalize_downscale(x: torch.Tensor, crop_size: Sequence[int], state
         t.cos_t, t.sin_t = (math.cos(theta), math.sin(theta)) if theta is not None else (1.0, 0.0)
         gamma = st.get("gamma")
         t.inv_gamma = 1.0 / gamma if gamma is not None else 0.0
+        flip = st.get("flip") or 0
+        if flip not in (0, 1, 2) or (flip == 2 and len(spatial) == 2):
+            raise ValueError(f"flip must be None / 0, 1 (columns) or 2 (slices of a 3-D volume), got {flip!r}")
+        t.flip = flip
     x = x.contiguous()
     b = x.shape[0]
     params = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(x.device)

@@ -129,13 +129,16 @@ def rotate_in_slice(vol, theta):
     return out.astype(f)
 
 
-def augment_chain(raw, offsets, crop_size, theta, gamma, mean, std, factor):
+def augment_chain(raw, offsets, crop_size, theta, gamma, mean, std, factor, flip=0):
     """One sample of the training loader (``koafusion/datasets/_data_provider.py:297-334``) and the on-GPU downscale:
     crop -> ``PTToUnitRange`` -> rotation (``theta`` or None) -> ``PTGammaCorrection`` (``gamma`` or None) ->
-    ``PTNormalize`` -> ``PTInterpolate``. ``raw``: stored (R, C[, S]) array; returns (1, R', C'[, S']) fp32."""
+    ``PTNormalize`` -> ``PTInterpolate``. ``raw``: stored (R, C[, S]) array; ``flip``: 0, 1 (columns) or 2 (slices), the
+    mirroring of RIGHT knees in front of the transforms; returns (1, R', C'[, S']) fp32."""
     f = np.float32
     raw = np.asarray(raw)
     two_d = raw.ndim == 2
+    if flip:                # RIGHT knee: mirrored before the transforms (koafusion/datasets/oai/_dataset.py:303-316)
+        raw = np.flip(raw, axis=flip)
     sel = tuple(slice(o, o + c) for o, c in zip(offsets, crop_size))
     vol = raw[sel].astype(f)
     vol = (vol - vol.min()) / (vol.max() - vol.min())

@@ -1,6 +1,6 @@
 // step_emul.cpp — TEST-ONLY host build of the per-element arithmetic of step_ops.cu (csrc/step_arith.cuh).
 //
-// g++ compiles the very functions the CUDA kernels call (resample_element, augment_element, crop_origin, split_index)
+// g++ compiles the very functions the CUDA kernels call (resample_element, augment_element, crop_view, split_index)
 // and loops over the output elements the way the grid-stride loops do; tests/test_kernel_arith_host.py checks the
 // result against the golden vectors of the unmodified reference. It verifies indexing, tap order and weights of the
 // kernels without a GPU. It is not part of the product: the Python package never loads it and libkoa_b200.so does not
@@ -35,14 +35,13 @@ template <typename T>
 void augment(const T* in, float* out, koa_augment_t* params, int batch, const int* s, const int* c, const int* o, float mean,
              float stdev) {
   const Dims3 src{s[0], s[1], s[2]}, crop{c[0], c[1], c[2]}, dout{o[0], o[1], o[2]};
-  const long long st_r = (long long)s[1] * s[2], st_c = s[2];
   for (int b = 0; b < batch; ++b) {  // crop_minmax_kernel + crop_minmax_finish_kernel
-    const T* vol = crop_origin(in, (long long)b, params[b], src);
+    const CropView<T> v = crop_view(in, (long long)b, params[b], src);
     float lo = std::numeric_limits<float>::infinity(), hi = -lo;
     for (int r = 0; r < c[0]; ++r)
       for (int cc = 0; cc < c[1]; ++cc)
         for (int z = 0; z < c[2]; ++z) {
-          const float f = ld_f(vol + r * st_r + cc * st_c + z);
+          const float f = ld_f(v.p + r * v.st_r + cc * v.st_c + z * v.st_s);
           lo = std::min(lo, f);
           hi = std::max(hi, f);
         }
@@ -55,7 +54,7 @@ void augment(const T* in, float* out, koa_augment_t* params, int batch, const in
     int x0, x1, x2;
     const long long b = split_index(i, dout, x0, x1, x2);
     const koa_augment_t a = params[b];
-    out[i] = augment_element<T>(crop_origin(in, b, a, src), a, src, crop, x0, x1, x2, rs0, rs1, rs2, mean, stdev);
+    out[i] = augment_element<T>(crop_view(in, b, a, src), a, crop, x0, x1, x2, rs0, rs1, rs2, mean, stdev);
   }
 }
 

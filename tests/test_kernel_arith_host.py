@@ -74,6 +74,7 @@ def _augment(lib, x, kind, crop, states, mean, std, factor):
         t.rotate = int(th is not None)
         t.cos_t, t.sin_t = (math.cos(th), math.sin(th)) if th is not None else (1.0, 0.0)
         t.inv_gamma = 1.0 / gm if gm is not None else 0.0
+        t.flip = st.get("flip") or 0
     out = np.empty((b, 1) + tuple(size_out), np.float32)
     rc = lib.emul_augment_resample(C.c_void_p(x.ctypes.data), _DT[kind], C.c_void_p(out.ctypes.data), table, b,
                                    _I3(*_pad3(x.shape[1:])), _I3(*_pad3(crop)), _I3(*_pad3(size_out)), C.c_float(mean),
@@ -108,7 +109,7 @@ def test_normalize_downscale_arithmetic_matches_reference_golden(emul, gold):
 def test_augment_arithmetic_matches_reference_golden(emul, gold):
     for case in gold["augment"]:
         x = seeded_volume(case["seed"], tuple(case["stored"]), case["kind"])
-        states = [{"offsets": case["offsets"], "theta": case["theta"], "gamma": case["gamma"]},
+        states = [{"offsets": case["offsets"], "theta": case["theta"], "gamma": case["gamma"], "flip": case["flip"]},
                   {"offsets": preproc.crop_offsets(case["stored"], case["crop"]), "theta": None, "gamma": None}]
         y, table = _augment(emul, np.stack([x, x]), case["kind"], case["crop"], states, case["mean"], case["std"],
                             case["factor"])
@@ -118,7 +119,8 @@ def test_augment_arithmetic_matches_reference_golden(emul, gold):
         plain = so.augment_chain(x, states[1]["offsets"], case["crop"], None, None, case["mean"], case["std"], case["factor"])
         np.testing.assert_allclose(y[1], plain, rtol=1e-5, atol=2e-5, err_msg=case["name"])
         sel = tuple(slice(o, o + c) for o, c in zip(case["offsets"], case["crop"]))
-        assert table[0].lo == float(x[sel].min()) and table[0].range == float(x[sel].max()) - float(x[sel].min())
+        xm = np.flip(x, axis=case["flip"]) if case["flip"] else x
+        assert table[0].lo == float(xm[sel].min()) and table[0].range == float(xm[sel].max()) - float(xm[sel].min())
 
 
 @pytest.mark.parametrize("stored,crop,kind,factor", [
@@ -138,9 +140,11 @@ def test_augment_arithmetic_matches_the_oracle_on_random_states(emul, stored, cr
         vols = np.stack([seeded_volume(900 + k, stored, kind) for k in range(4)])
     states = [preproc.draw_train_state(rng, stored, crop, rotate_prob=0.75, gamma_prob=0.75) for _ in range(4)]
     states[3] = {"offsets": preproc.crop_offsets(stored, crop), "theta": 0.26, "gamma": 0.5}   # extreme angle / gamma
+    states[1]["flip"] = 1                                   # RIGHT knees: mirrored columns / slices
+    states[2]["flip"] = 2 if len(stored) == 3 else 1
     y, _ = _augment(emul, vols, kind, crop, states, 0.4, 0.25, factor)
     for k, st in enumerate(states):
-        ref = so.augment_chain(vols[k], st["offsets"], crop, st["theta"], st["gamma"], 0.4, 0.25, factor)
+        ref = so.augment_chain(vols[k], st["offsets"], crop, st["theta"], st["gamma"], 0.4, 0.25, factor, st.get("flip") or 0)
         np.testing.assert_allclose(y[k], ref, rtol=1e-5, atol=5e-5, err_msg=f"volume {k}: {st}")
 
 

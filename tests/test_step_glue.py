@@ -78,7 +78,7 @@ class HostStandIn:
             theta = float(np.arctan2(t.sin_t, t.cos_t)) if t.rotate else None
             gamma = 1.0 / t.inv_gamma if t.inv_gamma != 0 else None
             factor = [o / c for o, c in zip(odims, cdims)]
-            res.append(so.augment_chain(x[b], [t.off0, t.off1, t.off2], cdims, theta, gamma, mean, std, factor))
+            res.append(so.augment_chain(x[b], [t.off0, t.off1, t.off2], cdims, theta, gamma, mean, std, factor, t.flip))
         y = np.stack(res)
         assert list(y.shape[2:]) == odims
         _view(out, y.size, np.float32)[:] = y.astype(np.float32).ravel()
@@ -212,7 +212,7 @@ def test_augment_glue(host):
     for case in gold["augment"]:
         x = torch.from_numpy(seeded_volume(case["seed"], tuple(case["stored"]), case["kind"]))
         batch = torch.stack([x, x])[:, None]     # two knees with different states: the second one is the plain chain
-        states = [{"offsets": case["offsets"], "theta": case["theta"], "gamma": case["gamma"]},
+        states = [{"offsets": case["offsets"], "theta": case["theta"], "gamma": case["gamma"], "flip": case["flip"]},
                   {"offsets": preproc.crop_offsets(case["stored"], case["crop"]), "theta": None, "gamma": None}]
         y = preproc.augment_normalize_downscale(batch, case["crop"], states, case["mean"], case["std"], case["factor"])
         ref = np.asarray(case["out"], dtype=np.float32).reshape(case["out_shape"])
@@ -226,3 +226,7 @@ def test_augment_glue(host):
                                             0.3, 0.2)
     with pytest.raises(ValueError):
         preproc.augment_normalize_downscale(batch, case["crop"], states[:1], 0.3, 0.2)
+    with pytest.raises(ValueError):       # no slice axis to mirror in a 2-D image
+        xr = torch.zeros(1, 1, 8, 8, dtype=torch.uint8)
+        preproc.augment_normalize_downscale(xr, (8, 8), [{"offsets": [0, 0], "theta": None, "gamma": None, "flip": 2}], 0.3, 0.2)
+    assert preproc.FLIP_AXIS == {"sag_3d_dess": 2, "cor_iw_tse": 1, "sag_t2_map": 2, "xr_pa": 1}

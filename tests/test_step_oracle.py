@@ -72,11 +72,12 @@ def test_affine_form_of_the_normalisation_commutes_with_resampling(gold):
 def test_augment_chain_oracle_matches_reference(gold):
     """crop -> unit range -> rotation -> gamma -> z-score -> downscale against the reference transform classes run with
     the same (hand-set) random state; every stage switched on and off, 2-D and 3-D, integer and fp32 storage."""
-    assert {c["name"] for c in gold["augment"]} >= {"dess_all", "tse_rot_only", "t2_gamma_only", "xr_2d", "val_center"}
+    assert {c["name"] for c in gold["augment"]} >= {"dess_all", "tse_rot_only", "t2_gamma_only", "xr_2d", "val_center",
+                                                        "dess_right", "tse_right", "xr_right", "t2_right_val"}
     for case in gold["augment"]:
         x = seeded_volume(case["seed"], tuple(case["stored"]), case["kind"])
         y = so.augment_chain(x, case["offsets"], case["crop"], case["theta"], case["gamma"], case["mean"], case["std"],
-                             case["factor"])
+                             case["factor"], case["flip"])
         ref = np.asarray(case["out"], dtype=np.float32).reshape(case["out_shape"])
         np.testing.assert_allclose(y, ref, rtol=1e-5, atol=1e-5, err_msg=case["name"])
     # offsets as the reference computes them

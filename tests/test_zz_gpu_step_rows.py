@@ -217,7 +217,7 @@ def test_augment_matches_reference_golden(cuda, gold):
     for case in gold["augment"]:
         x = torch.from_numpy(seeded_volume(case["seed"], tuple(case["stored"]), case["kind"]))
         batch = torch.stack([x, x])[:, None].to(cuda)
-        states = [{"offsets": case["offsets"], "theta": case["theta"], "gamma": case["gamma"]},
+        states = [{"offsets": case["offsets"], "theta": case["theta"], "gamma": case["gamma"], "flip": case["flip"]},
                   {"offsets": preproc.crop_offsets(case["stored"], case["crop"]), "theta": None, "gamma": None}]
         y = preproc.augment_normalize_downscale(batch, case["crop"], states, case["mean"], case["std"], case["factor"])
         assert list(y.shape) == [2] + case["out_shape"], case["name"]
@@ -247,15 +247,20 @@ def test_augment_matches_the_oracle_on_random_states(cuda, stored, crop, dtype, 
         x = torch.randint(lo, hi, (b, 1) + stored, generator=g, dtype=torch.int32).to(dtype)
     states = [preproc.draw_train_state(rng, stored, crop, rotate_prob=0.75, gamma_prob=0.75) for _ in range(b)]
     states[-1] = {"offsets": preproc.crop_offsets(stored, crop), "theta": 0.26, "gamma": 0.5}    # extreme angle / gamma
+    states[1]["flip"] = 1                                    # RIGHT knees: mirrored columns / slices
+    states[2]["flip"] = 2 if len(stored) == 3 else 1
     y = preproc.augment_normalize_downscale(x.to(cuda), crop, states, 0.4, 0.25, factor).cpu()
     for k, st in enumerate(states):
-        ref = so.augment_chain(x[k, 0].numpy(), st["offsets"], crop, st["theta"], st["gamma"], 0.4, 0.25, factor)
+        ref = so.augment_chain(x[k, 0].numpy(), st["offsets"], crop, st["theta"], st["gamma"], 0.4, 0.25, factor,
+                               st.get("flip") or 0)
         torch.testing.assert_close(y[k], torch.from_numpy(ref), rtol=1e-5, atol=5e-5, msg=f"volume {k}: {st}")
 
 
 def _torch_chain(vol, st, crop, mean, std, factor):
     """The reference chain written with the torch calls the reference makes (F.affine_grid / F.grid_sample /
     F.interpolate), on the device: the full-size counterpart of the numpy oracle."""
+    if st.get("flip"):
+        vol = vol.flip(st["flip"])
     sel = tuple(slice(o, o + c) for o, c in zip(st["offsets"], crop))
     v = vol[sel].float()
     v = (v - v.min()) / (v.max() - v.min())
@@ -285,7 +290,7 @@ def test_augment_recipe_sizes(cuda):
     dess = torch.randint(0, 256, (3, 1) + stored, dtype=torch.uint8, generator=g).to(cuda)
     states = [{"offsets": [7, 13, 5], "theta": None, "gamma": None},
               {"offsets": [32, 20, 8], "theta": 0.0, "gamma": None},
-              {"offsets": [0, 0, 0], "theta": -0.21, "gamma": 1.7}]
+              {"offsets": [0, 0, 0], "theta": -0.21, "gamma": 1.7, "flip": 2}]
     y = preproc.augment_normalize_downscale(dess, crop, states, 0.257, 0.235, (0.5, 0.5, 0.5))
     assert y.shape == (3, 1, 160, 160, 64)
     for k in (0, 1):
@@ -299,7 +304,7 @@ def test_augment_recipe_sizes(cuda):
     torch.testing.assert_close(y[2], _torch_chain(dess[2, 0], states[2], crop, 0.257, 0.235, (0.5, 0.5, 0.5)),
                                rtol=1e-4, atol=1e-3)
     xr = torch.randint(0, 4096, (2, 1, 720, 712), dtype=torch.int32, generator=g).to(torch.uint16).to(cuda)
-    states = [{"offsets": [20, 12], "theta": 0.15, "gamma": 0.6}, {"offsets": [3, 0], "theta": None, "gamma": 1.9}]
+    states = [{"offsets": [20, 12], "theta": 0.15, "gamma": 0.6, "flip": 1}, {"offsets": [3, 0], "theta": None, "gamma": 1.9}]
     y = preproc.augment_normalize_downscale(xr, (700, 700), states, 0.543, 0.296, (0.5, 0.5))
     assert y.shape == (2, 1, 350, 350)
     for k in range(2):
