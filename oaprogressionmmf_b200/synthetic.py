@@ -133,3 +133,129 @@ class DevicePrefetcher:
 
 def input_bytes(ins: Sequence[torch.Tensor], target: torch.Tensor) -> int:
     return sum(t.numel() * t.element_size() for t in ins) + target.numel() * target.element_size()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the item / batch contract of the reference datasets
+# ---------------------------------------------------------------------------------------------------------------------
+# per sequence: stored (on-disk) minimum size, storage type, PTNormalize statistics, gamma augmentation or not
+# (koafusion/datasets/oai/_dataset.py:277-291, koafusion/datasets/_data_provider.py:297-334)
+MODAL_SPECS = {
+    "sag_3d_dess": dict(stored=(320, 320, 128), dtype=torch.uint8, mean=0.257, std=0.235, gamma=True),
+    "cor_iw_tse": dict(stored=(320, 320, 32), dtype=torch.uint8, mean=0.455, std=0.290, gamma=True),
+    "sag_t2_map": dict(stored=(320, 320, 25), dtype=torch.uint8, mean=0.259, std=0.345, gamma=False),
+    "xr_pa": dict(stored=(700, 700), dtype=torch.uint16, mean=0.543, std=0.296, gamma=True),
+}
+
+
+def encode_clinical(age: float, sex: str, bmi: float, inj: int, surg: int, womac: float) -> torch.Tensor:
+    """The 9-element clinical vector of ``DatasetOAI3d.__getitem__`` (``koafusion/datasets/oai/_dataset.py:254-266``):
+    z-scored age, one-hot sex (MALE first), z-scored BMI, one-hot injury, one-hot surgery, z-scored WOMAC."""
+    vec = [(age - 60.945) / 9.209]
+    vec += [1, 0] if sex == "MALE" else [0, 1]
+    vec.append((bmi - 28.734) / 4.917)
+    for flag in (inj, surg):
+        onehot = [0.0, 0.0]
+        onehot[flag] = 1.0
+        vec += onehot
+    vec.append((womac - 10.940) / 14.573)
+    return torch.tensor(vec, dtype=torch.float32)
+
+
+class SyntheticKneeDataset(torch.utils.data.Dataset):
+    """Map-style dataset with the item contract of ``DatasetOAI3d.__getitem__`` (``_dataset.py:250-329``): a dict with
+    ``image__{modal}`` per modality ((CH, R, C[, S]) image, (1, 9) clinical vector), ``target`` (numpy array of one
+    element), ``("-", "exam_knee_id")``, ``("-", "side")``. A ``DataLoader`` with the default collate turns it into the
+    batches the reference's train / eval loops read (``run/train_prog_fus.py:136-140``, ``run/eval_prog_fus.py:250-312``).
+
+    ``stored=False``: images as the reference's CPU transform chain delivers them (z-normalised fp32 of ``sizes[modal]``).
+    ``stored=True``: images *as stored* (integer type and on-disk size of ``MODAL_SPECS``, or ``stored_sizes[modal]``) plus,
+    under ``state__{modal}``, the random state of the training transforms drawn like the reference draws it
+    (``preproc.draw_train_state``; centre crop and no augmentation when ``train=False``); the chain itself then runs on
+    the device (``device_transforms``). RIGHT knees carry their mirror axis in the state instead of being flipped here."""
+
+    def __init__(self, modals: Sequence[str], sizes: dict, n: int, seed: int = 779, stored: bool = False, train: bool = True,
+                 stored_sizes: dict = None):
+        self.modals, self.sizes, self.n, self.seed = list(modals), dict(sizes), int(n), int(seed)
+        self.stored, self.train = bool(stored), bool(train)
+        self.stored_sizes = dict(stored_sizes or {})
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, idx):
+        import random
+
+        import numpy as np
+
+        from . import preproc
+
+        g = torch.Generator().manual_seed(self.seed * 100003 + idx)
+        rng = random.Random(self.seed * 100003 + idx)
+        side = "RIGHT" if rng.random() < 0.5 else "LEFT"
+        item = {("-", "exam_knee_id"): f"{9000000 + idx}__{side}", ("-", "side"): side}
+        for m in self.modals:
+            if m == "clin":
+                vec = encode_clinical(rng.gauss(60.9, 9.2), rng.choice(["MALE", "FEMALE"]), rng.gauss(28.7, 4.9),
+                                      int(rng.random() < 0.3), int(rng.random() < 0.1), abs(rng.gauss(10.9, 14.6)))
+                item["image__clin"] = vec.unsqueeze(0)
+                continue
+            if not self.stored:
+                item[f"image__{m}"] = torch.randn((1,) + tuple(self.sizes[m]), generator=g)
+                continue
+            spec = MODAL_SPECS[m]
+            size = tuple(self.stored_sizes.get(m, spec["stored"]))
+            hi = 256 if spec["dtype"] == torch.uint8 else 4096
+            item[f"image__{m}"] = torch.randint(0, hi, (1,) + size, generator=g, dtype=torch.int32).to(spec["dtype"])
+            if self.train:
+                st = preproc.draw_train_state(rng, size, self.sizes[m], with_gamma=spec["gamma"])
+            else:
+                st = {"offsets": preproc.crop_offsets(size, self.sizes[m]), "theta": None, "gamma": None}
+            st["flip"] = preproc.FLIP_AXIS[m] if side == "RIGHT" else 0
+            item[f"state__{m}"] = st
+        item["target"] = np.asarray([int(rng.random() < 0.12)])
+        return item
+
+
+def preproc_flip_axis(modal: str) -> int:
+    """Axis mirrored for RIGHT knees of this sequence (``preproc.FLIP_AXIS``)."""
+    from . import preproc
+
+    return preproc.FLIP_AXIS[modal]
+
+
+def collate_knees(items: Sequence[dict]) -> dict:
+    """Collate for ``stored=True`` items: tensors are stacked like the default collate does, the per-sample transform
+    states stay a list of dicts (one per knee), identifiers a list."""
+    import numpy as np
+
+    out = {}
+    for k in items[0]:
+        vals = [it[k] for it in items]
+        if isinstance(vals[0], torch.Tensor):
+            out[k] = torch.stack(vals)
+        elif isinstance(vals[0], np.ndarray):
+            out[k] = torch.from_numpy(np.stack(vals))
+        else:
+            out[k] = vals
+    return out
+
+
+def device_transforms(batch: dict, modals: Sequence[str], sizes: dict, downscale=None, device=None) -> List[torch.Tensor]:
+    """Positional model inputs from a ``stored=True`` batch: per image modality ONE ``koa_augment_resample`` call (mirror,
+    crop, unit range, rotation, gamma, z-score of ``MODAL_SPECS`` and the downscale factor of the recipe,
+    ``run/train_prog_fus.py:143-146``) on the stored integers after their host-to-device copy; the clinical vector passes
+    through. ``sizes[modal]`` is the crop (``config.model.input_size`` before the downscale)."""
+    from . import preproc
+
+    xs = []
+    for i, m in enumerate(modals):
+        x = batch[f"image__{m}"]
+        if device is not None:
+            x = x.to(device, non_blocking=True)
+        if m != "clin":
+            spec = MODAL_SPECS[m]
+            factor = downscale[i] if downscale else None
+            x = preproc.augment_normalize_downscale(x, sizes[m], batch[f"state__{m}"], spec["mean"], spec["std"], factor)
+        xs.append(x)
+    return xs

@@ -313,6 +313,42 @@ def test_augment_recipe_sizes(cuda):
     assert torch.isfinite(y).all()
 
 
+def test_stored_batches_transformed_on_the_device(cuda):
+    """The loader contract end to end: stored integer volumes + per-sample transform state from the
+    dataset, one koa_augment_resample call per modality on the device, against the numpy oracle knee by knee."""
+    from oaprogressionmmf_b200 import synthetic as sy
+
+    modals = ["xr_pa", "sag_3d_dess", "cor_iw_tse", "sag_t2_map", "clin"]
+    sizes = {"xr_pa": (20, 20), "sag_3d_dess": (16, 16, 8), "cor_iw_tse": (16, 16, 4), "sag_t2_map": (16, 16, 3)}
+    stored = {"xr_pa": (24, 22), "sag_3d_dess": (18, 20, 9), "cor_iw_tse": (16, 18, 4), "sag_t2_map": (17, 16, 4)}
+    downscale = [(0.5, 0.5), (0.5, 0.5, 0.5), (0.5, 0.5, 1.0), (0.5, 0.5, 1.0), (1.0,)]
+    for train in (True, False):
+        ds = sy.SyntheticKneeDataset(modals, sizes, n=8, stored=True, train=train, stored_sizes=stored)
+        dl = torch.utils.data.DataLoader(ds, batch_size=4, drop_last=True, collate_fn=sy.collate_knees)
+        saw_right = saw_rot = saw_gamma = False
+        for batch in dl:
+            assert batch["image__sag_3d_dess"].dtype == torch.uint8 and batch["image__xr_pa"].dtype == torch.uint16
+            xs = [x.cpu() for x in sy.device_transforms(batch, modals, sizes, downscale, device=cuda)]
+            assert [tuple(x.shape) for x in xs] == [(4, 1, 10, 10), (4, 1, 8, 8, 4), (4, 1, 8, 8, 4), (4, 1, 8, 8, 3), (4, 1, 9)]
+            for m, x, f in zip(modals[:-1], xs, downscale):
+                spec = sy.MODAL_SPECS[m]
+                for k, st in enumerate(batch[f"state__{m}"]):
+                    side = batch[("-", "side")][k]
+                    assert st["flip"] == (sy.preproc_flip_axis(m) if side == "RIGHT" else 0)
+                    if not train:
+                        assert st["theta"] is None and st["gamma"] is None
+                    if m == "sag_t2_map":
+                        assert st["gamma"] is None              # no gamma augmentation for T2 maps
+                    saw_right |= side == "RIGHT"
+                    saw_rot |= st["theta"] is not None
+                    saw_gamma |= st["gamma"] is not None
+                    raw = batch[f"image__{m}"][k, 0].numpy()
+                    ref = so.augment_chain(raw, st["offsets"], sizes[m], st["theta"], st["gamma"], spec["mean"], spec["std"],
+                                           f, st["flip"])
+                    np.testing.assert_allclose(x[k].numpy(), ref, rtol=1e-5, atol=5e-5, err_msg=f"{m} knee {k}: {st}")
+        assert saw_right and (saw_rot and saw_gamma) == train
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # predictions
 # ---------------------------------------------------------------------------------------------------------------------
