@@ -349,6 +349,48 @@ def test_stored_batches_transformed_on_the_device(cuda):
         assert saw_right and (saw_rot and saw_gamma) == train
 
 
+def test_epoch_loops_on_the_cuda_path(cuda):
+    """trainpath.train_epoch / val_epoch (the reference trainer's loops with one read-back per epoch) around the CUDA
+    model, FocalLoss and the fused Adam: same losses as a replay that reads loss.item() every step, as the reference does
+    (weight gradients are summed with fp32 atomics, so equal up to summation order)."""
+    from oaprogressionmmf_b200 import koamodels, synthetic as sy, trainpath
+    from oaprogressionmmf_b200.losses import FocalLoss
+    from oracle import koa_oracle as ko
+    from tests.util import to_attr
+
+    cfg = ko.make_config("XR1Cnn", xr_size=64, xr_arch="resnet18")
+    modals, sizes = ["xr_pa"], {"xr_pa": (64, 64)}
+
+    def loader():
+        return torch.utils.data.DataLoader(sy.SyntheticKneeDataset(modals, sizes, n=12, seed=3), batch_size=4, drop_last=True)
+
+    def build():
+        torch.manual_seed(778)
+        model = koamodels.dict_models["XR1Cnn"](to_attr(cfg), None).to(cuda).train()
+        return model, koptim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+
+    loss_fn = FocalLoss(num_classes=2)
+    model, opt = build()
+    metrics = trainpath.train_epoch(model, loader(), modals, loss_fn, opt, device=cuda)
+    ref_model, ref_opt = build()
+    logged = []
+    for batch in loader():
+        ref_opt.zero_grad()
+        x = batch["image__xr_pa"].to(cuda)
+        loss = loss_fn(input=ref_model(x)["main"].squeeze(1), target=batch["target"].to(cuda).long().squeeze(1))
+        logged.append(loss.item())
+        loss.backward()
+        ref_opt.step()
+    got = metrics["batch-w"]["loss_prog"]
+    assert len(got) == 3 and all(np.isfinite(got))
+    np.testing.assert_allclose(got, logged, rtol=2e-2, atol=1e-3)
+    val = trainpath.val_epoch(model.eval(), loader(), modals, loss_fn, device=cuda)
+    assert len(val["batch-w"]["loss_prog"]) == 3
+    proba = val["epoch-w"]["predict_proba"]
+    assert proba.shape == (12, 2) and val["epoch-w"]["target"].shape == (12, 1)
+    np.testing.assert_allclose(proba.sum(1), np.ones(12), rtol=0, atol=1e-5)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # predictions
 # ---------------------------------------------------------------------------------------------------------------------
