@@ -54,6 +54,8 @@ __device__ __forceinline__ void stage_rows(const bf16* __restrict__ g, long long
 __global__ void __launch_bounds__(kWarps * 32)
 attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ probs, int n, int heads,
                      int hd, float scale) {
+  griddep_wait();  // KOA_PDL (koa_common.cuh)
+  griddep_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int ldk = hd + 8;
   bf16* sK = reinterpret_cast<bf16*>(smem);
@@ -123,6 +125,8 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float
 __global__ void __launch_bounds__(kWarps * 32)
 attention_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ probs, const bf16* __restrict__ dout,
                      bf16* __restrict__ dqkv, int n, int heads, int hd, float scale) {
+  griddep_wait();  // KOA_PDL (koa_common.cuh)
+  griddep_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int ldk = hd + 8;
   bf16* bufA = reinterpret_cast<bf16*>(smem);               // [n][hd+8]
@@ -232,8 +236,12 @@ int koa_k_attention_fwd(const void* qkv, void* out, float* probs, int batch, int
                                         (int)fwd_smem(kMaxN, 256)));
     attr_set = 1;
   }
-  attention_fwd_kernel<<<batch * heads, kWarps * 32, fwd_smem(n, head_dim), st>>>((const bf16*)qkv, (bf16*)out, probs, n,
-                                                                                  heads, head_dim, scale);
+  if (koa_pdl_enabled())
+    KOA_CHECK_CUDA(koa_launch_pdl(attention_fwd_kernel, dim3(batch * heads), dim3(kWarps * 32), fwd_smem(n, head_dim), st, 1u,
+                                  (const bf16*)qkv, (bf16*)out, probs, n, heads, head_dim, scale));
+  else
+    attention_fwd_kernel<<<batch * heads, kWarps * 32, fwd_smem(n, head_dim), st>>>((const bf16*)qkv, (bf16*)out, probs, n,
+                                                                                    heads, head_dim, scale);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -248,8 +256,12 @@ int koa_k_attention_bwd(const void* qkv, const float* probs, const void* dout, v
                                         (int)bwd_smem(kMaxN, 256)));
     attr_set = 1;
   }
-  attention_bwd_kernel<<<batch * heads, kWarps * 32, bwd_smem(n, head_dim), st>>>(
-      (const bf16*)qkv, probs, (const bf16*)dout, (bf16*)dqkv, n, heads, head_dim, scale);
+  if (koa_pdl_enabled())
+    KOA_CHECK_CUDA(koa_launch_pdl(attention_bwd_kernel, dim3(batch * heads), dim3(kWarps * 32), bwd_smem(n, head_dim), st, 1u,
+                                  (const bf16*)qkv, probs, (const bf16*)dout, (bf16*)dqkv, n, heads, head_dim, scale));
+  else
+    attention_bwd_kernel<<<batch * heads, kWarps * 32, bwd_smem(n, head_dim), st>>>(
+        (const bf16*)qkv, probs, (const bf16*)dout, (bf16*)dqkv, n, heads, head_dim, scale);
   KOA_LAUNCH_CHECK();
   return 0;
 }

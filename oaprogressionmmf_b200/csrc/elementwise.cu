@@ -863,6 +863,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ beta, bf16* __restrict__ out_bf16,
                                      float* __restrict__ out_f32, float* __restrict__ mean_out,
                                      float* __restrict__ rstd_out, int rows, int d, long long x_row_stride, float eps) {
+  griddep_wait();  // KOA_PDL (koa_common.cuh)
+  griddep_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -921,6 +923,8 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
                                      float* __restrict__ dx, bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int rows, int d, long long x_row_stride,
                                      long long dx_row_stride) {
+  griddep_wait();  // KOA_PDL (koa_common.cuh)
+  griddep_launch_dependents();
   extern __shared__ float sm[];  // [2][d]
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.0f;
   __syncthreads();
@@ -1365,7 +1369,10 @@ int koa_k_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
                         float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st) {
   KOA_REQUIRE(d % 256 == 0 && d <= 4096, "LayerNorm width %d must be a multiple of 256 and <= 4096", d);
   const int blocks = koa_cdiv((long long)rows * 32, kThreads);
-  if (d <= 2048)
+  if (koa_pdl_enabled())
+    KOA_CHECK_CUDA(koa_launch_pdl(d <= 2048 ? layernorm_fwd_kernel<8> : layernorm_fwd_kernel<16>, dim3(blocks), dim3(kThreads), 0,
+                                  st, 1u, x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d, x_row_stride, 1e-5f));
+  else if (d <= 2048)
     layernorm_fwd_kernel<8><<<blocks, kThreads, 0, st>>>(x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d,
                                                          x_row_stride, 1e-5f);
   else
@@ -1380,9 +1387,14 @@ int koa_k_layernorm_bwd(const float* dy, const float* x, const float* gamma, con
   KOA_REQUIRE(d % 256 == 0 && d <= 2048, "LayerNorm backward width %d must be a multiple of 256 and <= 2048", d);
   int blocks = koa_cdiv(rows, kThreads / 32);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  layernorm_bwd_kernel<8><<<blocks, kThreads, 2 * d * sizeof(float), st>>>(dy, x, gamma, mean, rstd, dres, dx,
-                                                                           (bf16*)dx_bf16, dgamma, dbeta, rows, d,
-                                                                           x_row_stride, dx_row_stride);
+  if (koa_pdl_enabled())
+    KOA_CHECK_CUDA(koa_launch_pdl(layernorm_bwd_kernel<8>, dim3(blocks), dim3(kThreads), 2 * d * sizeof(float), st, 1u, dy, x,
+                                  gamma, mean, rstd, dres, dx, (bf16*)dx_bf16, dgamma, dbeta, rows, d, x_row_stride,
+                                  dx_row_stride));
+  else
+    layernorm_bwd_kernel<8><<<blocks, kThreads, 2 * d * sizeof(float), st>>>(dy, x, gamma, mean, rstd, dres, dx,
+                                                                             (bf16*)dx_bf16, dgamma, dbeta, rows, d,
+                                                                             x_row_stride, dx_row_stride);
   KOA_LAUNCH_CHECK();
   return 0;
 }
