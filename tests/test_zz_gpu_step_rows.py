@@ -303,12 +303,13 @@ def test_augment_recipe_sizes(cuda):
     # coordinates ~320 carry an ulp of 3e-5, a unit-range difference between neighbours of up to 1, divided by std
     torch.testing.assert_close(y[2], _torch_chain(dess[2, 0], states[2], crop, 0.257, 0.235, (0.5, 0.5, 0.5)),
                                rtol=1e-4, atol=1e-3)
-    xr = torch.randint(0, 4096, (2, 1, 720, 712), dtype=torch.int32, generator=g).to(torch.uint16).to(cuda)
+    xr_i32 = torch.randint(0, 4096, (2, 1, 720, 712), dtype=torch.int32, generator=g)
+    xr = xr_i32.to(torch.uint16).to(cuda)         # uint16 only ever crosses to the device as bytes: no CUDA cast kernels
     states = [{"offsets": [20, 12], "theta": 0.15, "gamma": 0.6, "flip": 1}, {"offsets": [3, 0], "theta": None, "gamma": 1.9}]
     y = preproc.augment_normalize_downscale(xr, (700, 700), states, 0.543, 0.296, (0.5, 0.5))
     assert y.shape == (2, 1, 350, 350)
     for k in range(2):
-        ref = _torch_chain(xr[k, 0].to(torch.int32), states[k], (700, 700), 0.543, 0.296, (0.5, 0.5))
+        ref = _torch_chain(xr_i32[k, 0].to(cuda), states[k], (700, 700), 0.543, 0.296, (0.5, 0.5))
         torch.testing.assert_close(y[k], ref, rtol=1e-4, atol=1e-3)
     assert torch.isfinite(y).all()
 
