@@ -24,4 +24,9 @@ KOA_PDL=1 run bench_pdl 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseli
 KOA_IDX32=1 run parity_idx32 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu
 KOA_IDX32=1 run bench_idx32 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
 run step_ops_bench 300 python tools/step_ops_bench.py
+# 5. profiler passes last (numbers printed under ncu are never bench values): launch list + DRAM bytes of one timed step
+#    (the warm-up step is skipped), summarised by tools/launch_report.py into profiles/ by hand afterwards
+run ncu_launches 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+  --launch-skip 1760 --launch-count 1760 --csv --log-file gpurun_out/r2_launches.csv \
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --skip-e2e --no-full-step
 cat gpurun_out/r2_summary.log
