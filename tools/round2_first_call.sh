@@ -23,6 +23,7 @@ KOA_PDL=1 run parity_pdl 900 python -m pytest tests/test_gpu_parity.py -x -q -m 
 KOA_PDL=1 run bench_pdl 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
 KOA_IDX32=1 run parity_idx32 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu
 KOA_IDX32=1 run bench_idx32 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
+KOA_BRANCH_PRIORITY=1 run bench_prio 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
 run step_ops_bench 300 python tools/step_ops_bench.py
 # 5. profiler passes last (numbers printed under ncu are never bench values): launch list + DRAM bytes of one timed step
 #    (the warm-up step is skipped), summarised by tools/launch_report.py into profiles/ by hand afterwards
