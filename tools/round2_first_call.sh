@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2: everything that was written after round 1's GPU budget was spent, in one box visit.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash tools/round2_first_call.sh'   # ~30-40 min of box time
 # Results land in gpurun_out/r2_*.log. Each step has its own timeout and never stops the next one.
 mkdir -p gpurun_out
 run() { name=$1; shift; echo "== $name"; timeout "$@" > gpurun_out/r2_$name.log 2>&1; echo "rc=$? $name" | tee -a gpurun_out/r2_summary.log; tail -3 gpurun_out/r2_$name.log; }
