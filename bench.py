@@ -227,6 +227,39 @@ def measure_full_step(step, model, dev_batches, steps, knees, peaks):
                           frac=gbs / peaks["hbm"] if gbs else None))
 
 
+def measure_inference(model, cfg, dev, batch=64, chunk=32, iters=3):
+    """Eval-mode forward of `batch` knees in micro-batches of `chunk` (no coupling between knees in eval mode: BatchNorm
+    uses its running statistics), inputs from pinned host memory, class predictions read back per micro-batch as the
+    reference's eval loop does (koafusion/run/eval_prog_fus.py:286-304)."""
+    from oaprogressionmmf_b200.synthetic import synthetic_batch
+
+    was_training = model.training
+    model.eval()
+    try:
+        torch.cuda.empty_cache()
+        ins_h, _ = synthetic_batch(cfg, batch, 5, pin=True)
+
+        def one():
+            ins = [t.to(dev, non_blocking=True) for t in ins_h]
+            return torch.cat([model(*[t[i:i + chunk] for t in ins])["main"].argmax(1).cpu() for i in range(0, batch, chunk)])
+
+        with torch.no_grad():
+            one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                pred = one()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        return dict(value=batch / ms * 1e3, unit="knees/s", batch=batch, micro_batch=chunk, ms_per_batch=ms,
+                    h2d_bytes_per_batch=sum(t.numel() * t.element_size() for t in ins_h), predictions=int(pred.numel()),
+                    mode="eval, no_grad, H2D + prediction read-back inside the timed region")
+    finally:
+        model.train(was_training)
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -441,6 +474,15 @@ def run_ours(args):
             full_step = measure_full_step(step, model, dev_batches, args.steps, B, peaks)
         except Exception as e:  # noqa: BLE001
             full_step = dict(error=f"{type(e).__name__}: {e}"[:300])
+    # ---- batched inference (BASELINE.json config 5), same model in eval mode under no_grad: 64 knees as two micro-batches
+    # of 32, host -> device copy and the read-back of the predictions inside the timed region (tools/infer_sweep.py is the
+    # full sweep). Reported next to `value`; single GPU (the 8-GPU sweep is 8 replicas without a collective), guarded, last.
+    inference = None
+    if ws == 1 and not args.skip_e2e and not args.no_full_step:
+        try:
+            inference = measure_inference(model, cfg, dev)
+        except Exception as e:  # noqa: BLE001
+            inference = dict(error=f"{type(e).__name__}: {e}"[:300])
     line = dict(metric=METRIC, value=value, unit="knees/s", n_gpus=ws, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=args.workload, description=WORKLOAD_DESC.get(args.workload, args.workload),
@@ -456,7 +498,7 @@ def run_ours(args):
                 e2e=dict(value=e2e_value, unit="knees/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                          loss_readback=e2e_mode, blocking_value=e2e_blocking),
                 gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag, full_step=full_step,
-                switches={k: v for k, v in sorted(os.environ.items()) if k.startswith("KOA_")})
+                inference=inference, switches={k: v for k, v in sorted(os.environ.items()) if k.startswith("KOA_")})
     print(json.dumps(line), flush=True)
     if ws > 1:
         dist.destroy_process_group()
