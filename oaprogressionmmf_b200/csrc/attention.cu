@@ -236,7 +236,7 @@ int koa_k_attention_fwd(const void* qkv, void* out, float* probs, int batch, int
                                         (int)fwd_smem(kMaxN, 256)));
     attr_set = 1;
   }
-  if (koa_pdl_enabled())
+  if (koa_pdl_enabled() >= 3)
     KOA_CHECK_CUDA(koa_launch_pdl(attention_fwd_kernel, dim3(batch * heads), dim3(kWarps * 32), fwd_smem(n, head_dim), st, 1u,
                                   (const bf16*)qkv, (bf16*)out, probs, n, heads, head_dim, scale));
   else
@@ -256,7 +256,7 @@ int koa_k_attention_bwd(const void* qkv, const float* probs, const void* dout, v
                                         (int)bwd_smem(kMaxN, 256)));
     attr_set = 1;
   }
-  if (koa_pdl_enabled())
+  if (koa_pdl_enabled() >= 3)
     KOA_CHECK_CUDA(koa_launch_pdl(attention_bwd_kernel, dim3(batch * heads), dim3(kWarps * 32), bwd_smem(n, head_dim), st, 1u,
                                   (const bf16*)qkv, probs, (const bf16*)dout, (bf16*)dqkv, n, heads, head_dim, scale));
   else

@@ -1243,7 +1243,7 @@ int koa_k_bn_act_fin(const void* y, const KoaBnFwdFin* a, const void* res, const
                      void* out_bf16, long long rows, int c, int relu, double count, int training, cudaStream_t st) {
   KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm apply needs C/8 | %d (C=%d)", kThreads, c);
   KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
-  if (koa_pdl_enabled())
+  if (koa_pdl_enabled() >= 2)
     KOA_CHECK_CUDA(koa_launch_pdl(bn_act_fixed_kernel, dim3(grid_for(rows * (c / 8) / 2)), dim3(kThreads), 0, st, 1u,
                                   (const bf16*)y, nullptr, nullptr, (const bf16*)res, (const bf16*)y2, nullptr, nullptr,
                                   (bf16*)out, (bf16*)out_bf16, rows, c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training));
@@ -1259,7 +1259,7 @@ int koa_k_bn_bwd_apply_fin(const void* dout, const void* act, const void* y, con
                            cudaStream_t st) {
   KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm backward needs C/8 | %d (C=%d)", kThreads, c);
   KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
-  if (koa_pdl_enabled())
+  if (koa_pdl_enabled() >= 2)
     KOA_CHECK_CUDA(koa_launch_pdl(bn_bwd_apply_fixed_kernel, dim3(grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid)),
                                   dim3(kThreads), 0, st, 1u, (const bf16*)dout, (const bf16*)act, (const bf16*)y, nullptr,
                                   nullptr, nullptr, (bf16*)dy, (const bf16*)y2, nullptr, nullptr, nullptr, (bf16*)dy2, rows, c,
@@ -1278,7 +1278,7 @@ int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const 
   if (rc) return rc;
   const int threads = reduce_threads(c);
   const int lanes = threads / (c / 8);
-  if (koa_pdl_enabled())
+  if (koa_pdl_enabled() >= 2)
     KOA_CHECK_CUDA(koa_launch_pdl(bn_bwd_reduce_kernel, dim3(grid_for(rows, lanes, kDeepGrid)), dim3(threads),
                                   3 * c * sizeof(float), st, 1u, (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean,
                                   invstd, (const bf16*)y2, mean2, invstd2, sum_dz, sum_dzx, sum_dzx2, rows, c));
@@ -1369,7 +1369,7 @@ int koa_k_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
                         float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st) {
   KOA_REQUIRE(d % 256 == 0 && d <= 4096, "LayerNorm width %d must be a multiple of 256 and <= 4096", d);
   const int blocks = koa_cdiv((long long)rows * 32, kThreads);
-  if (koa_pdl_enabled())
+  if (koa_pdl_enabled() >= 3)
     KOA_CHECK_CUDA(koa_launch_pdl(d <= 2048 ? layernorm_fwd_kernel<8> : layernorm_fwd_kernel<16>, dim3(blocks), dim3(kThreads), 0,
                                   st, 1u, x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d, x_row_stride, 1e-5f));
   else if (d <= 2048)
@@ -1387,7 +1387,7 @@ int koa_k_layernorm_bwd(const float* dy, const float* x, const float* gamma, con
   KOA_REQUIRE(d % 256 == 0 && d <= 2048, "LayerNorm backward width %d must be a multiple of 256 and <= 2048", d);
   int blocks = koa_cdiv(rows, kThreads / 32);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  if (koa_pdl_enabled())
+  if (koa_pdl_enabled() >= 3)
     KOA_CHECK_CUDA(koa_launch_pdl(layernorm_bwd_kernel<8>, dim3(blocks), dim3(kThreads), 2 * d * sizeof(float), st, 1u, dy, x,
                                   gamma, mean, rstd, dres, dx, (bf16*)dx_bf16, dgamma, dbeta, rows, d, x_row_stride,
                                   dx_row_stride));

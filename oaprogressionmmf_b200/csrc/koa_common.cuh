@@ -75,7 +75,7 @@ typedef __nv_bfloat162 bf162;
 // koa_launch_pdl() therefore calls griddep_wait() before its first access to global memory, and griddep_launch_dependents()
 // AFTER it owns its TMEM columns (a successor CTA that became resident earlier could otherwise take the columns this CTA
 // is about to ask for and then wait for this grid: deadlock). Without the attribute both instructions do nothing.
-int koa_pdl_enabled();  // koa_tma.cu: getenv("KOA_PDL"), read once
+int koa_pdl_enabled();  // koa_tma.cu: getenv("KOA_PDL"), read once: 0 off, 1 GEMM kernels, 2 + BatchNorm, 3 + LayerNorm / attention
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t koa_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

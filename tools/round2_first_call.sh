@@ -19,8 +19,10 @@ if grep -q "MIXED OK" gpurun_out/r2_mixed_wgrad.log; then
 fi
 KOA_WGRAD_BULK_RED=1 run parity_bulkred 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu
 KOA_WGRAD_BULK_RED=1 run bench_bulkred 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
-KOA_PDL=1 run parity_pdl 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu
-KOA_PDL=1 run bench_pdl 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
+KOA_PDL=3 run parity_pdl3 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu
+for lvl in 1 2 3; do
+  KOA_PDL=$lvl run bench_pdl$lvl 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
+done
 KOA_IDX32=1 run parity_idx32 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu
 KOA_IDX32=1 run bench_idx32 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
 KOA_BRANCH_PRIORITY=1 run bench_prio 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-full-step
