@@ -1,4 +1,4 @@
-// step_arith.cuh — per-element arithmetic of the resampling / augmentation kernels of step_ops.cu.
+// step_arith.cuh — per-element arithmetic of the Adam, resampling and augmentation kernels of step_ops.cu.
 //
 // The functions are __host__ __device__ so that the *same source* the kernels run is also compiled by g++ into a
 // test-only harness (tests/host_emul/step_emul.cpp) and checked on the CPU against the golden vectors made from the
@@ -31,6 +31,47 @@ KOA_HD float div_rn(float a, float b) {  // IEEE division whatever the compiler 
 #else
   return a / b;
 #endif
+}
+
+KOA_HD float sqrt_rn(float a) {
+#if defined(__CUDA_ARCH__)
+  return __fsqrt_rn(a);
+#else
+  return sqrtf(a);
+#endif
+}
+
+// ---- Adam / AdamW ------------------------------------------------------------------------------------------------------
+struct AdamCoef {
+  float beta2, one_m_beta1, one_m_beta2, eps, step_size, bc2_sqrt, l2, decay_mul, grad_scale;
+};
+
+// scalars exactly as torch.optim.Adam forms them: in double on the host, rounded to fp32 where the tensor op takes them
+inline AdamCoef make_adam_coef(const koa_adam_hyper_t& h) {
+  const double bc1 = 1.0 - pow(h.beta1, (double)h.step), bc2 = 1.0 - pow(h.beta2, (double)h.step);
+  AdamCoef c;
+  c.beta2 = (float)h.beta2;
+  c.one_m_beta1 = (float)(1.0 - h.beta1);
+  c.one_m_beta2 = (float)(1.0 - h.beta2);
+  c.eps = (float)h.eps;
+  c.step_size = (float)(h.lr / bc1);
+  c.bc2_sqrt = (float)sqrt(bc2);
+  c.l2 = h.decoupled_weight_decay ? 0.f : (float)h.weight_decay;
+  c.decay_mul = h.decoupled_weight_decay ? (float)(1.0 - h.lr * h.weight_decay) : 1.f;
+  c.grad_scale = (float)(h.grad_scale == 0.0 ? 1.0 : h.grad_scale);
+  return c;
+}
+
+KOA_HD void adam_update(float& p, float g, float& m, float& v, const AdamCoef& c) {
+  // the order of torch.optim.adam._single_tensor_adam: L2 term into the gradient (Adam) or decay of the parameter
+  // (AdamW), exp_avg.lerp_(grad, 1 - beta1), exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2),
+  // denom = sqrt(exp_avg_sq) / sqrt(bias_correction2) + eps, param.addcdiv_(exp_avg, denom, -lr / bias_correction1)
+  g = fmaf(c.l2, p, g * c.grad_scale);
+  p *= c.decay_mul;
+  m = fmaf(g - m, c.one_m_beta1, m);
+  v = fmaf(c.one_m_beta2 * g, g, v * c.beta2);
+  const float denom = div_rn(sqrt_rn(v), c.bc2_sqrt) + c.eps;
+  p = fmaf(-c.step_size, div_rn(m, denom), p);
 }
 
 struct Tap { int i0, step; float l0, l1; };

@@ -38,21 +38,8 @@ struct AdamTable {
   unsigned long long vec_mask;      // bit i: the four pointers of slot i are 16-byte aligned
 };
 
-struct AdamCoef {
-  float beta2, one_m_beta1, one_m_beta2, eps, step_size, bc2_sqrt, l2, decay_mul, grad_scale;
-};
-
-__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamCoef& c) {
-  // the order of torch.optim.adam._single_tensor_adam: L2 term into the gradient (Adam) or decay of the parameter
-  // (AdamW), exp_avg.lerp_(grad, 1 - beta1), exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2),
-  // denom = sqrt(exp_avg_sq) / sqrt(bias_correction2) + eps, param.addcdiv_(exp_avg, denom, -lr / bias_correction1)
-  g = fmaf(c.l2, p, g * c.grad_scale);
-  p *= c.decay_mul;
-  m = fmaf(g - m, c.one_m_beta1, m);
-  v = fmaf(c.one_m_beta2 * g, g, v * c.beta2);
-  const float denom = __fdiv_rn(__fsqrt_rn(v), c.bc2_sqrt) + c.eps;
-  p = fmaf(-c.step_size, __fdiv_rn(m, denom), p);
-}
+using koa_arith::AdamCoef;
+using koa_arith::adam_update;
 
 __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamTable tab,
                                                          const __grid_constant__ AdamCoef c) {
@@ -358,18 +345,7 @@ extern "C" int koa_adam_step(const koa_adam_tensor_t* tensors, int n_tensors, co
   KOA_REQUIRE(h->lr >= 0.0 && h->eps >= 0.0 && h->weight_decay >= 0.0 && h->beta1 >= 0.0 && h->beta1 < 1.0 &&
                   h->beta2 >= 0.0 && h->beta2 < 1.0,
               "invalid Adam hyper-parameters");
-  // scalars exactly as torch.optim.Adam forms them: in double on the host, rounded to fp32 where the tensor op takes them
-  const double bc1 = 1.0 - pow(h->beta1, (double)h->step), bc2 = 1.0 - pow(h->beta2, (double)h->step);
-  AdamCoef c;
-  c.beta2 = (float)h->beta2;
-  c.one_m_beta1 = (float)(1.0 - h->beta1);
-  c.one_m_beta2 = (float)(1.0 - h->beta2);
-  c.eps = (float)h->eps;
-  c.step_size = (float)(h->lr / bc1);
-  c.bc2_sqrt = (float)sqrt(bc2);
-  c.l2 = h->decoupled_weight_decay ? 0.f : (float)h->weight_decay;
-  c.decay_mul = h->decoupled_weight_decay ? (float)(1.0 - h->lr * h->weight_decay) : 1.f;
-  c.grad_scale = (float)(h->grad_scale == 0.0 ? 1.0 : h->grad_scale);
+  const AdamCoef c = koa_arith::make_adam_coef(*h);  // step_arith.cuh (shared with the CPU check)
 
   AdamTable tab;
   int i = 0;

@@ -82,3 +82,14 @@ extern "C" int emul_augment_resample(const void* in, int in_dtype, float* out, k
   }
   return -1;
 }
+
+// koa_adam_step on host pointers: the same coefficient set-up and per-element update the kernel runs
+extern "C" int emul_adam_step(const koa_adam_tensor_t* tensors, int n_tensors, const koa_adam_hyper_t* h) {
+  const AdamCoef c = make_adam_coef(*h);
+  for (int t = 0; t < n_tensors; ++t) {
+    const koa_adam_tensor_t& a = tensors[t];
+    if (a.numel <= 0 || a.grad == nullptr) continue;  // torch skips parameters without a gradient
+    for (long long i = 0; i < a.numel; ++i) adam_update(a.param[i], a.grad[i], a.exp_avg[i], a.exp_avg_sq[i], c);
+  }
+  return 0;
+}

@@ -1,4 +1,4 @@
-"""The per-element arithmetic of the resampling / augmentation kernels, checked on the CPU.
+"""The per-element arithmetic of the resampling / augmentation / Adam kernels, checked on the CPU.
 
 ``csrc/step_arith.cuh`` holds the ``__host__ __device__`` functions the kernels of ``step_ops.cu`` call for one output
 element. ``tests/host_emul/step_emul.cpp`` compiles that same header with g++ and loops over the elements the way the
@@ -174,6 +174,9 @@ def test_gpu_tests_of_the_step_rows_dry_run_on_the_host(emul, gold, monkeypatch)
     emul.emul_resample_linear.argtypes = [_P, _I, _P, _I, C.POINTER(_I), C.POINTER(_I), _P, _P]
 
     class Stub(glue.HostStandIn):
+        def koa_adam_step(self, table, n, hyper, stream):          # the kernel's own coefficient set-up and update
+            return emul.emul_adam_step(table, n, hyper)
+
         def koa_augment_resample(self, src, dtype, out, params, batch, s, c, o, mean, std, ws, stream):
             return emul.emul_augment_resample(src, dtype, out, params, batch, s, c, o, mean, std)
 
@@ -196,10 +199,12 @@ def test_gpu_tests_of_the_step_rows_dry_run_on_the_host(emul, gold, monkeypatch)
     gpu_tests.test_interpolate_matches_the_oracle(cpu, (2, 2, 30, 31), (0.75, 0.4), torch.float32)
     gpu_tests.test_interpolate_matches_the_oracle(cpu, (2, 1, 16, 12, 5), (0.5, 0.5, 1.0), torch.int16)
     gpu_tests.test_recipe_sizes_box_mean_identity_and_minmax(cpu)
-    # the rows without host-compiled arithmetic: the test bodies run against the oracle stand-in (their logic, their
-    # bookkeeping assertions and their tolerances against torch.optim on the same device)
+    # Adam: adam_update / make_adam_coef of the kernel (host build) against torch.optim on the same device and against the
+    # numpy oracle, with the tolerances the GPU tests use; the predictions run against the oracle stand-in (test logic only)
     from oaprogressionmmf_b200 import optim as koptim
 
+    emul.emul_adam_step.argtypes = [_P, _I, _P]
+    gpu_tests.test_adam_matches_torch_optim(cpu, koptim.Adam, torch.optim.Adam, 0.0)
     gpu_tests.test_adam_matches_torch_optim(cpu, koptim.Adam, torch.optim.Adam, 1e-4)
     gpu_tests.test_adam_matches_torch_optim(cpu, koptim.AdamW, torch.optim.AdamW, 1e-2)
     gpu_tests.test_adam_matches_the_oracle(cpu)
