@@ -74,6 +74,39 @@ KOA_HD void adam_update(float& p, float g, float& m, float& v, const AdamCoef& c
   p = fmaf(-c.step_size, div_rn(m, denom), p);
 }
 
+// ---- predictions ---------------------------------------------------------------------------------------------------------
+// softmax + argmax of one row of logits (koafusion/run/eval_prog_fus.py:300-304); first maximum wins, as torch / numpy
+KOA_HD void predict_row(const float* x, int classes, float* proba, long long* pred) {
+  float mx = x[0];
+  int arg = 0;
+  for (int c = 1; c < classes; ++c)
+    if (x[c] > mx) { mx = x[c]; arg = c; }
+  float sum = 0.f;
+  for (int c = 0; c < classes; ++c) sum += expf(x[c] - mx);
+  if (proba != nullptr)
+    for (int c = 0; c < classes; ++c) proba[c] = expf(x[c] - mx) / sum;
+  if (pred != nullptr) *pred = arg;
+}
+
+// the fold ensemble of the reference for knee b: softmax over classes of the fold-mean of the per-fold probabilities
+// (sic, eval_prog_fus.py:330-336), then argmax; proba is [folds][batch][classes]
+KOA_HD void ensemble_row(const float* proba, int folds, int batch, int classes, int b, float* out, long long* pred) {
+  const float inv = 1.f / (float)folds;
+  float mx = 0.f, sum = 0.f;
+  int arg = 0;
+  for (int pass = 0; pass < 3; ++pass) {  // maximum, normaliser, output: the fold means are recomputed, not stored
+    for (int c = 0; c < classes; ++c) {
+      float s = 0.f;
+      for (int f = 0; f < folds; ++f) s += proba[((long long)f * batch + b) * classes + c];
+      s *= inv;
+      if (pass == 0) { if (c == 0 || s > mx) { mx = s; arg = c; } }
+      else if (pass == 1) sum += expf(s - mx);
+      else if (out != nullptr) out[c] = expf(s - mx) / sum;
+    }
+  }
+  if (pred != nullptr) *pred = arg;
+}
+
 struct Tap { int i0, step; float l0, l1; };
 KOA_HD Tap make_tap(int dst, float rscale, int n_in) {
   // area_pixel_compute_source_index: src = scale * (dst + 0.5) - 0.5, clamped at 0 (linear modes)

@@ -184,41 +184,17 @@ __global__ void predict_kernel(const float* __restrict__ logits, float* __restri
                                int batch, int classes) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  const float* x = logits + (long long)b * classes;
-  float mx = x[0];
-  int arg = 0;
-  for (int c = 1; c < classes; ++c)
-    if (x[c] > mx) { mx = x[c]; arg = c; }
-  float sum = 0.f;
-  for (int c = 0; c < classes; ++c) sum += expf(x[c] - mx);
-  if (proba != nullptr)
-    for (int c = 0; c < classes; ++c) proba[(long long)b * classes + c] = expf(x[c] - mx) / sum;
-  if (pred != nullptr) pred[b] = arg;
+  koa_arith::predict_row(logits + (long long)b * classes, classes, proba ? proba + (long long)b * classes : nullptr,
+                         pred ? pred + b : nullptr);
 }
 
-// the fold ensemble of the reference: softmax over classes of the fold-mean of the per-fold probabilities (sic),
-// then argmax; proba is [folds][batch][classes]
+// the fold ensemble of the reference (step_arith.cuh); proba is [folds][batch][classes]
 __global__ void ensemble_kernel(const float* __restrict__ proba, float* __restrict__ out, long long* __restrict__ pred,
                                 int folds, int batch, int classes) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
-  const float inv = 1.f / (float)folds;
-  auto mean_of = [&](int c) {
-    float s = 0.f;
-    for (int f = 0; f < folds; ++f) s += proba[((long long)f * batch + b) * classes + c];
-    return s * inv;
-  };
-  float mx = mean_of(0);
-  int arg = 0;
-  for (int c = 1; c < classes; ++c) {
-    const float t = mean_of(c);
-    if (t > mx) { mx = t; arg = c; }
-  }
-  float sum = 0.f;
-  for (int c = 0; c < classes; ++c) sum += expf(mean_of(c) - mx);
-  if (out != nullptr)
-    for (int c = 0; c < classes; ++c) out[(long long)b * classes + c] = expf(mean_of(c) - mx) / sum;
-  if (pred != nullptr) pred[b] = arg;
+  koa_arith::ensemble_row(proba, folds, batch, classes, b, out ? out + (long long)b * classes : nullptr,
+                          pred ? pred + b : nullptr);
 }
 
 // ======================================================================================================

@@ -93,3 +93,15 @@ extern "C" int emul_adam_step(const koa_adam_tensor_t* tensors, int n_tensors, c
   }
   return 0;
 }
+
+extern "C" int emul_predict(const float* logits, float* proba, long long* pred, int batch, int classes) {
+  for (int b = 0; b < batch; ++b)
+    predict_row(logits + (long long)b * classes, classes, proba ? proba + (long long)b * classes : nullptr, pred ? pred + b : nullptr);
+  return 0;
+}
+
+extern "C" int emul_ensemble_proba(const float* proba, float* out, long long* pred, int folds, int batch, int classes) {
+  for (int b = 0; b < batch; ++b)
+    ensemble_row(proba, folds, batch, classes, b, out ? out + (long long)b * classes : nullptr, pred ? pred + b : nullptr);
+  return 0;
+}

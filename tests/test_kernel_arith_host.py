@@ -180,6 +180,12 @@ def test_gpu_tests_of_the_step_rows_dry_run_on_the_host(emul, gold, monkeypatch)
         def koa_augment_resample(self, src, dtype, out, params, batch, s, c, o, mean, std, ws, stream):
             return emul.emul_augment_resample(src, dtype, out, params, batch, s, c, o, mean, std)
 
+        def koa_predict(self, logits, proba, pred, b, c, stream):
+            return emul.emul_predict(logits, proba, pred, b, c)
+
+        def koa_ensemble_proba(self, proba, out, pred, f, b, c, stream):
+            return emul.emul_ensemble_proba(proba, out, pred, f, b, c)
+
         def koa_resample_linear(self, src, dtype, out, batch, di, do, scale, shift, stream):
             return emul.emul_resample_linear(src, dtype, out, batch, di, do, scale, shift)
 
@@ -200,10 +206,12 @@ def test_gpu_tests_of_the_step_rows_dry_run_on_the_host(emul, gold, monkeypatch)
     gpu_tests.test_interpolate_matches_the_oracle(cpu, (2, 1, 16, 12, 5), (0.5, 0.5, 1.0), torch.int16)
     gpu_tests.test_recipe_sizes_box_mean_identity_and_minmax(cpu)
     # Adam: adam_update / make_adam_coef of the kernel (host build) against torch.optim on the same device and against the
-    # numpy oracle, with the tolerances the GPU tests use; the predictions run against the oracle stand-in (test logic only)
+    # numpy oracle, with the tolerances the GPU tests use; softmax / argmax / fold ensemble likewise (predict_row, ensemble_row)
     from oaprogressionmmf_b200 import optim as koptim
 
     emul.emul_adam_step.argtypes = [_P, _I, _P]
+    emul.emul_predict.argtypes = [_P, _P, _P, _I, _I]
+    emul.emul_ensemble_proba.argtypes = [_P, _P, _P, _I, _I, _I]
     gpu_tests.test_adam_matches_torch_optim(cpu, koptim.Adam, torch.optim.Adam, 0.0)
     gpu_tests.test_adam_matches_torch_optim(cpu, koptim.Adam, torch.optim.Adam, 1e-4)
     gpu_tests.test_adam_matches_torch_optim(cpu, koptim.AdamW, torch.optim.AdamW, 1e-2)
