@@ -107,6 +107,15 @@ KOA_HD void ensemble_row(const float* proba, int folds, int batch, int classes, 
   if (pred != nullptr) *pred = arg;
 }
 
+// ---- unit range + z-score as one affine map --------------------------------------------------------------------------
+// z = ((x - lo) / (hi - lo) - mean) / std = x * scale + shift (PTToUnitRange + PTNormalize, koafusion/preproc/_pt.py:75-124);
+// a constant volume gives inf / nan like the reference
+KOA_HD void unit_range_coef(float lo, float hi, float mean, float stdev, float* scale, float* shift) {
+  const float range = hi - lo;
+  *scale = 1.f / (range * stdev);
+  *shift = (-lo / range - mean) / stdev;
+}
+
 struct Tap { int i0, step; float l0, l1; };
 KOA_HD Tap make_tap(int dst, float rscale, int n_in) {
   // area_pixel_compute_source_index: src = scale * (dst + 0.5) - 0.5, clamped at 0 (linear modes)

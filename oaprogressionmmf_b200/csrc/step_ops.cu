@@ -169,10 +169,7 @@ __global__ void unit_range_affine_kernel(const unsigned* __restrict__ mm, float 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch) return;
   const float lo = from_ordered_u32(mm[2 * i]), hi = from_ordered_u32(mm[2 * i + 1]);
-  // z = ((x - lo) / (hi - lo) - mean) / std = x * scale + shift; a constant volume gives inf / nan like the reference
-  const float range = hi - lo;
-  scale[i] = 1.f / (range * stdev);
-  shift[i] = (-lo / range - mean) / stdev;
+  koa_arith::unit_range_coef(lo, hi, mean, stdev, scale + i, shift + i);
   if (minmax_out != nullptr) { minmax_out[2 * i] = lo; minmax_out[2 * i + 1] = hi; }
 }
 

@@ -105,3 +105,29 @@ extern "C" int emul_ensemble_proba(const float* proba, float* out, long long* pr
     ensemble_row(proba, folds, batch, classes, b, out ? out + (long long)b * classes : nullptr, pred ? pred + b : nullptr);
   return 0;
 }
+
+// koa_unit_range_affine on host pointers: per-volume minimum / maximum, then the kernel's coefficient formula
+template <typename T>
+static void unit_range(const T* in, int batch, long long n_per, float mean, float stdev, float* scale, float* shift, float* minmax) {
+  for (int b = 0; b < batch; ++b) {
+    float lo = std::numeric_limits<float>::infinity(), hi = -lo;
+    for (long long i = 0; i < n_per; ++i) {
+      const float f = ld_f(in + b * n_per + i);
+      lo = std::min(lo, f);
+      hi = std::max(hi, f);
+    }
+    unit_range_coef(lo, hi, mean, stdev, scale + b, shift + b);
+    if (minmax != nullptr) { minmax[2 * b] = lo; minmax[2 * b + 1] = hi; }
+  }
+}
+
+extern "C" int emul_unit_range_affine(const void* in, int in_dtype, int batch, long long n_per, float mean, float stdev,
+                                      float* scale, float* shift, float* minmax) {
+  switch (in_dtype) {
+    case KOA_DT_F32: unit_range((const float*)in, batch, n_per, mean, stdev, scale, shift, minmax); return 0;
+    case KOA_DT_U8: unit_range((const uint8_t*)in, batch, n_per, mean, stdev, scale, shift, minmax); return 0;
+    case KOA_DT_U16: unit_range((const uint16_t*)in, batch, n_per, mean, stdev, scale, shift, minmax); return 0;
+    case KOA_DT_I16: unit_range((const int16_t*)in, batch, n_per, mean, stdev, scale, shift, minmax); return 0;
+  }
+  return -1;
+}

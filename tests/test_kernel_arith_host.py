@@ -172,6 +172,10 @@ def test_gpu_tests_of_the_step_rows_dry_run_on_the_host(emul, gold, monkeypatch)
     _I, _P, _F = C.c_int, C.c_void_p, C.c_float
     emul.emul_augment_resample.argtypes = [_P, _I, _P, _P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), _F, _F]
     emul.emul_resample_linear.argtypes = [_P, _I, _P, _I, C.POINTER(_I), C.POINTER(_I), _P, _P]
+    emul.emul_adam_step.argtypes = [_P, _I, _P]
+    emul.emul_predict.argtypes = [_P, _P, _P, _I, _I]
+    emul.emul_unit_range_affine.argtypes = [_P, _I, _I, C.c_longlong, _F, _F, _P, _P, _P]
+    emul.emul_ensemble_proba.argtypes = [_P, _P, _P, _I, _I, _I]
 
     class Stub(glue.HostStandIn):
         def koa_adam_step(self, table, n, hyper, stream):          # the kernel's own coefficient set-up and update
@@ -179,6 +183,9 @@ def test_gpu_tests_of_the_step_rows_dry_run_on_the_host(emul, gold, monkeypatch)
 
         def koa_augment_resample(self, src, dtype, out, params, batch, s, c, o, mean, std, ws, stream):
             return emul.emul_augment_resample(src, dtype, out, params, batch, s, c, o, mean, std)
+
+        def koa_unit_range_affine(self, src, dtype, batch, n_per, mean, std, ws, scale, shift, minmax, stream):
+            return emul.emul_unit_range_affine(src, dtype, batch, n_per, mean, std, scale, shift, minmax)
 
         def koa_predict(self, logits, proba, pred, b, c, stream):
             return emul.emul_predict(logits, proba, pred, b, c)
@@ -209,9 +216,6 @@ def test_gpu_tests_of_the_step_rows_dry_run_on_the_host(emul, gold, monkeypatch)
     # numpy oracle, with the tolerances the GPU tests use; softmax / argmax / fold ensemble likewise (predict_row, ensemble_row)
     from oaprogressionmmf_b200 import optim as koptim
 
-    emul.emul_adam_step.argtypes = [_P, _I, _P]
-    emul.emul_predict.argtypes = [_P, _P, _P, _I, _I]
-    emul.emul_ensemble_proba.argtypes = [_P, _P, _P, _I, _I, _I]
     gpu_tests.test_adam_matches_torch_optim(cpu, koptim.Adam, torch.optim.Adam, 0.0)
     gpu_tests.test_adam_matches_torch_optim(cpu, koptim.Adam, torch.optim.Adam, 1e-4)
     gpu_tests.test_adam_matches_torch_optim(cpu, koptim.AdamW, torch.optim.AdamW, 1e-2)
