@@ -35,7 +35,7 @@ def _ref_models():
     return dict_models
 
 
-@pytest.mark.parametrize("name", ["XR1Cnn", "MR1CnnTrf", "XR1MR2C1CnnTrf"])
+@pytest.mark.parametrize("name", ["XR1Cnn", "XR1MR2C1CnnTrf"])
 def test_checkpoint_roundtrip_with_the_reference_handler(name, tmp_path):
     cfg = ko.make_config(name, xr_size=64, mr_size=64, slices=(3, 2, 2), depth=1)
     torch.manual_seed(778)
