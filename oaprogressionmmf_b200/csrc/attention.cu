@@ -230,12 +230,8 @@ int koa_k_attention_fwd(const void* qkv, void* out, float* probs, int batch, int
                         cudaStream_t st) {
   int rc = check(n, head_dim);
   if (rc) return rc;
-  static int attr_set = 0;
-  if (!attr_set) {
-    KOA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)fwd_smem(kMaxN, 256)));
-    attr_set = 1;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  KOA_CHECK_CUDA(koa_ensure_dyn_smem(attention_fwd_kernel, (int)fwd_smem(kMaxN, 256), attr_done));
   if (koa_pdl_enabled() >= 3)
     KOA_CHECK_CUDA(koa_launch_pdl(attention_fwd_kernel, dim3(batch * heads), dim3(kWarps * 32), fwd_smem(n, head_dim), st, 1u,
                                   (const bf16*)qkv, (bf16*)out, probs, n, heads, head_dim, scale));
@@ -250,12 +246,8 @@ int koa_k_attention_bwd(const void* qkv, const float* probs, const void* dout, v
                         int head_dim, float scale, cudaStream_t st) {
   int rc = check(n, head_dim);
   if (rc) return rc;
-  static int attr_set = 0;
-  if (!attr_set) {
-    KOA_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)bwd_smem(kMaxN, 256)));
-    attr_set = 1;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  KOA_CHECK_CUDA(koa_ensure_dyn_smem(attention_bwd_kernel, (int)bwd_smem(kMaxN, 256), attr_done));
   if (koa_pdl_enabled() >= 3)
     KOA_CHECK_CUDA(koa_launch_pdl(attention_bwd_kernel, dim3(batch * heads), dim3(kWarps * 32), bwd_smem(n, head_dim), st, 1u,
                                   (const bf16*)qkv, probs, (const bf16*)dout, (bf16*)dqkv, n, heads, head_dim, scale));

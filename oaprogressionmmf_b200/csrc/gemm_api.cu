@@ -159,13 +159,8 @@ template <int BN, int STAGES, bool IM2COL, bool CONV>
 static int launch_kmajor_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
                            const EpiParams& ep, cudaStream_t st) {
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  });
-  KOA_CHECK_CUDA(attr_err);
+  static std::atomic<unsigned long long> attr_done{0};
+  KOA_CHECK_CUDA(koa_ensure_dyn_smem(gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV>, (int)smem, attr_done));
   const long long tiles = (long long)koa_cdiv(m, BM) * koa_cdiv(n, BN);
   KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
   const unsigned grid = (unsigned)(tiles < koa_num_sms() ? tiles : koa_num_sms());  // persistent: one CTA per SM
@@ -189,10 +184,8 @@ static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
   constexpr size_t smem = conv_smem_bytes<BN, STAGES, MODE, CTA2>();
   static_assert(smem <= 232448, "shared memory budget of one CTA per SM");
   auto kern = gemm_conv_kernel<BN, STAGES, IM2COL, MODE, OF16, AF16, CTA2>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-  KOA_CHECK_CUDA(attr_err);
+  static std::atomic<unsigned long long> attr_done{0};
+  KOA_CHECK_CUDA(koa_ensure_dyn_smem(kern, (int)smem, attr_done));
   const int n_tiles = koa_cdiv(n, BN);
   const long long tiles = (long long)koa_cdiv(m, CTA2 ? 2 * BM : BM) * n_tiles;
   KOA_REQUIRE(tiles > 0 && tiles < 2147483647LL, "bad tile count");
@@ -346,10 +339,8 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
   const int a_f16 = x_f16 == 3 ? 0 : x_f16, b_f16 = x_f16 == 3 ? 1 : x_f16;  // dY, X
   constexpr size_t smem = wgrad_smem_bytes<CTA2 ? BN / 2 : BN, STAGES>();
   auto kern = gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT, CTA2>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-  KOA_CHECK_CUDA(attr_err);
+  static std::atomic<unsigned long long> attr_done{0};
+  KOA_CHECK_CUDA(koa_ensure_dyn_smem(kern, (int)smem, attr_done));
   const int tiles = (g.grouped ? 1 : koa_cdiv(cout, CTA2 ? 2 * BM : BM)) * koa_cdiv(cin, BN) * taps;
   const int num_kb = koa_cdiv(pixels, BK);
   // Split the pixel (reduction) range so that the grid covers the machine a few times over.

@@ -68,6 +68,24 @@ static __device__ unsigned int g_koa_debug_flag = 0;
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 
+// cudaFuncSetAttribute is per device: one thread per GPU in a single process (nn.DataParallel) needs the attribute on
+// every device it launches on, so "done" is remembered per (kernel instantiation, device), not once per process.
+// Setting it twice from two threads is harmless.
+#ifdef __CUDACC__
+#include <atomic>
+template <typename K>
+static inline cudaError_t koa_ensure_dyn_smem(K kern, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+#endif
+
 // ---- programmatic dependent launch (experiment KOA_PDL=1, default off) -----------------------------------------------
 // A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in the stream
 // is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in
