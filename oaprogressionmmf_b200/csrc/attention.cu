@@ -54,8 +54,6 @@ __device__ __forceinline__ void stage_rows(const bf16* __restrict__ g, long long
 __global__ void __launch_bounds__(kWarps * 32)
 attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ probs, int n, int heads,
                      int hd, float scale) {
-  griddep_wait();  // KOA_PDL (koa_common.cuh)
-  griddep_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int ldk = hd + 8;
   bf16* sK = reinterpret_cast<bf16*>(smem);
@@ -125,8 +123,6 @@ attention_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float
 __global__ void __launch_bounds__(kWarps * 32)
 attention_bwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ probs, const bf16* __restrict__ dout,
                      bf16* __restrict__ dqkv, int n, int heads, int hd, float scale) {
-  griddep_wait();  // KOA_PDL (koa_common.cuh)
-  griddep_launch_dependents();
   extern __shared__ __align__(16) uint8_t smem[];
   const int ldk = hd + 8;
   bf16* bufA = reinterpret_cast<bf16*>(smem);               // [n][hd+8]
@@ -232,11 +228,7 @@ int koa_k_attention_fwd(const void* qkv, void* out, float* probs, int batch, int
   if (rc) return rc;
   static std::atomic<unsigned long long> attr_done{0};
   KOA_CHECK_CUDA(koa_ensure_dyn_smem(attention_fwd_kernel, (int)fwd_smem(kMaxN, 256), attr_done));
-  if (koa_pdl_enabled() >= 3)
-    KOA_CHECK_CUDA(koa_launch_pdl(attention_fwd_kernel, dim3(batch * heads), dim3(kWarps * 32), fwd_smem(n, head_dim), st, 1u,
-                                  (const bf16*)qkv, (bf16*)out, probs, n, heads, head_dim, scale));
-  else
-    attention_fwd_kernel<<<batch * heads, kWarps * 32, fwd_smem(n, head_dim), st>>>((const bf16*)qkv, (bf16*)out, probs, n,
+  attention_fwd_kernel<<<batch * heads, kWarps * 32, fwd_smem(n, head_dim), st>>>((const bf16*)qkv, (bf16*)out, probs, n,
                                                                                     heads, head_dim, scale);
   KOA_LAUNCH_CHECK();
   return 0;
@@ -248,11 +240,7 @@ int koa_k_attention_bwd(const void* qkv, const float* probs, const void* dout, v
   if (rc) return rc;
   static std::atomic<unsigned long long> attr_done{0};
   KOA_CHECK_CUDA(koa_ensure_dyn_smem(attention_bwd_kernel, (int)bwd_smem(kMaxN, 256), attr_done));
-  if (koa_pdl_enabled() >= 3)
-    KOA_CHECK_CUDA(koa_launch_pdl(attention_bwd_kernel, dim3(batch * heads), dim3(kWarps * 32), bwd_smem(n, head_dim), st, 1u,
-                                  (const bf16*)qkv, probs, (const bf16*)dout, (bf16*)dqkv, n, heads, head_dim, scale));
-  else
-    attention_bwd_kernel<<<batch * heads, kWarps * 32, bwd_smem(n, head_dim), st>>>(
+  attention_bwd_kernel<<<batch * heads, kWarps * 32, bwd_smem(n, head_dim), st>>>(
         (const bf16*)qkv, probs, (const bf16*)dout, (bf16*)dqkv, n, heads, head_dim, scale);
   KOA_LAUNCH_CHECK();
   return 0;

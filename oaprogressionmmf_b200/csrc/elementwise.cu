@@ -19,16 +19,6 @@ constexpr int kDeepGrid = 148 * 2;
 // One element per thread and iteration with index arithmetic in front of every access (pooling, packing, resampling):
 // latency-bound, these keep the full grid (they ran 30-60 % slower with the cap).
 constexpr int kWideGrid = -148 * 16;
-// KOA_IDX32=1 (experiment, default off, not yet run on a B200): 32-bit work-item indices in the pooling kernels whenever
-// the item count and one grid stride both stay below 2^31
-inline bool koa_idx32_ok(long long items, int blocks, int threads) {
-  static const int on = [] {
-    const char* e = getenv("KOA_IDX32");
-    return e != nullptr && atoi(e) > 0 ? 1 : 0;
-  }();
-  return on && items < 0x7fffffffLL && (long long)blocks * threads < 0x7fffffffLL;
-}
-
 inline int grid_for(long long work_items, int threads = kThreads, int max_blocks = 148 * 16) {
   static const int env_cap = [] {
     const char* e = getenv("KOA_EW_MAX_BLOCKS");
@@ -411,8 +401,6 @@ bn_act_fixed_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                     const bf16* __restrict__ res, const bf16* __restrict__ y2, const float* __restrict__ scale2,
                     const float* __restrict__ shift2, bf16* __restrict__ out, bf16* __restrict__ out_bf, long long rows,
                     int c, int relu, KoaBnFwdFin fa, KoaBnFwdFin fb, double count, int training) {
-  griddep_wait();  // KOA_PDL (koa_common.cuh): launched early, the predecessor's data is visible from here
-  griddep_launch_dependents();
   const int cg = c / 8;
   const long long total = rows * cg;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -475,8 +463,6 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
                                      const float* __restrict__ mean2, const float* __restrict__ invstd2,
                                      float* __restrict__ sum_dz, float* __restrict__ sum_dzx,
                                      float* __restrict__ sum_dzx2, long long rows, int c) {
-  griddep_wait();  // KOA_PDL (koa_common.cuh): launched early, the predecessor's data is visible from here
-  griddep_launch_dependents();
   extern __shared__ float sm[];
   const int cg = c / 8;
   const int lanes = blockDim.x / cg;
@@ -619,8 +605,6 @@ bn_bwd_apply_fixed_kernel(const bf16* __restrict__ dout, const bf16* __restrict_
                           bf16* __restrict__ dy, const bf16* __restrict__ y2, const float* __restrict__ k0b,
                           const float* __restrict__ k1b, const float* __restrict__ k2b, bf16* __restrict__ dy2,
                           long long rows, int c, KoaBnBwdFin fa, KoaBnBwdFin fb, double count, int training) {
-  griddep_wait();  // KOA_PDL (koa_common.cuh): launched early, the predecessor's data is visible from here
-  griddep_launch_dependents();
   const int cg = c / 8;
   const long long total = rows * cg;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -679,19 +663,16 @@ bn_bwd_apply_fixed_kernel(const bf16* __restrict__ dout, const bf16* __restrict_
 // Pooling
 // ------------------------------------------------------------------------------------------------
 // 3x3 stride-2 pad-1 max pool, first maximum in scan order wins (as ATen); idx = r*3+s of the winner.
-// I: type of the flat work-item index. long long always works; unsigned (KOA_IDX32=1, launcher checks the range) replaces
-// the three 64-bit divisions per item, which make these kernels issue-bound (~400 instructions per 16 bytes), by 32-bit ones.
-template <typename I>
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, bf16* __restrict__ out_bf,
                                    uint8_t* __restrict__ idx,
                                    int n, int h, int w, int c, int ho, int wo) {
   const int cg = c / 8;
-  const I total = (I)((long long)n * ho * wo * cg);
-  for (I i = (I)(blockIdx.x * (long long)blockDim.x + threadIdx.x); i < total; i += (I)((long long)gridDim.x * blockDim.x)) {
-    I t = i;
-    const int g = (int)(t % (I)cg); t /= (I)cg;
-    const int ow = (int)(t % (I)wo); t /= (I)wo;
-    const int oh = (int)(t % (I)ho); t /= (I)ho;
+  const long long total = ((long long)n * ho * wo * cg);
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x); i < total; i += ((long long)gridDim.x * blockDim.x)) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int ow = (int)(t % wo); t /= wo;
+    const int oh = (int)(t % ho); t /= ho;
     const int ni = (int)t;
     float best[8];
     int bi[8];
@@ -723,16 +704,15 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict_
   }
 }
 
-template <typename I>
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dout, const uint8_t* __restrict__ idx, bf16* __restrict__ dx,
                                    int n, int h, int w, int c, int ho, int wo) {
   const int cg = c / 8;
-  const I total = (I)((long long)n * h * w * cg);
-  for (I i = (I)(blockIdx.x * (long long)blockDim.x + threadIdx.x); i < total; i += (I)((long long)gridDim.x * blockDim.x)) {
-    I t = i;
-    const int g = (int)(t % (I)cg); t /= (I)cg;
-    const int iw = (int)(t % (I)w); t /= (I)w;
-    const int ih = (int)(t % (I)h); t /= (I)h;
+  const long long total = ((long long)n * h * w * cg);
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x); i < total; i += ((long long)gridDim.x * blockDim.x)) {
+    long long t = i;
+    const int g = (int)(t % cg); t /= cg;
+    const int iw = (int)(t % w); t /= w;
+    const int ih = (int)(t % h); t /= h;
     const int ni = (int)t;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // windows (oh, ow) with 2*oh-1 <= ih <= 2*oh+1
@@ -863,8 +843,6 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
                                      const float* __restrict__ beta, bf16* __restrict__ out_bf16,
                                      float* __restrict__ out_f32, float* __restrict__ mean_out,
                                      float* __restrict__ rstd_out, int rows, int d, long long x_row_stride, float eps) {
-  griddep_wait();  // KOA_PDL (koa_common.cuh)
-  griddep_launch_dependents();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -923,8 +901,6 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
                                      float* __restrict__ dx, bf16* __restrict__ dx_bf16, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int rows, int d, long long x_row_stride,
                                      long long dx_row_stride) {
-  griddep_wait();  // KOA_PDL (koa_common.cuh)
-  griddep_launch_dependents();
   extern __shared__ float sm[];  // [2][d]
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.0f;
   __syncthreads();
@@ -1243,12 +1219,7 @@ int koa_k_bn_act_fin(const void* y, const KoaBnFwdFin* a, const void* res, const
                      void* out_bf16, long long rows, int c, int relu, double count, int training, cudaStream_t st) {
   KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm apply needs C/8 | %d (C=%d)", kThreads, c);
   KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
-  if (koa_pdl_enabled() >= 2)
-    KOA_CHECK_CUDA(koa_launch_pdl(bn_act_fixed_kernel, dim3(grid_for(rows * (c / 8) / 2)), dim3(kThreads), 0, st, 1u,
-                                  (const bf16*)y, nullptr, nullptr, (const bf16*)res, (const bf16*)y2, nullptr, nullptr,
-                                  (bf16*)out, (bf16*)out_bf16, rows, c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training));
-  else
-    bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
+  bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
         (const bf16*)y, nullptr, nullptr, (const bf16*)res, (const bf16*)y2, nullptr, nullptr, (bf16*)out, (bf16*)out_bf16, rows,
         c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training);
   KOA_LAUNCH_CHECK();
@@ -1259,13 +1230,7 @@ int koa_k_bn_bwd_apply_fin(const void* dout, const void* act, const void* y, con
                            cudaStream_t st) {
   KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm backward needs C/8 | %d (C=%d)", kThreads, c);
   KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
-  if (koa_pdl_enabled() >= 2)
-    KOA_CHECK_CUDA(koa_launch_pdl(bn_bwd_apply_fixed_kernel, dim3(grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid)),
-                                  dim3(kThreads), 0, st, 1u, (const bf16*)dout, (const bf16*)act, (const bf16*)y, nullptr,
-                                  nullptr, nullptr, (bf16*)dy, (const bf16*)y2, nullptr, nullptr, nullptr, (bf16*)dy2, rows, c,
-                                  *a, b ? *b : KoaBnBwdFin{}, count, training));
-  else
-    bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid), kThreads, 0, st>>>(
+  bn_bwd_apply_fixed_kernel<<<grid_for(rows * (c / 8) / 2, kThreads, kDeepGrid), kThreads, 0, st>>>(
         (const bf16*)dout, (const bf16*)act, (const bf16*)y, nullptr, nullptr, nullptr, (bf16*)dy, (const bf16*)y2, nullptr,
         nullptr, nullptr, (bf16*)dy2, rows, c, *a, b ? *b : KoaBnBwdFin{}, count, training);
   KOA_LAUNCH_CHECK();
@@ -1278,12 +1243,7 @@ int koa_k_bn_bwd_reduce(const void* dout, const void* act, const void* y, const 
   if (rc) return rc;
   const int threads = reduce_threads(c);
   const int lanes = threads / (c / 8);
-  if (koa_pdl_enabled() >= 2)
-    KOA_CHECK_CUDA(koa_launch_pdl(bn_bwd_reduce_kernel, dim3(grid_for(rows, lanes, kDeepGrid)), dim3(threads),
-                                  3 * c * sizeof(float), st, 1u, (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean,
-                                  invstd, (const bf16*)y2, mean2, invstd2, sum_dz, sum_dzx, sum_dzx2, rows, c));
-  else
-    bn_bwd_reduce_kernel<<<grid_for(rows, lanes, kDeepGrid), threads, 3 * c * sizeof(float), st>>>(
+  bn_bwd_reduce_kernel<<<grid_for(rows, lanes, kDeepGrid), threads, 3 * c * sizeof(float), st>>>(
         (const bf16*)dout, (const bf16*)act, (const bf16*)y, mean, invstd, (const bf16*)y2, mean2, invstd2, sum_dz,
         sum_dzx, sum_dzx2, rows, c);
   KOA_LAUNCH_CHECK();
@@ -1317,11 +1277,7 @@ int koa_k_maxpool_fwd(const void* x, void* out, void* out_bf16, void* idx, int n
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const long long items = (long long)n * ho * wo * (c / 8);
   const int blocks = grid_for(items, kThreads, kWideGrid);
-  if (koa_idx32_ok(items, blocks, kThreads))
-    maxpool_fwd_kernel<unsigned><<<blocks, kThreads, 0, st>>>((const bf16*)x, (bf16*)out, (bf16*)out_bf16, (uint8_t*)idx, n, h, w, c,
-                                                              ho, wo);
-  else
-    maxpool_fwd_kernel<long long><<<blocks, kThreads, 0, st>>>((const bf16*)x, (bf16*)out, (bf16*)out_bf16, (uint8_t*)idx, n, h, w,
+  maxpool_fwd_kernel<<<blocks, kThreads, 0, st>>>((const bf16*)x, (bf16*)out, (bf16*)out_bf16, (uint8_t*)idx, n, h, w,
                                                                c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
@@ -1331,10 +1287,7 @@ int koa_k_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h,
   const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
   const long long items = (long long)n * h * w * (c / 8);
   const int blocks = grid_for(items, kThreads, kWideGrid);
-  if (koa_idx32_ok(items, blocks, kThreads))
-    maxpool_bwd_kernel<unsigned><<<blocks, kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx, (bf16*)dx, n, h, w, c, ho, wo);
-  else
-    maxpool_bwd_kernel<long long><<<blocks, kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx, (bf16*)dx, n, h, w, c, ho, wo);
+  maxpool_bwd_kernel<<<blocks, kThreads, 0, st>>>((const bf16*)dout, (const uint8_t*)idx, (bf16*)dx, n, h, w, c, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1369,10 +1322,7 @@ int koa_k_layernorm_fwd(const float* x, const float* gamma, const float* beta, v
                         float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st) {
   KOA_REQUIRE(d % 256 == 0 && d <= 4096, "LayerNorm width %d must be a multiple of 256 and <= 4096", d);
   const int blocks = koa_cdiv((long long)rows * 32, kThreads);
-  if (koa_pdl_enabled() >= 3)
-    KOA_CHECK_CUDA(koa_launch_pdl(d <= 2048 ? layernorm_fwd_kernel<8> : layernorm_fwd_kernel<16>, dim3(blocks), dim3(kThreads), 0,
-                                  st, 1u, x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d, x_row_stride, 1e-5f));
-  else if (d <= 2048)
+  if (d <= 2048)
     layernorm_fwd_kernel<8><<<blocks, kThreads, 0, st>>>(x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d,
                                                          x_row_stride, 1e-5f);
   else
@@ -1387,12 +1337,7 @@ int koa_k_layernorm_bwd(const float* dy, const float* x, const float* gamma, con
   KOA_REQUIRE(d % 256 == 0 && d <= 2048, "LayerNorm backward width %d must be a multiple of 256 and <= 2048", d);
   int blocks = koa_cdiv(rows, kThreads / 32);
   if (blocks > 148 * 2) blocks = 148 * 2;
-  if (koa_pdl_enabled() >= 3)
-    KOA_CHECK_CUDA(koa_launch_pdl(layernorm_bwd_kernel<8>, dim3(blocks), dim3(kThreads), 2 * d * sizeof(float), st, 1u, dy, x,
-                                  gamma, mean, rstd, dres, dx, (bf16*)dx_bf16, dgamma, dbeta, rows, d, x_row_stride,
-                                  dx_row_stride));
-  else
-    layernorm_bwd_kernel<8><<<blocks, kThreads, 2 * d * sizeof(float), st>>>(dy, x, gamma, mean, rstd, dres, dx,
+  layernorm_bwd_kernel<8><<<blocks, kThreads, 2 * d * sizeof(float), st>>>(dy, x, gamma, mean, rstd, dres, dx,
                                                                              (bf16*)dx_bf16, dgamma, dbeta, rows, d,
                                                                              x_row_stride, dx_row_stride);
   KOA_LAUNCH_CHECK();

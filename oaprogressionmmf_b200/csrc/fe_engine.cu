@@ -32,9 +32,7 @@ namespace {
 // KOA_WGRAD_XCVT: 0 = copies everywhere; 1 = no copies (-25 % workspace, same step time as 0); 2 (default) = no copies
 // where the consuming weight gradient is HBM-bound anyway and the conversion is free: the pooled stem output and the
 // outputs of the bottleneck blocks with at most 512 channels (layer1 / layer2: consumed by 1x1 convolutions with
-// 50-170 FLOP per byte), copies for the rest; 3 (experiment, not yet run on a B200) = no copies anywhere and no
-// conversion either: the MMA is issued with dY in bf16 and X in fp16 (x_f16 = 3, separate format fields of the
-// instruction descriptor).
+// 50-170 FLOP per byte), copies for the rest.
 int wgrad_xcvt_mode() {
   static const int v = [] {
     const char* e = getenv("KOA_WGRAD_XCVT");
@@ -167,7 +165,7 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
   const bool bw = d->need_backward != 0;
   // bf16 copies of the activations (operands of the weight gradients): see wgrad_xcvt_mode()
   const int xm = wgrad_xcvt_mode();
-  const bool bwc = bw && xm != 1 && xm != 3;      // copies of the narrow a1 / a2 tensors
+  const bool bwc = bw && xm != 1;                 // copies of the narrow a1 / a2 tensors
   const bool bwc_p0 = bwc && !(xm == 2 && bottleneck);
   p.p0 = ws.take((size_t)n * ph * pw * 64 * 2);
   p.p0_bf = bwc_p0 ? ws.take((size_t)n * ph * pw * 64 * 2) : 0;
@@ -479,8 +477,7 @@ int conv_wgrad(const Plan& p, const Unit& u, size_t x_bf, size_t x_f16, const vo
   float* gw = (float*)grads[u.idx * 3 + 0];
   if (gw == nullptr) return 0;
   const void* x = at(ws, x_bf ? x_bf : x_f16);
-  // 2: x is the fp16 activation, converted inside the kernel; 3: multiplied as fp16 (mixed-format MMA)
-  const int xf = x_bf ? 0 : (wgrad_xcvt_mode() == 3 ? 3 : 2);
+  const int xf = x_bf ? 0 : 2;  // 2: x is the fp16 activation, converted to bf16 inside the kernel
   if (u.k == 1 && u.stride == 1) return koa_gemm_wgrad_launch(dy, x, gw, (int)u.rows_out, u.cout, u.cin, xf, st);
   if (u.k == 1) return koa_conv_wgrad_launch(dy, x, gw, p.n_img, u.hin, u.win, u.cin, u.cout, 1, 1, u.stride, 0, xf, st);
   float* scratch = (float*)at(ws, u.dw_scratch);
@@ -748,8 +745,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     // the forward pass kept its fp16 im2col operand; the weight-gradient kernel converts it to bf16 in shared memory
     // (x_f16 = 2) to pair it with the bf16 dy. This GEMM is HBM-bound (64 x 64 outputs over millions of pixels), so the
     // conversion is free and the second im2col pass (1 ms per step) is gone.
-    KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64,
-                                  wgrad_xcvt_mode() == 3 ? 3 : 2, st));
+    KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64, 2, st));
     KOA_TRY(koa_k_stem_unfold_dwb((const float*)at(ws, p.dwstem), (float*)grads[0], st));
   }
   KOA_TRY(side.join());  // every weight gradient is complete in the order of the caller's stream

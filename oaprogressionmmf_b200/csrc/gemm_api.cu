@@ -166,11 +166,7 @@ static int launch_kmajor_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, 
   const unsigned grid = (unsigned)(tiles < koa_num_sms() ? tiles : koa_num_sms());  // persistent: one CTA per SM
   {
     ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep));
-    if (koa_pdl_enabled())
-      KOA_CHECK_CUDA(koa_launch_pdl(gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV>, dim3(grid), dim3(kKmajorThreads), smem, st, 1u,
-                                    ta, tb, m, n, k, g, ep));
-    else
-      gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV><<<grid, kKmajorThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
+    gemm_kmajor_kernel<BN, STAGES, IM2COL, CONV><<<grid, kKmajorThreads, smem, st>>>(ta, tb, m, n, k, g, ep);
   }
   KOA_LAUNCH_CHECK();
   return 0;
@@ -210,10 +206,7 @@ static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
   }
   {
     ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep) | (CTA2 ? 256 : 0));
-    if (koa_pdl_enabled()) {
-      KOA_CHECK_CUDA(koa_launch_pdl(kern, dim3(CTA2 ? 2 * units : units), dim3(kConvThreads), smem, st, CTA2 ? 2u : 1u, ta, tb,
-                                    t_out, t_add, t_gate, t_y, m, n, k, g, ep));
-    } else if (CTA2) {
+    if (CTA2) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2 * units, 1, 1);
       cfg.blockDim = dim3(kConvThreads, 1, 1);
@@ -327,16 +320,15 @@ int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_
   return dispatch_kmajor<true>(ta, w, (int)m, cout, filt_r * filt_s * cin, g, to_epi(ep, cout), st);
 }
 
-// x_f16: 0 = dY and X bf16; 1 = both fp16; 2 = dY bf16, X fp16 converted to bf16 inside the kernel (XCVT);
-// 3 = dY bf16, X fp16, multiplied as they are: the instruction descriptor of tcgen05.mma kind::f16 carries one format
-// field per operand (experiment, KOA_WGRAD_XCVT=3: written without a GPU, to be confirmed on a B200 by
-// tools/try_mixed_wgrad.py before anything relies on it)
+// x_f16: 0 = dY and X bf16; 1 = both fp16; 2 = dY bf16, X fp16 converted to bf16 inside the kernel (XCVT). (A mixed
+// bf16 x fp16 MMA, one format field per operand in the instruction descriptor, faults with an illegal instruction on
+// B200: measured in round 2, removed.)
 // CTA2: CTA pairs on 256 x BN tiles (the tensor map of X then has boxes of 64 columns as always; each CTA loads BN / 2)
 template <int BN, int STAGES, bool IM2COL, bool XCVT = false, bool CTA2 = false>
 static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, int cin, int pixels, int taps,
                         const ConvGeom& g, float* dw, int x_f16, cudaStream_t st) {
   if (!XCVT && !CTA2 && x_f16 == 2) return launch_wgrad<BN, STAGES, IM2COL, true, false>(ta, tb, cout, cin, pixels, taps, g, dw, 0, st);
-  const int a_f16 = x_f16 == 3 ? 0 : x_f16, b_f16 = x_f16 == 3 ? 1 : x_f16;  // dY, X
+  const int a_f16 = x_f16, b_f16 = x_f16;  // dY, X
   constexpr size_t smem = wgrad_smem_bytes<CTA2 ? BN / 2 : BN, STAGES>();
   auto kern = gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT, CTA2>;
   static std::atomic<unsigned long long> attr_done{0};
@@ -356,18 +348,12 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
   splits = koa_cdiv(num_kb, kb_per_split);
   dim3 grid((unsigned)tiles * (CTA2 ? 2 : 1), (unsigned)splits);
   const unsigned threads = XCVT ? kWgradCvtThreads : kGemmThreads;
-  // experiment (default off, not yet measured): split-K partial sums leave through cp.reduce.async.bulk, one 256 / 512-byte
-  // reduction per output row instead of 16-byte red instructions (gemm_tc.cuh)
-  static const int bulk_red = env_int("KOA_WGRAD_BULK_RED", 0);
   {
     // grouped: only the diagonal 64x64 blocks are algorithmic work
     const double n_eff = g.grouped ? 64.0 : (double)cin;
     ProfScope prof(st, 1, 2.0 * (double)pixels * (double)cout * n_eff * (double)taps, cout, cin * taps, pixels,
                    (IM2COL ? 1 : 0) | (CTA2 ? 256 : 0));
-    if (koa_pdl_enabled()) {
-      KOA_CHECK_CUDA(koa_launch_pdl(kern, grid, dim3(threads), smem, st, CTA2 ? 2u : 1u, ta, tb, cout, cin, pixels, taps, g, dw,
-                                    kb_per_split, s_wgrad_desc, a_f16, b_f16, CTA2 ? 0 : bulk_red));
-    } else if (CTA2) {
+    if (CTA2) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = grid;
       cfg.blockDim = dim3(threads, 1, 1);
@@ -380,9 +366,9 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, a_f16, b_f16, 0));
+      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, a_f16, b_f16));
     } else {
-      kern<<<grid, threads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, a_f16, b_f16, bulk_red);
+      kern<<<grid, threads, smem, st>>>(ta, tb, cout, cin, pixels, taps, g, dw, kb_per_split, s_wgrad_desc, a_f16, b_f16);
     }
   }
   KOA_LAUNCH_CHECK();

@@ -150,8 +150,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  griddep_wait();                // KOA_PDL: everything above overlapped the predecessor's tail; its data is visible from here
-  griddep_launch_dependents();   // this CTA owns its TMEM columns: the successor's CTAs may become resident
 
   if (warp == 0) {
     if (lane == 0) {

@@ -439,8 +439,6 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  griddep_wait();                // KOA_PDL (koa_common.cuh): the prologue above overlapped the predecessor's tail
-  griddep_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -606,7 +604,7 @@ template <int BN, int STAGES, bool B_IM2COL, bool XCVT, bool CTA2 = false>
 __global__ void __launch_bounds__(XCVT ? kWgradCvtThreads : kGemmThreads)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int cout, int cin,
                   int pixels, int taps, ConvGeom g, float* __restrict__ dw, int kb_per_split, WgradDesc wd, int a_f16,
-                  int b_f16, int bulk_red) {
+                  int b_f16) {
   // g.grouped: dw is [C][taps][64] (per-64-channel-chunk dense blocks); tile n_t pairs input chunk n_t with
   // output chunk n_t only (BN must be 64; the upper 64 accumulator rows are discarded).
   static_assert(!(CTA2 && XCVT), "the in-kernel conversion is not combined with CTA pairs");
@@ -665,8 +663,6 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (CTA2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  griddep_wait();                // KOA_PDL (koa_common.cuh): the prologue above overlapped the predecessor's tail
-  griddep_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -767,35 +763,6 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int ldw = g.grouped ? 64 : cin;
     const int col0 = g.grouped ? 0 : n0_tile;
     float* dst_row = dw + ((long long)row * taps + tap) * ldw;
-    if (!CTA2 && bulk_red) {
-      // Split-K reduction through the bulk-copy engine (experiment, KOA_WGRAD_BULK_RED=1): the thread stages its output
-      // row in the shared memory of the finished pipeline (every MMA that read it has completed: tmem_full_bar) and
-      // issues ONE cp.reduce.async.bulk (fp32 add, BN * 4 contiguous bytes of dW) instead of BN / 4 16-byte red
-      // instructions that each touch a different line per lane. Rows are padded by 16 bytes so that the 32 lanes of a
-      // warp (one row each) store to different banks.
-      constexpr uint32_t ROW_BYTES = BN * 4 + 16;
-      static_assert(CTA2 || BM * ROW_BYTES <= STAGES * (A_BYTES + B_BYTES), "the staging tile fits in the pipeline stages");
-      const uint32_t stage_row = smem_u32(smem) + (uint32_t)(q * 32 + lane) * ROW_BYTES;
-      const int valid = g.grouped ? 64 : min(BN, cin - n0_tile);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (c0 >= valid) break;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) sts128(stage_row + (uint32_t)(c0 + j) * 4, make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]));
-      }
-      fence_proxy_async_smem();  // this thread's generic-proxy stores -> visible to its bulk (async-proxy) read
-      if (row_ok) {
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst_row + col0),
-                     "r"(stage_row), "r"((uint32_t)valid * 4u)
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging rows are read before the CTA exits
-      }
-      goto done;
-    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0_tile + c0 >= cin) break;

@@ -86,44 +86,8 @@ static inline cudaError_t koa_ensure_dyn_smem(K kern, int bytes, std::atomic<uns
 }
 #endif
 
-// ---- programmatic dependent launch (experiment KOA_PDL=1, default off) -----------------------------------------------
-// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in the stream
-// is still draining: its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in
-// griddep_wait() until the predecessor has completed and its writes are visible. Every kernel launched through
-// koa_launch_pdl() therefore calls griddep_wait() before its first access to global memory, and griddep_launch_dependents()
-// AFTER it owns its TMEM columns (a successor CTA that became resident earlier could otherwise take the columns this CTA
-// is about to ask for and then wait for this grid: deadlock). Without the attribute both instructions do nothing.
-int koa_pdl_enabled();  // koa_tma.cu: getenv("KOA_PDL"), read once: 0 off, 1 GEMM kernels, 2 + BatchNorm, 3 + LayerNorm / attention
-
-template <typename... KArgs, typename... Args>
-static inline cudaError_t koa_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                         unsigned cluster_x, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  unsigned na = 0;
-  if (cluster_x > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = cluster_x;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = 1;
-    ++na;
-  }
-  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[na].val.programmaticStreamSerializationAllowed = 1;
-  ++na;
-  cfg.attrs = attr;
-  cfg.numAttrs = na;
-  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
-}
-
 namespace koa {
 
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

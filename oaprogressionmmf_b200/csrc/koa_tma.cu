@@ -130,11 +130,3 @@ int koa_num_sms() {
   }
   return n;
 }
-
-int koa_pdl_enabled() {
-  static const int v = [] {
-    const char* e = getenv("KOA_PDL");
-    return e != nullptr && atoi(e) > 0 ? atoi(e) : 0;  // 1: tcgen05 GEMM kernels; 2: + BatchNorm kernels; 3: + LayerNorm / attention
-  }();
-  return v;
-}

@@ -53,17 +53,16 @@ __global__ void stem_unfold_dw_kernel(const float* __restrict__ dwfold, float* _
 // Tensor-core form of the stem: img fp32 [n][h][w] -> A fp16 [n*ho*wo][64], column k = r*7 + s holds
 // img[2*oh - 3 + r][2*ow - 3 + s] (zero outside the image and for the 15 padding columns k >= 49). The convolution
 // is then the plain GEMM A . Wb^T with Wb[64 co][64 k] (koa_k_stem_pack_wb), its weight gradient dy^T . A.
-// I: type of the flat work-item index (unsigned with KOA_IDX32=1 when the range allows: 32-bit divisions)
-template <bool F16, typename I>
+template <bool F16>
 __global__ void stem_im2col_kernel(const float* __restrict__ img, bf16* __restrict__ a, long long total_ll, int h, int w,
                                    int ho, int wo) {
-  const I total = (I)total_ll;
-  for (I i = (I)(blockIdx.x * (long long)blockDim.x + threadIdx.x); i < total; i += (I)((long long)gridDim.x * blockDim.x)) {
+  const long long total = total_ll;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x); i < total; i += ((long long)gridDim.x * blockDim.x)) {
     const int kg = (int)(i & 7);
-    I pix = i >> 3;
-    const int ow = (int)(pix % (I)wo); pix /= (I)wo;
-    const int oh = (int)(pix % (I)ho);
-    const long long ni = (long long)(pix / (I)ho);
+    long long pix = i >> 3;
+    const int ow = (int)(pix % wo); pix /= wo;
+    const int oh = (int)(pix % ho);
+    const long long ni = (long long)(pix / ho);
     const float* src = img + ni * h * w;
     float f[8];
 #pragma unroll
@@ -254,15 +253,8 @@ int koa_k_stem_im2col(const float* img, void* a, int n, int h, int w, int f16, c
   const long long total = (long long)n * ho * wo * 8;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  static const int idx32 = [] {  // KOA_IDX32 (elementwise.cu): experiment, default off
-    const char* e = getenv("KOA_IDX32");
-    return e != nullptr && atoi(e) > 0 ? 1 : 0;
-  }();
-  const bool narrow = idx32 && total < 0x7fffffffLL && blocks * 256 < 0x7fffffffLL;
-  if (f16 && narrow) stem_im2col_kernel<true, unsigned><<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
-  else if (f16) stem_im2col_kernel<true, long long><<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
-  else if (narrow) stem_im2col_kernel<false, unsigned><<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
-  else stem_im2col_kernel<false, long long><<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
+  if (f16) stem_im2col_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
+  else stem_im2col_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(img, (bf16*)a, total, h, w, ho, wo);
   KOA_LAUNCH_CHECK();
   return 0;
 }

@@ -82,14 +82,7 @@ def _run_branches(fns):
     main = torch.cuda.current_stream()
     key = (main.device.index, len(fns))
     if key not in _BRANCH_STREAMS:
-        import os
-
-        # KOA_BRANCH_PRIORITY=1 (experiment, default off, not yet run on a B200): the first branch — the longest chain in
-        # every fusion model (SAG 3D DESS: 62 % of the FLOPs) — gets a high-priority stream, so that its CTAs are placed
-        # first and the shorter branches only fill what it leaves idle instead of time-slicing with it
-        first_high = os.environ.get("KOA_BRANCH_PRIORITY", "0") == "1"
-        _BRANCH_STREAMS[key] = [torch.cuda.Stream(device=main.device, priority=-1 if (first_high and i == 0) else 0)
-                                for i in range(len(fns))]
+        _BRANCH_STREAMS[key] = [torch.cuda.Stream(device=main.device) for _ in range(len(fns))]
         # parameters shared by runs with and without branch streams keep their AccumulateGrad node: intentional
         if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
