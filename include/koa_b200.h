@@ -76,6 +76,16 @@ typedef struct koa_epilogue {
   float drop_p;              /* > 0: dropout after the activation, before the residual add: value *= mask / (1 - p), */
   unsigned int drop_site;    /* mask = koa_dropout_mask(drop_seed, drop_site, M, N, drop_p) (counter-based Philox, */
   unsigned long long drop_seed; /* regenerated in backward instead of stored) */
+  /* BatchNorm folded into the convolution (koafusion/models/_torchvision.py:118-138 conv -> bn -> [+ identity] -> relu as
+   * ONE kernel; eval mode, or train mode once the batch statistics are known): value = acc * bn_scale[col] + bn_shift[col],
+   * + add_bf16 read as a 16-bit residual in the act_f16 format (itself * res_scale[col] + res_shift[col] when res_scale is
+   * set: the downsample branch's raw convolution output), act = KOA_ACT_NONE / KOA_ACT_RELU; needs out_f16 = 1;
+   * out_bf16_copy receives a bf16 copy of the same values. */
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* res_scale;
+  const float* res_shift;
+  const float* col_bias;     /* backward flavour: fp32 [N] added per column before the gate */
 } koa_epilogue_t;
 
 /* out[M,N] = epilogue(A[M,K] . B[N,K]^T); A, B bf16 row-major. tcgen05/TMEM tiles fed by TMA.
@@ -83,6 +93,12 @@ typedef struct koa_epilogue {
  * stride-1 nn.Conv2d of the bottlenecks (koafusion/models/_torchvision.py:29-31,108,112) in forward
  * and in data-gradient form. Requires K % 8 == 0 and N % 32 == 0. */
 int koa_gemm_bf16(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep, void* stream);
+/* Same with the reduction dimension split over two A tensors: out = epilogue([A1[M,K1] | A2[M,K2]] . B[N,K1+K2]^T),
+ * K1 and K2 multiples of 64. The data gradient through a train-mode BatchNorm whose input was never stored is one such
+ * GEMM over [G | a2] (autograd of koafusion/models/_torchvision.py:130-131). Convolution-flavour epilogues
+ * only (16-bit output; addend / gate / statistics / col_bias). */
+int koa_gemm_kcat_bf16(const void* a1, int k1, const void* a2, int k2, const void* b, int m, int n,
+                       const koa_epilogue_t* ep, void* stream);
 
 /* y[N,Ho,Wo,Cout] = epilogue(conv(x[N,H,W,Cin], w[Cout,R,S,Cin])): implicit GEMM, the activation
  * operand is fetched by im2col-mode TMA. Replaces nn.Conv2d 3x3 (stride 1/2) and 1x1 stride 2
@@ -93,9 +109,7 @@ int koa_conv_fprop_bf16(const void* x, const void* w, int n_img, int h, int w_in
 
 /* dw[Cout,Cin] += dy[P,Cout]^T . x[P,Cin] (fp32 accumulate with atomics; caller zeroes dw). Both operands bf16, or
  * both fp16 with x_f16 == 1 (tcgen05 kind::f16 takes one 16-bit format per instruction); x_f16 == 2: dy bf16 and x fp16,
- * x is converted to bf16 in shared memory inside the kernel (no bf16 copy of the forward activations in HBM);
- * x_f16 == 3 (experiment, unconfirmed on hardware): dy bf16 and x fp16 multiplied as they are, one format field per
- * operand in the tcgen05 instruction descriptor.
+ * x is converted to bf16 in shared memory inside the kernel (no bf16 copy of the forward activations in HBM).
  * Weight gradient of nn.Linear and of 1x1 stride-1 convolutions (autograd of the call sites above). */
 int koa_gemm_wgrad_bf16(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, int x_f16, void* stream);
 

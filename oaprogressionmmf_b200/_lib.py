@@ -44,6 +44,11 @@ class Epilogue(C.Structure):
         ("drop_p", C.c_float),
         ("drop_site", C.c_uint),
         ("drop_seed", C.c_ulonglong),
+        ("bn_scale", C.c_void_p),
+        ("bn_shift", C.c_void_p),
+        ("res_scale", C.c_void_p),
+        ("res_shift", C.c_void_p),
+        ("col_bias", C.c_void_p),
     ]
 
 
@@ -150,6 +155,7 @@ SIGNATURES = {
     "koa_profile_read": (_I, [C.POINTER(C.c_double)]),
     "koa_profile_dump": (_I, [C.c_char_p]),
     "koa_gemm_bf16": (_I, [_P, _P, _I, _I, _I, C.POINTER(Epilogue), _P]),
+    "koa_gemm_kcat_bf16": (_I, [_P, _I, _P, _I, _P, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_conv_fprop_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_gemm_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "koa_conv_wgrad_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -400,7 +400,10 @@ __global__ void __launch_bounds__(256)
 bn_act_fixed_kernel(const bf16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     const bf16* __restrict__ res, const bf16* __restrict__ y2, const float* __restrict__ scale2,
                     const float* __restrict__ shift2, bf16* __restrict__ out, bf16* __restrict__ out_bf, long long rows,
-                    int c, int relu, KoaBnFwdFin fa, KoaBnFwdFin fb, double count, int training) {
+                    int c, int relu, KoaBnFwdFin fa, KoaBnFwdFin fb, double count, int training,
+                    float* __restrict__ out_colsum) {
+  __shared__ float s_cs[2048];  // out_colsum: per-block column sums (C <= 2048: C / 8 divides 256)
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int cg = c / 8;
   const long long total = rows * cg;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -448,9 +451,24 @@ bn_act_fixed_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
         for (int u = 0; u < 8; ++u) f[u] = fmaxf(f[u], 0.0f);
       }
       const long long o = e == 0 ? i : j;
-      *reinterpret_cast<uint4*>(out + o * 8) = pack8h(f);
+      const uint4 pk = pack8h(f);
+      *reinterpret_cast<uint4*>(out + o * 8) = pk;
       if (out_bf != nullptr) *reinterpret_cast<uint4*>(out_bf + o * 8) = pack8(f);
+      if (out_colsum != nullptr) {  // sums of the values as stored (fp16)
+        float fr[8];
+        unpack8h(pk, fr);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cs[u] += fr[u];
+      }
     }
+  }
+  if (out_colsum != nullptr) {  // uniform over the grid
+    for (int i = threadIdx.x; i < c; i += blockDim.x) s_cs[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) atomicAdd(&s_cs[g * 8 + u], cs[u]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&out_colsum[i], s_cs[i]);
   }
 }
 
@@ -1206,7 +1224,7 @@ int koa_k_bn_act(const void* y, const float* scale, const float* shift, const vo
     bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
                                                                            (const bf16*)y2, scale2, shift2, (bf16*)out,
                                                                            (bf16*)out_bf16, rows, c, relu, KoaBnFwdFin{},
-                                                                           KoaBnFwdFin{}, 1.0, 0);
+                                                                           KoaBnFwdFin{}, 1.0, 0, nullptr);
   else
     bn_act_kernel<<<grid_for(rows * (c / 8)), kThreads, 0, st>>>((const bf16*)y, scale, shift, (const bf16*)res,
                                                                  (const bf16*)y2, scale2, shift2, (bf16*)out,
@@ -1216,12 +1234,13 @@ int koa_k_bn_act(const void* y, const float* scale, const float* shift, const vo
 }
 int koa_k_bn_fused_ok(int c) { return c % 8 == 0 && c / 8 <= kThreads && kThreads % (c / 8) == 0; }
 int koa_k_bn_act_fin(const void* y, const KoaBnFwdFin* a, const void* res, const void* y2, const KoaBnFwdFin* b, void* out,
-                     void* out_bf16, long long rows, int c, int relu, double count, int training, cudaStream_t st) {
+                     void* out_bf16, float* out_colsum, long long rows, int c, int relu, double count, int training,
+                     cudaStream_t st) {
   KOA_REQUIRE(koa_k_bn_fused_ok(c) && a != nullptr && a->gamma != nullptr, "fused BatchNorm apply needs C/8 | %d (C=%d)", kThreads, c);
   KOA_REQUIRE((y2 != nullptr) == (b != nullptr), "second BatchNorm: y2 and its sums go together");
   bn_act_fixed_kernel<<<grid_for(rows * (c / 8) / 2), kThreads, 0, st>>>(
         (const bf16*)y, nullptr, nullptr, (const bf16*)res, (const bf16*)y2, nullptr, nullptr, (bf16*)out, (bf16*)out_bf16, rows,
-        c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training);
+        c, relu, *a, b ? *b : KoaBnFwdFin{}, count, training, out_colsum);
   KOA_LAUNCH_CHECK();
   return 0;
 }

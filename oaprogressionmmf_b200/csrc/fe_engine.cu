@@ -40,6 +40,25 @@ int wgrad_xcvt_mode() {
   }();
   return v;
 }
+// KOA_BN_GRAM (default 1): train-mode bottlenecks never store the output of their last 1x1 convolution; its BatchNorm runs
+// from the Gram matrix of the convolution's input (bn_gram.cu). 0: the round-1 dataflow (y3 stored, separate
+// BatchNorm apply / backward-apply passes over the widest tensor of the block).
+bool bn_gram_enabled() {
+  static const int v = [] {
+    const char* e = getenv("KOA_BN_GRAM");
+    return e == nullptr ? 1 : atoi(e);
+  }();
+  return v != 0;
+}
+// KOA_EVAL_FUSED (default 1): inference (eval mode, no backward) applies every BatchNorm (+ residual + ReLU) in the epilogue
+// of its convolution (gemm_conv.cuh MODE 2): no raw convolution output is stored and no BatchNorm pass runs.
+bool eval_fused_enabled() {
+  static const int v = [] {
+    const char* e = getenv("KOA_EVAL_FUSED");
+    return e == nullptr ? 1 : atoi(e);
+  }();
+  return v != 0;
+}
 }  // namespace
 
 namespace {
@@ -61,6 +80,10 @@ struct Block {
   size_t a1_bf, a2_bf, out_bf;     // bf16 copies, kept only when backward will run: operands of the weight gradients
   size_t in, in_bf;                // activation feeding the block
   int stride;
+  // y-free tail (Plan::gram): s = colsum(a2) [w], Gram = a2^T a2 [w][w] (both fp32, zeroed with the forward statistics),
+  // fp16 head / tail of Gram / N, Q = W3 . Gram / N [C][w] fp32 (kept for backward), T = G^T a2 [C][w] fp32 (zeroed with the
+  // backward statistics), wext = [k0 * W3^T | -W3^T diag(k2) W3] bf16 [w][C + w], k2w = -k2 * W3^T bf16 [w][C], bias fp32 [w]
+  size_t sa2, gram, gram_hi, gram_lo, q, tq, wext, k2w, cbias;
 };
 struct Plan {
   int n_img, h, w, out_c, out_h, out_w;
@@ -71,6 +94,8 @@ struct Plan {
   size_t bstat_begin, bstat_end;
   size_t g[2], t[5];               // backward scratch (block gradients ping-pong + temporaries)
   size_t total;
+  bool gram;                       // train-mode bottlenecks without y3 (bn_gram.cu)
+  bool fused_eval;                 // inference: BatchNorm in the convolution epilogues, no y at all
 };
 
 enum { S_SUM = 0, S_SUMSQ, S_SDZ, S_SDZX, S_SCALE, S_SHIFT, S_MEAN, S_INVSTD, S_K0, S_K1, S_K2 };
@@ -97,6 +122,8 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
   const int expansion = bottleneck ? 4 : 1;
   p.n_img = d->n_img; p.h = d->h; p.w = d->w;
   p.units.clear(); p.blocks.clear();
+  p.gram = bottleneck && d->training != 0 && bn_gram_enabled();
+  p.fused_eval = d->training == 0 && d->need_backward == 0 && eval_fused_enabled();
   Bump ws;
   const long long n = d->n_img;
   auto conv_out = [](int x, int k, int s, int pad) { return (x + 2 * pad - k) / s + 1; };
@@ -158,10 +185,20 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
     u.w_dgrad = ws.take(wcount * 2);
     u.dw_scratch = (u.k > 1) ? ws.take(wcount * 4) : 0;
   }
-  for (Unit& u : p.units) u.y = ws.take((size_t)u.rows_out * u.cout * 2);
+  for (const Block& b : p.blocks)  // the coefficient kernels of the y-free tail want power-of-two widths <= 1024
+    if (p.gram && !(koa_k_bn_fused_ok(p.units[b.u2].cout) && p.units[b.u2].cout <= 1024)) p.gram = false;
+  {
+    std::vector<char> no_y(p.units.size(), p.fused_eval ? 1 : 0);
+    for (const Block& b : p.blocks) {
+      if (p.gram) no_y[b.u3] = 1;
+      if (p.fused_eval && b.ud >= 0) no_y[b.ud] = 0;  // holds bn_d(conv_d(x)), the residual of the block's last convolution
+    }
+    for (Unit& u : p.units) u.y = no_y[u.idx] ? 0 : ws.take((size_t)u.rows_out * u.cout * 2);
+  }
   const Unit& us = p.units[stem];
   p.a_stem = ws.take((size_t)us.rows_out * 64 * 2);  // im2col operand of the stem GEMM (kept for its weight gradient)
   p.a0 = ws.take((size_t)us.rows_out * 64 * 2);
+  const bool gram_bw = p.gram && d->need_backward != 0;
   const bool bw = d->need_backward != 0;
   // bf16 copies of the activations (operands of the weight gradients): see wgrad_xcvt_mode()
   const int xm = wgrad_xcvt_mode();
@@ -181,7 +218,8 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
     b.a1_bf = bwc ? ws.take((size_t)u1.rows_out * u1.cout * 2) : 0;
     if (b.kind == 0) {
       b.a2 = ws.take((size_t)u2.rows_out * u2.cout * 2);
-      b.a2_bf = bwc ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
+      // (the y-free tail reads a2 in bf16 as the second K segment of its data-gradient GEMM: always a copy)
+      b.a2_bf = (bwc || gram_bw) ? ws.take((size_t)u2.rows_out * u2.cout * 2) : 0;
       const Unit& u3 = p.units[b.u3];
       b.out = ws.take((size_t)u3.rows_out * u3.cout * 2);
       const bool wide_hbm_bound = xm == 2 && u3.cout <= 512;  // consumers: 1x1 conv1 / downsample of the next block
@@ -200,11 +238,31 @@ int build_plan(const koa_fe_desc_t* d, Plan& p) {
   }
   p.fstat_begin = ws.off;
   for (Unit& u : p.units) u.fstat = ws.take((size_t)2 * u.cout * 4);
+  if (p.gram)
+    for (Block& b : p.blocks) {
+      const size_t w = (size_t)p.units[b.u2].cout;
+      b.sa2 = ws.take(w * 4);
+      b.gram = ws.take(w * w * 4);
+    }
   p.fstat_end = ws.off;
   p.bstat_begin = ws.off;
   p.dwstem = ws.take(64 * 64 * 4);
   for (Unit& u : p.units) u.bstat = ws.take((size_t)2 * u.cout * 4);
+  if (gram_bw)
+    for (Block& b : p.blocks) b.tq = ws.take((size_t)p.units[b.u3].cout * p.units[b.u2].cout * 4);
   p.bstat_end = ws.off;
+  if (p.gram)
+    for (Block& b : p.blocks) {
+      const size_t w = (size_t)p.units[b.u2].cout, c = (size_t)p.units[b.u3].cout;
+      b.gram_hi = ws.take(w * w * 2);
+      b.gram_lo = ws.take(w * w * 2);
+      b.q = ws.take(c * w * 4);
+      if (gram_bw) {
+        b.wext = ws.take(w * (c + w) * 2);
+        b.k2w = ws.take(w * c * 2);
+        b.cbias = ws.take(w * 4);
+      }
+    }
   for (Unit& u : p.units) u.coef = ws.take((size_t)COEF_SLOTS * u.cout * 4);
   for (int i = 0; i < 2; ++i) p.g[i] = ws.take(max_act * 2);
   for (int i = 0; i < 5; ++i) p.t[i] = ws.take(max_act * 2);
@@ -266,6 +324,29 @@ int conv_forward(const Plan& p, const Unit& u, const void* x, void* ws, int trai
   return koa_conv_fprop_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, &ep, st);
 }
 
+// out = act(bn(conv(x)) [+ res [* rscale + rshift]]) in ONE kernel: the BatchNorm coefficients are already known (eval mode, or
+// the y-free tail in train mode) and applied by the GEMM epilogue (gemm_conv.cuh MODE 2); y never exists in HBM.
+int conv_bn_forward(const Plan& p, const Unit& u, const void* x, void* ws, const void* res, const Unit* res_bn, int relu,
+                    void* out, void* out_bf, cudaStream_t st) {
+  koa_epilogue_t ep{};
+  ep.out = out;
+  ep.ldo = u.cout;
+  ep.a_f16 = ep.b_f16 = ep.out_f16 = ep.act_f16 = 1;
+  ep.bn_scale = bn_slot(ws, u, S_SCALE);
+  ep.bn_shift = bn_slot(ws, u, S_SHIFT);
+  ep.add_bf16 = res;
+  if (res_bn != nullptr) {
+    ep.res_scale = bn_slot(ws, *res_bn, S_SCALE);
+    ep.res_shift = bn_slot(ws, *res_bn, S_SHIFT);
+  }
+  ep.act = relu ? KOA_ACT_RELU : KOA_ACT_NONE;
+  ep.out_bf16_copy = out_bf;
+  if (u.groups > 1)
+    return koa_conv_grouped_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.stride, &ep, st);
+  if (u.k == 1 && u.stride == 1) return koa_gemm_launch(x, at(ws, u.w_fwd), (int)u.rows_out, u.cout, u.cin, &ep, st);
+  return koa_conv_fprop_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, &ep, st);
+}
+
 int bn_finalize(const Unit& u, const ParamView& pv, void* ws, int training, cudaStream_t st) {
   return koa_k_bn_finalize(bn_slot(ws, u, S_SUM), bn_slot(ws, u, S_SUMSQ), pv.gamma(u), pv.beta(u), pv.run_mean(u),
                            pv.run_var(u), bn_slot(ws, u, S_SCALE), bn_slot(ws, u, S_SHIFT), bn_slot(ws, u, S_MEAN),
@@ -280,19 +361,82 @@ KoaBnFwdFin fwd_fin(const Unit& u, const ParamView& pv, void* ws) {
 // out = relu(bn(y) [+ res | + bn_d(y_d)]) with the BatchNorm coefficients derived inside the apply kernel (one launch
 // per BatchNorm instead of finalize + apply) whenever the channel count allows it.
 int bn_apply(const Unit& u, const Unit* ud, const ParamView& pv, void* ws, const void* res, void* out, void* out_bf,
-             int training, cudaStream_t st) {
+             int training, cudaStream_t st, float* out_colsum = nullptr) {
   if (koa_k_bn_fused_ok(u.cout)) {
     const KoaBnFwdFin fa = fwd_fin(u, pv, ws);
     KoaBnFwdFin fb{};
     if (ud) fb = fwd_fin(*ud, pv, ws);
-    return koa_k_bn_act_fin(at(ws, u.y), &fa, res, ud ? at(ws, ud->y) : nullptr, ud ? &fb : nullptr, out, out_bf, u.rows_out,
-                            u.cout, 1, (double)u.rows_out, training, st);
+    return koa_k_bn_act_fin(at(ws, u.y), &fa, res, ud ? at(ws, ud->y) : nullptr, ud ? &fb : nullptr, out, out_bf, out_colsum,
+                            u.rows_out, u.cout, 1, (double)u.rows_out, training, st);
   }
+  KOA_REQUIRE(out_colsum == nullptr, "column sums need the fused BatchNorm-apply kernel (C = %d)", u.cout);
   KOA_TRY(bn_finalize(u, pv, ws, training, st));
   if (ud) KOA_TRY(bn_finalize(*ud, pv, ws, training, st));
   return koa_k_bn_act(at(ws, u.y), bn_slot(ws, u, S_SCALE), bn_slot(ws, u, S_SHIFT), res, ud ? at(ws, ud->y) : nullptr,
                       ud ? bn_slot(ws, *ud, S_SCALE) : nullptr, ud ? bn_slot(ws, *ud, S_SHIFT) : nullptr, out, out_bf,
                       u.rows_out, u.cout, 1, st);
+}
+
+// Forward of the y-free bottleneck tail (bn_gram.cu): batch statistics of conv3's output from the Gram matrix of its input a2
+// (column sums `sa2` come from the BatchNorm-apply pass that wrote a2), then conv3 with BatchNorm + residual + ReLU in its
+// epilogue. `res`: the identity x, or the raw output of the downsample convolution (whose BatchNorm the epilogue applies).
+int gram_tail_forward(const Plan& p, const Block& b, const ParamView& pv, void* ws, const void* x, cudaStream_t st) {
+  const Unit& u2 = p.units[b.u2];
+  const Unit& u3 = p.units[b.u3];
+  const int w = u2.cout, c = u3.cout;
+  const double count = (double)u3.rows_out;
+  float* gram = (float*)at(ws, b.gram);
+  float* q = (float*)at(ws, b.q);
+  // Gram = a2^T a2: a weight-gradient-shaped GEMM over the pixels, both operands the fp16 tensor itself (products exact in fp32)
+  KOA_TRY(koa_gemm_wgrad_launch(at(ws, b.a2), at(ws, b.a2), gram, (int)u2.rows_out, w, w, 1, st));
+  KOA_TRY(koa_k_gram_split(gram, at(ws, b.gram_hi), at(ws, b.gram_lo), w, count, st));
+  // Q = W3 . (hi + lo): two small GEMMs with fp16 operands and an fp32 result (the second accumulates onto the first)
+  for (int part = 0; part < 2; ++part) {
+    koa_epilogue_t ep{};
+    ep.out = q;
+    ep.ldo = w;
+    ep.out_fp32 = 1;
+    ep.a_f16 = ep.b_f16 = 1;
+    if (part == 1) ep.residual_f32 = q;
+    KOA_TRY(koa_gemm_launch(at(ws, u3.w_fwd), at(ws, part == 0 ? b.gram_hi : b.gram_lo), c, w, w, &ep, st));
+  }
+  KOA_TRY(koa_k_bn_gram_stats(at(ws, u3.w_fwd), (const float*)at(ws, b.sa2), q, pv.gamma(u3), pv.beta(u3), pv.run_mean(u3),
+                              pv.run_var(u3), bn_slot(ws, u3, S_SCALE), bn_slot(ws, u3, S_SHIFT), bn_slot(ws, u3, S_MEAN),
+                              bn_slot(ws, u3, S_INVSTD), c, w, count, st));
+  const void* res = x;
+  const Unit* res_bn = nullptr;
+  if (b.ud >= 0) {
+    const Unit& ud = p.units[b.ud];
+    KOA_TRY(conv_forward(p, ud, x, ws, 1, st));
+    KOA_TRY(bn_finalize(ud, pv, ws, 1, st));
+    res = at(ws, ud.y);
+    res_bn = &ud;
+  }
+  return conv_bn_forward(p, u3, at(ws, b.a2), ws, res, res_bn, 1, at(ws, b.out), b.out_bf ? at(ws, b.out_bf) : nullptr, st);
+}
+
+// Inference forward of one block: every BatchNorm in the epilogue of its convolution.
+int fused_eval_block(const Plan& p, const Block& b, const ParamView& pv, void* ws, const void* x, cudaStream_t st) {
+  const Unit& u1 = p.units[b.u1];
+  const Unit& u2 = p.units[b.u2];
+  const Unit* last = b.kind == 0 ? &p.units[b.u3] : &u2;
+  KOA_TRY(bn_finalize(u1, pv, ws, 0, st));
+  KOA_TRY(conv_bn_forward(p, u1, x, ws, nullptr, nullptr, 1, at(ws, b.a1), nullptr, st));
+  const void* last_in = at(ws, b.a1);
+  if (b.kind == 0) {
+    KOA_TRY(bn_finalize(u2, pv, ws, 0, st));
+    KOA_TRY(conv_bn_forward(p, u2, at(ws, b.a1), ws, nullptr, nullptr, 1, at(ws, b.a2), nullptr, st));
+    last_in = at(ws, b.a2);
+  }
+  const void* res = x;
+  if (b.ud >= 0) {  // r = bn_d(conv_d(x)) (no activation), stored where the raw output would have gone
+    const Unit& ud = p.units[b.ud];
+    KOA_TRY(bn_finalize(ud, pv, ws, 0, st));
+    KOA_TRY(conv_bn_forward(p, ud, x, ws, nullptr, nullptr, 0, at(ws, ud.y), nullptr, st));
+    res = at(ws, ud.y);
+  }
+  KOA_TRY(bn_finalize(*last, pv, ws, 0, st));
+  return conv_bn_forward(p, *last, last_in, ws, res, nullptr, 1, at(ws, b.out), nullptr, st);
 }
 
 }  // namespace
@@ -326,7 +470,8 @@ extern "C" int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, 
   if (what == 0 || what == 6) {
     KOA_REQUIRE(index >= 0 && index < (int)p.units.size(), "unit index out of range");
     const Unit& u = p.units[index];
-    if (what == 0) { *offset = u.y; *bytes = (size_t)u.rows_out * u.cout * 2; }
+    // (no y: inference with fused BatchNorm epilogues, and the last convolution of a train-mode bottleneck)
+    if (what == 0) { *offset = u.y; *bytes = (u.y == 0 && u.idx != 0) ? 0 : (size_t)u.rows_out * u.cout * 2; }
     else { *offset = u.coef; *bytes = (size_t)COEF_SLOTS * u.cout * 4; }
     return 0;
   }
@@ -350,6 +495,15 @@ extern "C" int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, 
     if (what == 8) { *offset = b.out_bf; *bytes = b.out_bf ? (size_t)last.rows_out * last.cout * 2 : 0; }
     if (what == 9) { *offset = b.a1_bf; *bytes = b.a1_bf ? (size_t)u1.rows_out * u1.cout * 2 : 0; }
     if (what == 10) { *offset = b.a2_bf; *bytes = b.a2_bf ? (size_t)u2.rows_out * u2.cout * 2 : 0; }
+    return 0;
+  }
+  if (what == 12 || what == 13) {  // y-free tail: colsum(a2) [w] fp32 / Q = W3 . Gram / N [C][w] fp32 of block `index`
+    KOA_REQUIRE(index >= 0 && index < (int)p.blocks.size(), "block index out of range");
+    const Block& b = p.blocks[index];
+    if (!p.gram) { *offset = 0; *bytes = 0; return 0; }
+    const size_t w = (size_t)p.units[b.u2].cout, c = (size_t)p.units[b.u3].cout;
+    if (what == 12) { *offset = b.sa2; *bytes = w * 4; }
+    else { *offset = b.q; *bytes = c * w * 4; }
     return 0;
   }
   if (what == 11) { *offset = p.p0_bf; *bytes = !p.p0_bf ? 0 : (size_t)p.n_img * p.units[p.blocks[0].u1].hin * p.units[p.blocks[0].u1].win * 64 * 2; return 0; }
@@ -392,9 +546,17 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
       ep.col_sum = bn_slot(ws, us, S_SUM);
       ep.col_sumsq = bn_slot(ws, us, S_SUMSQ);
     }
+    if (p.fused_eval) {  // BatchNorm (running statistics) + ReLU in the epilogue: a0 directly
+      KOA_TRY(bn_finalize(us, pv, ws, 0, st));
+      ep.out = at(ws, p.a0);
+      ep.act_f16 = 1;
+      ep.bn_scale = bn_slot(ws, us, S_SCALE);
+      ep.bn_shift = bn_slot(ws, us, S_SHIFT);
+      ep.act = KOA_ACT_RELU;
+    }
     KOA_TRY(koa_gemm_launch(at(ws, p.a_stem), at(ws, p.wstem), (int)us.rows_out, 64, 64, &ep, st));
   }
-  KOA_TRY(bn_apply(us, nullptr, pv, ws, nullptr, at(ws, p.a0), nullptr, training, st));
+  if (!p.fused_eval) KOA_TRY(bn_apply(us, nullptr, pv, ws, nullptr, at(ws, p.a0), nullptr, training, st));
   KOA_TRY(koa_k_maxpool_fwd(at(ws, p.a0), at(ws, p.p0), p.p0_bf ? at(ws, p.p0_bf) : nullptr, at(ws, p.idx0), p.n_img, us.hout,
                             us.wout, 64, st));
 
@@ -403,13 +565,22 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
     const Unit& u1 = p.units[b.u1];
     const Unit& u2 = p.units[b.u2];
     const void* x = at(ws, b.in);
+    if (p.fused_eval) {
+      KOA_TRY(fused_eval_block(p, b, pv, ws, x, st));
+      continue;
+    }
     KOA_TRY(conv_forward(p, u1, x, ws, training, st));
     KOA_TRY(bn_apply(u1, nullptr, pv, ws, nullptr, at(ws, b.a1), b.a1_bf ? at(ws, b.a1_bf) : nullptr, training, st));
     KOA_TRY(conv_forward(p, u2, at(ws, b.a1), ws, training, st));
     const Unit* last = &u2;
     if (b.kind == 0) {
       const Unit& u3 = p.units[b.u3];
-      KOA_TRY(bn_apply(u2, nullptr, pv, ws, nullptr, at(ws, b.a2), b.a2_bf ? at(ws, b.a2_bf) : nullptr, training, st));
+      KOA_TRY(bn_apply(u2, nullptr, pv, ws, nullptr, at(ws, b.a2), b.a2_bf ? at(ws, b.a2_bf) : nullptr, training, st,
+                       p.gram ? (float*)at(ws, b.sa2) : nullptr));
+      if (p.gram) {
+        KOA_TRY(gram_tail_forward(p, b, pv, ws, x, st));
+        continue;
+      }
       KOA_TRY(conv_forward(p, u3, at(ws, b.a2), ws, training, st));
       last = &u3;
     }
@@ -521,6 +692,16 @@ void gate_and_stats(koa_epilogue_t& ep, void* ws, size_t act_off, const Unit* u,
     ep.stat_y = at(ws, u->y);
     ep.stat_mean = bn_slot(ws, *u, S_MEAN);
     ep.stat_invstd = bn_slot(ws, *u, S_INVSTD);
+  }
+}
+
+// Producer-side statistics of the y-free tail: only sum(G) is needed from the epilogue that produces G (sum(G * y3) comes
+// out of the weight-gradient GEMM, bn_gram.cu); the sum-of-squares slot the kernel also fills is scratch.
+void gate_and_colsum(koa_epilogue_t& ep, void* ws, size_t act_off, const Unit* u, bool fuse) {
+  ep.gate_bf16 = at(ws, act_off);
+  if (fuse && u != nullptr) {
+    ep.col_sum = bn_slot(ws, *u, S_SDZ);
+    ep.col_sumsq = bn_slot(ws, *u, S_SDZX);
   }
 }
 
@@ -660,8 +841,49 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     void* dy_down = at(ws, p.t[1]);
     KOA_TRY(side.before_write(0));
     KOA_TRY(side.before_write(1));
-    KOA_TRY(bn_backward(last, ud, pv, grads, ws, g_out, nullptr, dy_last, ud ? dy_down : nullptr, training, g_stats_done, st));
     void* d_a1 = at(ws, p.t[3]);
+    if (p.gram) {
+      // y-free tail (bn_gram.cu): no dy3 tensor. T = G^T a2 -> coefficients, dW3, the extended data-gradient operand ->
+      // dz2 = ([G | a2] . wext^T + bias) * (a2 > 0) in ONE GEMM.
+      const int w = u2.cout, c = u3->cout;
+      const double count = (double)u3->rows_out;
+      if (!g_stats_done)  // sum(G) per channel (the producer of G did not reduce it)
+        KOA_TRY(koa_k_col_stats(g_out, bn_slot(ws, *u3, S_SDZ), bn_slot(ws, *u3, S_SDZX), u3->rows_out, c, st));
+      if (ud) KOA_TRY(bn_backward(*ud, nullptr, pv, grads, ws, g_out, nullptr, dy_down, nullptr, training, false, st));
+      float* tq = (float*)at(ws, b.tq);
+      KOA_TRY(koa_gemm_wgrad_launch(g_out, at(ws, b.a2_bf), tq, (int)u3->rows_out, c, w, 0, st));
+      KOA_TRY(koa_k_bn_gram_bwd(tq, at(ws, u3->w_fwd), pv.w(*u3), (const float*)at(ws, b.sa2), (const float*)at(ws, b.q),
+                                bn_slot(ws, *u3, S_SDZ), pv.gamma(*u3), bn_slot(ws, *u3, S_MEAN), bn_slot(ws, *u3, S_INVSTD),
+                                (float*)grads[u3->idx * 3 + 1], (float*)grads[u3->idx * 3 + 2], (float*)grads[u3->idx * 3 + 0],
+                                at(ws, b.wext), at(ws, b.k2w), bn_slot(ws, *u3, S_K0), bn_slot(ws, *u3, S_K1),
+                                bn_slot(ws, *u3, S_K2), c, w, c + w, count, st));
+      KOA_TRY(koa_k_bn_gram_bias(at(ws, u3->w_dgrad), bn_slot(ws, *u3, S_K1), (float*)at(ws, b.cbias), w, c, st));
+      {  // -M = W3^T . (-k2 * W3) [w][w], stored as the last w columns of every wext row
+        koa_epilogue_t em{};
+        em.out = (uint8_t*)at(ws, b.wext) + (size_t)c * 2;
+        em.ldo = c + w;
+        KOA_TRY(koa_gemm_launch(at(ws, u3->w_dgrad), at(ws, b.k2w), w, w, c, &em, st));
+      }
+      void* d_a2 = at(ws, p.t[2]);
+      koa_epilogue_t ep{};
+      ep.out = d_a2;
+      ep.ldo = w;
+      ep.act_f16 = 1;
+      ep.col_bias = (const float*)at(ws, b.cbias);
+      gate_and_stats(ep, ws, b.a2, &u2, fuse);  // dz2 = (...) * (a2 > 0) + sums for bn2
+      KOA_TRY(side.before_write(2));
+      KOA_TRY(koa_gemm_kcat_launch(g_out, c, at(ws, b.a2_bf), w, at(ws, b.wext), (int)u3->rows_out, w, &ep, st));
+      KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, nullptr, d_a2, nullptr, training, fuse, st));  // in place -> dy2
+      KOA_TRY(side.begin(&sw));
+      KOA_TRY(conv_wgrad(p, u2, b.a1_bf, b.a1, d_a2, grads, ws, sw));
+      KOA_TRY(side.reads(2));
+      koa_epilogue_t ep2{};
+      ep2.out = d_a1;
+      gate_and_stats(ep2, ws, b.a1, &u1, fuse);
+      KOA_TRY(side.before_write(3));
+      KOA_TRY(conv_dgrad(p, u2, d_a2, ws, &ep2, at(ws, p.t[4]), st));
+    } else {
+    KOA_TRY(bn_backward(last, ud, pv, grads, ws, g_out, nullptr, dy_last, ud ? dy_down : nullptr, training, g_stats_done, st));
     if (u3) {
       KOA_TRY(side.begin(&sw));
       KOA_TRY(conv_wgrad(p, *u3, b.a2_bf, b.a2, dy_last, grads, ws, sw));
@@ -691,6 +913,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       KOA_TRY(side.before_write(3));
       KOA_TRY(conv_dgrad(p, u2, dy_last, ws, &ep2, at(ws, p.t[4]), st));
     }
+    }
     KOA_TRY(bn_backward(u1, nullptr, pv, grads, ws, d_a1, nullptr, d_a1, nullptr, training, fuse, st));  // in place -> dy1
     KOA_TRY(side.begin(&sw));
     KOA_TRY(conv_wgrad(p, u1, b.in_bf, b.in, d_a1, grads, ws, sw));
@@ -700,12 +923,17 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     const Block* prev = bi > 0 ? &p.blocks[bi - 1] : nullptr;
     const Unit* prev_last = prev ? &p.units[prev->kind == 0 ? prev->u3 : prev->u2] : nullptr;
     const bool single_producer = !(ud && ud->stride != 1);
-    const bool fuse_prev = fuse && prev != nullptr && prev->ud < 0 && single_producer;
+    // (y-free tail: the previous block only needs sum(G) from this epilogue, also when it has a downsample branch)
+    const bool fuse_prev = fuse && prev != nullptr && (p.gram || prev->ud < 0) && single_producer;
+    auto gate_prev = [&](koa_epilogue_t& e) {
+      if (p.gram) gate_and_colsum(e, ws, b.in, prev_last, fuse_prev);
+      else gate_and_stats(e, ws, b.in, prev_last, fuse_prev);
+    };
     if (!ud) {
       koa_epilogue_t ep{};
       ep.out = g_in;
       ep.add_bf16 = g_out;  // identity path: G of this block
-      gate_and_stats(ep, ws, b.in, prev_last, fuse_prev);
+      gate_prev(ep);
       KOA_TRY(conv_dgrad(p, u1, d_a1, ws, &ep, at(ws, p.t[4]), st));
     } else {
       KOA_TRY(side.begin(&sw));
@@ -718,7 +946,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
         koa_epilogue_t ep2{};
         ep2.out = g_in;
         ep2.add_bf16 = g_in;  // accumulate in place, then gate the sum
-        gate_and_stats(ep2, ws, b.in, prev_last, fuse_prev);
+        gate_prev(ep2);
         KOA_TRY(conv_dgrad(p, *ud, dy_down, ws, &ep2, nullptr, st));
       } else {
         koa_epilogue_t ep{};

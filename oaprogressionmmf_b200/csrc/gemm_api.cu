@@ -122,6 +122,8 @@ static EpiParams to_epi(const koa_epilogue_t* e, int n) {
   p.stat_mean = e->stat_mean;
   p.stat_invstd = e->stat_invstd;
   p.a_f16 = e->a_f16; p.b_f16 = e->b_f16; p.out_f16 = e->out_f16; p.act_f16 = e->act_f16;
+  p.bn_scale = e->bn_scale; p.bn_shift = e->bn_shift; p.res_scale = e->res_scale; p.res_shift = e->res_shift;
+  p.col_bias = e->col_bias;
   p.drop_on = e->drop_p > 0.0f ? 1 : 0;
   p.drop_cols = n;
   p.drop = make_drop_spec(e->drop_seed, e->drop_site, e->drop_p);
@@ -140,19 +142,42 @@ static int check_epi(const koa_epilogue_t* ep, int n) {
   KOA_REQUIRE(ep->drop_p >= 0.0f && ep->drop_p < 1.0f, "dropout probability %f out of range", (double)ep->drop_p);
   KOA_REQUIRE(ep->stat_y == nullptr || (ep->col_sum != nullptr && ep->stat_mean != nullptr && ep->stat_invstd != nullptr),
               "stat_y needs col_sum/col_sumsq and stat_mean/stat_invstd");
+  KOA_REQUIRE((ep->bn_scale == nullptr) == (ep->bn_shift == nullptr), "bn_scale and bn_shift go together");
+  KOA_REQUIRE((ep->res_scale == nullptr) == (ep->res_shift == nullptr), "res_scale and res_shift go together");
+  if (ep->bn_scale != nullptr) {
+    KOA_REQUIRE(ep->out_f16 && !ep->out_fp32, "the BatchNorm-apply epilogue stores fp16 (out_f16 = 1)");
+    KOA_REQUIRE(ep->act == KOA_ACT_NONE || ep->act == KOA_ACT_RELU, "the BatchNorm-apply epilogue takes no activation but ReLU");
+    KOA_REQUIRE(ep->add_bf16 == nullptr || ep->act_f16, "the residual of the BatchNorm-apply epilogue is an fp16 activation");
+    KOA_REQUIRE(ep->res_scale == nullptr || ep->add_bf16 != nullptr, "res_scale needs the residual (add_bf16)");
+    KOA_REQUIRE(ep->gate_bf16 == nullptr && ep->col_sum == nullptr && ep->col_bias == nullptr && ep->bias == nullptr &&
+                    ep->pre_out_bf16 == nullptr && ep->residual_f32 == nullptr && ep->drop_p == 0.0f,
+                "the BatchNorm-apply epilogue combines with add_bf16 / act / out_bf16_copy only");
+  } else {
+    KOA_REQUIRE(ep->res_scale == nullptr, "res_scale needs bn_scale");
+  }
   return 0;
 }
 
 // The convolution flavour of the epilogue (bf16 output, optional addend / gate / statistics) is a separate, leaner
 // instantiation; everything else (bias, activations, fp32 residual stream) takes the full one.
 static bool conv_epilogue(const EpiParams& ep) {
+  if (ep.bn_scale != nullptr) return true;  // BatchNorm-apply flavour (MODE 2): act / out_bf16_copy belong to it (check_epi)
   return !ep.out_fp32 && ep.act == ACT_NONE && ep.bias == nullptr && ep.pre_out == nullptr && ep.res_f32 == nullptr &&
          ep.out_bf16_copy == nullptr && !ep.drop_on;
 }
+// features only gemm_conv_kernel implements: there is no fallback kernel for them
+static bool conv_only(const EpiParams& ep) { return ep.bn_scale != nullptr || ep.col_bias != nullptr; }
+
+// second A tensor of a K-concatenated GEMM (k-blocks >= kb_split read it); kb_split < 0: none
+struct AExt {
+  const CUtensorMap* ta2 = nullptr;
+  int kb_split = -1;
+};
 
 static int prof_flavor(bool im2col, const EpiParams& ep) {
   return (im2col ? 1 : 0) | (ep.col_sum ? 2 : 0) | (ep.add_bf16 ? 4 : 0) | (ep.gate_bf16 ? 8 : 0) | (ep.res_f32 ? 16 : 0) |
-         (ep.out_fp32 ? 32 : 0) | (ep.act ? 64 : 0) | (ep.stat_y ? 128 : 0);
+         (ep.out_fp32 ? 32 : 0) | (ep.act ? 64 : 0) | (ep.stat_y ? 128 : 0) | (ep.bn_scale ? 512 : 0) |
+         (ep.col_bias ? 1024 : 0);
 }
 
 template <int BN, int STAGES, bool IM2COL, bool CONV>
@@ -176,7 +201,7 @@ static int launch_kmajor_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, 
 // CTA2: CTA pairs (cluster of 2, tcgen05 cta_group::2) on 256-row tiles; `tb` then has a box of BN / 2 rows.
 template <int BN, int STAGES, bool IM2COL, int MODE, bool OF16, bool AF16, bool CTA2>
 static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
-                         const EpiParams& ep, cudaStream_t st) {
+                         const EpiParams& ep, cudaStream_t st, const AExt& ax) {
   constexpr size_t smem = conv_smem_bytes<BN, STAGES, MODE, CTA2>();
   static_assert(smem <= 232448, "shared memory budget of one CTA per SM");
   auto kern = gemm_conv_kernel<BN, STAGES, IM2COL, MODE, OF16, AF16, CTA2>;
@@ -190,20 +215,25 @@ static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
   const unsigned units = (unsigned)(cap / n_tiles * n_tiles);
   KOA_REQUIRE(units > 0, "more n-tiles than SMs");
   // MODE 1 moves its epilogue operands and its output with the TMA unit: [M, N] views with row pitch ldo
-  CUtensorMap t_out = ta, t_add = ta, t_gate = ta, t_y = ta;
+  CUtensorMap t_out = ta, t_add = ta, t_gate = ta, t_y = ta, t_out2 = ta;
   {
     const uint64_t pitch = (uint64_t)ep.ldo * 2;
     int rc = koa_tmap_2d_sw64(&t_out, ep.out, (uint64_t)n, (uint64_t)m, pitch);
     if (rc) return rc;
   }
-  if (MODE == 1) {
+  if (MODE >= 1) {
     const uint64_t pitch = (uint64_t)ep.ldo * 2;
     int rc;
-    t_add = t_gate = t_y = t_out;
+    t_add = t_gate = t_y = t_out2 = t_out;
     if (ep.add_bf16 && (rc = koa_tmap_2d_sw64(&t_add, ep.add_bf16, (uint64_t)n, (uint64_t)m, pitch))) return rc;
-    if (ep.gate_bf16 && (rc = koa_tmap_2d_sw64(&t_gate, ep.gate_bf16, (uint64_t)n, (uint64_t)m, pitch))) return rc;
-    if (ep.stat_y && (rc = koa_tmap_2d_sw64(&t_y, ep.stat_y, (uint64_t)n, (uint64_t)m, pitch))) return rc;
+    if (MODE == 1 && ep.gate_bf16 && (rc = koa_tmap_2d_sw64(&t_gate, ep.gate_bf16, (uint64_t)n, (uint64_t)m, pitch))) return rc;
+    if (MODE == 1 && ep.stat_y && (rc = koa_tmap_2d_sw64(&t_y, ep.stat_y, (uint64_t)n, (uint64_t)m, pitch))) return rc;
+    if (MODE == 2 && ep.out_bf16_copy && (rc = koa_tmap_2d_sw64(&t_out2, ep.out_bf16_copy, (uint64_t)n, (uint64_t)m, pitch)))
+      return rc;
   }
+  KOA_REQUIRE(ax.kb_split < 0 || (MODE == 1 && !IM2COL), "K concatenation: backward flavour of a plain GEMM only");
+  const CUtensorMap& ta2 = ax.kb_split >= 0 ? *ax.ta2 : ta;
+  const int kb_split = ax.kb_split >= 0 ? ax.kb_split : 0x7fffffff;
   {
     ProfScope prof(st, 0, 2.0 * (double)m * (double)n * (double)k, m, n, k, prof_flavor(IM2COL, ep) | (CTA2 ? 256 : 0));
     if (CTA2) {
@@ -219,9 +249,9 @@ static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, int m, in
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t_out, t_add, t_gate, t_y, m, n, k, g, ep));
+      KOA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, t_out, t_add, t_gate, t_y, ta2, t_out2, m, n, k, kb_split, g, ep));
     } else {
-      kern<<<units, kConvThreads, smem, st>>>(ta, tb, t_out, t_add, t_gate, t_y, m, n, k, g, ep);
+      kern<<<units, kConvThreads, smem, st>>>(ta, tb, t_out, t_add, t_gate, t_y, ta2, t_out2, m, n, k, kb_split, g, ep);
     }
   }
   KOA_LAUNCH_CHECK();
@@ -240,36 +270,42 @@ static int conv_cta2_min_k() { static const int v = env_int("KOA_CONV_CTA2_MINK"
 // mode / format dispatch of the convolution flavour; returns 1 when no instantiation matches (caller falls back)
 template <int BN, int ST0, int ST1, bool IM2COL, bool CTA2>
 static int launch_conv_fmt(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
-                           const EpiParams& ep, cudaStream_t st) {
-  const bool mode1 = ep.add_bf16 != nullptr || ep.gate_bf16 != nullptr || ep.stat_y != nullptr;
+                           const EpiParams& ep, cudaStream_t st, const AExt& ax) {
+  if (ep.bn_scale != nullptr)  // BatchNorm apply (+ residual) + ReLU, fp16 activations (check_epi)
+    return launch_conv_t<BN, ST1, IM2COL, 2, true, true, CTA2>(ta, tb, m, n, k, g, ep, st, ax);
+  const bool mode1 = ep.add_bf16 != nullptr || ep.gate_bf16 != nullptr || ep.stat_y != nullptr || ep.col_bias != nullptr ||
+                     ax.kb_split >= 0;
   if (!mode1) {
-    if (ep.out_f16) return launch_conv_t<BN, ST0, IM2COL, 0, true, false, CTA2>(ta, tb, m, n, k, g, ep, st);
-    return launch_conv_t<BN, ST0, IM2COL, 0, false, false, CTA2>(ta, tb, m, n, k, g, ep, st);
+    if (ep.out_f16) return launch_conv_t<BN, ST0, IM2COL, 0, true, false, CTA2>(ta, tb, m, n, k, g, ep, st, ax);
+    return launch_conv_t<BN, ST0, IM2COL, 0, false, false, CTA2>(ta, tb, m, n, k, g, ep, st, ax);
   }
   if (!ep.out_f16 && conv_mode1_enabled()) {
-    if (ep.act_f16) return launch_conv_t<BN, ST1, IM2COL, 1, false, true, CTA2>(ta, tb, m, n, k, g, ep, st);
-    return launch_conv_t<BN, ST1, IM2COL, 1, false, false, CTA2>(ta, tb, m, n, k, g, ep, st);
+    if (ep.act_f16) return launch_conv_t<BN, ST1, IM2COL, 1, false, true, CTA2>(ta, tb, m, n, k, g, ep, st, ax);
+    return launch_conv_t<BN, ST1, IM2COL, 1, false, false, CTA2>(ta, tb, m, n, k, g, ep, st, ax);
   }
   return 1;
 }
 
 template <int BN, int STAGES, bool IM2COL>
 static int launch_kmajor(const CUtensorMap& ta, const CUtensorMap& tb, int m, int n, int k, const ConvGeom& g,
-                         const EpiParams& ep, cudaStream_t st) {
+                         const EpiParams& ep, cudaStream_t st, const AExt& ax) {
+  const bool only = conv_only(ep) || ax.kb_split >= 0;
   if (conv_epilogue(ep)) {
     const int n_tiles = koa_cdiv(n, BN);
-    if (n_tiles <= conv_max_ntiles() && n_tiles <= koa_num_sms()) {
-      const int rc = launch_conv_fmt<BN, (BN == 128 ? 5 : 6), (BN == 128 ? 4 : 5), IM2COL, false>(ta, tb, m, n, k, g, ep, st);
+    if ((n_tiles <= conv_max_ntiles() || only) && n_tiles <= koa_num_sms()) {
+      const int rc = launch_conv_fmt<BN, (BN == 128 ? 5 : 6), (BN == 128 ? 4 : 5), IM2COL, false>(ta, tb, m, n, k, g, ep, st, ax);
       if (rc != 1) return rc;
     }
+    KOA_REQUIRE(!only, "BatchNorm-apply / col_bias / K-concatenated epilogues: no kernel for %d x %d x %d", m, n, k);
     return launch_kmajor_t<BN, STAGES, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
   }
+  KOA_REQUIRE(!only, "col_bias / K concatenation need a convolution-flavour epilogue");
   return launch_kmajor_t<BN, STAGES, IM2COL, false>(ta, tb, m, n, k, g, ep, st);
 }
 
 template <bool IM2COL>
 static int dispatch_kmajor(const CUtensorMap& ta, const void* b, int m, int n, int k, const ConvGeom& g,
-                           const EpiParams& ep, cudaStream_t st) {
+                           const EpiParams& ep, cudaStream_t st, const AExt& ax = AExt{}) {
   const bool bn128 = (n % 128 == 0);
   CUtensorMap tb;
   int rc;
@@ -279,15 +315,15 @@ static int dispatch_kmajor(const CUtensorMap& ta, const void* b, int m, int n, i
     if (n % 256 == 0 && n / 256 <= koa_num_sms() / 2) {
       rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, 128);
       if (rc) return rc;
-      rc = launch_conv_fmt<256, 5, 4, IM2COL, true>(ta, tb, m, n, k, g, ep, st);
+      rc = launch_conv_fmt<256, 5, 4, IM2COL, true>(ta, tb, m, n, k, g, ep, st, ax);
       if (rc != 1) return rc;
     }
   }
   rc = koa_tmap_2d_bf16(&tb, b, (uint64_t)k, (uint64_t)n, (uint64_t)k * 2, 64, bn128 ? 128 : 64);
   if (rc) return rc;
   // persistent kernel, one CTA per SM: a deep smem ring lets the TMA producer run ahead across tiles
-  if (bn128) return launch_kmajor<128, 5, IM2COL>(ta, tb, m, n, k, g, ep, st);
-  return launch_kmajor<64, 6, IM2COL>(ta, tb, m, n, k, g, ep, st);
+  if (bn128) return launch_kmajor<128, 5, IM2COL>(ta, tb, m, n, k, g, ep, st, ax);
+  return launch_kmajor<64, 6, IM2COL>(ta, tb, m, n, k, g, ep, st, ax);
 }
 
 int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep, cudaStream_t st) {
@@ -300,6 +336,25 @@ int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa
   if (rc) return rc;
   ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
   return dispatch_kmajor<false>(ta, b, m, n, k, g, to_epi(ep, n), st);
+}
+
+// out = epilogue([A1 | A2] . B^T): the k-blocks of A2 follow those of A1 (B has K = k1 + k2 columns)
+int koa_gemm_kcat_launch(const void* a1, int k1, const void* a2, int k2, const void* b, int m, int n,
+                         const koa_epilogue_t* ep, cudaStream_t st) {
+  int rc = check_epi(ep, n);
+  if (rc) return rc;
+  KOA_REQUIRE(m > 0 && n > 0 && k1 > 0 && k2 > 0, "empty GEMM %dx%dx(%d+%d)", m, n, k1, k2);
+  KOA_REQUIRE(k1 % BK == 0 && k2 % BK == 0, "K concatenation needs K1, K2 multiples of %d (got %d, %d)", BK, k1, k2);
+  CUtensorMap ta, ta2;
+  rc = koa_tmap_2d_bf16(&ta, a1, (uint64_t)k1, (uint64_t)m, (uint64_t)k1 * 2, 64, 128);
+  if (rc) return rc;
+  rc = koa_tmap_2d_bf16(&ta2, a2, (uint64_t)k2, (uint64_t)m, (uint64_t)k2 * 2, 64, 128);
+  if (rc) return rc;
+  ConvGeom g = {1, 1, 1, 0, 1, 1, 0};
+  AExt ax;
+  ax.ta2 = &ta2;
+  ax.kb_split = k1 / BK;
+  return dispatch_kmajor<false>(ta, b, m, n, k1 + k2, g, to_epi(ep, n), st, ax);
 }
 
 int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_in, int cin, int cout, int filt_r,
@@ -434,7 +489,7 @@ int koa_conv_grouped_launch(const void* x, const void* w, int n_img, int h, int 
   rc = koa_tmap_2d_bf16(&tb, w, 576, (uint64_t)c, 576 * 2, 64, 64);
   if (rc) return rc;
   ConvGeom g = {hout, wout, stride, 1, 3, 1, 1};
-  return launch_kmajor<64, 6, true>(ta, tb, (int)m, c, 576, g, to_epi(ep, c), st);
+  return launch_kmajor<64, 6, true>(ta, tb, (int)m, c, 576, g, to_epi(ep, c), st, AExt{});
 }
 
 // dw[C][9][64] += per-chunk dense weight gradient of the grouped convolution.
@@ -457,6 +512,10 @@ int koa_conv_grouped_wgrad_launch(const void* dy, const void* x, float* dw, int 
 extern "C" int koa_gemm_bf16(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep,
                              void* stream) {
   return koa_gemm_launch(a, b, m, n, k, ep, (cudaStream_t)stream);
+}
+extern "C" int koa_gemm_kcat_bf16(const void* a1, int k1, const void* a2, int k2, const void* b, int m, int n,
+                                  const koa_epilogue_t* ep, void* stream) {
+  return koa_gemm_kcat_launch(a1, k1, a2, k2, b, m, n, ep, (cudaStream_t)stream);
 }
 extern "C" int koa_conv_fprop_bf16(const void* x, const void* w, int n_img, int h, int w_in, int cin, int cout,
                                    int filt_r, int filt_s, int stride, int pad, const koa_epilogue_t* ep,

@@ -16,6 +16,13 @@
 //     sum(dz * xhat) is accumulated as sum(dz * y) and corrected once per CTA: invstd * (sum(dz*y) - mean * sum(dz)).
 //   * MODE 1 (backward) moves its epilogue operands and its output with the TMA unit ([32 x 32] boxes in the 64-byte
 //     swizzle, which IS the staging layout): no operand registers, no address arithmetic, no row predicates.
+//   * MODE 2 (forward with the BatchNorm already known: eval mode, and the y-free last convolution of a bottleneck in
+//     train mode, fe_engine.cu): value = acc * scale[col] + shift[col] (+ residual [* rscale[col] + rshift[col]]), ReLU,
+//     stored as fp16 and optionally once more as bf16 (the weight-gradient operand of the backward pass): the raw
+//     convolution output never reaches HBM and no BatchNorm-apply pass follows. The residual tile arrives by TMA like the
+//     MODE 1 operands; the per-column coefficients sit in shared memory and are read as warp-wide broadcasts.
+//   * K concatenation (MODE 1, 1x1 only): k-blocks >= kb_split come from a second A tensor (tmA2): the data gradient of the
+//     y-free BatchNorm is ONE GEMM over [G | a2] (fe_engine.cu); `col_bias` is added per column before the gate.
 //   * CTA2: the compute-bound layers run as CTA pairs (cluster of 2 along M, tcgen05.mma.cta_group::2, M = 256): each
 //     CTA stages its own 128 A rows and HALF of the B tile, the pair's tensor cores read both halves, so the
 //     shared-memory fill per FLOP drops from (128 + BN) to (128 + BN / 2) rows per k-block. Only the rank-0 CTA
@@ -28,14 +35,23 @@ namespace koa {
 constexpr int kConvEpiWarps = 16;
 constexpr int kConvThreads = 64 + 32 * kConvEpiWarps;  // TMA warp, MMA warp, 16 epilogue warps
 
-// MODE 0: forward (statistics optional). MODE 1: backward (addend / gate / BatchNorm-backward statistics).
+// MODE 0: forward (statistics optional). MODE 1: backward (addend / gate / BatchNorm-backward statistics / column bias).
+// MODE 2: forward with BatchNorm apply (+ residual) + ReLU in the epilogue, fp16 output + optional bf16 copy.
+template <int BN, int MODE>
+constexpr int conv_coef_floats() {
+  // MODE 0: end-of-kernel statistics exchange; MODE 2: scale, shift, residual scale, residual shift
+  return MODE == 0 ? kConvEpiWarps * 128 : (MODE == 1 ? 0 : 4 * BN);
+}
+template <int MODE>
+constexpr int conv_stage_bufs() { return MODE == 0 ? 1 : (MODE == 1 ? 3 : 2); }
 template <int BN, int STAGES, int MODE, bool CTA2>
 constexpr size_t conv_smem_bytes() {
   // MODE 0: one staging buffer per epilogue warp + the end-of-kernel statistics exchange; MODE 1: three staging
-  // buffers per warp (addend -> output, gate, y), the statistics exchange re-uses them
+  // buffers per warp (addend -> output, gate, y), the statistics exchange re-uses them; MODE 2: two (residual -> fp16
+  // output, bf16 copy)
   return 1024 /*align slack*/ + (size_t)STAGES * (BM * BK * 2 + (CTA2 ? BN / 2 : BN) * BK * 2) + (2 * STAGES + 4) * 8 + 16 +
-         kConvEpiWarps * 8 /*operand mbarriers*/ + (MODE == 0 ? kConvEpiWarps * 128 * sizeof(float) : 0) + 1024 +
-         (size_t)kConvEpiWarps * (MODE == 0 ? 1 : 3) * kStageBytesPerWarp;
+         kConvEpiWarps * 8 /*operand mbarriers*/ + conv_coef_floats<BN, MODE>() * sizeof(float) + 1024 +
+         (size_t)kConvEpiWarps * conv_stage_bufs<MODE>() * kStageBytesPerWarp;
 }
 
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
@@ -66,15 +82,16 @@ template <int BN, int STAGES, bool A_IM2COL, int MODE, bool OF16, bool AF16, boo
 __global__ void __launch_bounds__(kConvThreads, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
-                 const __grid_constant__ CUtensorMap tmGate, const __grid_constant__ CUtensorMap tmY, int M, int N, int K,
-                 ConvGeom g, EpiParams ep) {
+                 const __grid_constant__ CUtensorMap tmGate, const __grid_constant__ CUtensorMap tmY,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmOut2, int M, int N, int K,
+                 int kb_split, ConvGeom g, EpiParams ep) {
   static_assert(BN == 64 || BN == 128 || BN == 256, "tile widths");
   static_assert(BN != 256 || CTA2, "BN = 256 needs the CTA pair (shared-memory budget)");
   constexpr uint32_t B_ROWS = CTA2 ? BN / 2 : BN;    // B rows staged by this CTA
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = B_ROWS * BK * 2;
   constexpr int ACC = 2;
-  constexpr int NSTG = MODE == 0 ? 1 : 3;            // staging buffers per epilogue warp
+  constexpr int NSTG = conv_stage_bufs<MODE>();      // staging buffers per epilogue warp
   constexpr int CH = BN == 256 ? 2 : 1;              // 32-column chunks per epilogue warp and tile
   constexpr int kDrainWarps = BN == 64 ? 8 : 16;     // warps (of one CTA) that read one accumulator stage
   constexpr int kEpiThreads = kConvEpiWarps * 32;
@@ -98,7 +115,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* s_fin0 = reinterpret_cast<float*>(op_bar + kConvEpiWarps);
   // staging buffers: 1024-byte aligned (the 64-byte TMA swizzle pattern is a function of the address bits 4..8)
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(
-      ((uintptr_t)(s_fin0 + (MODE == 0 ? kConvEpiWarps * 128 : 0)) + 1023) & ~(uintptr_t)1023);
+      ((uintptr_t)(s_fin0 + conv_coef_floats<BN, MODE>()) + 1023) & ~(uintptr_t)1023);
+  float* s_coef = s_fin0;  // MODE 2: [4][BN] scale, shift, residual scale, residual shift
   // end-of-kernel statistics exchange [16 warps][CH][16 lanes][4]; MODE 1 re-uses the first staging buffer of each warp
   float* s_fin = MODE == 0 ? s_fin0 : reinterpret_cast<float*>(s_stage);
   constexpr int kFinStride = MODE == 0 ? 128 : NSTG * kStageBytesPerWarp / 4;  // floats between two warps' slots
@@ -124,6 +142,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     if (MODE == 1) {
       tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmAdd); tma_prefetch_desc(&tmGate); tma_prefetch_desc(&tmY);
+      tma_prefetch_desc(&tmA2);
+    } else if (MODE == 2) {
+      tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmAdd); tma_prefetch_desc(&tmOut2);
     } else if (TMA_OUT) {
       tma_prefetch_desc(&tmOut);
     }
@@ -182,13 +203,17 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             fs = (uint16_t)(tap - fr * g.filt_s);
             ca = g.grouped ? n_t * 64 : cb * 64;
           }
+          // K concatenation: the k-blocks from kb_split on read the second A tensor (same rows)
+          const bool second = !A_IM2COL && MODE == 1 && kb >= kb_split;
+          const CUtensorMap* ta = second ? &tmA2 : &tmA;
+          if (second) ca = (kb - kb_split) * BK;
           if (!CTA2) {
             if (A_IM2COL) tma_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], ca, pw, ph, pn, fs, fr);
-            else tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], ca, m0);
+            else tma_load_2d(sA + s * A_BYTES, ta, &full_bar[s], ca, m0);
             tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0);
           } else {
             if (A_IM2COL) tma2_load_im2col_4d(sA + s * A_BYTES, &tmA, &full_bar[s], ca, pw, ph, pn, fs, fr);
-            else tma2_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], ca, m0);
+            else tma2_load_2d(sA + s * A_BYTES, ta, &full_bar[s], ca, m0);
             tma2_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], kb * BK, n0 + (int)(rank * B_ROWS));
           }
         }
@@ -236,8 +261,24 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t stage_y = stage + (NSTG > 2 ? 2 : 0) * kStageBytesPerWarp;
     const LaneMap lm = make_lane_map(lane);
     const bool stats = ep.col_sum != nullptr;
-    const bool has_add = MODE == 1 && ep.add_bf16 != nullptr, has_gate = MODE == 1 && ep.gate_bf16 != nullptr;
+    const bool has_add = MODE >= 1 && ep.add_bf16 != nullptr, has_gate = MODE == 1 && ep.gate_bf16 != nullptr;
     const bool bwd = MODE == 1 && ep.stat_y != nullptr;
+    const bool has_bias = MODE == 1 && ep.col_bias != nullptr;
+    const bool has_out2 = MODE == 2 && ep.out_bf16_copy != nullptr;
+    const bool res_affine = MODE == 2 && ep.res_scale != nullptr;
+    const bool relu = MODE == 2 && ep.act == ACT_RELU;
+    if (MODE == 2) {  // per-column coefficients of this CTA's n-tile -> shared memory (broadcast reads later)
+      for (int i = e * 32 + lane; i < BN; i += kEpiThreads) {
+        const int col = n0 + i;
+        const bool ok = col < N;
+        s_coef[i] = ok ? __ldg(ep.bn_scale + col) : 0.f;
+        s_coef[BN + i] = ok ? __ldg(ep.bn_shift + col) : 0.f;
+        s_coef[2 * BN + i] = (ok && res_affine) ? __ldg(ep.res_scale + col) : 1.f;
+        s_coef[3 * BN + i] = (ok && res_affine) ? __ldg(ep.res_shift + col) : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    }
+    const uint32_t coef_s = smem_u32(s_coef);
     const uint32_t op_bytes = (uint32_t)((has_add ? 1 : 0) + (has_gate ? 1 : 0) + (bwd ? 1 : 0)) * kStageBytesPerWarp;
     uint32_t op_phase = 0;
     // statistics lane mapping: lane = (h, p): column pair (2p, 2p + 1) of the chunk over the 16 rows 2i + h
@@ -261,7 +302,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool col_ok = n < N;
         const bool last = j == CH - 1;
         if (MODE == 0 && TMA_OUT && col_ok && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (MODE == 1 && col_ok && lane == 0) {
+        if (MODE >= 1 && col_ok && lane == 0) {
           // The TMA unit fetches the operand tiles of this chunk ([32 rows][32 columns], 64-byte swizzle = the staging
           // layout; rows past M arrive as zeros) while the accumulator is still being computed. The previous
           // output store must have finished reading the buffer the addend lands in.
@@ -274,7 +315,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // (lane 0 has waited for the previous TMA store to finish reading the staging buffer: no lane may write it earlier)
-        if (MODE == 1 || TMA_OUT) __syncwarp();
+        if (MODE >= 1 || TMA_OUT) __syncwarp();
         if (!waited) {
           mbar_wait(&tmem_full_bar[acc], acc_phase, 0xc00 + acc);
           tc_fence_after();
@@ -295,7 +336,28 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (!col_ok) continue;
 
-        if (MODE == 1 && op_bytes != 0) {
+        if (MODE == 2) {  // BatchNorm apply: acc * scale + shift (coefficients: warp-wide shared-memory broadcasts)
+          const uint32_t cb = coef_s + (uint32_t)cj * 4;
+#pragma unroll
+          for (int t4 = 0; t4 < 8; ++t4) {
+            const uint4 sc = lds128(cb + t4 * 16), sh = lds128(cb + BN * 4 + t4 * 16);
+            r[4 * t4 + 0] = __float_as_uint(fmaf(__uint_as_float(r[4 * t4 + 0]), __uint_as_float(sc.x), __uint_as_float(sh.x)));
+            r[4 * t4 + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * t4 + 1]), __uint_as_float(sc.y), __uint_as_float(sh.y)));
+            r[4 * t4 + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * t4 + 2]), __uint_as_float(sc.z), __uint_as_float(sh.z)));
+            r[4 * t4 + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * t4 + 3]), __uint_as_float(sc.w), __uint_as_float(sh.w)));
+          }
+        }
+        if (has_bias) {  // every lane reads the same 128 bytes: L1 broadcasts (N is a multiple of 32: no column guard)
+#pragma unroll
+          for (int t4 = 0; t4 < 8; ++t4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.col_bias + n) + t4);
+            r[4 * t4 + 0] = __float_as_uint(__uint_as_float(r[4 * t4 + 0]) + b.x);
+            r[4 * t4 + 1] = __float_as_uint(__uint_as_float(r[4 * t4 + 1]) + b.y);
+            r[4 * t4 + 2] = __float_as_uint(__uint_as_float(r[4 * t4 + 2]) + b.z);
+            r[4 * t4 + 3] = __float_as_uint(__uint_as_float(r[4 * t4 + 3]) + b.w);
+          }
+        }
+        if (MODE >= 1 && op_bytes != 0) {
           mbar_wait(&op_bar[e], op_phase, 0xd00 + e);
           op_phase ^= 1;
         }
@@ -305,13 +367,31 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int pc = 0; pc < 4; ++pc) {
             const uint32_t w[4] = {qa[pc].x, qa[pc].y, qa[pc].z, qa[pc].w};
+            float a8[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const float2 a = unpack_bf16x2(w[u]);
-              r[pc * 8 + 2 * u] = __float_as_uint(__uint_as_float(r[pc * 8 + 2 * u]) + a.x);
-              r[pc * 8 + 2 * u + 1] = __float_as_uint(__uint_as_float(r[pc * 8 + 2 * u + 1]) + a.y);
+              // MODE 1: bf16 gradient addend; MODE 2: residual in the forward activation format
+              const float2 a = MODE == 2 ? unpack16<AF16>(w[u]) : unpack_bf16x2(w[u]);
+              a8[2 * u] = a.x; a8[2 * u + 1] = a.y;
             }
+            if (res_affine) {  // the residual is a raw convolution output with its own BatchNorm (downsample branch)
+              const uint32_t cb = coef_s + (uint32_t)(2 * BN + cj + pc * 8) * 4;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const uint4 sc = lds128(cb + hh * 16), sh = lds128(cb + BN * 4 + hh * 16);
+                a8[4 * hh + 0] = fmaf(a8[4 * hh + 0], __uint_as_float(sc.x), __uint_as_float(sh.x));
+                a8[4 * hh + 1] = fmaf(a8[4 * hh + 1], __uint_as_float(sc.y), __uint_as_float(sh.y));
+                a8[4 * hh + 2] = fmaf(a8[4 * hh + 2], __uint_as_float(sc.z), __uint_as_float(sh.z));
+                a8[4 * hh + 3] = fmaf(a8[4 * hh + 3], __uint_as_float(sc.w), __uint_as_float(sh.w));
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[pc * 8 + u] = __float_as_uint(__uint_as_float(r[pc * 8 + u]) + a8[u]);
           }
+        }
+        if (relu) {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) r[u] = __float_as_uint(fmaxf(__uint_as_float(r[u]), 0.f));
         }
         uint4 qv[4];
 #pragma unroll
@@ -336,7 +416,18 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (has_add) __syncwarp();  // every lane has read its addend row: the buffer becomes the output buffer
         row_sts(stage, qv, lm);
-        if (MODE == 1 || TMA_OUT) {
+        if (has_out2) {  // bf16 copy of the same values (weight-gradient operand of the backward pass)
+          uint4 qb[4];
+#pragma unroll
+          for (int pc = 0; pc < 4; ++pc) {
+            qb[pc].x = pack_bf16x2(__uint_as_float(r[pc * 8 + 0]), __uint_as_float(r[pc * 8 + 1]));
+            qb[pc].y = pack_bf16x2(__uint_as_float(r[pc * 8 + 2]), __uint_as_float(r[pc * 8 + 3]));
+            qb[pc].z = pack_bf16x2(__uint_as_float(r[pc * 8 + 4]), __uint_as_float(r[pc * 8 + 5]));
+            qb[pc].w = pack_bf16x2(__uint_as_float(r[pc * 8 + 6]), __uint_as_float(r[pc * 8 + 7]));
+          }
+          row_sts(stage_g, qb, lm);
+        }
+        if (MODE >= 1 || TMA_OUT) {
           fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
           __syncwarp();
           if (lane == 0) {  // rows past M / columns past N are clipped by the TMA unit
@@ -344,6 +435,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              reinterpret_cast<uint64_t>(&tmOut)),
                          "r"(n), "r"(row0), "r"(stage)
                          : "memory");
+            if (has_out2)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmOut2)),
+                           "r"(n), "r"(row0), "r"(stage_g)
+                           : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         } else {
@@ -391,7 +487,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-    if ((MODE == 1 || TMA_OUT) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
+    if ((MODE >= 1 || TMA_OUT) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
     __syncwarp();
 
     if (stats) {

@@ -43,6 +43,12 @@ struct EpiParams {
   int a_f16, b_f16;       // operand format (0 = bf16, 1 = fp16); the launcher enforces a_f16 == b_f16
   int out_f16;            // out / pre_out (16-bit outputs) are fp16 instead of bf16
   int act_f16;            // gate and stat_y (forward activations) are fp16 instead of bf16
+  // convolution flavour only (gemm_conv.cuh):
+  const float* bn_scale;  // MODE 2: value = acc * bn_scale[col] + bn_shift[col] (+ add_bf16 as the 16-bit residual in the
+  const float* bn_shift;  //   act_f16 format, optionally * res_scale[col] + res_shift[col]); act = ACT_RELU; fp16 output
+  const float* res_scale; //   (+ out_bf16_copy)
+  const float* res_shift;
+  const float* col_bias;  // MODE 1: added per column before the gate
   int drop_on;            // dropout (applied after the activation, before the residual add); element index of the
   int drop_cols;          // mask = row * drop_cols + column
   DropSpec drop;

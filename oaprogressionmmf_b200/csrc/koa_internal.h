@@ -8,6 +8,8 @@
 int koa_num_sms();
 
 int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep, cudaStream_t st);
+int koa_gemm_kcat_launch(const void* a1, int k1, const void* a2, int k2, const void* b, int m, int n,
+                         const koa_epilogue_t* ep, cudaStream_t st);
 int koa_conv_fprop_launch(const void* x, const void* w, int n_img, int h, int w_in, int cin, int cout, int filt_r,
                           int filt_s, int stride, int pad, const koa_epilogue_t* ep, cudaStream_t st);
 int koa_gemm_wgrad_launch(const void* dy, const void* x, float* dw, int pixels, int cout, int cin, int x_f16,

@@ -46,9 +46,11 @@ struct KoaBnBwdFin {
   float* dgamma; float* dbeta; float* k0; float* k1; float* k2;
 };
 int koa_k_bn_fused_ok(int c);
-// out = act(bn_a(y) [+ res | + bn_b(y2)]); b may be NULL
+// out = act(bn_a(y) [+ res | + bn_b(y2)]); b may be NULL. out_colsum (optional, fp32 [c], caller zeroes): per-channel sums
+// of the stored fp16 values of `out` (the `s` of the y-free bottleneck tail, bn_gram.cu)
 int koa_k_bn_act_fin(const void* y, const KoaBnFwdFin* a, const void* res, const void* y2, const KoaBnFwdFin* b, void* out,
-                     void* out_bf16, long long rows, int c, int relu, double count, int training, cudaStream_t st);
+                     void* out_bf16, float* out_colsum, long long rows, int c, int relu, double count, int training,
+                     cudaStream_t st);
 // dy = BatchNorm-backward of a (and dy2 of b, sharing dz = dout * (act > 0)); b may be NULL
 int koa_k_bn_bwd_apply_fin(const void* dout, const void* act, const void* y, const KoaBnBwdFin* a, void* dy, const void* y2,
                            const KoaBnBwdFin* b, void* dy2, long long rows, int c, double count, int training,
@@ -62,6 +64,21 @@ int koa_k_bn_bwd_finalize(const float* sum_dz, const float* sum_dzx, const float
 int koa_k_bn_bwd_apply(const void* dout, const void* act, const void* y, const float* k0, const float* k1,
                        const float* k2, void* dy, const void* y2, const float* k0b, const float* k1b, const float* k2b,
                        void* dy2, long long rows, int c, cudaStream_t st);
+
+// ---- y-free bottleneck tail (bn_gram.cu; formulas in its header) -------------------------------------------------
+// hi + lo = gram / count as two fp16 [w][w] matrices
+int koa_k_gram_split(const float* gram, void* hi, void* lo, int w, double count, cudaStream_t st);
+// statistics of y3 = a2 . W3^T from s = colsum(a2) and Q = W3 . Gram / N; w3h: the fp16 forward operand [C][w]
+int koa_k_bn_gram_stats(const void* w3h, const float* sa2, const float* q, const float* gamma, const float* beta,
+                        float* run_mean, float* run_var, float* scale, float* shift, float* mean, float* invstd, int c_out,
+                        int w, double count, cudaStream_t st);
+// t = G^T a2 [C][w]; w3m: fp32 master weights [C][w]; wext: bf16 [w][ld_ext] (columns 0..C-1 written), k2w: bf16 [w][C]
+int koa_k_bn_gram_bwd(const float* t, const void* w3h, const float* w3m, const float* sa2, const float* q, const float* sdz,
+                      const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta, float* dw,
+                      void* wext, void* k2w, float* k0, float* k1, float* k2, int c_out, int w, int ld_ext, double count,
+                      cudaStream_t st);
+// bias[j] = -(k1 . W3)[j]; w3t: bf16 [w][C]
+int koa_k_bn_gram_bias(const void* w3t, const float* k1, float* bias, int w, int c_out, cudaStream_t st);
 
 // ---- pooling / resampling -------------------------------------------------------------------------
 int koa_k_maxpool_fwd(const void* x, void* out, void* out_bf16, void* idx, int n, int h, int w, int c, cudaStream_t st);

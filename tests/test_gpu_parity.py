@@ -260,6 +260,112 @@ def test_gemm_conv_forward_epilogue_fp16(cuda, m, n, k):
     assert _lib.debug_flag() == 0
 
 
+
+@pytest.mark.parametrize("m,n,k", [(333, 256, 64), (40000, 64, 64), (6, 1024, 256), (128 * 148 * 2 + 77, 128, 64), (96, 96, 128),
+                                   (3000, 128, 1024), (1000, 768, 512), (257, 2048, 512), (128 * 74 * 4 + 300, 512, 512)])
+def test_gemm_conv_bn_apply_epilogue(cuda, m, n, k):
+    """conv -> bn -> (+ identity | + bn_d(downsample)) -> relu as ONE kernel (reference _torchvision.py:118-138; here
+    gemm_conv.cuh MODE 2, used by inference and by the y-free tail of a train-mode bottleneck): fp16 operands, per-column
+    scale / shift, fp16 residual with its own optional per-column affine map, fp16 output + bf16 copy; single CTAs and
+    CTA pairs, 1..16 n-tiles, ragged row tiles."""
+    lib = _lib.load()
+    a = _randn(m, k, seed=3).half().contiguous()
+    b = _randn(n, k, seed=4, scale=k ** -0.5).half().contiguous()
+    acc = a.float() @ b.float().t()
+    scale = torch.rand(n, generator=torch.Generator().manual_seed(5)).to(cuda) + 0.5
+    shift = _randn(n, seed=6, scale=0.3)
+    res = _randn(m, n, seed=7).half().contiguous()
+    rs = torch.rand(n, generator=torch.Generator().manual_seed(8)).to(cuda) + 0.5
+    rt = _randn(n, seed=9, scale=0.3)
+    out = torch.empty(m, n, dtype=torch.float16, device=cuda)
+    cp = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+    fmt = dict(a_f16=1, b_f16=1, out_f16=1, act_f16=1)
+    # bn + relu (conv1 / conv2 in inference)
+    ep = _epi(out=out, ldo=n, bn_scale=scale, bn_shift=shift, act=_lib.ACT_RELU, **fmt)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "bn relu")
+    ref = (acc * scale + shift).relu()
+    assert rel(out.float(), ref) < 6e-4, rel(out.float(), ref)
+    # bn, no activation (downsample branch in inference)
+    ep = _epi(out=out, ldo=n, bn_scale=scale, bn_shift=shift, **fmt)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "bn")
+    assert rel(out.float(), acc * scale + shift) < 6e-4
+    # bn + identity + relu, with the bf16 copy (last convolution of an identity block)
+    ep = _epi(out=out, ldo=n, bn_scale=scale, bn_shift=shift, add_bf16=res, act=_lib.ACT_RELU, out_bf16_copy=cp, **fmt)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "bn res relu")
+    ref = (acc * scale + shift + res.float()).relu()
+    assert rel(out.float(), ref) < 6e-4
+    _close_bf16(cp, ref, "bf16 copy of the block output")
+    # bn + bn_d(raw downsample output) + relu (first block of a stage, train mode)
+    ep = _epi(out=out, ldo=n, bn_scale=scale, bn_shift=shift, add_bf16=res, res_scale=rs, res_shift=rt, act=_lib.ACT_RELU, **fmt)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "bn res-affine relu")
+    ref = (acc * scale + shift + res.float() * rs + rt).relu()
+    assert rel(out.float(), ref) < 6e-4
+    # in place over the residual (not used by the engine, but nothing forbids it)
+    io = res.clone()
+    ep = _epi(out=io, ldo=n, bn_scale=scale, bn_shift=shift, add_bf16=io, act=_lib.ACT_RELU, **fmt)
+    _lib.check(lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(ep), _stream()), "bn res in place")
+    assert rel(io.float(), (acc * scale + shift + res.float()).relu()) < 6e-4
+    # a request the flavour cannot serve is rejected, not silently served by another kernel
+    bad = _epi(out=cp, ldo=n, bn_scale=scale, bn_shift=shift)
+    assert lib.koa_gemm_bf16(a.data_ptr(), b.data_ptr(), m, n, k, C.byref(bad), _stream()) == -1
+    assert _lib.debug_flag() == 0
+
+
+@pytest.mark.parametrize("n_img,h,w,cin,cout,k,stride", [(3, 20, 20, 64, 64, 3, 1), (2, 16, 16, 128, 128, 3, 2),
+                                                         (2, 22, 22, 256, 512, 1, 2)])
+def test_conv_bn_apply_epilogue(cuda, n_img, h, w, cin, cout, k, stride):
+    """The same epilogue behind the implicit-GEMM convolutions (3x3 stride 1 / 2, strided 1x1 downsample)."""
+    lib = _lib.load()
+    pad = k // 2
+    x = _randn(n_img, cin, h, w, seed=1).half()
+    wt = _randn(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5).half()
+    scale = torch.rand(cout, generator=torch.Generator().manual_seed(5)).to(cuda) + 0.5
+    shift = _randn(cout, seed=6, scale=0.3)
+    y = F.conv2d(x.float(), wt.float(), stride=stride, padding=pad)
+    ref = (y * scale[None, :, None, None] + shift[None, :, None, None]).relu()
+    xn = _nhwc(x).half().contiguous()
+    wp = wt.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty(ref.shape[0] * ref.shape[2] * ref.shape[3], cout, dtype=torch.float16, device=cuda)
+    ep = _epi(out=out, ldo=cout, bn_scale=scale, bn_shift=shift, act=_lib.ACT_RELU, a_f16=1, b_f16=1, out_f16=1, act_f16=1)
+    _lib.check(lib.koa_conv_fprop_bf16(xn.data_ptr(), wp.data_ptr(), n_img, h, w, cin, cout, k, k, stride, pad, C.byref(ep),
+                                       _stream()), "conv bn relu")
+    assert rel(out.float(), ref.permute(0, 2, 3, 1).reshape(-1, cout)) < 6e-4
+    assert _lib.debug_flag() == 0
+
+
+@pytest.mark.parametrize("m,k1,k2,n", [(333, 256, 64, 64), (40000, 256, 64, 64), (5000, 512, 128, 128), (2500, 2048, 512, 512),
+                                       (128 * 74 * 4 + 300, 1024, 256, 256), (700, 2048, 1024, 1024)])
+def test_gemm_kcat_bias_gate_stats(cuda, m, k1, k2, n):
+    """out = (([A1 | A2] . B^T + bias) * (gate > 0)) with the BatchNorm-backward sums: the data gradient of the y-free
+    bottleneck tail (fe_engine.cu; autograd of _torchvision.py:130-133), K split over two tensors."""
+    lib = _lib.load()
+    a1, a2 = _bf(_randn(m, k1, seed=1)), _bf(_randn(m, k2, seed=2))
+    b = _bf(_randn(n, k1 + k2, seed=3, scale=(k1 + k2) ** -0.5))
+    bias = _randn(n, seed=4, scale=0.2)
+    gate = _randn(m, n, seed=5).relu().half().contiguous()
+    y = (_randn(m, n, seed=6) * 2 + 0.5).half().contiguous()
+    mean = _randn(n, seed=7, scale=0.3)
+    invstd = torch.rand(n, generator=torch.Generator().manual_seed(8)).to(cuda) + 0.5
+    acc = torch.cat([a1, a2], 1).float() @ b.float().t() + bias
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=cuda)
+    s, q = torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    ep = _epi(out=out, ldo=n, col_bias=bias, gate_bf16=gate, col_sum=s, col_sumsq=q, stat_y=y, stat_mean=mean,
+              stat_invstd=invstd, act_f16=1)
+    _lib.check(lib.koa_gemm_kcat_bf16(a1.data_ptr(), k1, a2.data_ptr(), k2, b.data_ptr(), m, n, C.byref(ep), _stream()), "kcat")
+    _close_bf16(out, acc * (gate.float() > 0), "kcat gated")
+    dz = out.double()
+    xhat = ((y.float() - mean) * invstd).double()
+    tol = 2e-4 * float(dz.abs().sum(0).max()) + 1e-3
+    assert float((s.double() - dz.sum(0)).abs().max()) < tol
+    assert float((q.double() - (dz * xhat).sum(0)).abs().max()) < 4 * tol
+    # plain concatenation, no epilogue operands
+    ep = _epi(out=out, ldo=n)
+    _lib.check(lib.koa_gemm_kcat_bf16(a1.data_ptr(), k1, a2.data_ptr(), k2, b.data_ptr(), m, n, C.byref(ep), _stream()), "kcat plain")
+    _close_bf16(out, acc - bias, "kcat plain")
+    assert lib.koa_gemm_kcat_bf16(a1.data_ptr(), 72, a2.data_ptr(), k2, b.data_ptr(), m, n, C.byref(ep), _stream()) == -1
+    assert _lib.debug_flag() == 0
+
+
 def _nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous()
 
@@ -624,7 +730,9 @@ def test_fe_backward_teacher_forced(cuda, arch, xr, b, s, size):
             ykeys.append(f"{p}.downsample.0.y")
     for ui, key in enumerate(ykeys):
         y = taps[key].detach()
-        _ws_view(lib, desc, ws, 0, ui, torch.float16).copy_(_nhwc_f16(y))
+        yv = _ws_view(lib, desc, ws, 0, ui, torch.float16)
+        if yv.numel():  # (the last convolution of a train-mode bottleneck stores no y: bn_gram.cu)
+            yv.copy_(_nhwc_f16(y))
         coef = _ws_view(lib, desc, ws, 6, ui, torch.float32).view(7, -1)
         coef[2].copy_(y.mean(dim=(0, 2, 3)))
         coef[3].copy_(torch.rsqrt(y.var(dim=(0, 2, 3), unbiased=False) + 1e-5))
@@ -639,6 +747,12 @@ def test_fe_backward_teacher_forced(cuda, arch, xr, b, s, size):
         if blk["kind"] == "bottleneck":
             _ws_view(lib, desc, ws, 3, bi, torch.float16).copy_(_nhwc_f16(taps[f"{p}.a2"]))
             _set_bf16_copy(lib, desc, ws, 10, bi, _nhwc_f16(taps[f"{p}.a2"]).bfloat16())
+            sa2 = _ws_view(lib, desc, ws, 12, bi, torch.float32)
+            if sa2.numel():  # y-free tail: its forward state is s = colsum(a2) and Q = W3 . (a2^T a2) / N
+                a2 = _nhwc_f16(taps[f"{p}.a2"]).double().view(-1, sa2.numel())
+                w3 = sd[f"{p}.conv3.weight"].detach().half().double().flatten(1)
+                sa2.copy_(a2.sum(0))
+                _ws_view(lib, desc, ws, 13, bi, torch.float32).copy_((w3 @ (a2.t() @ a2 / a2.shape[0])).flatten())
     a0 = _ws_view(lib, desc, ws, 4, 0, torch.float16)
     p0 = _ws_view(lib, desc, ws, 5, 0, torch.float16)
     idx0 = _ws_view(lib, desc, ws, 7, 0, torch.uint8)
