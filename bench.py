@@ -339,7 +339,7 @@ def run_ours(args):
     # every tcgen05 launch is bracketed by events on its stream. Same model, same batches, still inside a long step.
     from oaprogressionmmf_b200.koamodels import set_branch_streams
 
-    prof_steps = max(1, min(3, args.steps))
+    prof_steps = 0 if args.no_roofline_pass else max(1, min(3, args.steps))
     set_branch_streams(False)
     if not args.skip_e2e:  # (profiler runs replay every launch: no extra warm-up step for them)
         step(*dev_batches[0])
@@ -448,11 +448,12 @@ def run_ours(args):
                     traffic_source=traffic_src,
                     dram_gbs=(traffic / (k_ms / max(1.0, k_n) * 1e-3) / 1e9) if traffic and k_ms > 0 else None,
                     peak_source=peaks["source"], avg_launch_ms=k_ms / max(1.0, k_n), launches_timed=int(k_n),
-                    share_of_step=k_ms / ms_serial_total,
+                    share_of_step=k_ms / max(ms_serial_total, 1e-9),
                     wgrad=dict(kernel="gemm_wgrad_kernel (tcgen05 MN-major split-K)",
                                achieved=(w_flops / (w_ms / 1e3)) / 1e12 if w_ms > 0 else 0.0,
-                               avg_launch_ms=w_ms / max(1.0, w_n), launches_timed=int(w_n), share_of_step=w_ms / ms_serial_total),
-                    timing_pass=dict(steps=prof_steps, ms_per_step=ms_serial_total / prof_steps,
+                               avg_launch_ms=w_ms / max(1.0, w_n), launches_timed=int(w_n),
+                               share_of_step=w_ms / max(ms_serial_total, 1e-9)),
+                    timing_pass=dict(steps=prof_steps, ms_per_step=ms_serial_total / max(1, prof_steps),
                                      note="per-launch CUDA events with the modality branches run one after the other; "
                                           "`value` is measured with the branches on concurrent streams"),
                     whole_step=dict(achieved=value / ws * flops_knee / 1e12, frac=value / ws * flops_knee / 1e12 / peaks["tflops"],
@@ -518,6 +519,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiler runs: skip the end-to-end pass")
     ap.add_argument("--no-full-step", action="store_true", help="skip the forward+backward+Adam measurement")
+    ap.add_argument("--no-roofline-pass", action="store_true", help="profiler runs: skip the per-launch CUDA-event pass")
     ap.add_argument("--profile-dump", default=None, help="write the per-shape tcgen05 kernel timing table to this file")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -72,7 +72,7 @@ typedef struct koa_epilogue {
   const float* stat_invstd;  /* [M, ldo], the forward conv output), i.e. col_sum / col_sumsq = dbeta / dgamma */
   int a_f16, b_f16;          /* operand format: 0 = bf16, 1 = fp16; must be equal (one format per tcgen05 kind::f16 MMA) */
   int out_f16;               /* out / pre_out_bf16 hold fp16 instead of bf16 */
-  int act_f16;               /* gate_bf16 / stat_y (forward activations) hold fp16 instead of bf16 */
+  int act_f16;               /* gate_bf16 / stat_y / aux_bf16 (forward activations) hold fp16 instead of bf16 */
   float drop_p;              /* > 0: dropout after the activation, before the residual add: value *= mask / (1 - p), */
   unsigned int drop_site;    /* mask = koa_dropout_mask(drop_seed, drop_site, M, N, drop_p) (counter-based Philox, */
   unsigned long long drop_seed; /* regenerated in backward instead of stored) */
@@ -196,6 +196,13 @@ int koa_attention_fwd(const void* qkv, void* out, float* probs, int batch, int n
                       void* stream);
 int koa_attention_bwd(const void* qkv, const float* probs, const void* dout, void* dqkv, int batch, int n, int heads,
                       int head_dim, float scale, void* stream);
+/* Same with the format of the forward tensors as an argument: f16 != 0: qkv and out hold fp16 (the transformer's forward
+ * format, KOA_FEAT_F16); dout / dqkv are bf16 either way. n <= 128 tokens with head_dim a multiple of 64 (<= 256) runs
+ * on tcgen05 (one UMMA tile per contraction, attention_tc.cu), other head sizes on CUDA cores. */
+int koa_attention_fwd_fmt(const void* qkv, void* out, float* probs, int batch, int n, int heads, int head_dim, float scale,
+                          int f16, void* stream);
+int koa_attention_bwd_fmt(const void* qkv, const float* probs, const void* dout, void* dqkv, int batch, int n, int heads,
+                          int head_dim, float scale, int f16, void* stream);
 /* (B,1,R,C,S) -> [B*S][R*C]: einops "b ch r c s -> (b s) ch r c" (koafusion/models/_xrNmrMcP.py:209-210). */
 int koa_stem_pack(const float* vol, float* img, int batch, int rc, int slices, void* stream);
 /* nn.MaxPool2d(3, 2, 1) on NHWC (koafusion/models/_torchvision.py:174); idx keeps the winning tap. Forward: fp16
@@ -207,6 +214,12 @@ int koa_maxpool_bwd(const void* dout, const void* idx, void* dx, int n, int h, i
  * counter-based generator). FeaT sites: 4*layer + {0: to_out, 1: ff GELU, 2: ff out}, 0xE000: embedding, 0xF000: head. */
 int koa_dropout_mask(unsigned long long seed, unsigned int site, long long rows, int cols, float p, float* out,
                      void* stream);
+/* nn.Dropout2d on the extractor output (koafusion/models/_xrNmrMcP.py:62-74,226-229: applied to (B*S, C, h, w)), on the
+ * token layout x [n_img][positions][c] fp32: out = x * m[img][ch] with ONE draw per (image, channel) shared by all
+ * positions; m = koa_dropout_mask(seed, site, n_img, c, p). The backward pass is the same call on the gradient.
+ * out may alias x. Site 0xD000 + extractor index in the model classes. */
+int koa_channel_dropout(const float* x, float* out, long long n_img, int positions, int c, unsigned long long seed,
+                        unsigned int site, float p, void* stream);
 /* per-channel sum / sum of squares of a bf16 [rows][c] tensor (stand-alone BatchNorm statistics). */
 int koa_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, void* stream);
 

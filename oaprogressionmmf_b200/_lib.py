@@ -177,10 +177,13 @@ SIGNATURES = {
     "koa_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "koa_attention_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "koa_attention_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "koa_attention_fwd_fmt": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
+    "koa_attention_bwd_fmt": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P]),
     "koa_stem_pack": (_I, [_P, _P, _I, _I, _I, _P]),
     "koa_maxpool_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "koa_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "koa_col_stats": (_I, [_P, _P, _P, C.c_longlong, _I, _P]),
+    "koa_channel_dropout": (_I, [_P, _P, C.c_longlong, _I, _I, C.c_ulonglong, C.c_uint, _F, _P]),
     "koa_dropout_mask": (_I, [C.c_ulonglong, C.c_uint, C.c_longlong, _I, _F, _P, _P]),
     "koa_adam_step": (_I, [_P, _I, C.POINTER(AdamHyper), _P]),
     "koa_resample_linear": (_I, [_P, _I, _P, _I, C.POINTER(_I), C.POINTER(_I), _P, _P, _P]),
@@ -251,6 +254,24 @@ def require_cuda(t, what: str) -> None:
     """The product has no CPU path: a host tensor is an error, never a silent fallback."""
     if not t.is_cuda:
         raise KoaError(f"{what} needs a CUDA tensor: this path has no CPU fallback")
+
+
+def require_same_device(what: str, *tensors):
+    """Every tensor argument of a C call lives on ONE CUDA device (None entries are skipped); returns that device.
+    A host tensor would hand the kernels a host pointer (a sticky illegal-address fault, not an exception); a tensor on
+    another GPU would be read from the wrong device."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        require_cuda(t, what)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise KoaError(f"{what}: tensors on different devices ({dev} and {t.device})")
+    if dev is None:
+        raise KoaError(f"{what}: no tensor argument")
+    return dev
 
 
 def on_device(device):

@@ -200,7 +200,7 @@ __global__ void unpack_conv_dw_kernel(const float* __restrict__ src, float* __re
 
 // bf16 copy and bf16 transpose of a row-major fp32 matrix [rows][cols].
 __global__ void pack_matrix_kernel(const float* __restrict__ src, bf16* __restrict__ dst, bf16* __restrict__ dst_t,
-                                   int rows, int cols) {
+                                   int rows, int cols, int dst_f16) {
   __shared__ float tile[32][33];
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -208,7 +208,10 @@ __global__ void pack_matrix_kernel(const float* __restrict__ src, bf16* __restri
     float v = 0.0f;
     if (r < rows && c < cols) {
       v = src[(long long)r * cols + c];
-      if (dst != nullptr) dst[(long long)r * cols + c] = __float2bfloat16_rn(v);
+      if (dst != nullptr) {  // forward operand: fp16 (transformer forward) or bf16; the transpose (data-gradient operand) is bf16
+        if (dst_f16) reinterpret_cast<__half*>(dst)[(long long)r * cols + c] = __float2half_rn(v);
+        else dst[(long long)r * cols + c] = __float2bfloat16_rn(v);
+      }
     }
     tile[j][threadIdx.x] = v;
   }
@@ -221,11 +224,11 @@ __global__ void pack_matrix_kernel(const float* __restrict__ src, bf16* __restri
   }
 }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n8) {
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n8, int f16) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8];
     load8f(src + i * 8, f);
-    *reinterpret_cast<uint4*>(dst + i * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(dst + i * 8) = f16 ? pack8h(f) : pack8(f);
   }
 }
 
@@ -860,7 +863,8 @@ template <int MAXV>
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, bf16* __restrict__ out_bf16,
                                      float* __restrict__ out_f32, float* __restrict__ mean_out,
-                                     float* __restrict__ rstd_out, int rows, int d, long long x_row_stride, float eps) {
+                                     float* __restrict__ rstd_out, int rows, int d, long long x_row_stride, float eps,
+                                     int out_f16) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -899,7 +903,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
       load8f(beta + col, b);
 #pragma unroll
       for (int u = 0; u < 8; ++u) o[u] = (v[i][u] - mean) * rstd * g[u] + b[u];
-      if (out_bf16 != nullptr) *reinterpret_cast<uint4*>(out_bf16 + (long long)warp * d + col) = pack8(o);
+      if (out_bf16 != nullptr) *reinterpret_cast<uint4*>(out_bf16 + (long long)warp * d + col) = out_f16 ? pack8h(o) : pack8(o);
       if (out_f32 != nullptr) {
         float* dst = out_f32 + (long long)warp * d + col;
         *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
@@ -1103,32 +1107,54 @@ __global__ void linear_small_dw_kernel(const float* __restrict__ dpre, const flo
 __global__ void focal_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                   float* __restrict__ loss, float* __restrict__ dlogits, int batch, int classes,
                                   float gamma) {
-  __shared__ float sacc;
-  if (threadIdx.x == 0) sacc = 0.0f;
-  __syncthreads();
+  // fixed-order reduction (per-thread partial -> warp shuffle -> warp partials summed in order): the loss is
+  // bit-reproducible from run to run
+  __shared__ float s_part[32];
+  float part = 0.0f;
+  bool bad = false;
   for (int b = threadIdx.x; b < batch; b += blockDim.x) {
     const float* z = logits + (long long)b * classes;
+    const long long tl = target[b];
+    if (tl < 0 || tl >= classes) {  // F.cross_entropy of the reference trips a device assert here: NaN loss + diagnostic word
+      bad = true;
+      if (dlogits != nullptr)
+        for (int j = 0; j < classes; ++j) dlogits[(long long)b * classes + j] = __int_as_float(0x7fc00000);
+      continue;
+    }
+    const int t = (int)tl;
     float mx = -INFINITY;
     for (int j = 0; j < classes; ++j) mx = fmaxf(mx, z[j]);
     float se = 0.0f;
     for (int j = 0; j < classes; ++j) se += expf(z[j] - mx);
-    const int t = (int)target[b];
     const float logpt = z[t] - mx - logf(se);
     const float pt = expf(logpt);
-    const float om = 1.0f - pt;
-    const float l = -powf(om, gamma) * logpt;
-    atomicAdd(&sacc, l);
+    const float om = fmaxf(1.0f - pt, 0.0f);
+    const float omg = gamma == 0.0f ? 1.0f : powf(om, gamma);
+    part += -omg * logpt;
     if (dlogits != nullptr) {
-      // dl/dlogpt = gamma*(1-pt)^(gamma-1)*pt*logpt - (1-pt)^gamma ; dlogpt/dz_j = [j==t] - p_j
-      const float dl = gamma * powf(om, gamma - 1.0f) * pt * logpt - powf(om, gamma);
+      // dl/dlogpt = gamma*(1-pt)^(gamma-1)*pt*logpt - (1-pt)^gamma ; dlogpt/dz_j = [j==t] - p_j.
+      // pt -> 1: logpt ~ -(1-pt), so the first term -> -gamma*(1-pt)^gamma*pt (finite for every gamma > 0; the literal
+      // expression is inf * 0 for gamma < 1)
+      const float first = om > 0.0f ? gamma * powf(om, gamma - 1.0f) * pt * logpt : 0.0f;
+      const float dl = first - omg;
       for (int j = 0; j < classes; ++j) {
         const float pj = expf(z[j] - mx) / se;
         dlogits[(long long)b * classes + j] = dl * ((j == t ? 1.0f : 0.0f) - pj) / (float)batch;
       }
     }
   }
+  if (bad) {
+    atomicOr(&g_koa_debug_flag, 0xF0CA1u);  // koa_debug_flag(): a target outside [0, classes)
+    part = __int_as_float(0x7fc00000);
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
   __syncthreads();
-  if (threadIdx.x == 0) *loss = sacc / (float)batch;
+  if (threadIdx.x == 0) {
+    float tot = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
+    *loss = tot / (float)batch;
+  }
 }
 
 }  // namespace
@@ -1180,15 +1206,15 @@ int koa_k_unpack_conv_dw(const float* src, float* dst, int cout, int cin, int fr
   KOA_LAUNCH_CHECK();
   return 0;
 }
-int koa_k_pack_matrix(const float* src, void* dst, void* dst_t, int rows, int cols, cudaStream_t st) {
+int koa_k_pack_matrix(const float* src, void* dst, void* dst_t, int rows, int cols, cudaStream_t st, int dst_f16) {
   dim3 grid(koa_cdiv(cols, 32), koa_cdiv(rows, 32)), block(32, 8);
-  pack_matrix_kernel<<<grid, block, 0, st>>>(src, (bf16*)dst, (bf16*)dst_t, rows, cols);
+  pack_matrix_kernel<<<grid, block, 0, st>>>(src, (bf16*)dst, (bf16*)dst_t, rows, cols, dst_f16);
   KOA_LAUNCH_CHECK();
   return 0;
 }
-int koa_k_cast_bf16(const float* src, void* dst, long long n, cudaStream_t st) {
+int koa_k_cast_bf16(const float* src, void* dst, long long n, cudaStream_t st, int f16) {
   KOA_REQUIRE(n % 8 == 0, "cast length must be a multiple of 8");
-  cast_f32_bf16_kernel<<<grid_for(n / 8), kThreads, 0, st>>>(src, (bf16*)dst, n / 8);
+  cast_f32_bf16_kernel<<<grid_for(n / 8), kThreads, 0, st>>>(src, (bf16*)dst, n / 8, f16);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1338,15 +1364,15 @@ int koa_k_scatter_add2(const void* src, const void* gate, void* dx, int n, int h
   return 0;
 }
 int koa_k_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
-                        float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st) {
+                        float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st, int out_f16) {
   KOA_REQUIRE(d % 256 == 0 && d <= 4096, "LayerNorm width %d must be a multiple of 256 and <= 4096", d);
   const int blocks = koa_cdiv((long long)rows * 32, kThreads);
   if (d <= 2048)
     layernorm_fwd_kernel<8><<<blocks, kThreads, 0, st>>>(x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d,
-                                                         x_row_stride, 1e-5f);
+                                                         x_row_stride, 1e-5f, out_f16);
   else
     layernorm_fwd_kernel<16><<<blocks, kThreads, 0, st>>>(x, gamma, beta, (bf16*)out_bf16, out_f32, mean, rstd, rows, d,
-                                                          x_row_stride, 1e-5f);
+                                                          x_row_stride, 1e-5f, out_f16);
   KOA_LAUNCH_CHECK();
   return 0;
 }
@@ -1439,6 +1465,33 @@ __global__ void dropout_apply_kernel(DropSpec d, long long quads, float* __restr
   }
 }
 }  // namespace
+namespace {
+// nn.Dropout2d on the (N, C, h, w) extractor output, stored here as tokens [n_img][positions][c]: ONE mask value per
+// (image, channel), shared by every spatial position. Mask element (img, ch) = element img * c + ch of the (seed, site)
+// stream, i.e. koa_dropout_mask(seed, site, n_img, c, p) is exactly the mask applied.
+__global__ void channel_dropout_kernel(DropSpec d, const float* __restrict__ x, float* __restrict__ out, long long n_img,
+                                       int positions, int c) {
+  const int cq = c / 4;
+  const long long total = n_img * positions * cq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % cq);
+    const long long img = i / ((long long)cq * positions);
+    float s[4];
+    drop_scales4(d, (unsigned long long)(img * cq + q), s);
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4(v.x * s[0], v.y * s[1], v.z * s[2], v.w * s[3]);
+  }
+}
+}  // namespace
+int koa_k_channel_dropout(const float* x, float* out, long long n_img, int positions, int c, unsigned long long seed,
+                          unsigned int site, float p, cudaStream_t st) {
+  KOA_REQUIRE(n_img > 0 && positions > 0 && c > 0 && c % 4 == 0, "channel dropout needs C %% 4 == 0 (got %d)", c);
+  KOA_REQUIRE(p >= 0.0f && p < 1.0f, "dropout probability %f out of range", (double)p);
+  const long long total = n_img * positions * (c / 4);
+  channel_dropout_kernel<<<grid_for(total), kThreads, 0, st>>>(make_drop_spec(seed, site, p), x, out, n_img, positions, c);
+  KOA_LAUNCH_CHECK();
+  return 0;
+}
 int koa_k_dropout_mask(unsigned long long seed, unsigned int site, long long n, float p, float* out, cudaStream_t st) {
   KOA_REQUIRE(n > 0 && p >= 0.0f && p < 1.0f && out != nullptr, "bad dropout mask request");
   dropout_mask_kernel<<<grid_for((n + 3) / 4), kThreads, 0, st>>>(make_drop_spec(seed, site, p), n, out);
@@ -1450,6 +1503,12 @@ int koa_k_dropout_apply(float* x_inplace, const float* x, void* out_bf16, unsign
   KOA_REQUIRE(n > 0 && n % 4 == 0 && p >= 0.0f && p < 1.0f && (x_inplace != nullptr || x != nullptr), "bad dropout request");
   dropout_apply_kernel<<<grid_for(n / 4), kThreads, 0, st>>>(make_drop_spec(seed, site, p), n / 4, x_inplace, x, (bf16*)out_bf16);
   KOA_LAUNCH_CHECK();
+  return 0;
+}
+int koa_k_debug_flag_elementwise(unsigned int* out) {
+  unsigned int zero = 0;
+  KOA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_koa_debug_flag, sizeof(unsigned int)));
+  KOA_CHECK_CUDA(cudaMemcpyToSymbol(g_koa_debug_flag, &zero, sizeof(unsigned int)));
   return 0;
 }
 int koa_k_focal_loss(const float* logits, const long long* target, float* loss, float* dlogits, int batch, int classes,

@@ -4,8 +4,13 @@
 // LayerNorm/Linear/GELU/Linear classification head on token 0.
 //
 // Every Linear is a tcgen05 GEMM (gemm_api.cu) with its bias / GELU / residual fused in the epilogue;
-// the residual stream stays fp32, GEMM operands are bf16. LayerNorm, attention (n <= 128 tokens), token
-// assembly and bias gradients are the kernels of elementwise.cu / attention.cu.
+// the residual stream stays fp32. Forward GEMM operands (weights, LayerNorm outputs, q/k/v, attention output, GELU
+// output) are fp16 (KOA_FEAT_F16, default 1): everything here sits behind a LayerNorm or a softmax, so the fp16 range is
+// not an issue, and the 11-bit significand brings the logits within BASELINE.json's 1e-2 of the fp32 reference where
+// bf16 operands left them at 2e-2 (the head's hidden activations alone carried 2^-9 per element). Gradients are bf16;
+// the weight-gradient GEMMs convert their fp16 activation operand in shared memory (gemm_wgrad_kernel XCVT).
+// LayerNorm, attention (n <= 128 tokens), token assembly and bias gradients are the kernels of elementwise.cu /
+// attention.cu.
 //
 // Parameter / gradient tables (fp32 device pointers, reference state_dict order, _core_trf.py:99-116,189-193):
 //   [0] cls_token (NULL when with_cls == 0)  [1] pos_embedding  [2] patch_to_embedding.weight  [3] .bias
@@ -52,6 +57,15 @@ struct Bump {
     return o;
   }
 };
+
+// forward operand format of the transformer: 1 = fp16 (default), 0 = bf16 (the round-1 arithmetic)
+int feat_f16() {
+  static const int v = [] {
+    const char* e = getenv("KOA_FEAT_F16");
+    return e == nullptr ? 1 : (atoi(e) != 0 ? 1 : 0);
+  }();
+  return v;
+}
 
 int build_plan(const koa_feat_desc_t* d, Plan& p) {
   KOA_REQUIRE(d != nullptr, "null descriptor");
@@ -155,9 +169,11 @@ struct Drop {
 };
 
 __global__ void gelu_bwd_rows_kernel(const float* __restrict__ d, const bf16* __restrict__ pre, bf16* __restrict__ out,
-                                     long long total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16_rn(d[i] * koa::gelu_erf_grad(__bfloat162float(pre[i])));
+                                     long long total, int pre_f16) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float h = pre_f16 ? __half2float(reinterpret_cast<const __half*>(pre)[i]) : __bfloat162float(pre[i]);
+    out[i] = __float2bfloat16_rn(d[i] * koa::gelu_erf_grad(h));
+  }
 }
 
 }  // namespace
@@ -190,11 +206,14 @@ extern "C" int koa_feat_forward(const koa_feat_desc_t* d, const void* const* par
   const bool bw = d->need_backward != 0;
   const float scale = 1.0f / sqrtf((float)D);  // reference quirk: model dim, not head dim (_core_trf.py:160)
   const Drop drop(d);
+  const int hf = feat_f16();  // forward operands in fp16
+  auto fmt = [hf](koa_epilogue_t& e) { e.a_f16 = e.b_f16 = e.out_f16 = hf; };
 
-  KOA_TRY(koa_k_cast_bf16(tokens, at(ws, p.tok_bf16), p.Mp * D, st));
-  KOA_TRY(koa_k_pack_matrix(pr.pe_w(), at(ws, p.w_pe), bw ? at(ws, p.w_pe_t) : nullptr, D, D, st));
+  KOA_TRY(koa_k_cast_bf16(tokens, at(ws, p.tok_bf16), p.Mp * D, st, hf));
+  KOA_TRY(koa_k_pack_matrix(pr.pe_w(), at(ws, p.w_pe), bw ? at(ws, p.w_pe_t) : nullptr, D, D, st, hf));
   {
     koa_epilogue_t ep{};
+    fmt(ep);
     ep.out = at(ws, p.emb); ep.out_fp32 = 1; ep.bias = pr.pe_b();
     KOA_TRY(linear(at(ws, p.tok_bf16), at(ws, p.w_pe), p.Mp, D, D, &ep, st));
   }
@@ -207,35 +226,39 @@ extern "C" int koa_feat_forward(const koa_feat_desc_t* d, const void* const* par
     float* x_in = atf(ws, L.x_in);
     float* x_mid = atf(ws, L.x_mid);
     float* x_next = atf(ws, l + 1 < p.depth ? p.L[l + 1].x_in : p.x_final);
-    KOA_TRY(koa_k_pack_matrix(pr.layer(l, P_QKV_W), at(ws, L.w_qkv), bw ? at(ws, L.w_qkv_t) : nullptr, 3 * D, D, st));
-    KOA_TRY(koa_k_pack_matrix(pr.layer(l, P_OUT_W), at(ws, L.w_out), bw ? at(ws, L.w_out_t) : nullptr, D, D, st));
-    KOA_TRY(koa_k_pack_matrix(pr.layer(l, P_FF0_W), at(ws, L.w_ff0), bw ? at(ws, L.w_ff0_t) : nullptr, mlp, D, st));
-    KOA_TRY(koa_k_pack_matrix(pr.layer(l, P_FF3_W), at(ws, L.w_ff3), bw ? at(ws, L.w_ff3_t) : nullptr, D, mlp, st));
+    KOA_TRY(koa_k_pack_matrix(pr.layer(l, P_QKV_W), at(ws, L.w_qkv), bw ? at(ws, L.w_qkv_t) : nullptr, 3 * D, D, st, hf));
+    KOA_TRY(koa_k_pack_matrix(pr.layer(l, P_OUT_W), at(ws, L.w_out), bw ? at(ws, L.w_out_t) : nullptr, D, D, st, hf));
+    KOA_TRY(koa_k_pack_matrix(pr.layer(l, P_FF0_W), at(ws, L.w_ff0), bw ? at(ws, L.w_ff0_t) : nullptr, mlp, D, st, hf));
+    KOA_TRY(koa_k_pack_matrix(pr.layer(l, P_FF3_W), at(ws, L.w_ff3), bw ? at(ws, L.w_ff3_t) : nullptr, D, mlp, st, hf));
     KOA_TRY(koa_k_layernorm_fwd(x_in, pr.layer(l, P_LN0_W), pr.layer(l, P_LN0_B), at(ws, L.ln0), nullptr, atf(ws, L.st0),
-                                atf(ws, L.st0) + p.M, (int)p.M, D, D, st));
+                                atf(ws, L.st0) + p.M, (int)p.M, D, D, st, hf));
     {
       koa_epilogue_t ep{};
+      fmt(ep);
       ep.out = at(ws, L.qkv);
       KOA_TRY(linear(at(ws, L.ln0), at(ws, L.w_qkv), p.M, 3 * D, D, &ep, st));
     }
     KOA_TRY(koa_k_attention_fwd(at(ws, L.qkv), at(ws, L.attn_out), atf(ws, L.probs), p.B, p.n, p.heads, D / p.heads,
-                                scale, st));
+                                scale, st, hf));
     {
       koa_epilogue_t ep{};
+      fmt(ep);
       ep.out = x_mid; ep.out_fp32 = 1; ep.bias = pr.layer(l, P_OUT_B); ep.residual_f32 = x_in;
       drop.set(ep, site_attn_out(l));
       KOA_TRY(linear(at(ws, L.attn_out), at(ws, L.w_out), p.M, D, D, &ep, st));
     }
     KOA_TRY(koa_k_layernorm_fwd(x_mid, pr.layer(l, P_LN1_W), pr.layer(l, P_LN1_B), at(ws, L.ln1), nullptr, atf(ws, L.st1),
-                                atf(ws, L.st1) + p.M, (int)p.M, D, D, st));
+                                atf(ws, L.st1) + p.M, (int)p.M, D, D, st, hf));
     {
       koa_epilogue_t ep{};
+      fmt(ep);
       ep.out = at(ws, L.g); ep.bias = pr.layer(l, P_FF0_B); ep.act = KOA_ACT_GELU; ep.pre_out_bf16 = at(ws, L.h_pre);
       drop.set(ep, site_ff_act(l));
       KOA_TRY(linear(at(ws, L.ln1), at(ws, L.w_ff0), p.M, mlp, D, &ep, st));
     }
     {
       koa_epilogue_t ep{};
+      fmt(ep);
       ep.out = x_next; ep.out_fp32 = 1; ep.bias = pr.layer(l, P_FF3_B); ep.residual_f32 = x_mid;
       drop.set(ep, site_ff_out(l));
       KOA_TRY(linear(at(ws, L.g), at(ws, L.w_ff3), p.M, D, mlp, &ep, st));
@@ -247,10 +270,11 @@ extern "C" int koa_feat_forward(const koa_feat_desc_t* d, const void* const* par
   if (d->compute_head) {
     KOA_REQUIRE(logits_out != nullptr, "compute_head needs logits_out");
     const float* xf = atf(ws, p.x_final);
-    KOA_TRY(koa_k_pack_matrix(pr.head(H_1_W), at(ws, p.w_h1), bw ? at(ws, p.w_h1_t) : nullptr, mlp, D, st));
+    KOA_TRY(koa_k_pack_matrix(pr.head(H_1_W), at(ws, p.w_h1), bw ? at(ws, p.w_h1_t) : nullptr, mlp, D, st, hf));
     KOA_TRY(koa_k_layernorm_fwd(xf, pr.head(H_LN_W), pr.head(H_LN_B), at(ws, p.cls_ln), nullptr, atf(ws, p.st_h),
-                                atf(ws, p.st_h) + p.B, p.B, D, (long long)p.n * D, st));
+                                atf(ws, p.st_h) + p.B, p.B, D, (long long)p.n * D, st, hf));
     koa_epilogue_t ep{};
+    fmt(ep);
     ep.out = at(ws, p.hh); ep.out_fp32 = 1; ep.bias = pr.head(H_1_B); ep.act = KOA_ACT_GELU;
     ep.pre_out_bf16 = at(ws, p.hh_pre);
     drop.set(ep, kSiteHead);
@@ -274,6 +298,8 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
   const long long M = p.M;
   const float scale = 1.0f / sqrtf((float)D);
   const Drop drop(d);
+  const int hf = feat_f16();
+  const int xf = hf ? 2 : 0;  // weight gradients: the saved forward activation is fp16, converted to bf16 inside the kernel
 
   float* dx = atf(ws, p.dxa);
   float* dx_other = atf(ws, p.dxb);
@@ -287,10 +313,10 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
     const long long tot = (long long)p.B * mlp;
     if (drop.mlp) KOA_TRY(koa_k_dropout_apply(atf(ws, p.d_hh), nullptr, nullptr, drop.seed, kSiteHead, tot, drop.p_mlp, st));
     gelu_bwd_rows_kernel<<<koa_cdiv(tot, 256), 256, 0, st>>>(atf(ws, p.d_hh), (const bf16*)at(ws, p.hh_pre),
-                                                             (bf16*)at(ws, p.d_hpre), tot);
+                                                             (bf16*)at(ws, p.d_hpre), tot, hf);
     KOA_LAUNCH_CHECK();
     KOA_TRY(koa_k_col_sum(at(ws, p.d_hpre), 1, gr.head(H_1_B), p.B, mlp, mlp, st));
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.d_hpre), at(ws, p.cls_ln), gr.head(H_1_W), p.B, mlp, D, 0, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.d_hpre), at(ws, p.cls_ln), gr.head(H_1_W), p.B, mlp, D, xf, st));
     koa_epilogue_t ep{};
     ep.out = at(ws, p.d_clsln); ep.out_fp32 = 1;
     KOA_TRY(linear(at(ws, p.d_hpre), at(ws, p.w_h1_t), p.B, D, mlp, &ep, st));
@@ -311,15 +337,15 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
     } else {
       KOA_TRY(koa_k_col_sum(dx, 0, gr.layer(l, P_FF3_B), M, D, D, st));
     }
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.g), gr.layer(l, P_FF3_W), (int)M, D, mlp, 0, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.g), gr.layer(l, P_FF3_W), (int)M, D, mlp, xf, st));
     {
       koa_epilogue_t ep{};
-      ep.out = at(ws, p.dh); ep.act = KOA_ACT_GELU_GRAD; ep.aux_bf16 = at(ws, L.h_pre);
+      ep.out = at(ws, p.dh); ep.act = KOA_ACT_GELU_GRAD; ep.aux_bf16 = at(ws, L.h_pre); ep.act_f16 = hf;
       drop.set(ep, site_ff_act(l));
       KOA_TRY(linear(at(ws, p.dx_bf16), at(ws, L.w_ff3_t), M, mlp, D, &ep, st));
     }
     KOA_TRY(koa_k_col_sum(at(ws, p.dh), 1, gr.layer(l, P_FF0_B), M, mlp, mlp, st));
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dh), at(ws, L.ln1), gr.layer(l, P_FF0_W), (int)M, mlp, D, 0, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dh), at(ws, L.ln1), gr.layer(l, P_FF0_W), (int)M, mlp, D, xf, st));
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, p.d_ln); ep.out_fp32 = 1;
@@ -335,15 +361,15 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
     } else {
       KOA_TRY(koa_k_col_sum(dx_other, 0, gr.layer(l, P_OUT_B), M, D, D, st));
     }
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.attn_out), gr.layer(l, P_OUT_W), (int)M, D, D, 0, st));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dx_bf16), at(ws, L.attn_out), gr.layer(l, P_OUT_W), (int)M, D, D, xf, st));
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, p.dattn);
       KOA_TRY(linear(at(ws, p.dx_bf16), at(ws, L.w_out_t), M, D, D, &ep, st));
     }
     KOA_TRY(koa_k_attention_bwd(at(ws, L.qkv), atf(ws, L.probs), at(ws, p.dattn), at(ws, p.dqkv), p.B, p.n, p.heads,
-                                D / p.heads, scale, st));
-    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dqkv), at(ws, L.ln0), gr.layer(l, P_QKV_W), (int)M, 3 * D, D, 0, st));
+                                D / p.heads, scale, st, hf));
+    KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.dqkv), at(ws, L.ln0), gr.layer(l, P_QKV_W), (int)M, 3 * D, D, xf, st));
     {
       koa_epilogue_t ep{};
       ep.out = at(ws, p.d_ln); ep.out_fp32 = 1;
@@ -358,7 +384,7 @@ extern "C" int koa_feat_backward(const koa_feat_desc_t* d, const void* const* pa
   float* dcls = p.n_cls ? gr.at(0) : nullptr;
   KOA_TRY(koa_k_token_assemble_bwd(dx, gr.at(1), dcls, at(ws, p.d_emb), p.B, p.n, p.n_cls, D, st));
   KOA_TRY(koa_k_col_sum(at(ws, p.d_emb), 1, gr.at(3), p.Mp, D, D, st));
-  KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.d_emb), at(ws, p.tok_bf16), gr.at(2), (int)p.Mp, D, D, 0, st));
+  KOA_TRY(koa_gemm_wgrad_launch(at(ws, p.d_emb), at(ws, p.tok_bf16), gr.at(2), (int)p.Mp, D, D, xf, st));
   if (d_tokens != nullptr) {
     koa_epilogue_t ep{};
     ep.out = d_tokens; ep.out_fp32 = 1;

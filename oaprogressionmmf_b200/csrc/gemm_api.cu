@@ -90,9 +90,13 @@ extern "C" int koa_profile_read(double* out) {
 extern "C" int koa_version(void) { return 1; }
 
 extern "C" int koa_debug_flag(unsigned int* out) {
-  unsigned int zero = 0;
+  unsigned int zero = 0, other = 0;
   KOA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_koa_debug_flag, sizeof(unsigned int)));
   KOA_CHECK_CUDA(cudaMemcpyToSymbol(g_koa_debug_flag, &zero, sizeof(unsigned int)));
+  // the diagnostic word is one variable per translation unit: fold in the element-wise kernels' copy (focal-loss targets)
+  int rc = koa_k_debug_flag_elementwise(&other);
+  if (rc) return rc;
+  *out |= other;
   return 0;
 }
 

@@ -166,13 +166,25 @@ __device__ __forceinline__ void pack_row_16(uint4 (&q)[4], const float (&v)[32],
   }
 }
 // staged coalesced tile -> this thread's row as 32 floats (whole warp; syncs on both sides)
-__device__ __forceinline__ void tile_to_row_bf16(float (&f)[32], uint32_t stage, const uint4 (&t)[4], const LaneMap& lm) {
+__device__ __forceinline__ void tile_to_row_bf16(float (&f)[32], uint32_t stage, const uint4 (&t)[4], const LaneMap& lm,
+                                                 bool f16 = false) {
   tile_sts(stage, t, lm);
   __syncwarp();
   uint4 q[4];
   row_lds(q, stage, lm);
   __syncwarp();
-  unpack_row_bf16(f, q);
+  if (!f16) {
+    unpack_row_bf16(f, q);
+  } else {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float2 a;
+      a = unpack_f16x2(q[p].x); f[p * 8 + 0] = a.x; f[p * 8 + 1] = a.y;
+      a = unpack_f16x2(q[p].y); f[p * 8 + 2] = a.x; f[p * 8 + 3] = a.y;
+      a = unpack_f16x2(q[p].z); f[p * 8 + 4] = a.x; f[p * 8 + 5] = a.y;
+      a = unpack_f16x2(q[p].w); f[p * 8 + 6] = a.x; f[p * 8 + 7] = a.y;
+    }
+  }
 }
 
 // Coalesced write-back of a staged [32 rows][64 bytes] tile; rows >= rows_valid are skipped.
@@ -261,7 +273,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint64_t* release
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
     } else if (ep.act == ACT_GELU_GRAD) {
       float h[32];
-      tile_to_row_bf16(h, stage, t_y, lm);
+      tile_to_row_bf16(h, stage, t_y, lm, ep.act_f16 != 0);  // the saved pre-activation is a forward tensor
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= gelu_erf_grad(h[j]);
     }

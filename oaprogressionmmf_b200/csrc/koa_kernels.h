@@ -20,8 +20,9 @@ struct KoaPackJob {
 };
 constexpr int kKoaMaxPackJobs = 64;
 int koa_k_pack_fe_weights(const KoaPackJob* jobs, int n_jobs, cudaStream_t st);
-int koa_k_pack_matrix(const float* src, void* dst, void* dst_t, int rows, int cols, cudaStream_t st);
-int koa_k_cast_bf16(const float* src, void* dst, long long n, cudaStream_t st);
+// dst: 16-bit copy (fp16 when dst_f16, else bf16), dst_t: bf16 transpose (data-gradient operand); either may be NULL
+int koa_k_pack_matrix(const float* src, void* dst, void* dst_t, int rows, int cols, cudaStream_t st, int dst_f16 = 0);
+int koa_k_cast_bf16(const float* src, void* dst, long long n, cudaStream_t st, int f16 = 0);
 
 // ---- BatchNorm ------------------------------------------------------------------------------------
 int koa_k_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, float* run_mean,
@@ -91,7 +92,7 @@ int koa_k_scatter_add2(const void* src, const void* gate, void* dx, int n, int h
 
 // ---- transformer pieces ---------------------------------------------------------------------------
 int koa_k_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* out_bf16, float* out_f32,
-                        float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st);
+                        float* mean, float* rstd, int rows, int d, long long x_row_stride, cudaStream_t st, int out_f16 = 0);
 int koa_k_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                         const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int rows, int d,
                         long long x_row_stride, long long dx_row_stride, cudaStream_t st);
@@ -111,15 +112,26 @@ int koa_k_dropout_mask(unsigned long long seed, unsigned int site, long long n, 
 // x *= mask in place (fp32) and/or out_bf16 = bf16(x * mask); n % 4 == 0
 int koa_k_dropout_apply(float* x_inplace, const float* x, void* out_bf16, unsigned long long seed, unsigned int site,
                         long long n, float p, cudaStream_t st);
+// out = x * mask[img][ch] for tokens x [n_img][positions][c] (nn.Dropout2d: one draw per image and channel)
+int koa_k_channel_dropout(const float* x, float* out, long long n_img, int positions, int c, unsigned long long seed,
+                          unsigned int site, float p, cudaStream_t st);
 int koa_k_focal_loss(const float* logits, const long long* target, float* loss, float* dlogits, int batch, int classes,
                      float gamma, cudaStream_t st);
 
 // ---- attention (attention.cu) -----------------------------------------------------------------------
 // qkv: bf16 [B*n][3*D] with feature index = (qkv, head, d); out: bf16 [B*n][D]; probs: fp32 [B][H][n][n].
+// f16: qkv and out are fp16 (the transformer's forward format); gradients (dout, dqkv) are always bf16
 int koa_k_attention_fwd(const void* qkv, void* out, float* probs, int batch, int n, int heads, int head_dim, float scale,
-                        cudaStream_t st);
+                        cudaStream_t st, int f16 = 0);
 int koa_k_attention_bwd(const void* qkv, const float* probs, const void* dout, void* dqkv, int batch, int n, int heads,
-                        int head_dim, float scale, cudaStream_t st);
+                        int head_dim, float scale, cudaStream_t st, int f16 = 0);
+
+// tcgen05 form (attention_tc.cu): one UMMA tile per contraction; n <= 128, head_dim a multiple of 64 up to 256
+bool koa_attention_tc_ok(int n, int head_dim);
+int koa_k_attention_tc_fwd(const void* qkv, void* out, float* probs, int batch, int n, int heads, int head_dim, float scale,
+                           cudaStream_t st, int f16);
+int koa_k_attention_tc_bwd(const void* qkv, const float* probs, const void* dout, void* dqkv, int batch, int n, int heads,
+                           int head_dim, float scale, cudaStream_t st, int f16);
 
 // ---- stem (stem.cu) -----------------------------------------------------------------------------------
 // vol (B,1,R,C,S) fp32 slice-innermost -> img [B*S][R][C] fp32

@@ -40,6 +40,14 @@ extern "C" int koa_attention_bwd(const void* qkv, const float* probs, const void
                                  int heads, int head_dim, float scale, void* stream) {
   return koa_k_attention_bwd(qkv, probs, dout, dqkv, batch, n, heads, head_dim, scale, ST);
 }
+extern "C" int koa_attention_fwd_fmt(const void* qkv, void* out, float* probs, int batch, int n, int heads, int head_dim,
+                                     float scale, int f16, void* stream) {
+  return koa_k_attention_fwd(qkv, out, probs, batch, n, heads, head_dim, scale, ST, f16);
+}
+extern "C" int koa_attention_bwd_fmt(const void* qkv, const float* probs, const void* dout, void* dqkv, int batch, int n,
+                                     int heads, int head_dim, float scale, int f16, void* stream) {
+  return koa_k_attention_bwd(qkv, probs, dout, dqkv, batch, n, heads, head_dim, scale, ST, f16);
+}
 extern "C" int koa_stem_pack(const float* vol, float* img, int batch, int rc, int slices, void* stream) {
   return koa_k_stem_pack(vol, img, batch, rc, slices, ST);
 }
@@ -51,6 +59,11 @@ extern "C" int koa_maxpool_bwd(const void* dout, const void* idx, void* dx, int 
 }
 extern "C" int koa_col_stats(const void* y, float* sum, float* sumsq, long long rows, int c, void* stream) {
   return koa_k_col_stats(y, sum, sumsq, rows, c, ST);
+}
+extern "C" int koa_channel_dropout(const float* x, float* out, long long n_img, int positions, int c,
+                                   unsigned long long seed, unsigned int site, float p, void* stream) {
+  KOA_REQUIRE(x != nullptr && out != nullptr, "null pointer argument");
+  return koa_k_channel_dropout(x, out, n_img, positions, c, seed, site, p, ST);
 }
 extern "C" int koa_dropout_mask(unsigned long long seed, unsigned int site, long long rows, int cols, float p, float* out,
                                 void* stream) {

@@ -172,15 +172,26 @@ class KneeParallel(nn.Module):
             p.register_hook(_loose_hook)
 
     def forward(self, *args, **kwargs):
+        # A backward pass that raised (e.g. an out-of-memory error the caller caught) never ran its final callback: drain
+        # what it left behind so that this step queues its own callback and no stale collective is mistaken for a new one.
+        st = _state
+        if st.callback_queued or st.handles:
+            for work, _ in st.handles:
+                work.wait()
+            st.handles.clear()
+            st.covered.clear()
+            st.callback_queued = False
         return self.module(*args, **kwargs)
 
     def sync_buffers(self) -> None:
         """Rank 0's BatchNorm running statistics to every rank (DataParallel keeps replica 0's)."""
         import torch.distributed as dist
 
+        group = _state.group
+        src = dist.get_global_rank(group, 0) if group is not None else 0  # group rank 0, as in __init__
         with torch.no_grad():
             for b in self.module.buffers():
-                dist.broadcast(b, src=0, group=_state.group)
+                dist.broadcast(b, src=src, group=group)
 
 
 def wrap(model: nn.Module, device_ids=None, process_group=None) -> nn.Module:

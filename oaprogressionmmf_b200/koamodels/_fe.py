@@ -127,6 +127,7 @@ class _FEFunction(torch.autograd.Function):
     def forward(ctx, enc: "SliceEncoder", x: torch.Tensor, n_img: int, h: int, w: int, slices: int, need_bw: bool,
                 *params):
         lib = _lib.load()
+        dev = _lib.require_same_device("SliceEncoder", x, *params)
         desc = _lib.FeDesc(arch=_lib.ARCH_IDS[enc.arch], n_img=n_img, h=h, w=w, slices=slices,
                            with_gap=1 if enc.with_gap else 0, training=1 if enc.training else 0,
                            need_backward=1 if need_bw else 0,
@@ -140,10 +141,11 @@ class _FEFunction(torch.autograd.Function):
         feat = torch.empty((n_img, ch.value) if enc.with_gap else (n_img, oh.value * ow.value, ch.value),
                            dtype=torch.float32, device=x.device)
         table = enc._param_table()
-        _lib.check(lib.koa_fe_forward(C.byref(desc), table, x.data_ptr(), ws.data_ptr(), feat.data_ptr(),
-                                      _lib.current_stream()), "koa_fe_forward")
-        if enc.training:
-            torch._foreach_add_(enc._nbt(), 1)
+        with _lib.on_device(dev):
+            _lib.check(lib.koa_fe_forward(C.byref(desc), table, x.data_ptr(), ws.data_ptr(), feat.data_ptr(),
+                                          _lib.current_stream()), "koa_fe_forward")
+            if enc.training:
+                torch._foreach_add_(enc._nbt(), 1)
         ctx.enc, ctx.desc, ctx.ws, ctx.table, ctx.x = enc, desc, ws, table, x
         ctx.n_params = len(params)
         return feat
@@ -155,9 +157,11 @@ class _FEFunction(torch.autograd.Function):
         params = enc._trainable()
         grads, flat = _lib.zeros_like_flat([p if p.requires_grad else None for p in params])
         gtable = _lib.ptr_table(grads)
+        dev = _lib.require_same_device("SliceEncoder backward", dfeat, ctx.ws)
         dfeat = dfeat.contiguous().float()
-        _lib.check(lib.koa_fe_backward(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(), dfeat.data_ptr(),
-                                       _lib.current_stream()), "koa_fe_backward")
+        with _lib.on_device(dev):
+            _lib.check(lib.koa_fe_backward(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(), dfeat.data_ptr(),
+                                           _lib.current_stream()), "koa_fe_backward")
         ctx.ws = None
         dataparallel.sync_flat(flat, [p for p in params if p.requires_grad])  # no-op outside a data-parallel run
         return (None, None, None, None, None, None, None, *grads)

@@ -69,6 +69,7 @@ class _FeaTFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mod: "FeaT", tokens: torch.Tensor, compute_head: bool, need_bw: bool, seed: int, *params):
         lib = _lib.load()
+        dev = _lib.require_same_device("FeaT", tokens, *params)
         b, n_p, dim = tokens.shape
         tr = mod.transformer
         desc = _lib.FeatDesc(batch=b, n_patches=n_p, dim=dim, depth=tr.depth, heads=tr.heads, mlp_dim=tr.mlp_dim,
@@ -85,9 +86,10 @@ class _FeaTFunction(torch.autograd.Function):
         logits = torch.empty((b, mod.num_classes), dtype=torch.float32, device=tokens.device) if compute_head else None
         table = _lib.ptr_table(mod._param_list())
         tokens = tokens.contiguous().float()
-        _lib.check(lib.koa_feat_forward(C.byref(desc), table, tokens.data_ptr(), ws.data_ptr(), states.data_ptr(),
-                                        None if logits is None else logits.data_ptr(), _lib.current_stream()),
-                   "koa_feat_forward")
+        with _lib.on_device(dev):
+            _lib.check(lib.koa_feat_forward(C.byref(desc), table, tokens.data_ptr(), ws.data_ptr(), states.data_ptr(),
+                                            None if logits is None else logits.data_ptr(), _lib.current_stream()),
+                       "koa_feat_forward")
         ctx.mod, ctx.desc, ctx.ws, ctx.table = mod, desc, ws, table
         ctx.tokens_need_grad = ctx.needs_input_grad[1]
         ctx.token_shape = tokens.shape
@@ -121,10 +123,12 @@ class _FeaTFunction(torch.autograd.Function):
         d_tokens = torch.empty(ctx.token_shape, dtype=torch.float32, device=ctx.ws.device) if ctx.tokens_need_grad else None
         ds = None if d_states is None else d_states.contiguous().float()
         dl = None if d_logits is None else d_logits.contiguous().float()
-        _lib.check(lib.koa_feat_backward(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(),
-                                         None if ds is None else ds.data_ptr(), None if dl is None else dl.data_ptr(),
-                                         None if d_tokens is None else d_tokens.data_ptr(), _lib.current_stream()),
-                   "koa_feat_backward")
+        dev = _lib.require_same_device("FeaT backward", ctx.ws, ds, dl)
+        with _lib.on_device(dev):
+            _lib.check(lib.koa_feat_backward(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(),
+                                             None if ds is None else ds.data_ptr(), None if dl is None else dl.data_ptr(),
+                                             None if d_tokens is None else d_tokens.data_ptr(), _lib.current_stream()),
+                       "koa_feat_backward")
         ctx.ws = None
         dataparallel.sync_flat(flat, [p for g, p in zip(grads, params) if g is not None])
         out_grads = [g for g, p in zip(grads, params) if p is not None]

@@ -45,12 +45,45 @@ def _drop2d(p):
     return nn.Dropout2d(p=p) if p else nn.Identity()
 
 
-def _apply_drop2d(drop, tokens):
-    """Dropout2d on the (N, C, 1, 1) extractor output == channel dropout on the (B, S, C) tokens."""
-    if isinstance(drop, nn.Identity) or not drop.training:
+class _ChannelDropout(torch.autograd.Function):
+    """``nn.Dropout2d`` of the reference on the extractor output ``(B*S, C, h, w)`` (``_xrNmrMcP.py:62-74,226-229``), on
+    the engine's token layout ``(B, S*positions, C)``: one Philox draw per (slice, channel), shared by every spatial
+    position of that slice; the backward pass regenerates the mask (``koa_channel_dropout``)."""
+
+    @staticmethod
+    def forward(ctx, tokens, n_img, positions, p, seed, site):
+        lib = _lib.load()
+        _lib.require_cuda(tokens, "channel dropout")
+        x = tokens.contiguous().float()
+        out = torch.empty_like(x)
+        with _lib.on_device(x.device):
+            _lib.check(lib.koa_channel_dropout(x.data_ptr(), out.data_ptr(), n_img, positions, x.shape[-1], seed, site,
+                                               float(p), _lib.current_stream()), "koa_channel_dropout")
+        ctx.args = (n_img, positions, float(p), seed, site)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        n_img, positions, p, seed, site = ctx.args
+        g = g.contiguous().float()
+        out = torch.empty_like(g)
+        with _lib.on_device(g.device):
+            _lib.check(lib.koa_channel_dropout(g.data_ptr(), out.data_ptr(), n_img, positions, g.shape[-1], seed, site, p,
+                                               _lib.current_stream()), "koa_channel_dropout")
+        return out, None, None, None, None, None
+
+
+def _apply_drop2d(drop, tokens, n_img, site=0):
+    """Dropout2d on the (N, C, h, w) extractor output == per-(image, channel) dropout on the (B, S * positions, C) tokens.
+    ``drop.last_seed`` keeps the Philox seed of the call (tests replay the mask with ``koa_dropout_mask``)."""
+    if isinstance(drop, nn.Identity) or not drop.training or drop.p == 0:
         return tokens
-    b, s, c = tokens.shape
-    return drop(tokens.reshape(b * s, c, 1, 1)).reshape(b, s, c)
+    b, sp, c = tokens.shape
+    positions = (b * sp) // n_img
+    seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())  # torch's CPU generator: torch.manual_seed replays
+    drop.last_seed, drop.last_site = seed, 0xD000 + site
+    return _ChannelDropout.apply(tokens, n_img, positions, drop.p, seed, 0xD000 + site)
 
 
 _BRANCH_STREAMS = {}
@@ -186,7 +219,7 @@ class MR1CnnTrf(_Base):
             vol = input.permute(0, 1, 3, 4, 2)
         elif view == "rs":  # slice along columns: images are (r, s)
             vol = input.permute(0, 1, 2, 4, 3)
-        tok = _apply_drop2d(self._fe_drop, self._fe.encode_volume(vol))
+        tok = _apply_drop2d(self._fe_drop, self._fe.encode_volume(vol), vol.shape[0] * vol.shape[-1])
         out, _, _ = self._agg.run(tok, compute_head=True)
         return _output(self.config, out.flatten(1))
 
@@ -217,8 +250,8 @@ class MR2CnnTrf(_Base):
         self._finish(path_weights)
 
     def forward(self, input0, input1):
-        t0 = _apply_drop2d(self._fe0_drop, self._fe0.encode_volume(input0))
-        t1 = _apply_drop2d(self._fe1_drop, self._fe1.encode_volume(input1))
+        t0 = _apply_drop2d(self._fe0_drop, self._fe0.encode_volume(input0), input0.shape[0] * input0.shape[-1], 0)
+        t1 = _apply_drop2d(self._fe1_drop, self._fe1.encode_volume(input1), input1.shape[0] * input1.shape[-1], 1)
         out, _, _ = self._agg.run(torch.cat([t0, t1], dim=1), compute_head=True)
         return _output(self.config, out.flatten(1))
 
@@ -257,10 +290,11 @@ class _XRMRBase(_Base):
         self.vs["agg_in_depth"] = FE_OUT_CH[fe["mr"]["arch"]]
 
     def _mr_tokens(self, i, vol):
-        return _apply_drop2d(getattr(self, f"_fe{i}_drop"), getattr(self, f"_fe{i}").encode_volume(vol))
+        return _apply_drop2d(getattr(self, f"_fe{i}_drop"), getattr(self, f"_fe{i}").encode_volume(vol),
+                             vol.shape[0] * vol.shape[-1], i)
 
     def _xr_tokens(self, img):
-        return _apply_drop2d(self._fe0_drop, self._fe0.encode_image(img))
+        return _apply_drop2d(self._fe0_drop, self._fe0.encode_image(img), img.shape[0], 0)
 
 
 class XR1MR1CnnTrf(_XRMRBase):
@@ -344,7 +378,8 @@ class MR3CnnTrf(_Base):
     def forward(self, input0, input1, input2):
         states = []
         for i, vol in enumerate((input0, input1, input2), start=1):
-            tok = _apply_drop2d(getattr(self, f"_fe{i}_drop"), getattr(self, f"_fe{i}").encode_volume(vol))
+            tok = _apply_drop2d(getattr(self, f"_fe{i}_drop"), getattr(self, f"_fe{i}").encode_volume(vol),
+                                vol.shape[0] * vol.shape[-1], i)
             states.append(getattr(self, f"_agg_{i}").run(tok, compute_head=False)[1])
         out, _, _ = self._agg_final.run(torch.cat(states, dim=1), compute_head=True)
         return _output(self.config, out.flatten(1))

@@ -55,20 +55,26 @@ class Adam(optim.Optimizer):
                 loss = closure()
         lib = _lib.load()
         for group in self.param_groups:
-            by_step = {}
+            # validate the whole group first: a parameter that fails a check must not leave the step counters of the
+            # parameters before it advanced without an update
+            live = []
             for p in group["params"]:
                 g = p.grad
                 if g is None:
                     continue
                 _lib.require_cuda(p, "koa_adam_step")
+                _lib.require_cuda(g, "koa_adam_step")
                 if g.is_sparse:
                     raise RuntimeError("Adam does not support sparse gradients")
                 if p.dtype != torch.float32 or g.dtype != torch.float32:
                     raise _lib.KoaError("koa_adam_step updates fp32 master parameters with fp32 gradients")
                 if not p.is_contiguous():
                     raise _lib.KoaError("koa_adam_step needs contiguous parameters")
-                if not g.is_contiguous():
-                    g = g.contiguous()
+                live.append((p, g if g.is_contiguous() else g.contiguous()))
+            if live and any(p.device != live[0][0].device or g.device != live[0][0].device for p, g in live):
+                raise _lib.KoaError("one parameter group must live on one device")
+            by_step = {}
+            for p, g in live:
                 st = self._init_state(p)
                 st["step"] += 1
                 by_step.setdefault(int(st["step"]), []).append((p, g, st))
@@ -84,10 +90,7 @@ class Adam(optim.Optimizer):
                 hyper = _lib.AdamHyper(lr=lr, beta1=group["betas"][0], beta2=group["betas"][1], eps=group["eps"],
                                        weight_decay=group["weight_decay"], grad_scale=grad_scale, step=step,
                                        decoupled_weight_decay=int(self._decoupled))
-                dev = entries[0][0].device
-                if any(p.device != dev for p, _, _ in entries):
-                    raise _lib.KoaError("one parameter group must live on one device")
-                with _lib.on_device(dev):
+                with _lib.on_device(entries[0][0].device):
                     _lib.check(lib.koa_adam_step(C.cast(table, C.c_void_p), len(entries), C.byref(hyper),
                                                  _lib.current_stream()), "koa_adam_step")
         return loss

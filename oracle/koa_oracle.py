@@ -143,21 +143,24 @@ def model_param_spec(name: str, cfg: dict) -> List[Tuple[str, Tuple[int, ...]]]:
     xr, mr = cfg["fe"]["xr"]["arch"], cfg["fe"]["mr"]["arch"]
     c = FE_OUT_CH[mr]
     ns = agg["num_slices"]
+    p0, p1 = (1, 1)
+    if name in ("XR1MR1CnnTrf", "XR1MR2CnnTrf", "XR1MR2C1CnnTrf"):
+        p0, p1, _ = _xrmr_positions(cfg)
     if name == "XR1MR1CnnTrf":  # _xr1mrN.py:19-100
         return (fe_param_spec(xr, "_fe0") + fe_param_spec(mr, "_fe1") +
-                feat_param_spec("_agg", 1 + ns[1], c, depth, mlp, nc, True))
+                feat_param_spec("_agg", p0 + ns[1] * p1, c, depth, mlp, nc, True))
     if name == "XR1MR2CnnTrf":  # _xr1mrN.py:169-296
         return (fe_param_spec(xr, "_fe0") + fe_param_spec(mr, "_fe1") + fe_param_spec(mr, "_fe2") +
-                feat_param_spec("_agg_1", ns[1], c, depth, mlp, nc, False) +
-                feat_param_spec("_agg_2", ns[2], c, depth, mlp, nc, False) +
-                feat_param_spec("_agg_final", 1 + ns[1] + ns[2], c, depth, mlp, nc, True))
+                feat_param_spec("_agg_1", ns[1] * p1, c, depth, mlp, nc, False) +
+                feat_param_spec("_agg_2", ns[2] * p1, c, depth, mlp, nc, False) +
+                feat_param_spec("_agg_final", p0 + (ns[1] + ns[2]) * p1, c, depth, mlp, nc, True))
     if name == "XR1MR2C1CnnTrf":  # _xrNmrMcP.py:40-179
         clin = cfg["fe"]["clin"]
         return (fe_param_spec(xr, "_fe0") + fe_param_spec(mr, "_fe1") + fe_param_spec(mr, "_fe2") +
                 [("_fe3._fe.0.weight", (clin["dim_out"], clin["dim_in"])), ("_fe3._fe.0.bias", (clin["dim_out"],))] +
-                feat_param_spec("_agg_1", ns[1], c, depth, mlp, nc, False) +
-                feat_param_spec("_agg_2", ns[2], c, depth, mlp, nc, False) +
-                feat_param_spec("_agg_final", 1 + ns[1] + ns[2] + ns[3], c, depth, mlp, nc, True))
+                feat_param_spec("_agg_1", ns[1] * p1, c, depth, mlp, nc, False) +
+                feat_param_spec("_agg_2", ns[2] * p1, c, depth, mlp, nc, False) +
+                feat_param_spec("_agg_final", p0 + (ns[1] + ns[2]) * p1 + ns[3], c, depth, mlp, nc, True))
     # ---- pattern extensions (not in the reference; SURVEY.md §8 row a-ext) -----------------------
     if name == "MR3CnnTrf":  # three sequences, hierarchical like _xrNmrMcP.py without XR / clin
         return (fe_param_spec(mr, "_fe1") + fe_param_spec(mr, "_fe2") + fe_param_spec(mr, "_fe3") +
@@ -177,12 +180,32 @@ def model_param_spec(name: str, cfg: dict) -> List[Tuple[str, Tuple[int, ...]]]:
     raise ValueError(f"unknown model {name}")
 
 
+# spatial size of the extractor output without GAP, as the reference tabulates it (_mrN_cnn_trf.py:56, _xrNmrMcP.py:104-105)
+_SPATIAL = {320: 10, 160: 5, 128: 4, 96: 3, 64: 2, 32: 1, 350: 11, 25: 1}
+
+
 def _mr1_num_tokens(cfg: dict) -> int:
-    """``vs['agg_in_len']`` of MR1CnnTrf with GAP (_mrN_cnn_trf.py:46-71)."""
+    """``vs['agg_in_len']`` of MR1CnnTrf (_mrN_cnn_trf.py:46-71)."""
     shape = list(cfg["input_size"][0])
     if cfg["downscale"]:
         shape = [round(s * d) for s, d in zip(shape, cfg["downscale"][0])]
-    return {"rc": shape[2], "cs": shape[0], "rs": shape[1]}[cfg["fe"]["dims_view"]]
+    sp = (1, 1, 1) if cfg["fe"]["with_gap"] else tuple(_SPATIAL[e] for e in shape)
+    return {"rc": shape[2] * sp[0] * sp[1], "cs": shape[0] * sp[1] * sp[2], "rs": shape[1] * sp[0] * sp[2]}[cfg["fe"]["dims_view"]]
+
+
+def _xrmr_positions(cfg: dict) -> Tuple[int, int, bool]:
+    """(positions per XR image, positions per MRI slice, GAP kept) of the XR + MRI classes: the extractors keep their GAP
+    when EITHER modality asks for it, while the token counts follow each modality's own flag (_xrNmrMcP.py:47-55,112-122);
+    only the two consistent settings (both with GAP, both without) are meaningful."""
+    fe = cfg["fe"]
+    gap = bool(fe["xr"]["with_gap"] or fe["mr"]["with_gap"])
+    assert gap == bool(fe["xr"]["with_gap"] and fe["mr"]["with_gap"]), "mixed with_gap settings are inconsistent in the reference"
+    shapes = [list(t) for t in cfg["input_size"]]
+    if cfg["downscale"]:
+        shapes = [[round(a * d) for a, d in zip(t, dd)] for t, dd in zip(shapes, cfg["downscale"])]
+    p0 = 1 if gap else _SPATIAL[shapes[0][0]] * _SPATIAL[shapes[0][1]]
+    p1 = 1 if gap else _SPATIAL[shapes[1][0]] * _SPATIAL[shapes[1][1]]
+    return p0, p1, gap
 
 
 def make_state_dict(spec: Sequence[Tuple[str, Tuple[int, ...]]], seed: int, pos_scale: float = 1.0,
@@ -403,12 +426,13 @@ def _slices_to_images(vol: Tensor) -> Tensor:
     return vol.permute(0, 4, 1, 2, 3).reshape(b * s, ch, r, c).expand(-1, 3, -1, -1)
 
 
-def _fe_tokens(sd, prefix, arch, images, training, batch, drop_p, taps=None, emulate_16bit=False):
-    """FE → Dropout2d → tokens "(b s) ch 1 1 -> b s ch" (_xrNmrMcP.py:226-232)."""
-    f = fe_forward(sd, prefix, arch, images, training, True, taps, emulate_16bit=emulate_16bit)
+def _fe_tokens(sd, prefix, arch, images, training, batch, drop_p, taps=None, emulate_16bit=False, with_gap=True):
+    """FE → Dropout2d → tokens "(b s) ch d0 d1 -> b (s d0 d1) ch" (_xrNmrMcP.py:226-232; d0 = d1 = 1 with GAP)."""
+    f = fe_forward(sd, prefix, arch, images, training, with_gap, taps, emulate_16bit=emulate_16bit)
     if drop_p:
         f = F.dropout2d(f, drop_p, training)
-    return f.reshape(batch, -1, f.shape[1])
+    n, ch = f.shape[0], f.shape[1]
+    return f.reshape(batch, n // batch, ch, -1).permute(0, 1, 3, 2).reshape(batch, -1, ch)
 
 
 def model_forward(name: str, cfg: dict, sd: StateDict, inputs: Sequence[Tensor], training: bool,
@@ -445,7 +469,8 @@ def model_forward(name: str, cfg: dict, sd: StateDict, inputs: Sequence[Tensor],
         perm = {"rc": (0, 4, 1, 2, 3), "cs": (0, 2, 1, 3, 4), "rs": (0, 3, 1, 2, 4)}[view]
         imgs = v3.permute(*perm)
         imgs = imgs.reshape(-1, *imgs.shape[2:])
-        tok = _fe_tokens(sd, "_fe", cfg["fe"]["arch"], imgs, training, b, cfg["fe"]["dropout"], taps)
+        tok = _fe_tokens(sd, "_fe", cfg["fe"]["arch"], imgs, training, b, cfg["fe"]["dropout"], taps,
+                         with_gap=cfg["fe"]["with_gap"])
         if taps is not None:
             taps["tokens"] = tok
         out, states = feat("_agg", tok)
@@ -468,14 +493,17 @@ def model_forward(name: str, cfg: dict, sd: StateDict, inputs: Sequence[Tensor],
         return feat("_agg_final", torch.cat(st, dim=1))[0].flatten(1)
 
     b = inputs[0].shape[0]
-    t0 = _fe_tokens(sd, "_fe0", xr_cfg["arch"], inputs[0].expand(-1, 3, -1, -1), training, b, xr_cfg["dropout"], taps)
+    gap = bool(xr_cfg["with_gap"] or mr_cfg["with_gap"])  # one flag for every extractor (_xrNmrMcP.py:47)
+    t0 = _fe_tokens(sd, "_fe0", xr_cfg["arch"], inputs[0].expand(-1, 3, -1, -1), training, b, xr_cfg["dropout"], taps,
+                    with_gap=gap)
     if name == "XR1MR1CnnTrf":  # _xr1mrN.py:108-158
-        t1 = _fe_tokens(sd, "_fe1", mr_cfg["arch"], _slices_to_images(inputs[1]), training, b, mr_cfg["dropout"], taps)
+        t1 = _fe_tokens(sd, "_fe1", mr_cfg["arch"], _slices_to_images(inputs[1]), training, b, mr_cfg["dropout"], taps,
+                        with_gap=gap)
         return feat("_agg", torch.cat([t0, t1], dim=1))[0].flatten(1)
 
     n_mr = 3 if name == "XR1MR3C1CnnTrf" else 2
     toks = [_fe_tokens(sd, f"_fe{i + 1}", mr_cfg["arch"], _slices_to_images(inputs[i + 1]), training, b,
-                       mr_cfg["dropout"], taps) for i in range(n_mr)]
+                       mr_cfg["dropout"], taps, with_gap=gap) for i in range(n_mr)]
     # per-sequence transformers: all token states are forwarded, their heads are dead compute
     # (_xrNmrMcP.py:239-240, _xr1mrN.py:347-348)
     states = [feat(f"_agg_{i + 1}", toks[i])[1] for i in range(n_mr)]
@@ -522,7 +550,7 @@ def train_step(name: str, cfg: dict, sd: StateDict, inputs: Sequence[Tensor], ta
 # ------------------------------------------------------------------------------------------------
 def make_config(name: str, *, xr_size=350, mr_size=160, slices=(64, 32, 25), depth=4, heads=8, mlp_dim=2048,
                 xr_arch="resnext50_32x4d", mr_arch="resnet50", dropout=0.0, clin_dim=9, dim_out=2048,
-                output_type="dict") -> dict:
+                output_type="dict", with_gap=True, dims_view="rc") -> dict:
     """Model config dicts with the keys the reference constructors read. ``slices``
     are the per-sequence slice counts in the order the class takes its MRI inputs."""
     base = dict(name=name, debug=False, downscale=False, input_channels=1, output_channels=2,
@@ -534,14 +562,14 @@ def make_config(name: str, *, xr_size=350, mr_size=160, slices=(64, 32, 25), dep
                     agg=dict(hidden_size=512, dropout=0.5 if dropout else 0.0))
     if name == "MR1CnnTrf":
         return dict(base, input_size=[[mr_size, mr_size, slices[0]]],
-                    fe=dict(arch=mr_arch, pretrained=False, with_gap=True, dropout=dropout, dims_view="rc"),
+                    fe=dict(arch=mr_arch, pretrained=False, with_gap=with_gap, dropout=dropout, dims_view=dims_view),
                     agg=dict(agg, num_slices=slices[0]))
     if name == "MR2CnnTrf":
         return dict(base, input_size=[[mr_size, mr_size, slices[0]], [mr_size, mr_size, slices[1]]],
                     fe=dict(arch=mr_arch, pretrained=False, with_gap=True, dropout=dropout),
                     agg=dict(agg, num_slices=[slices[0], slices[1]]))
-    fe = dict(xr=dict(arch=xr_arch, pretrained=False, with_gap=True, dropout=dropout),
-              mr=dict(arch=mr_arch, pretrained=False, with_gap=True, dropout=dropout))
+    fe = dict(xr=dict(arch=xr_arch, pretrained=False, with_gap=with_gap, dropout=dropout),
+              mr=dict(arch=mr_arch, pretrained=False, with_gap=with_gap, dropout=dropout))
     if name == "XR1MR1CnnTrf":
         return dict(base, input_size=[[xr_size, xr_size], [mr_size, mr_size, slices[0]]], fe=fe,
                     agg=dict(agg, num_slices=[1, slices[0]]))

@@ -51,6 +51,14 @@ def to_attr(d):
     return d
 
 
+def tensor_summary(t):
+    """What a fixture keeps of an intermediate tensor: shape, L2 norm, mean and five values at fixed flat positions."""
+    flat = t.flatten().double()
+    n = flat.numel()
+    idx = [0, n // 4, n // 2, (3 * n) // 4, n - 1]
+    return dict(shape=list(t.shape), norm=float(flat.norm()), mean=float(flat.mean()), samples=[float(flat[i]) for i in idx])
+
+
 def load_ref_focal_loss():
     spec = importlib.util.spec_from_file_location("ref_losses", os.path.join(REF, "koafusion/various/_losses.py"))
     mod = importlib.util.module_from_spec(spec)
@@ -70,6 +78,14 @@ CASES = {
     "XR1MR2C1CnnTrf": dict(kw=dict(xr_size=64, mr_size=32, slices=(3, 2), depth=1), batch=2),
     "MR3CnnTrf": dict(kw=dict(mr_size=32, slices=(3, 2, 2), depth=1), batch=2),
     "XR1MR3C1CnnTrf": dict(kw=dict(xr_size=64, mr_size=32, slices=(3, 2, 2), depth=1), batch=2),
+    # the other slicing axes of MR1CnnTrf (_mrN_cnn_trf.py:114-117): the volume is cubic so that every view gives 32 x 32 images
+    "MR1CnnTrf_cs": dict(model="MR1CnnTrf", kw=dict(mr_size=32, slices=(32,), depth=1, dims_view="cs"), batch=1),
+    "MR1CnnTrf_rs": dict(model="MR1CnnTrf", kw=dict(mr_size=32, slices=(32,), depth=1, dims_view="rs"), batch=1),
+    # extractors without the global average pool: one token per spatial position (64 -> 2 x 2, 32 -> 1 x 1). MR1CnnTrf looks
+    # up all three dimensions in its size table (_mrN_cnn_trf.py:55-56), so the slice count must be one of its keys
+    "MR1CnnTrf_nogap": dict(model="MR1CnnTrf", kw=dict(mr_size=32, slices=(32,), depth=1, with_gap=False), batch=1),
+    "XR1MR2C1CnnTrf_nogap": dict(model="XR1MR2C1CnnTrf",
+                                 kw=dict(xr_size=64, mr_size=64, slices=(3, 2), depth=1, with_gap=False), batch=2),
 }
 
 
@@ -159,11 +175,26 @@ def run_case(case_name, case):
         r = m(*ins)
         return r["main"] if isinstance(r, dict) else r
 
-    # eval mode
+    # eval mode, with the intermediates the logits hide (at random initialisation the logits barely depend on
+    # the input): every extractor output and every transformer's token states, as norm / mean / five sampled values
     model.load_state_dict(ko.make_state_dict(spec, seed_w), strict=True)
     model.eval()
+    taps = {}
+
+    def tap(key):
+        def hook(_m, _i, o):
+            t = o[1] if isinstance(o, tuple) else o          # FeaT returns (outputs, states, attentions)
+            taps[key] = tensor_summary(t.detach())
+        return hook
+
+    handles = [m.register_forward_hook(tap(k)) for k, m in model.named_children()
+               if (k.startswith("_fe") or k.startswith("_agg")) and not k.endswith("_drop") and k != "_agg" or
+               (k == "_agg" and not isinstance(m, torch.nn.Sequential))]
     with torch.no_grad():
         out["eval_logits"] = logits_of(model, inputs).tolist()
+    for h in handles:
+        h.remove()
+    out["taps"] = taps
     # sensitised eval
     model.load_state_dict(ko.make_state_dict(spec, seed_w, pos_scale=0.02), strict=True)
     with torch.no_grad():
@@ -185,6 +216,10 @@ def run_case(case_name, case):
             flat = p.grad.flatten()
             idx = [0, flat.numel() // 2, flat.numel() - 1]
             grads[k] = dict(norm=float(flat.norm()), samples=[float(flat[i]) for i in idx])
+            # direction, not only magnitude: the projection of the gradient on a fixed seeded probe of the same shape
+            # (a sign or permutation error inside a tensor leaves the norm alone and destroys this number)
+            probe = torch.randn(flat.numel(), generator=torch.Generator().manual_seed(flat.numel() % 9973 + 17))
+            grads[k]["probe"] = float((flat.double() * probe.double()).sum())
     out["grads"] = grads
     sd_after = model.state_dict()
     bn_keys = [k for k in sd_after if k.endswith("running_mean") or k.endswith("running_var")]

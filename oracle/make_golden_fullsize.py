@@ -23,6 +23,10 @@ CASES = {
     "XR1MR3C1CnnTrf_full": dict(model="XR1MR3C1CnnTrf", kw=dict(), batch=2),   # 3-MRI extension (bench workload)
     "MR1CnnTrf_full": dict(model="MR1CnnTrf", kw=dict(), batch=2),             # BASELINE.json config 2
     "XR1Cnn_full": dict(model="XR1Cnn", kw=dict(), batch=8),                   # BASELINE.json config 1
+    "MR2CnnTrf_full": dict(model="MR2CnnTrf", kw=dict(), batch=2),             # BASELINE.json config 3 (strict): DESS + TSE, flat
+    "XR1MR1CnnTrf_full": dict(model="XR1MR1CnnTrf", kw=dict(), batch=2),       # XR + DESS, flat
+    "XR1MR2CnnTrf_full": dict(model="XR1MR2CnnTrf", kw=dict(slices=(64, 25, 25)), batch=2),  # XR + DESS + T2, no clinical token
+    "MR3CnnTrf_full": dict(model="MR3CnnTrf", kw=dict(), batch=2),             # 3-MRI extension without XR / clinical
 }
 
 

@@ -464,30 +464,45 @@ def test_layernorm(cuda, rows, d):
     assert rel(dx, xr.grad) < 1e-4 and rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
 
 
-@pytest.mark.parametrize("b,n,heads,hd", [(2, 65, 8, 256), (3, 25, 8, 256), (1, 124, 8, 256), (2, 7, 4, 64), (1, 1, 8, 32)])
-def test_attention(cuda, b, n, heads, hd):
+@pytest.mark.parametrize("f16", [0, 1])
+@pytest.mark.parametrize("b,n,heads,hd", [(2, 65, 8, 256), (3, 25, 8, 256), (1, 124, 8, 256), (16, 92, 8, 256), (2, 128, 8, 256),
+                                          (3, 64, 2, 128), (2, 7, 4, 64), (1, 1, 8, 256), (1, 1, 8, 32), (2, 33, 4, 96)])
+def test_attention(cuda, b, n, heads, hd, f16):
     """softmax(Q K^T * scale) V with the reference's (qkv, head, d) feature split and model-dim scale
-    (_core_trf.py:160,167-182), forward + backward, including the single-token and 124-token (3-MRI) cases."""
+    (_core_trf.py:160,167-182), forward + backward: the tcgen05 kernels (head_dim a multiple of 64: one UMMA tile per
+    contraction, probabilities / dS rounded to 16 bit as MMA operands) and the CUDA-core kernels (other head sizes), with
+    fp16 or bf16 forward tensors; single-token, 25 / 64 / 92 / 124 / 128-token sequences (the last rows of a 128-row TMA box
+    belong to the next sequence or lie past the end of the matrix)."""
     lib = _lib.load()
     d = heads * hd
     scale = float(d) ** -0.5
-    qkv = _bf(_randn(b * n, 3 * d, seed=41))
-    out = torch.empty(b * n, d, dtype=torch.bfloat16, device=cuda)
+    fdt = torch.float16 if f16 else torch.bfloat16
+    qkv = _randn(b * n, 3 * d, seed=41).to(fdt).contiguous()
+    out = torch.empty(b * n, d, dtype=fdt, device=cuda)
     probs = torch.empty(b, heads, n, n, device=cuda)
-    _lib.check(lib.koa_attention_fwd(qkv.data_ptr(), out.data_ptr(), probs.data_ptr(), b, n, heads, hd, scale, _stream()),
-               "attn fwd")
+    _lib.check(lib.koa_attention_fwd_fmt(qkv.data_ptr(), out.data_ptr(), probs.data_ptr(), b, n, heads, hd, scale, f16,
+                                         _stream()), "attn fwd")
     qf = qkv.float().requires_grad_(True)
     q, k, v = qf.view(b, n, 3, heads, hd).permute(2, 0, 3, 1, 4)
     pr = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
     ref = (pr @ v).permute(0, 2, 1, 3).reshape(b * n, d)
-    assert rel(probs, pr) < 1e-4
-    _close_bf16(out, ref.detach(), "attention out")
+    assert torch.isfinite(probs).all() and rel(probs, pr) < 1e-4, rel(probs, pr)
+    assert rel(out.float(), ref.detach()) < (1.5e-3 if f16 else BF16_REL_L2), rel(out.float(), ref.detach())
     dout = _bf(_randn(b * n, d, seed=42))
     ref.backward(dout.float())
-    dqkv = torch.empty_like(qkv)
-    _lib.check(lib.koa_attention_bwd(qkv.data_ptr(), probs.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), b, n, heads, hd,
-                                     scale, _stream()), "attn bwd")
-    assert rel(dqkv.float(), qf.grad) < BF16_REL_L2
+    dqkv = torch.full_like(qkv, float("nan"), dtype=torch.bfloat16)
+    _lib.check(lib.koa_attention_bwd_fmt(qkv.data_ptr(), probs.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), b, n, heads, hd,
+                                         scale, f16, _stream()), "attn bwd")
+    assert torch.isfinite(dqkv.float()).all()
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        e = rel(dqkv[:, sl].float(), qf.grad[:, sl])
+        assert e < 6e-3, (name, e)
+    if f16 == 0:   # the original entry points are the bf16 form of the same call
+        out2 = torch.empty_like(out)
+        _lib.check(lib.koa_attention_fwd(qkv.data_ptr(), out2.data_ptr(), probs.data_ptr(), b, n, heads, hd, scale, _stream()),
+                   "attn fwd (bf16 entry point)")
+        assert torch.equal(out2, out)
+    assert _lib.debug_flag() == 0
 
 
 @pytest.mark.parametrize("n,h,w", [(3, 32, 32), (2, 175, 175), (1, 80, 80)])
@@ -527,6 +542,79 @@ def test_focal_loss(cuda, batch):
     ref.backward()
     assert abs(float(loss) - float(ref)) < 1e-6 + 1e-5 * abs(float(ref))
     assert rel(dl, lr.grad) < 1e-5
+
+
+def test_channel_dropout_is_dropout2d(cuda):
+    """nn.Dropout2d on the extractor output (reference _xrNmrMcP.py:62-74,226-229: applied to (B*S, C, h, w)) on the
+    engine's token layout: ONE draw per (slice, channel) shared by all spatial positions of the slice (not one per
+    position), scale 1 / (1 - p), the mask replayed by koa_dropout_mask, backward = the same mask on the gradient,
+    identity in eval mode; and the model classes call it that way (with and without the global average pool)."""
+    from oaprogressionmmf_b200.koamodels import _models as km
+
+    lib = _lib.load()
+    n_img, pos, c, p = 12, 4, 256, 0.3
+    x = (_randn(3, 4 * pos, c, seed=1).abs() + 0.1).requires_grad_(True)   # (B = 3, S * positions = 16, C): 4 slices per knee
+    drop = torch.nn.Dropout2d(p)
+    torch.manual_seed(5)
+    y = km._apply_drop2d(drop, x, n_img, site=2)
+    mask = torch.empty(n_img, c, device=cuda)
+    _lib.check(lib.koa_dropout_mask(drop.last_seed, drop.last_site, n_img, c, p, mask.data_ptr(), _stream()), "mask")
+    assert all(v == 0.0 or abs(v - 1 / (1 - p)) < 1e-6 for v in mask.unique().tolist())
+    keep = float((mask > 0).float().mean())
+    assert abs(keep - (1 - p)) < 0.05, keep
+    want = x.detach().reshape(n_img, pos, c) * mask[:, None, :]
+    assert torch.equal(y.detach().reshape(n_img, pos, c), want)          # every position of a slice shares the draw
+    gy = _randn(*y.shape, seed=2)
+    y.backward(gy)
+    assert torch.equal(x.grad.reshape(n_img, pos, c), gy.reshape(n_img, pos, c) * mask[:, None, :])
+    torch.manual_seed(5)
+    assert torch.equal(km._apply_drop2d(drop, x.detach(), n_img, site=2), y.detach())   # torch.manual_seed replays it
+    drop.eval()
+    assert km._apply_drop2d(drop, x, n_img) is x
+    # distribution matches nn.Dropout2d on the reference's (B*S, C, h, w) layout: zero fraction per (slice, channel)
+    ref = torch.nn.Dropout2d(p)(torch.ones(4000, 64, 2, 2, device=cuda))
+    assert abs(float((ref[:, :, 0, 0] == 0).float().mean()) - p) < 0.02
+    assert bool((ref == ref[:, :, :1, :1]).all())
+
+
+def test_focal_loss_edge_cases(cuda):
+    """What F.cross_entropy-based FocalLoss of the reference does at the edges (various/_losses.py:89-108): a target
+    outside [0, classes) is an error there (device assert); here it is a NaN loss plus the diagnostic word, never a
+    silent out-of-bounds read. gamma < 1 with a saturated prediction (pt -> 1) has a finite (zero) gradient.
+    reduction='sum' and the rejected class_weight."""
+    from oaprogressionmmf_b200.losses import FocalLoss
+
+    logits = torch.tensor([[0.3, -0.2], [40.0, -40.0], [-1.0, 2.0]], device=cuda, requires_grad=True)
+    target = torch.tensor([[0], [0], [1]], device=cuda)
+    for gamma in (0.5, 2.0):
+        ref_in = logits.detach().clone().requires_grad_(True)
+        logpt = -F.cross_entropy(ref_in, target.reshape(-1), reduction="none")
+        ref = (-((1 - logpt.exp()) ** gamma) * logpt)
+        for red in ("mean", "sum"):
+            lg = logits.detach().clone().requires_grad_(True)
+            loss = FocalLoss(gamma=gamma, reduction=red)(lg, target)
+            loss.backward()
+            want = ref.mean() if red == "mean" else ref.sum()
+            assert torch.isfinite(lg.grad).all(), (gamma, red)
+            assert abs(float(loss) - float(want)) < 1e-6 + 1e-5 * abs(float(want))
+            assert float(lg.grad[1].abs().max()) < 1e-6   # saturated sample: no gradient, no NaN
+    # the loss is bit-reproducible (fixed-order reduction)
+    big = _randn(4096, 2, seed=3)
+    tg = (torch.arange(4096, device=cuda) % 2).reshape(-1, 1)
+    l0 = float(FocalLoss()(big, tg))
+    assert all(float(FocalLoss()(big, tg)) == l0 for _ in range(5))
+    assert _lib.debug_flag() == 0
+    bad = torch.tensor([[0], [2], [1]], device=cuda)
+    loss = FocalLoss()(logits, bad)
+    assert torch.isnan(loss)
+    assert _lib.debug_flag() == 0xF0CA1
+    assert _lib.debug_flag() == 0   # read clears
+    with pytest.raises(ValueError):
+        FocalLoss(class_weight=torch.ones(2))
+    with pytest.raises(ValueError):
+        FocalLoss(reduction="max")
+    with pytest.raises(_lib.KoaError):
+        FocalLoss()(logits.detach().cpu(), target.cpu())
 
 
 @pytest.mark.parametrize("m,n,k,act", [(16, 2048, 9, _lib.ACT_GELU), (8, 512, 2048, _lib.ACT_RELU), (5, 2, 512, _lib.ACT_NONE)])
@@ -955,42 +1043,94 @@ def test_model_train_step_matches_reference_structure(cuda, golden_dir, case):
 
 
 GOLDEN_FULL = sorted(f[:-5] for f in os.listdir(os.path.join(os.path.dirname(__file__), "golden_full")) if f.endswith(".json"))
-LOGIT_SCALE = 0.25  # typical |logit| of these heads at initialisation (fixtures: 0.13 .. 0.58)
-
-
 def logit_err(got, ref):
-    """rms(got - ref) / max(rms(ref), LOGIT_SCALE): BASELINE.json's relative logit error with an absolute floor, so a
-    fixture whose logits happen to be ~0.03 does not turn a 1e-3 absolute error into a 3 % "relative" one."""
+    """BASELINE.json's metric, literally: ||got - ref|| / ||ref|| over the logit tensor, no absolute floor."""
     got, ref = got.detach().double(), ref.detach().double()
-    return float((got - ref).pow(2).mean().sqrt() / max(float(ref.pow(2).mean().sqrt()), LOGIT_SCALE))
+    return float((got - ref).norm() / ref.norm())
+
+
+class _Taps:
+    """Records what the fixtures' ``taps`` hold for the reference: the output of every extractor (``_fe*``) and the token
+    states of every transformer (``_agg*``) of one forward pass, keyed by the child-module name."""
+
+    def __init__(self, model):
+        from oaprogressionmmf_b200.koamodels import _feat, _fe, _small
+
+        self.out, self.names, self.saved = {}, {id(m): k for k, m in model.named_children()}, []
+        t = self
+
+        def wrap(cls, attr, pick):
+            orig = getattr(cls, attr)
+            self.saved.append((cls, attr, orig))
+
+            def f(mod, *a, **k):
+                r = orig(mod, *a, **k)
+                if id(mod) in t.names:
+                    t.out[t.names[id(mod)]] = pick(r).detach()
+                return r
+
+            setattr(cls, attr, f)
+
+        wrap(_fe.SliceEncoder, "encode_volume", lambda r: r)
+        wrap(_fe.SliceEncoder, "encode_image", lambda r: r)
+        wrap(_feat.FeaT, "run", lambda r: r[1])
+        wrap(_small.FeatC1, "forward", lambda r: r)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        for cls, attr, orig in self.saved:
+            setattr(cls, attr, orig)
+
+
+def _probe(numel, device):
+    return torch.randn(numel, generator=torch.Generator().manual_seed(numel % 9973 + 17)).to(device)
 
 
 @pytest.mark.parametrize("case", GOLDEN_FULL)
 def test_full_size_logits_match_reference(cuda, case):
     """BASELINE.json's sizes (XR 350x350 ResNeXt-50, DESS 160x160x64 / TSE x32 / T2 x25 ResNet-50s, D 2048, depth 4)
-    against logits, loss and gradient norms recorded from the UNMODIFIED reference on the same seeded weights and
-    inputs (oracle/make_golden_fullsize.py): eval logits within 1e-2 (2e-2 with the sensitised weights) and identical
-    class predictions; one train step: loss within 2 %, every gradient present exactly where the reference has one,
-    gradient norms within [0.6, 2.0] x reference with the median within 5 %."""
+    against what the UNMODIFIED reference produced for the same seeded weights and inputs
+    (oracle/make_golden_fullsize.py), all six reference classes and the two 3-MRI extensions.
+
+    * eval logits: ||delta|| / ||ref|| < 1e-2, the north-star tolerance as written (no floor), also with the sensitised
+      weights (pos_embedding / cls_token x 0.02, where the logits depend on the input), identical class predictions;
+    * the intermediates the logits hide: every extractor output and every transformer's states within 1e-2 (norm and
+      the five recorded values);
+    * one train step: loss within 1 %, a gradient exactly where the reference has one, and per tensor: the norm within
+      [0.6, 2.0] x reference (median within 5 %) and the DIRECTION: the projection of the gradient on a seeded probe
+      vector, which estimates the relative L2 error of the tensor (a sign or permutation error inside a tensor keeps the
+      norm and destroys the projection)."""
     from oaprogressionmmf_b200.losses import FocalLoss
 
     gold_dir = os.path.join(os.path.dirname(__file__), "golden_full")
     for tag, ps in (("eval_logits", 1.0), ("eval_logits_sensitised", 0.02)):
         gold, cfg, model, inputs, target = _golden_case(case, gold_dir, cuda, pos_scale=ps)
         model.eval()
-        with torch.no_grad():
+        with torch.no_grad(), _Taps(model) as taps:
             lg = model(*inputs)["main"]
         ref = torch.tensor(gold[tag], device=cuda)
-        # the sensitised weights (pos_embedding / cls_token x 0.02) are a stress variant: 2e-2
-        assert logit_err(lg, ref) < (LOGIT_TOL if ps == 1.0 else 2 * LOGIT_TOL), (tag, logit_err(lg, ref), rel(lg, ref))
+        assert logit_err(lg, ref) < LOGIT_TOL, (tag, logit_err(lg, ref))
         assert bool((lg.argmax(1) == ref.argmax(1)).all()), tag
+        if ps == 1.0 and "taps" in gold:
+            assert set(gold["taps"]) == set(taps.out), (sorted(gold["taps"]), sorted(taps.out))
+            for k, g in gold["taps"].items():
+                t = taps.out[k].flatten().double()
+                assert t.numel() == int(torch.tensor(g["shape"]).prod()), k
+                n = t.numel()
+                idx = [0, n // 4, n // 2, (3 * n) // 4, n - 1]
+                rms = g["norm"] / n ** 0.5
+                assert abs(float(t.norm()) - g["norm"]) < 1e-2 * g["norm"], (k, float(t.norm()), g["norm"])
+                for i, want in zip(idx, g["samples"]):
+                    assert abs(float(t[i]) - want) < 1e-2 * abs(want) + 2e-2 * rms, (k, i, float(t[i]), want)
     model.train()  # the reference's train step ran on the sensitised weights
     lg = model(*inputs)["main"]
     loss = FocalLoss(gamma=2)(lg, target)
     loss.backward()
-    assert abs(float(loss) - gold["train_loss"]) < 0.02 * gold["train_loss"], (float(loss), gold["train_loss"])
+    assert abs(float(loss) - gold["train_loss"]) < 0.01 * gold["train_loss"], (float(loss), gold["train_loss"])
     assert logit_err(lg, torch.tensor(gold["train_logits"], device=cuda)) < 3e-2
-    ratios = []
+    ratios, proj = [], []
     for k, p in model.named_parameters():
         gref = gold["grads"][k]
         if gref is None:
@@ -998,9 +1138,75 @@ def test_full_size_logits_match_reference(cuda, case):
             continue
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
         ratios.append(float(p.grad.norm()) / (gref["norm"] + 1e-30))
+        if "probe" in gref and gref["norm"] > 0:
+            got = float((p.grad.flatten().double() * _probe(p.grad.numel(), cuda).double()).sum())
+            proj.append((got - gref["probe"]) / gref["norm"])   # ~ N(0, 1) x relative L2 error of this tensor
     r = torch.tensor(ratios)
     assert float(r.min()) > 0.6 and float(r.max()) < 2.0, (float(r.min()), float(r.max()))
     assert abs(float(r.median()) - 1) < 0.05, float(r.median())
+    if proj:
+        # What 16-bit storage alone does to these projections: the same step with the oracle rounding every stored
+        # activation / operand of the extractors like the CUDA path stores it (no CUDA-path code involved). At random
+        # initialisation a train-mode BatchNorm ResNet amplifies any perturbation from block to block (ReLU masks flip),
+        # so the early convolutions' gradients move by tens of percent under ANY 16-bit arithmetic; the CUDA path must
+        # stay at that floor, and below 5e-2 wherever the floor is below 2e-2 (the transformers).
+        spec = ko.model_param_spec(gold["model"], cfg)
+        sd = ko.make_state_dict(spec, gold["seed_weights"], pos_scale=0.02, device=cuda)
+        _, _, g_emu = ko.train_step(gold["model"], cfg, sd, inputs, target, emulate_16bit=True)
+        floor, mine = [], []
+        for (k, p), e in zip([(k, p) for k, p in model.named_parameters() if gold["grads"][k] is not None and
+                              "probe" in gold["grads"][k] and gold["grads"][k]["norm"] > 0], proj):
+            gref = gold["grads"][k]
+            f = float((g_emu[k].flatten().double() * _probe(p.grad.numel(), cuda).double()).sum())
+            floor.append(abs(f - gref["probe"]) / gref["norm"])
+            mine.append(abs(e))
+        floor, mine = torch.tensor(floor), torch.tensor(mine)
+        rms = lambda t: float(t.pow(2).mean().sqrt())  # noqa: E731
+        assert rms(mine) <= 1.5 * rms(floor) + 0.05, (rms(mine), rms(floor))
+        assert float(mine.median()) <= 1.5 * float(floor.median()) + 0.03, (float(mine.median()), float(floor.median()))
+        quiet = floor < 2e-2
+        if bool(quiet.any()):
+            assert float(mine[quiet].max()) < 5e-2, float(mine[quiet].max())
+
+
+@pytest.mark.parametrize("name", ["XR1MR2C1CnnTrf", "XR1MR3C1CnnTrf"])
+def test_trained_weights_logits_match_oracle(cuda, name):
+    """at random initialisation the logits barely depend on the input, so a parity claim on them says little.
+    Here the full-size model (the reference's real one and the bench workload) is first TRAINED for 10 Adam steps (lr 1e-3)
+    on four knees with the fp32 oracle on this GPU (the oracle is pinned to the unmodified reference by the CPU fixtures;
+    a training trajectory cannot be replayed bit for bit across machines, so the trained weights are made here, not
+    shipped), then evaluated on two unseen knees: logits O(0.1 .. 1) that differ between knees, CUDA path within 1e-2 of
+    the oracle (literal ||delta|| / ||ref||) and the same class predictions."""
+    from oaprogressionmmf_b200.koamodels import dict_models
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = ko.make_config(name)
+    spec = ko.model_param_spec(name, cfg)
+    sd = ko.make_state_dict(spec, 4242, pos_scale=0.02, device=cuda)
+    params = [v for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))]
+    for v in params:
+        v.requires_grad_(True)
+    opt = torch.optim.Adam(params, lr=1e-3)
+    inputs, _ = ko.make_inputs(name, cfg, 4, 99, device=cuda)
+    target = torch.tensor([0, 1, 1, 0], device=cuda)
+    for _ in range(10):
+        opt.zero_grad(set_to_none=True)
+        loss = ko.focal_loss(ko.model_forward(name, cfg, sd, inputs, training=True), target)
+        loss.backward()
+        opt.step()
+    sd = {k: v.detach() for k, v in sd.items()}
+    test_in, _ = ko.make_inputs(name, cfg, 2, 100, device=cuda)
+    with torch.no_grad():
+        ref = ko.model_forward(name, cfg, sd, test_in, training=False)
+    model = dict_models[name](to_attr(cfg), None).to(cuda)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    with torch.no_grad():
+        got = model(*test_in)["main"]
+    assert float(ref.abs().max()) > 0.05, ref
+    assert logit_err(got, ref) < LOGIT_TOL, (logit_err(got, ref), got, ref)
+    assert bool((got.argmax(1) == ref.argmax(1)).all())
 
 
 def test_output_type_main_returns_bare_tensor(cuda, golden_dir):
