@@ -150,44 +150,77 @@ def dist_info():
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm: the reference's algorithm (oracle port, fp32 eager torch) on the host cores
+# reference arm: the reference's own implementation of the path on the host cores. oracle/_ref holds the verbatim copy
+# of koafusion/models + FocalLoss that oracle/build_ref.py makes in the build container (kind "reference"); without it
+# the oracle port (fp32 eager restatement, pinned to the reference by the golden fixtures) is timed (kind "port").
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_step(workload, knees, steps, warmup, threads, dropout=0.1):
+    """Times zero_grad -> forward -> FocalLoss -> backward (koafusion/run/train_prog_fus.py:133-165) of `workload` on
+    `knees` synthetic knees; returns (seconds per timed step, kind)."""
     from oracle import koa_oracle as ko
 
-    torch.set_num_threads(threads)
+    torch.set_num_threads(threads)  # the reference's OMP_NUM_THREADS=1 is a DataLoader-worker setting (train_prog_fus.py:7-9)
     cfg = ko.make_config(workload, dropout=dropout)
-    spec = ko.model_param_spec(workload, cfg)
-    sd = ko.make_state_dict(spec, 778)
     inputs, target = ko.make_inputs(workload, cfg, knees, 779)
+    try:
+        from oracle import ref_loader
+
+        torch.manual_seed(778)
+        model = ref_loader.build_model(workload, cfg)
+        loss_fn = ref_loader.focal_loss(gamma=2)
+        model.train()
+
+        def one():
+            model.zero_grad(set_to_none=True)
+            out = model(*inputs)
+            loss_fn(out["main"] if isinstance(out, dict) else out, target).backward()
+
+        kind = "reference"
+    except ImportError:
+        spec = ko.model_param_spec(workload, cfg)
+        sd = ko.make_state_dict(spec, 778)
+
+        def one():
+            ko.train_step(workload, cfg, sd, inputs, target)
+
+        kind = "port"
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        ko.train_step(workload, cfg, sd, inputs, target)
+        one()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return times
+    return times, kind
+
+
+def cpu_baseline_record(workload, knees, steps, warmup, dropout):
+    threads = os.cpu_count() or 1
+    times, kind = cpu_reference_step(workload, knees, steps, warmup, threads, dropout)
+    med, best = statistics.median(times), min(times)
+    what = ("the unmodified reference (oracle/_ref: koafusion.models + FocalLoss)" if kind == "reference" else
+            "the fp32 eager PyTorch restatement of the reference (oracle port)")
+    return dict(value=knees / med, unit="knees/s", cores=threads, kind=kind, median_s_per_step=med, min_s_per_step=best,
+                best_value=knees / best, steps=len(times), warmup=warmup, knees_per_step=knees, workload=workload,
+                sample=f"{warmup} warm-up + {len(times)} timed steps of zero_grad+forward+FocalLoss+backward on {knees} knee(s) "
+                       f"of {workload} with {what}, {threads} threads; value = knees / median step time")
 
 
 def run_reference(args):
     ws, rank, _ = dist_info()
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
     knees = args.cpu_knees
-    times = cpu_reference_step(args.workload, knees, max(1, args.steps), max(0, min(args.warmup, 1)), threads, args.dropout)
-    ms = 1e3 * sum(times) / len(times)
-    value = knees / (ms / 1e3)
-    sample = (f"{len(times)} timed steps (after {max(0, min(args.warmup, 1))} warm-up) of zero_grad+forward+FocalLoss+backward on "
-              f"{knees} knee(s) of the same workload, fp32 eager PyTorch restatement of the reference (oracle port)")
-    line = dict(metric=METRIC, value=value, unit="knees/s", impl="reference", n_gpus=args.gpus, steps=len(times),
-                warmup=max(0, min(args.warmup, 1)), ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="f32", data="synthetic",
+    warm = max(0, min(args.warmup, 1))
+    rec = cpu_baseline_record(args.workload, knees, max(1, args.steps), warm, args.dropout)
+    line = dict(metric=METRIC, value=rec["value"], unit="knees/s", impl="reference", n_gpus=args.gpus, steps=rec["steps"],
+                warmup=warm, ms_per_step=1e3 * rec["median_s_per_step"], higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=args.workload, description=WORKLOAD_DESC.get(args.workload, args.workload),
                             knees_per_step=knees, device="host CPU", dropout=args.dropout),
-                cpu_baseline=dict(value=value, unit="knees/s", cores=threads, kind="port", sample=sample),
-                e2e=dict(value=value, unit="knees/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+                cpu_baseline={k: rec[k] for k in ("value", "unit", "cores", "kind", "sample", "median_s_per_step",
+                                                  "min_s_per_step", "best_value")},
+                e2e=dict(value=rec["value"], unit="knees/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
 
 
@@ -424,6 +457,50 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001
                 e2e_mode += f" (pipelined read-back failed: {type(e).__name__}: {e})"[:200]
 
+    # ---- N > 1: what the gradient all-reduce costs. The same K steps with the synchronisation switched off (every rank
+    # then trains on its own: timing only); exposed = time with the all-reduce - time without it.
+    comm = None
+    if ws > 1:
+        from oaprogressionmmf_b200 import dataparallel as _dp
+
+        _dp._state.enabled = False
+        step(*dev_batches[0])
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step(*dev_batches[i % 2])
+        ev1.record()
+        barrier()
+        _dp._state.enabled = True
+        t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_nosync = float(t.item()) / args.steps
+        n_live = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        comm = dict(exposed_ms=ms_step - ms_nosync, ms_per_step_without_allreduce=ms_nosync,
+                    allreduce_bytes_per_step=4 * n_live, dtype="f32",
+                    schedule="one async NCCL all-reduce per finished backward stage: fusion transformer, per-sequence "
+                             "transformers, then layer4 / layer3 / layer2 / layer1+stem of every extractor")
+
+    # ---- batched inference (BASELINE.json config 5), same model in eval mode under no_grad: 64 knees per GPU as two
+    # micro-batches of 32, host -> device copy and the read-back of the predictions inside the timed region, no collective
+    # (tools/infer_sweep.py is the full sweep). Every rank runs its replica; the slowest rank sets the time.
+    inference = None
+    if not args.skip_e2e and not args.no_full_step:
+        try:
+            inference = measure_inference(model, cfg, dev)
+            if ws > 1:
+                t = torch.tensor([inference["ms_per_batch"]], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                inference["ms_per_batch"] = float(t.item())
+                inference["value"] = ws * inference["batch"] / float(t.item()) * 1e3
+                inference["batch_per_gpu"] = inference["batch"]
+                inference["batch"] = ws * inference["batch"]
+                inference["mode"] += f"; {ws} replicas, no collective, time = slowest rank"
+        except Exception as e:  # noqa: BLE001
+            inference = dict(error=f"{type(e).__name__}: {e}"[:300])
+            if ws > 1:
+                dist.barrier()
+
     if rank != 0:
         if ws > 1:
             dist.destroy_process_group()
@@ -438,34 +515,43 @@ def run_ours(args):
     achieved = (k_flops / (k_ms / 1e3)) / 1e12 if k_ms > 0 else 0.0
     # DRAM bytes per launch of the same kernel family from the committed ncu capture of this command (profiles/)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if args.workload == "XR1MR3C1CnnTrf" and B == 16 and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r01_traffic.json (ncu dram__bytes_read+write.sum per launch, same workload)"
-    roofline = dict(bound="tensor", kernel="gemm_conv_kernel + gemm_kmajor_kernel (tcgen05 GEMM / im2col implicit-GEMM conv, fwd + dgrad)",
-                    achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"], traffic=traffic,
-                    traffic_source=traffic_src,
-                    dram_gbs=(traffic / (k_ms / max(1.0, k_n) * 1e-3) / 1e9) if traffic and k_ms > 0 else None,
-                    peak_source=peaks["source"], avg_launch_ms=k_ms / max(1.0, k_n), launches_timed=int(k_n),
-                    share_of_step=k_ms / max(ms_serial_total, 1e-9),
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r02_traffic.json (ncu dram__bytes_read+write.sum per launch of the GEMM family, same workload)"
+    step_tflops = value / ws * flops_knee / 1e12
+    # `frac` is the number the north star targets: algorithmic FLOPs of the WHOLE step (what the
+    # reference computes, nothing this implementation adds) / step time / sustained bf16 peak, per GPU. The dominant kernel
+    # family and the weight gradients follow with their own per-launch numbers (CUDA events around every launch,
+    # algorithmic FLOPs per launch: zero-inserted rows, block-diagonal padding, K padding and the Gram bookkeeping GEMMs
+    # are not counted).
+    roofline = dict(bound="tensor", kernel="whole training step (forward + FocalLoss + backward), all kernels",
+                    achieved=step_tflops, peak=peaks["tflops"], unit="TFLOP/s", frac=step_tflops / peaks["tflops"],
+                    flops_per_knee=flops_knee, peak_source=peaks["source"], traffic=traffic, traffic_source=traffic_src,
+                    gemm_family=dict(kernel="gemm_conv_kernel + gemm_kmajor_kernel (tcgen05 GEMM / im2col implicit-GEMM conv, "
+                                            "forward + data gradient)",
+                                     achieved=achieved, frac=achieved / peaks["tflops"], avg_launch_ms=k_ms / max(1.0, k_n),
+                                     launches_timed=int(k_n), share_of_step=k_ms / max(ms_serial_total, 1e-9),
+                                     dram_gbs=(traffic / (k_ms / max(1.0, k_n) * 1e-3) / 1e9) if traffic and k_ms > 0 else None),
                     wgrad=dict(kernel="gemm_wgrad_kernel (tcgen05 MN-major split-K)",
                                achieved=(w_flops / (w_ms / 1e3)) / 1e12 if w_ms > 0 else 0.0,
                                avg_launch_ms=w_ms / max(1.0, w_n), launches_timed=int(w_n),
                                share_of_step=w_ms / max(ms_serial_total, 1e-9)),
                     timing_pass=dict(steps=prof_steps, ms_per_step=ms_serial_total / max(1, prof_steps),
                                      note="per-launch CUDA events with the modality branches run one after the other; "
-                                          "`value` is measured with the branches on concurrent streams"),
-                    whole_step=dict(achieved=value / ws * flops_knee / 1e12, frac=value / ws * flops_knee / 1e12 / peaks["tflops"],
-                                    note="algorithmic FLOPs of the whole step / step time, per GPU"))
+                                          "`value` is measured with the branches on concurrent streams"))
     roofline["by_bound"] = split_by_bound(dump_path, peaks, ms_serial_total)
     cpu = None
     if ws == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        times = cpu_reference_step(args.workload, args.cpu_knees, 1, 0, threads, args.dropout)
-        cpu = dict(value=args.cpu_knees / times[0], unit="knees/s", cores=threads, kind="port",
-                   sample=f"1 step (no warm-up) of forward+FocalLoss+backward on {args.cpu_knees} knee(s) of the same "
-                          f"workload with the fp32 eager PyTorch restatement of the reference (oracle port), {times[0]:.1f} s")
+        # 1 warm-up + 3 timed steps, median and minimum, of the bench workload at 2 knees and of
+        # BASELINE.json's config 1 (XR1Cnn, batch 8), on all host cores
+        cpu = cpu_baseline_record(args.workload, args.cpu_knees, 3, 1, args.dropout)
+        try:
+            c1 = cpu_baseline_record("XR1Cnn", 8, 3, 1, args.dropout)
+            cpu["config1"] = {k: c1[k] for k in ("value", "best_value", "median_s_per_step", "min_s_per_step", "kind", "sample")}
+        except Exception as e:  # noqa: BLE001
+            cpu["config1"] = dict(error=f"{type(e).__name__}: {e}"[:200])
     # ---- full training step: the same step followed by the optimiser update of the reference's training
     # configuration (Adam, lr 1e-4, weight decay 1e-4: conf/prog_fus.yaml:47-48) through koa_adam_step. Reported next to
     # `value`, never instead of it; single GPU only and last, so that nothing above depends on it.
@@ -475,15 +561,6 @@ def run_ours(args):
             full_step = measure_full_step(step, model, dev_batches, args.steps, B, peaks)
         except Exception as e:  # noqa: BLE001
             full_step = dict(error=f"{type(e).__name__}: {e}"[:300])
-    # ---- batched inference (BASELINE.json config 5), same model in eval mode under no_grad: 64 knees as two micro-batches
-    # of 32, host -> device copy and the read-back of the predictions inside the timed region (tools/infer_sweep.py is the
-    # full sweep). Reported next to `value`; single GPU (the 8-GPU sweep is 8 replicas without a collective), guarded, last.
-    inference = None
-    if ws == 1 and not args.skip_e2e and not args.no_full_step:
-        try:
-            inference = measure_inference(model, cfg, dev)
-        except Exception as e:  # noqa: BLE001
-            inference = dict(error=f"{type(e).__name__}: {e}"[:300])
     line = dict(metric=METRIC, value=value, unit="knees/s", n_gpus=ws, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
                 config=dict(workload=args.workload, description=WORKLOAD_DESC.get(args.workload, args.workload),
@@ -498,7 +575,7 @@ def run_ours(args):
                 roofline=roofline, cpu_baseline=cpu,
                 e2e=dict(value=e2e_value, unit="knees/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
                          loss_readback=e2e_mode, blocking_value=e2e_blocking),
-                gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag, full_step=full_step,
+                gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag, full_step=full_step, comm=comm,
                 inference=inference, switches={k: v for k, v in sorted(os.environ.items()) if k.startswith("KOA_")})
     print(json.dumps(line), flush=True)
     if ws > 1:
@@ -515,7 +592,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="knees per GPU (runner.sh:342 trains the full model at 16)")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="fe.*.dropout / agg.emb_dropout / agg.mlp_dropout (authors' recipe: 0.1, runner.sh:352 + conf/model/*.yaml)")
-    ap.add_argument("--cpu-knees", type=int, default=1, help="knees in the bounded CPU sample")
+    ap.add_argument("--cpu-knees", type=int, default=2, help="knees per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiler runs: skip the end-to-end pass")
     ap.add_argument("--no-full-step", action="store_true", help="skip the forward+backward+Adam measurement")

@@ -149,6 +149,14 @@ int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params, const floa
 /* grads[3*u + {0,1,2}] = d conv weight, d bn weight, d bn bias (fp32, accumulated into; NULL skips). */
 int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params, void* const* grads, void* workspace,
                     const float* dfeat, void* stream);
+/* The same backward pass in pieces: residual blocks [block_begin, block_end) from the last to the first. block_end < 0 (or
+ * the block count, koa_fe_num_blocks) starts the pass; with_stem != 0 (needs block_begin == 0) ends it with the max-pool /
+ * stem backward. Adjacent ranges issued in order on one stream compute exactly what koa_fe_backward computes; the
+ * data-parallel wrapper puts the gradient all-reduce of a finished stage between two calls, so that it overlaps the rest of
+ * the backward pass (nn.DataParallel reduces on the way back through the replicas: koafusion/run/train_prog_fus.py:84). */
+int koa_fe_backward_range(const koa_fe_desc_t* d, const void* const* params, void* const* grads, void* workspace,
+                          const float* dfeat, int block_begin, int block_end, int with_stem, void* stream);
+int koa_fe_num_blocks(const koa_fe_desc_t* d);
 int koa_fe_debug_offset(const koa_fe_desc_t* d, int what, int index, size_t* offset, size_t* bytes);
 
 /* ---- whole token transformer (FeaT) --------------------------------------------------------------- */

@@ -164,6 +164,8 @@ SIGNATURES = {
     "koa_fe_num_units": (_I, [C.POINTER(FeDesc)]),
     "koa_fe_forward": (_I, [C.POINTER(FeDesc), _PP, _P, _P, _P, _P]),
     "koa_fe_backward": (_I, [C.POINTER(FeDesc), _PP, _PP, _P, _P, _P]),
+    "koa_fe_backward_range": (_I, [C.POINTER(FeDesc), _PP, _PP, _P, _P, _I, _I, _I, _P]),
+    "koa_fe_num_blocks": (_I, [C.POINTER(FeDesc)]),
     "koa_fe_debug_offset": (_I, [C.POINTER(FeDesc), _I, _I, _SZ, _SZ]),
     "koa_feat_workspace_bytes": (C.c_size_t, [C.POINTER(FeatDesc)]),
     "koa_feat_num_params": (_I, [C.POINTER(FeatDesc)]),

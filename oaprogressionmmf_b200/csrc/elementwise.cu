@@ -522,20 +522,20 @@ __global__ void bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* 
         }
         unpack8h(qy[j], yy);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { a[u] += dz[u]; b[u] = fmaf(dz[u], yy[u], b[u]); }
+        for (int u = 0; u < 8; ++u) { a[u] += dz[u]; b[u] = fmaf(dz[u], yy[u] - mu[u], b[u]); }
         if (has_y2) {
           unpack8h(qz[j], yy);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) b2[u] = fmaf(dz[u], yy[u], b2[u]);
+          for (int u = 0; u < 8; ++u) b2[u] = fmaf(dz[u], yy[u] - mu2[u], b2[u]);
         }
       }
     }
-    // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)): one correction per thread instead of three operations
-    // per element (the sums are linear, so correcting the per-thread partials is exact)
+    // sum(dz * xhat) = invstd * sum(dz * (y - mean)): the mean is subtracted per element (subtracting mean * sum(dz) from
+    // sum(dz * y) at the end cancels catastrophically for channels with |mean| >> std)
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      b[u] = is[u] * (b[u] - mu[u] * a[u]);
-      if (has_y2) b2[u] = is2[u] * (b2[u] - mu2[u] * a[u]);
+      b[u] *= is[u];
+      if (has_y2) b2[u] *= is2[u];
     }
   }
   for (int i = threadIdx.x; i < 3 * c; i += blockDim.x) sm[i] = 0.0f;

@@ -318,8 +318,10 @@ int conv_forward(const Plan& p, const Unit& u, const void* x, void* ws, int trai
     ep.col_sum = bn_slot(ws, u, S_SUM);
     ep.col_sumsq = bn_slot(ws, u, S_SUMSQ);
   }
-  if (u.groups > 1)
+  if (u.groups > 1) {
+    const KoaFlopScale fs((double)(u.cin / u.groups) / 64.0);  // block-diagonal chunks: cin / groups of 64 columns are real
     return koa_conv_grouped_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.stride, &ep, st);
+  }
   if (u.k == 1 && u.stride == 1) return koa_gemm_launch(x, at(ws, u.w_fwd), (int)u.rows_out, u.cout, u.cin, &ep, st);
   return koa_conv_fprop_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, &ep, st);
 }
@@ -341,8 +343,10 @@ int conv_bn_forward(const Plan& p, const Unit& u, const void* x, void* ws, const
   }
   ep.act = relu ? KOA_ACT_RELU : KOA_ACT_NONE;
   ep.out_bf16_copy = out_bf;
-  if (u.groups > 1)
+  if (u.groups > 1) {
+    const KoaFlopScale fs((double)(u.cin / u.groups) / 64.0);  // block-diagonal chunks: cin / groups of 64 columns are real
     return koa_conv_grouped_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.stride, &ep, st);
+  }
   if (u.k == 1 && u.stride == 1) return koa_gemm_launch(x, at(ws, u.w_fwd), (int)u.rows_out, u.cout, u.cin, &ep, st);
   return koa_conv_fprop_launch(x, at(ws, u.w_fwd), p.n_img, u.hin, u.win, u.cin, u.cout, u.k, u.k, u.stride, u.pad, &ep, st);
 }
@@ -388,6 +392,7 @@ int gram_tail_forward(const Plan& p, const Block& b, const ParamView& pv, void* 
   float* gram = (float*)at(ws, b.gram);
   float* q = (float*)at(ws, b.q);
   // Gram = a2^T a2: a weight-gradient-shaped GEMM over the pixels, both operands the fp16 tensor itself (products exact in fp32)
+  const KoaFlopScale bookkeeping(0.0);  // Gram and Q are not part of the reference's arithmetic: 0 algorithmic FLOPs
   KOA_TRY(koa_gemm_wgrad_launch(at(ws, b.a2), at(ws, b.a2), gram, (int)u2.rows_out, w, w, 1, st));
   KOA_TRY(koa_k_gram_split(gram, at(ws, b.gram_hi), at(ws, b.gram_lo), w, count, st));
   // Q = W3 . (hi + lo): two small GEMMs with fp16 operands and an fp32 result (the second accumulates onto the first)
@@ -403,6 +408,7 @@ int gram_tail_forward(const Plan& p, const Block& b, const ParamView& pv, void* 
   KOA_TRY(koa_k_bn_gram_stats(at(ws, u3.w_fwd), (const float*)at(ws, b.sa2), q, pv.gamma(u3), pv.beta(u3), pv.run_mean(u3),
                               pv.run_var(u3), bn_slot(ws, u3, S_SCALE), bn_slot(ws, u3, S_SHIFT), bn_slot(ws, u3, S_MEAN),
                               bn_slot(ws, u3, S_INVSTD), c, w, count, st));
+  koa_profile_flop_scale(1.0);  // (the scope object restores the caller's value at return)
   const void* res = x;
   const Unit* res_bn = nullptr;
   if (b.ud >= 0) {
@@ -554,6 +560,7 @@ extern "C" int koa_fe_forward(const koa_fe_desc_t* d, const void* const* params,
       ep.bn_shift = bn_slot(ws, us, S_SHIFT);
       ep.act = KOA_ACT_RELU;
     }
+    const KoaFlopScale fs(49.0 / 64.0);  // 49 taps of the folded grey channel, padded to K = 64
     KOA_TRY(koa_gemm_launch(at(ws, p.a_stem), at(ws, p.wstem), (int)us.rows_out, 64, 64, &ep, st));
   }
   if (!p.fused_eval) KOA_TRY(bn_apply(us, nullptr, pv, ws, nullptr, at(ws, p.a0), nullptr, training, st));
@@ -654,7 +661,10 @@ int conv_wgrad(const Plan& p, const Unit& u, size_t x_bf, size_t x_f16, const vo
   float* scratch = (float*)at(ws, u.dw_scratch);
   if (u.groups > 1) {
     KOA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)u.cout * 9 * 64 * 4, st));
-    KOA_TRY(koa_conv_grouped_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.stride, xf, st));
+    {
+      const KoaFlopScale fs((double)(u.cin / u.groups) / 64.0);
+      KOA_TRY(koa_conv_grouped_wgrad_launch(dy, x, scratch, p.n_img, u.hin, u.win, u.cin, u.stride, xf, st));
+    }
     return koa_k_unpack_grouped_dw(scratch, gw, u.cout, u.cin / u.groups, st);
   }
   KOA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)u.cout * u.k * u.k * u.cin * 4, st));
@@ -674,11 +684,17 @@ int conv_dgrad(const Plan& p, const Unit& u, const void* dy, void* ws, koa_epilo
     return koa_gemm_launch(dy, at(ws, u.w_dgrad), (int)u.rows_out, u.cin, u.cout, ep, st);
   }
   const void* src = dy;
-  if (u.stride == 2) {
+  double alg = 1.0;
+  if (u.stride == 2) {  // three of four rows of the zero-inserted gradient are structural zeros
     KOA_TRY(koa_k_zero_insert2(dy, tmp, p.n_img, u.hin, u.win, u.cout, u.hout, u.wout, st));
     src = tmp;
+    alg = 0.25;
   }
-  if (u.groups > 1) return koa_conv_grouped_launch(src, at(ws, u.w_dgrad), p.n_img, u.hin, u.win, u.cout, 1, ep, st);
+  if (u.groups > 1) {
+    const KoaFlopScale fs(alg * (double)(u.cin / u.groups) / 64.0);
+    return koa_conv_grouped_launch(src, at(ws, u.w_dgrad), p.n_img, u.hin, u.win, u.cout, 1, ep, st);
+  }
+  const KoaFlopScale fs(alg);
   return koa_conv_fprop_launch(src, at(ws, u.w_dgrad), p.n_img, u.hin, u.win, u.cout, u.cin, u.k, u.k, 1, u.pad, ep, st);
 }
 
@@ -806,28 +822,62 @@ int get_wgrad_side(cudaStream_t main, WgradSide* out) {
 // gradients assembled by more than one kernel (stride-2 downsample) and for the stem.
 extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params, void* const* grads, void* ws,
                                const float* dfeat, void* stream) {
+  return koa_fe_backward_range(d, params, grads, ws, dfeat, 0, -1, 1, stream);
+}
+
+extern "C" int koa_fe_num_blocks(const koa_fe_desc_t* d) {
+  Plan p;
+  if (build_plan(d, p)) return -1;
+  return (int)p.blocks.size();
+}
+
+namespace {
+// does the epilogue that produces G for block `bi` (the conv1 / downsample data gradient of block bi + 1) also reduce it
+// for the last BatchNorm of block `bi`? A pure function of the plan, so that a backward pass split over several calls
+// (koa_fe_backward_range) needs no state besides the workspace.
+bool producer_reduces_g(const Plan& p, int bi, bool fuse) {
+  if (bi + 1 >= (int)p.blocks.size()) return false;  // G of the last block comes from the pooling backward
+  const Block& nb = p.blocks[bi + 1];
+  const Unit* ud = nb.ud >= 0 ? &p.units[nb.ud] : nullptr;
+  const bool single_producer = !(ud && ud->stride != 1);
+  return fuse && (p.gram || p.blocks[bi].ud < 0) && single_producer;
+}
+}  // namespace
+
+// Blocks [block_begin, block_end) of the backward pass, from the last to the first; block_end < 0 or == the block count
+// starts the pass (statistics reset + pooling backward), with_stem != 0 ends it (max-pool / stem backward after block 0;
+// needs block_begin == 0). Successive calls on the same stream with adjacent ranges compute exactly what one call does:
+// the data-parallel wrapper issues the gradient all-reduce of a stage between two calls (dataparallel.py).
+extern "C" int koa_fe_backward_range(const koa_fe_desc_t* d, const void* const* params, void* const* grads, void* ws,
+                                     const float* dfeat, int block_begin, int block_end, int with_stem, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   Plan p;
   KOA_TRY(build_plan(d, p));
   KOA_REQUIRE(params != nullptr && grads != nullptr && ws != nullptr && dfeat != nullptr, "null pointer argument");
   KOA_REQUIRE(d->need_backward, "forward was not run with need_backward");
+  const int n_blocks = (int)p.blocks.size();
+  if (block_end < 0) block_end = n_blocks;
+  KOA_REQUIRE(block_begin >= 0 && block_begin <= block_end && block_end <= n_blocks, "bad block range [%d, %d) of %d",
+              block_begin, block_end, n_blocks);
+  KOA_REQUIRE(!with_stem || block_begin == 0, "the stem follows block 0");
   const ParamView pv{params};
   const int training = d->training;
   const int hw = p.out_h * p.out_w;
   const bool fuse = fuse_bn_bwd_stats();
-  KOA_CHECK_CUDA(cudaMemsetAsync(at(ws, p.bstat_begin), 0, p.bstat_end - p.bstat_begin, st));
   WgradSide side;
   KOA_TRY(get_wgrad_side(st, &side));
   cudaStream_t sw = st;  // stream of the next weight-gradient GEMM
-  int cur = 0;  // p.g[cur] holds G of the current block
-  {
+  int cur = (n_blocks - block_end) & 1;  // p.g[cur] holds G of the current block (flips once per block)
+  if (block_end == n_blocks) {
+    KOA_CHECK_CUDA(cudaMemsetAsync(at(ws, p.bstat_begin), 0, p.bstat_end - p.bstat_begin, st));
     const Block& lb = p.blocks.back();
     if (d->with_gap) KOA_TRY(koa_k_gap_bwd(dfeat, at(ws, lb.out), at(ws, p.g[cur]), p.n_img, hw, p.out_c, st));
     else KOA_TRY(koa_k_gap_bwd(dfeat, at(ws, lb.out), at(ws, p.g[cur]), p.n_img * hw, 1, p.out_c, st));
   }
-  bool g_stats_done = false;  // the producer of G already reduced it for the last BatchNorm of the current block
+  // the producer of G already reduced it for the last BatchNorm of the current block
+  bool g_stats_done = block_end > 0 && producer_reduces_g(p, block_end - 1, fuse);
 
-  for (int bi = (int)p.blocks.size() - 1; bi >= 0; --bi) {
+  for (int bi = block_end - 1; bi >= block_begin; --bi) {
     const Block& b = p.blocks[bi];
     const Unit& u1 = p.units[b.u1];
     const Unit& u2 = p.units[b.u2];
@@ -859,6 +909,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
                                 bn_slot(ws, *u3, S_K2), c, w, c + w, count, st));
       KOA_TRY(koa_k_bn_gram_bias(at(ws, u3->w_dgrad), bn_slot(ws, *u3, S_K1), (float*)at(ws, b.cbias), w, c, st));
       {  // -M = W3^T . (-k2 * W3) [w][w], stored as the last w columns of every wext row
+        const KoaFlopScale bookkeeping(0.0);
         koa_epilogue_t em{};
         em.out = (uint8_t*)at(ws, b.wext) + (size_t)c * 2;
         em.ldo = c + w;
@@ -872,7 +923,10 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
       ep.col_bias = (const float*)at(ws, b.cbias);
       gate_and_stats(ep, ws, b.a2, &u2, fuse);  // dz2 = (...) * (a2 > 0) + sums for bn2
       KOA_TRY(side.before_write(2));
-      KOA_TRY(koa_gemm_kcat_launch(g_out, c, at(ws, b.a2_bf), w, at(ws, b.wext), (int)u3->rows_out, w, &ep, st));
+      {
+        const KoaFlopScale fs((double)c / (double)(c + w));  // the reference's data gradient has K = C; the a2 segment is ours
+        KOA_TRY(koa_gemm_kcat_launch(g_out, c, at(ws, b.a2_bf), w, at(ws, b.wext), (int)u3->rows_out, w, &ep, st));
+      }
       KOA_TRY(bn_backward(u2, nullptr, pv, grads, ws, d_a2, nullptr, d_a2, nullptr, training, fuse, st));  // in place -> dy2
       KOA_TRY(side.begin(&sw));
       KOA_TRY(conv_wgrad(p, u2, b.a1_bf, b.a1, d_a2, grads, ws, sw));
@@ -924,7 +978,8 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     const Unit* prev_last = prev ? &p.units[prev->kind == 0 ? prev->u3 : prev->u2] : nullptr;
     const bool single_producer = !(ud && ud->stride != 1);
     // (y-free tail: the previous block only needs sum(G) from this epilogue, also when it has a downsample branch)
-    const bool fuse_prev = fuse && prev != nullptr && (p.gram || prev->ud < 0) && single_producer;
+    const bool fuse_prev = prev != nullptr && producer_reduces_g(p, bi - 1, fuse);
+    (void)single_producer;
     auto gate_prev = [&](koa_epilogue_t& e) {
       if (p.gram) gate_and_colsum(e, ws, b.in, prev_last, fuse_prev);
       else gate_and_stats(e, ws, b.in, prev_last, fuse_prev);
@@ -963,6 +1018,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     g_stats_done = fuse_prev;
     cur ^= 1;
   }
+  if (!with_stem) return side.join();
   // ---- stem -----------------------------------------------------------------------------------------
   const Unit& us = p.units[0];
   void* d_a0 = at(ws, p.t[0]);
@@ -973,6 +1029,7 @@ extern "C" int koa_fe_backward(const koa_fe_desc_t* d, const void* const* params
     // the forward pass kept its fp16 im2col operand; the weight-gradient kernel converts it to bf16 in shared memory
     // (x_f16 = 2) to pair it with the bf16 dy. This GEMM is HBM-bound (64 x 64 outputs over millions of pixels), so the
     // conversion is free and the second im2col pass (1 ms per step) is gone.
+    const KoaFlopScale fs(49.0 / 64.0);
     KOA_TRY(koa_gemm_wgrad_launch(d_a0, at(ws, p.a_stem), (float*)at(ws, p.dwstem), (int)us.rows_out, 64, 64, 2, st));
     KOA_TRY(koa_k_stem_unfold_dwb((const float*)at(ws, p.dwstem), (float*)grads[0], st));
   }

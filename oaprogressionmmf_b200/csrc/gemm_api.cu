@@ -24,10 +24,16 @@ bool s_prof_on = false;
 std::vector<ProfRec> s_prof;
 std::mutex s_prof_mu;
 
+// Algorithmic share of the FLOPs of the next launches of this thread (koa_profile_flop_scale): the engines set it where a
+// launch multiplies structural zeros or does bookkeeping work (zero-inserted stride-2 data gradients: 1/4; grouped 3x3 as
+// block-diagonal 64-channel chunks: channels per group / 64; stem K = 49 of 64; the Gram / coefficient GEMMs of the y-free
+// BatchNorm: 0), so that the roofline counts what the reference computes, not what was launched.
+thread_local double t_flop_scale = 1.0;
+
 struct ProfScope {
   cudaStream_t st; int cls; double flops; int m, n, k, tag; cudaEvent_t a = nullptr, b = nullptr;
   ProfScope(cudaStream_t st_, int cls_, double flops_, int m_ = 0, int n_ = 0, int k_ = 0, int tag_ = 0)
-      : st(st_), cls(cls_), flops(flops_), m(m_), n(n_), k(k_), tag(tag_) {
+      : st(st_), cls(cls_), flops(flops_ * t_flop_scale), m(m_), n(n_), k(k_), tag(tag_) {
     if (!s_prof_on) return;
     cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a, st);
@@ -40,6 +46,12 @@ struct ProfScope {
   }
 };
 }  // namespace
+
+double koa_profile_flop_scale(double scale) {
+  const double old = t_flop_scale;
+  t_flop_scale = scale;
+  return old;
+}
 
 extern "C" int koa_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(s_prof_mu);

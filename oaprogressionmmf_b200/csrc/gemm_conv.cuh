@@ -13,7 +13,10 @@
 //     column and CTA at the end.
 //   * formats are template parameters (no per-element format selects), the statistics use packed fp32x2 math
 //     (FADD2 / FFMA2), the ReLU gate is one HSET2 + AND per element pair on the packed output,
-//     sum(dz * xhat) is accumulated as sum(dz * y) and corrected once per CTA: invstd * (sum(dz*y) - mean * sum(dz)).
+//     sum(dz * xhat) is accumulated as sum(dz * (y - mean)) (the mean of the warp's fixed column pair sits in two
+//     registers; subtracting it per element instead of correcting the total once avoids the cancellation
+//     sum(dz*y) - mean*sum(dz), which turned the summation-order noise of the atomics into 1e-3 of dgamma for channels
+//     with |mean| >> std) and scaled by invstd once per CTA.
 //   * MODE 1 (backward) moves its epilogue operands and its output with the TMA unit ([32 x 32] boxes in the 64-byte
 //     swizzle, which IS the staging layout): no operand registers, no address arithmetic, no row predicates.
 //   * MODE 2 (forward with the BatchNorm already known: eval mode, and the y-free last convolution of a bottleneck in
@@ -285,8 +288,17 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int h = lane >> 4, p = lane & 15;
     const uint32_t st_base = (uint32_t)(h * 64 + (p & 3) * 4);
     float2 s_a[CH], s_b[CH], q_a[CH], q_b[CH];  // two chains per chunk: sums over even / odd steps
+    float2 neg_mu[CH];                          // -mean of this lane's column pair (backward statistics)
 #pragma unroll
-    for (int j = 0; j < CH; ++j) s_a[j] = s_b[j] = q_a[j] = q_b[j] = make_float2(0.f, 0.f);
+    for (int j = 0; j < CH; ++j) {
+      s_a[j] = s_b[j] = q_a[j] = q_b[j] = make_float2(0.f, 0.f);
+      neg_mu[j] = make_float2(0.f, 0.f);
+      const int n = n0 + c0 + j * 128;
+      if (bwd && n < N) {
+        const float2 mu = __ldg(reinterpret_cast<const float2*>(ep.stat_mean + n + 2 * p));
+        neg_mu[j] = make_float2(-mu.x, -mu.y);
+      }
+    }
 
     for (int lt = lt_first; lt < my_tiles; lt += lt_step) {
       const int m0 = (m_start + lt * m_step) * BMT + m_off;
@@ -460,7 +472,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = 0; i < 16; i += 2) {
               const float2 x0 = unpack16<OF16>(w[i]), x1 = unpack16<OF16>(w[i + 1]);
               s_a[j] = add2(s_a[j], x0); s_b[j] = add2(s_b[j], x1);
-              q_a[j] = fma2(x0, unpack16<AF16>(wy[i]), q_a[j]); q_b[j] = fma2(x1, unpack16<AF16>(wy[i + 1]), q_b[j]);
+              q_a[j] = fma2(x0, add2(unpack16<AF16>(wy[i]), neg_mu[j]), q_a[j]);
+              q_b[j] = fma2(x1, add2(unpack16<AF16>(wy[i + 1]), neg_mu[j]), q_b[j]);
             }
           } else {
 #pragma unroll
@@ -497,11 +510,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float2 s = add2(s_a[j], s_b[j]), qq = add2(q_a[j], q_b[j]);
         s.x += __shfl_xor_sync(0xffffffffu, s.x, 16); s.y += __shfl_xor_sync(0xffffffffu, s.y, 16);
         qq.x += __shfl_xor_sync(0xffffffffu, qq.x, 16); qq.y += __shfl_xor_sync(0xffffffffu, qq.y, 16);
-        if (bwd && n < N) {  // sum(dz * xhat) = invstd * (sum(dz * y) - mean * sum(dz)); linear: per-CTA partials are fine
-          const float2 mu = __ldg(reinterpret_cast<const float2*>(ep.stat_mean + n + 2 * p));
+        if (bwd && n < N) {  // sum(dz * xhat) = invstd * sum(dz * (y - mean)); linear: per-CTA partials are fine
           const float2 is = __ldg(reinterpret_cast<const float2*>(ep.stat_invstd + n + 2 * p));
-          qq.x = is.x * (qq.x - mu.x * s.x);
-          qq.y = is.y * (qq.y - mu.y * s.y);
+          qq.x *= is.x;
+          qq.y *= is.y;
         }
         if (h == 0) *reinterpret_cast<float4*>(s_fin + e * kFinStride + j * 64 + p * 4) = make_float4(s.x, qq.x, s.y, qq.y);
       }

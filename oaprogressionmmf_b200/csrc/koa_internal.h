@@ -6,6 +6,13 @@
 #include "../../include/koa_b200.h"
 
 int koa_num_sms();
+// algorithmic share of the FLOPs of this thread's next GEMM launches in the per-launch profile (returns the previous value)
+double koa_profile_flop_scale(double scale);
+struct KoaFlopScale {  // RAII form
+  double old;
+  explicit KoaFlopScale(double s) : old(koa_profile_flop_scale(s)) {}
+  ~KoaFlopScale() { koa_profile_flop_scale(old); }
+};
 // reads and clears the diagnostic word of elementwise.cu (koa_debug_flag() in gemm_api.cu folds it into its own)
 int koa_k_debug_flag_elementwise(unsigned int* out);
 

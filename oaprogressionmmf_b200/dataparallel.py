@@ -77,11 +77,16 @@ class _SyncState:
 _state = _SyncState()
 
 
+def active() -> bool:
+    """True while a data-parallel wrapper synchronises gradients (the extractors then run their backward in stages)."""
+    return _state.enabled
+
+
 def sync_flat(flat: Optional[torch.Tensor], params: Sequence[nn.Parameter]) -> None:
-    """Called by the engine autograd Functions right after their backward call returned: ``flat`` holds the freshly
-    computed gradients of ``params`` (contiguous fp32). No-op unless ``wrap`` activated the synchronisation."""
+    """Called by the engine autograd Functions right after (a stage of) their backward call returned: ``flat`` holds
+    the freshly computed gradients of ``params`` (contiguous fp32). No-op unless ``wrap`` activated the synchronisation."""
     st = _state
-    if not st.enabled or flat is None:
+    if not st.enabled or flat is None or flat.numel() == 0:
         return
     import torch.distributed as dist
 

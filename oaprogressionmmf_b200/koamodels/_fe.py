@@ -160,10 +160,21 @@ class _FEFunction(torch.autograd.Function):
         dev = _lib.require_same_device("SliceEncoder backward", dfeat, ctx.ws)
         dfeat = dfeat.contiguous().float()
         with _lib.on_device(dev):
-            _lib.check(lib.koa_fe_backward(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(), dfeat.data_ptr(),
-                                           _lib.current_stream()), "koa_fe_backward")
+            if not dataparallel.active() or flat is None:
+                _lib.check(lib.koa_fe_backward(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(), dfeat.data_ptr(),
+                                               _lib.current_stream()), "koa_fe_backward")
+            else:
+                # Data-parallel run: the backward pass goes stage by stage (layer4 -> layer1 + stem), and the gradients
+                # of a finished stage, a contiguous slice of the flat buffer (units are laid out in network order), go on
+                # the wire while the earlier stages still compute. Only the last, smallest slice (stem + layer1, 0.9 MB
+                # of the 94 MB of a ResNet-50) is reduced after this extractor's compute has ended.
+                bounds = enc._stage_bounds(params, grads, flat)
+                for begin, end, with_stem, lo, hi, stage_params in bounds:
+                    _lib.check(lib.koa_fe_backward_range(C.byref(ctx.desc), ctx.table, gtable, ctx.ws.data_ptr(),
+                                                         dfeat.data_ptr(), begin, end, with_stem, _lib.current_stream()),
+                               "koa_fe_backward_range")
+                    dataparallel.sync_flat(flat[lo:hi], stage_params)
         ctx.ws = None
-        dataparallel.sync_flat(flat, [p for p in params if p.requires_grad])  # no-op outside a data-parallel run
         return (None, None, None, None, None, None, None, *grads)
 
 
@@ -194,6 +205,35 @@ class SliceEncoder(nn.Sequential):
         out = []
         for conv, bn in self._units():
             out += [conv.weight, bn.weight, bn.bias]
+        return out
+
+    def _stage_bounds(self, params, grads, flat):
+        """(block_begin, block_end, with_stem, flat_lo, flat_hi, parameters) per backward stage, last stage first: layer4,
+        layer3, layer2, then layer1 together with the stem. The flat gradient buffer holds the units in network order."""
+        blocks = [len(self[li]) for li in range(4, 8)]
+        units_per_layer = [sum(len(b.units()) for b in self[li]) for li in range(4, 8)]
+        offs = {}
+        base = flat.data_ptr()
+        for i, g in enumerate(grads):
+            if g is not None:
+                offs[i] = ((g.data_ptr() - base) // 4, g.numel())
+        live = sorted(offs)
+
+        def span(u_lo, u_hi):  # flat range and parameters of units [u_lo, u_hi)
+            idx = [i for i in live if 3 * u_lo <= i < 3 * u_hi]
+            if not idx:
+                return 0, 0, []
+            lo = offs[idx[0]][0]
+            hi = offs[idx[-1]][0] + offs[idx[-1]][1]
+            return lo, hi, [params[i] for i in idx]
+
+        out = []
+        b_hi, u_hi = sum(blocks), 1 + sum(units_per_layer)
+        for li in (3, 2, 1):
+            b_lo, u_lo = b_hi - blocks[li], u_hi - units_per_layer[li]
+            out.append((b_lo, b_hi, 0, *span(u_lo, u_hi)))
+            b_hi, u_hi = b_lo, u_lo
+        out.append((0, b_hi, 1, *span(0, u_hi)))
         return out
 
     def _nbt(self):

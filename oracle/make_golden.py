@@ -17,7 +17,6 @@ the reference's own FeaT + dict_fes blocks, assembled the way _xrNmrMcP.py:40-17
 """
 from __future__ import annotations
 
-import importlib.util
 import json
 import os
 import sys
@@ -26,29 +25,12 @@ import time
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = "/root/reference"
 sys.path.insert(0, ROOT)
-sys.path.insert(0, REF)
 
 from oracle import koa_oracle as ko  # noqa: E402
 
 
-class AttrDict(dict):
-    """item + attribute access, as the reference reads its OmegaConf config both ways."""
-
-    def __getattr__(self, k):
-        try:
-            return self[k]
-        except KeyError as e:
-            raise AttributeError(k) from e
-
-
-def to_attr(d):
-    if isinstance(d, dict):
-        return AttrDict({k: to_attr(v) for k, v in d.items()})
-    if isinstance(d, (list, tuple)):
-        return [to_attr(v) for v in d]
-    return d
+from oracle.ref_loader import build_model, focal_loss, to_attr  # noqa: E402
 
 
 def tensor_summary(t):
@@ -60,10 +42,7 @@ def tensor_summary(t):
 
 
 def load_ref_focal_loss():
-    spec = importlib.util.spec_from_file_location("ref_losses", os.path.join(REF, "koafusion/various/_losses.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod.FocalLoss(gamma=2)
+    return focal_loss(gamma=2)
 
 
 # Small but structurally complete cases (CPU seconds each). Sizes must be keys of the reference's
@@ -89,76 +68,11 @@ CASES = {
 }
 
 
-def build_extension_model(name, cfg):
-    """3-MRI pattern extension assembled from the reference's own blocks."""
-    from einops import rearrange, repeat
-    from koafusion.models._core_fes import dict_fes
-    from koafusion.models._core_trf import FeaT
-    from koafusion.models._xrNmrMcP import FeatC1
-    from torch import nn
-
-    agg = cfg["agg"]
-    ns = agg["num_slices"]
-
-    def fe(arch):
-        return nn.Sequential(*list(dict_fes[arch](pretrained=False).children())[:-1])
-
-    def feat(n, with_cls):
-        return FeaT(num_patches=n, patch_dim=2048, emb_dim=2048, depth=agg["depth"], heads=agg["heads"],
-                    mlp_dim=agg["mlp_dim"], num_classes=cfg["output_channels"], emb_dropout=agg["emb_dropout"],
-                    with_cls=with_cls, mlp_dropout=agg["mlp_dropout"])
-
-    class Ext(nn.Module):
-        def __init__(self):
-            super().__init__()
-            mr = cfg["fe"]["mr"]["arch"]
-            if name == "XR1MR3C1CnnTrf":
-                self._fe0 = fe(cfg["fe"]["xr"]["arch"])
-                self._fe1, self._fe2, self._fe3 = fe(mr), fe(mr), fe(mr)
-                self._fe4 = FeatC1(config=cfg["fe"]["clin"])
-                self._agg_1, self._agg_2, self._agg_3 = feat(ns[1], False), feat(ns[2], False), feat(ns[3], False)
-                self._agg_final = feat(1 + ns[1] + ns[2] + ns[3] + ns[4], True)
-            else:
-                self._fe1, self._fe2, self._fe3 = fe(mr), fe(mr), fe(mr)
-                self._agg_1, self._agg_2, self._agg_3 = feat(ns[0], False), feat(ns[1], False), feat(ns[2], False)
-                self._agg_final = feat(ns[0] + ns[1] + ns[2], True)
-
-        def forward(self, *ins):
-            def mri(fe_, agg_, vol):
-                b = vol.shape[0]
-                t = rearrange(vol, "b ch r c s -> (b s) ch r c")
-                t = repeat(t, "bs ch r c -> bs (k ch) r c", k=3)
-                t = rearrange(fe_(t), "(b s) ch d0 d1 -> b (s d0 d1) ch", b=b)
-                return agg_(t)[1]
-
-            parts = []
-            vols = ins
-            if name == "XR1MR3C1CnnTrf":
-                x = repeat(ins[0], "b ch r c -> b (k ch) r c", k=3)
-                parts.append(rearrange(self._fe0(x), "b ch d0 d1 -> b (d0 d1) ch"))
-                vols = ins[1:4]
-            parts.append(mri(self._fe1, self._agg_1, vols[0]))
-            parts.append(mri(self._fe2, self._agg_2, vols[1]))
-            parts.append(mri(self._fe3, self._agg_3, vols[2]))
-            if name == "XR1MR3C1CnnTrf":
-                parts.append(self._fe4(ins[4]))
-            out, _, _ = self._agg_final(torch.cat(parts, dim=1))
-            return {"main": rearrange(out, "b head cls -> b (head cls)")}
-
-    return Ext()
-
-
 def run_case(case_name, case):
-    from koafusion.models import dict_models
-
     name = case.get("model", case_name)
     cfg = ko.make_config(name, **case["kw"])
-    acfg = to_attr(cfg)
     torch.manual_seed(778)
-    if name in dict_models:
-        model = dict_models[name](config=acfg, path_weights=None)
-    else:
-        model = build_extension_model(name, acfg)
+    model = build_model(name, cfg)
 
     spec = ko.model_param_spec(name, cfg)
     ref_sd = model.state_dict()

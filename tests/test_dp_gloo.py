@@ -38,7 +38,10 @@ class _EngineFn(torch.autograd.Function):
         (gw, gb), flat = _lib.zeros_like_flat([w, gy.new_zeros(w.shape[0])])
         gw.copy_(gy.t() @ x)
         gb.copy_(gy.sum(0))
-        dp.sync_flat(flat, [ctx.w_param, ctx.b_param])
+        # in two slices of the one buffer, as the extractors hand over their stages (koamodels/_fe.py: layer4 first)
+        cut = (gb.data_ptr() - flat.data_ptr()) // 4
+        dp.sync_flat(flat[:cut], [ctx.w_param])
+        dp.sync_flat(flat[cut:], [ctx.b_param])
         return gy @ w, gw, gb
 
 
@@ -143,7 +146,7 @@ def test_ddp_wrapper_world2_gloo():
         acc = gs if acc is None else {n: acc[n] + gs[n] for n in gs}
     for n, g in acc.items():
         assert torch.allclose(r0["grads"][n], g / world, rtol=1e-5, atol=1e-6), n
-    assert r0["collectives"] == 2  # one flat engine buffer + one flat buffer of loose parameters
+    assert r0["collectives"] == 3  # two stage slices of the engine buffer + one flat buffer of loose parameters
     assert "zero_grad" in r0["second_backward"]
     # checkpoint keys are those of the unwrapped module (no "module." prefix)
     assert all(not k.startswith("module.") for k in r0["keys"])

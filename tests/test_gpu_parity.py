@@ -764,6 +764,62 @@ def test_fe_train_at_bf16_floor(cuda, arch, res_gain, b, s, size):
             assert int(msd[k[len("_fe."):]]) == int(v) == 1
 
 
+@pytest.mark.parametrize("arch,size,s", [("resnet50", 64, 3), ("resnext50_32x4d", 64, 0), ("resnet18", 64, 2)])
+def test_fe_backward_in_stages_equals_one_call(cuda, arch, size, s):
+    """koa_fe_backward_range over adjacent block ranges (how the data-parallel wrapper runs the backward pass, one
+    gradient all-reduce per finished stage) computes what koa_fe_backward computes: same gradients up to the summation
+    order of the split-K atomics, for any split of the block list."""
+    from oaprogressionmmf_b200 import dataparallel
+
+    lib = _lib.load()
+    sd, enc = _fe_pair(arch, cuda)
+    enc.train()
+    x = _randn(2, 1, size, size, max(s, 1), seed=5) if s else _randn(3, 1, size, size, seed=5)
+    tok = enc.encode_volume(x) if s else enc.encode_image(x)
+    gy = _randn(*tok.shape, seed=7)
+    fn = tok.grad_fn
+    while fn is not None and not hasattr(fn, "ws"):
+        fn = fn.next_functions[0][0] if fn.next_functions else None
+    ws, desc, table = fn.ws, fn.desc, fn.table
+    params = enc._trainable()
+    n_blocks = lib.koa_fe_num_blocks(C.byref(desc))
+    assert n_blocks == sum(len(enc[li]) for li in range(4, 8))
+
+    def run(ranges):
+        grads, flat = _lib.zeros_like_flat(params)
+        gt = _lib.ptr_table(grads)
+        d = gy.reshape(-1, gy.shape[-1]).contiguous()
+        for begin, end, stem in ranges:
+            _lib.check(lib.koa_fe_backward_range(C.byref(desc), table, gt, ws.data_ptr(), d.data_ptr(), begin, end, stem,
+                                                 _stream()), "range")
+        torch.cuda.synchronize()
+        return flat.clone()
+
+    whole = run([(0, -1, 1)])
+    # two runs of the same backward pass differ by the summation order of the statistics atomics, amplified through the
+    # BatchNorm backward of ~50 layers on this tiny batch: that run-to-run scatter is the yardstick
+    scatter = max(rel(run([(0, -1, 1)]), whole) for _ in range(2))
+    stages = [(b, e, st) for b, e, st, *_ in enc._stage_bounds(params, *_lib.zeros_like_flat(params))]
+    assert stages[0][1] == n_blocks and stages[-1][0] == 0 and stages[-1][2] == 1
+    for ranges in (stages, [(bi, bi + 1, 1 if bi == 0 else 0) for bi in range(n_blocks - 1, -1, -1)]):
+        got = run(ranges)
+        assert rel(got, whole) < 2 * scatter + 1e-5, (rel(got, whole), scatter)
+    assert scatter < 3e-2, scatter
+    # the slices the wrapper hands to the all-reduce cover every gradient exactly once
+    grads, flat = _lib.zeros_like_flat(params)
+    covered = torch.zeros_like(flat, dtype=torch.int32)
+    seen = []
+    for _, _, _, lo, hi, ps in enc._stage_bounds(params, grads, flat):
+        covered[lo:hi] += 1
+        seen += ps
+    assert int(covered.max()) == 1 and len(seen) == len(params) and len({id(p) for p in seen}) == len(params)
+    for g in grads:
+        off = (g.data_ptr() - flat.data_ptr()) // 4
+        assert bool((covered[off:off + g.numel()] == 1).all())
+    assert not dataparallel.active()
+    assert _lib.debug_flag() == 0
+
+
 def _ws_view(lib, desc, ws, what, index, dtype):
     off, nb = C.c_size_t(), C.c_size_t()
     _lib.check(lib.koa_fe_debug_offset(C.byref(desc), what, index, C.byref(off), C.byref(nb)), "koa_fe_debug_offset")
@@ -1130,7 +1186,7 @@ def test_full_size_logits_match_reference(cuda, case):
     loss.backward()
     assert abs(float(loss) - gold["train_loss"]) < 0.01 * gold["train_loss"], (float(loss), gold["train_loss"])
     assert logit_err(lg, torch.tensor(gold["train_logits"], device=cuda)) < 3e-2
-    ratios, proj = [], []
+    ratios, proj = [], {}
     for k, p in model.named_parameters():
         gref = gold["grads"][k]
         if gref is None:
@@ -1140,33 +1196,46 @@ def test_full_size_logits_match_reference(cuda, case):
         ratios.append(float(p.grad.norm()) / (gref["norm"] + 1e-30))
         if "probe" in gref and gref["norm"] > 0:
             got = float((p.grad.flatten().double() * _probe(p.grad.numel(), cuda).double()).sum())
-            proj.append((got - gref["probe"]) / gref["norm"])   # ~ N(0, 1) x relative L2 error of this tensor
+            proj[k] = (got - gref["probe"]) / gref["norm"]   # ~ N(0, 1) x relative L2 error of this tensor
     r = torch.tensor(ratios)
     assert float(r.min()) > 0.6 and float(r.max()) < 2.0, (float(r.min()), float(r.max()))
     assert abs(float(r.median()) - 1) < 0.05, float(r.median())
-    if proj:
-        # What 16-bit storage alone does to these projections: the same step with the oracle rounding every stored
-        # activation / operand of the extractors like the CUDA path stores it (no CUDA-path code involved). At random
-        # initialisation a train-mode BatchNorm ResNet amplifies any perturbation from block to block (ReLU masks flip),
-        # so the early convolutions' gradients move by tens of percent under ANY 16-bit arithmetic; the CUDA path must
-        # stay at that floor, and below 5e-2 wherever the floor is below 2e-2 (the transformers).
-        spec = ko.model_param_spec(gold["model"], cfg)
+    # DIRECTION of the gradients, tensor by tensor. At random initialisation a train-mode BatchNorm ResNet is chaotic in
+    # its gradients: the fp32 oracle on this GPU and the fp32 reference on the build container's CPU already disagree by
+    # ~70 % (relative L2) on the early convolutions of the 2-knee fixtures, and so does ANY 16-bit arithmetic. So the bar
+    # is (a) the floor: per tensor, the CUDA path is as close to the fp32 oracle (run here, same device, TF32 off) as the
+    # oracle with 16-bit storage emulated (no CUDA-path code involved) is; (b) wherever that floor is low (every
+    # transformer tensor: < 5e-2), the CUDA path itself is within 5e-2, the whole tensor compared element by element;
+    # (c) the recorded projections of the reference's gradients on seeded probe vectors agree wherever the fp32 oracle
+    # reproduces them on this machine.
+    spec = ko.model_param_spec(gold["model"], cfg)
+    runs = {}
+    for tag, emu in (("f32", False), ("emu", True)):
         sd = ko.make_state_dict(spec, gold["seed_weights"], pos_scale=0.02, device=cuda)
-        _, _, g_emu = ko.train_step(gold["model"], cfg, sd, inputs, target, emulate_16bit=True)
-        floor, mine = [], []
-        for (k, p), e in zip([(k, p) for k, p in model.named_parameters() if gold["grads"][k] is not None and
-                              "probe" in gold["grads"][k] and gold["grads"][k]["norm"] > 0], proj):
-            gref = gold["grads"][k]
-            f = float((g_emu[k].flatten().double() * _probe(p.grad.numel(), cuda).double()).sum())
-            floor.append(abs(f - gref["probe"]) / gref["norm"])
-            mine.append(abs(e))
-        floor, mine = torch.tensor(floor), torch.tensor(mine)
-        rms = lambda t: float(t.pow(2).mean().sqrt())  # noqa: E731
-        assert rms(mine) <= 1.5 * rms(floor) + 0.05, (rms(mine), rms(floor))
-        assert float(mine.median()) <= 1.5 * float(floor.median()) + 0.03, (float(mine.median()), float(floor.median()))
-        quiet = floor < 2e-2
-        if bool(quiet.any()):
-            assert float(mine[quiet].max()) < 5e-2, float(mine[quiet].max())
+        runs[tag] = ko.train_step(gold["model"], cfg, sd, inputs, target, emulate_16bit=emu)[2]
+    mine_e, floor_e, quiet_bad, probe_bad = [], [], [], []
+    for k, p in model.named_parameters():
+        if gold["grads"][k] is None:
+            continue
+        g32, gem = runs["f32"][k], runs["emu"][k]
+        if float(g32.norm()) == 0:
+            continue
+        em, ef = rel(p.grad, g32), rel(gem, g32)
+        mine_e.append(em)
+        floor_e.append(ef)
+        if ef < 5e-2 and em >= 5e-2:
+            quiet_bad.append((k, em, ef))
+        gref = gold["grads"][k]
+        if k in proj:
+            o32 = abs(float((g32.flatten().double() * _probe(g32.numel(), cuda).double()).sum()) - gref["probe"]) / gref["norm"]
+            if o32 < 2e-2 and abs(proj[k]) > 8e-2:
+                probe_bad.append((k, abs(proj[k]), o32))
+    mine_e, floor_e = torch.tensor(mine_e), torch.tensor(floor_e)
+    assert float(mine_e.median()) <= 1.25 * float(floor_e.median()) + 1e-2, (float(mine_e.median()), float(floor_e.median()))
+    assert float(mine_e.mean()) <= 1.25 * float(floor_e.mean()) + 1e-2, (float(mine_e.mean()), float(floor_e.mean()))
+    assert int((floor_e < 5e-2).sum()) >= 40, "the transformer tensors must be in the low-floor set"
+    assert not quiet_bad, quiet_bad[:5]
+    assert not probe_bad, probe_bad[:5]
 
 
 @pytest.mark.parametrize("name", ["XR1MR2C1CnnTrf", "XR1MR3C1CnnTrf"])
