@@ -260,7 +260,7 @@ def measure_full_step(step, model, dev_batches, steps, knees, peaks):
                           frac=gbs / peaks["hbm"] if gbs else None))
 
 
-def measure_inference(model, cfg, dev, batch=64, chunk=32, iters=3):
+def measure_inference(model, cfg, dev, batch=64, chunk=16, iters=3):
     """Eval-mode forward of `batch` knees in micro-batches of `chunk` (no coupling between knees in eval mode: BatchNorm
     uses its running statistics), inputs from pinned host memory, class predictions read back per micro-batch as the
     reference's eval loop does (koafusion/run/eval_prog_fus.py:286-304)."""
@@ -272,9 +272,10 @@ def measure_inference(model, cfg, dev, batch=64, chunk=32, iters=3):
         torch.cuda.empty_cache()
         ins_h, _ = synthetic_batch(cfg, batch, 5, pin=True)
 
-        def one():
-            ins = [t.to(dev, non_blocking=True) for t in ins_h]
-            return torch.cat([model(*[t[i:i + chunk] for t in ins])["main"].argmax(1).cpu() for i in range(0, batch, chunk)])
+        from oaprogressionmmf_b200.evalpath import predict_batched
+
+        def one():  # copy of micro-batch i + 1 overlaps the compute of micro-batch i; one read-back per batch
+            return predict_batched(model, ins_h, dev, micro_batch=chunk)[0]
 
         with torch.no_grad():
             one()
@@ -288,7 +289,8 @@ def measure_inference(model, cfg, dev, batch=64, chunk=32, iters=3):
         ms = e0.elapsed_time(e1) / iters
         return dict(value=batch / ms * 1e3, unit="knees/s", batch=batch, micro_batch=chunk, ms_per_batch=ms,
                     h2d_bytes_per_batch=sum(t.numel() * t.element_size() for t in ins_h), predictions=int(pred.numel()),
-                    mode="eval, no_grad, H2D + prediction read-back inside the timed region")
+                    mode="eval, no_grad, H2D (pipelined per micro-batch on a copy stream) + prediction read-back inside the "
+                         "timed region, through evalpath.predict_batched")
     finally:
         model.train(was_training)
 

@@ -52,6 +52,44 @@ def ensemble_proba(proba_foldw: torch.Tensor):
 
 
 @torch.no_grad()
+def predict_batched(model, inputs_host: Sequence[torch.Tensor], device, micro_batch: int = 32):
+    """Class predictions and probabilities of an eval-mode model for a batch that lives in (pinned) host memory, in
+    micro-batches of ``micro_batch`` knees (eval mode has no coupling between knees: BatchNorm uses its running
+    statistics): the host -> device copy of micro-batch i + 1 runs on a copy stream while micro-batch i computes, and
+    the predictions of the whole batch cross to the host once (the reference reads them per batch,
+    ``eval_prog_fus.py:286-304``). Returns ``(pred int64 (B,), proba fp32 (B, classes))`` on the host."""
+    if model.training:
+        raise ValueError("predict_batched runs an eval-mode model (call model.eval() first)")
+    device = torch.device(device)
+    n = inputs_host[0].shape[0]
+    main = torch.cuda.current_stream(device)
+    copy = torch.cuda.Stream(device)
+
+    def fetch(i):
+        with torch.cuda.stream(copy):
+            chunk = [t[i:i + micro_batch].to(device, non_blocking=True) for t in inputs_host]
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        return chunk, ev
+
+    nxt = fetch(0)
+    probas, preds = [], []
+    for i in range(0, n, micro_batch):
+        chunk, ev = nxt
+        if i + micro_batch < n:
+            nxt = fetch(i + micro_batch)
+        main.wait_event(ev)
+        for t in chunk:
+            t.record_stream(main)
+        out = model(*chunk)
+        logits = out["main"] if isinstance(out, dict) else out
+        proba, pred = predict(logits.reshape(logits.shape[0], -1))
+        probas.append(proba)
+        preds.append(pred)
+    return torch.cat(preds).cpu(), torch.cat(probas).cpu()
+
+
+@torch.no_grad()
 def eval_epoch(model, loader: Iterable[dict], modals: Sequence[str], downscale=None, device=None) -> Dict[str, list]:
     """One pass of a fold model over a loader with the reference's batch contract (``image__{modal}``, ``target``,
     ``("-", "exam_knee_id")``; ``eval_prog_fus.py:250-312``). Returns the reference's accumulator: lists under

@@ -94,8 +94,15 @@ class KoaResNet(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
-    def forward(self, x):  # pragma: no cover
-        raise RuntimeError("wrap the children in a SliceEncoder (as the koafusion model classes do)")
+    def forward(self, x):
+        """The classifier the reference's ``dict_fes[arch]()`` returns (``_torchvision.py:227-242``): extractor -> global
+        average pool -> ``fc``. The koafusion model classes never call it (they keep ``children()[:-1]``); here it runs the
+        CUDA extractor on this module's own children (shared, not copied) and the fp32 small-linear kernel for ``fc``."""
+        from ._small import small_linear
+
+        enc = SliceEncoder(self, with_gap=True)
+        enc.train(self.training)
+        return small_linear(enc(x).flatten(1), self.fc.weight, self.fc.bias)
 
 
 def _make_fe(arch: str):

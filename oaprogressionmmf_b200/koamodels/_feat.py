@@ -1,7 +1,9 @@
 """``FeaT`` / ``Transformer`` / ``Attention`` / ``FeedForward`` with the reference's module tree and
 ``state_dict`` keys (``koafusion/models/_core_trf.py:74-205``); ``FeaT.forward`` is one call into
 ``koa_feat_forward`` (tcgen05 GEMMs + fused attention/LayerNorm kernels), backward one call into
-``koa_feat_backward``. The sub-modules are parameter holders: the engine owns the compute.
+``koa_feat_backward``: inside ``FeaT`` the sub-modules only hold the parameters, the engine owns the compute. Used on
+their own (the reference exports them, ``koafusion/models/__init__.py:1``), ``Transformer`` / ``Attention`` /
+``FeedForward`` run operator by operator through ``_ops`` (same arithmetic, one launch per GEMM / LayerNorm / attention).
 """
 from __future__ import annotations
 
@@ -11,6 +13,7 @@ import torch
 from torch import nn
 
 from .. import _lib, dataparallel
+from . import _ops
 
 
 class FeedForward(nn.Module):
@@ -21,8 +24,9 @@ class FeedForward(nn.Module):
         self.net = nn.Sequential(nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout), nn.Linear(hidden_dim, dim),
                                  nn.Dropout(dropout))
 
-    def forward(self, x):  # pragma: no cover
-        raise RuntimeError("parameter holder; FeaT.forward runs the fused CUDA transformer")
+    def forward(self, x):
+        h = nn.functional.gelu(_ops.linear(x, self.net[0].weight, self.net[0].bias))
+        return self.net[4](_ops.linear(self.net[2](h), self.net[3].weight, self.net[3].bias))
 
 
 class Attention(nn.Module):
@@ -35,8 +39,13 @@ class Attention(nn.Module):
         self.to_qkv = nn.Linear(dim, dim * 3, bias=False)
         self.to_out = nn.Sequential(nn.Linear(dim, dim), nn.Dropout(dropout))
 
-    def forward(self, x, mask=None):  # pragma: no cover
-        raise RuntimeError("parameter holder; FeaT.forward runs the fused CUDA transformer")
+    def forward(self, x, mask=None):
+        """``(out (B, n, dim), attn (B, heads, n, n))`` as the reference returns them. ``mask`` is rejected: the reference's
+        mask branch cannot run (``import torch.functional as F`` has no ``pad``, ``_core_trf.py:2,173``)."""
+        if mask is not None:
+            raise ValueError("mask is unsupported (the reference's mask branch is dead code, _core_trf.py:172-177)")
+        out, attn = _ops.attention(_ops.linear(x, self.to_qkv.weight), self.heads, self.scale)
+        return self.to_out[1](_ops.linear(out, self.to_out[0].weight, self.to_out[0].bias)), attn
 
 
 class Transformer(nn.Module):
@@ -61,8 +70,15 @@ class Transformer(nn.Module):
         return [ln0.weight, ln0.bias, attn.to_qkv.weight, attn.to_out[0].weight, attn.to_out[0].bias, ln1.weight, ln1.bias,
                 ff.net[0].weight, ff.net[0].bias, ff.net[3].weight, ff.net[3].bias]
 
-    def forward(self, x, mask=None):  # pragma: no cover
-        raise RuntimeError("parameter holder; FeaT.forward runs the fused CUDA transformer")
+    def forward(self, x, mask=None):
+        """``(x, attentions)``: pre-norm blocks without a final norm (``_core_trf.py:195-205``)."""
+        attentions = []
+        for d in range(self.depth):
+            o, attn = getattr(self, f"attn_{d}")(_ops.layer_norm(x, getattr(self, f"prenorm_0_{d}")), mask)
+            attentions.append(attn)
+            x = o + x
+            x = getattr(self, f"ff_{d}")(_ops.layer_norm(x, getattr(self, f"prenorm_1_{d}"))) + x
+        return x, attentions
 
 
 class _FeaTFunction(torch.autograd.Function):

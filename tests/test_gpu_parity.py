@@ -953,6 +953,78 @@ def test_feat_forward_backward(cuda, b, n_p, depth, with_cls, head):
         assert rel(gm, v.grad) < 1e-2, (k, rel(gm, v.grad))
 
 
+def test_exported_transformer_classes_run_on_their_own(cuda):
+    """``koafusion.models`` exports ``Transformer``, ``Attention`` and ``FeedForward`` next to ``FeaT``
+    (``models/__init__.py:1``): used on their own they compute what the reference classes compute
+    (``_core_trf.py:141-205``), forward and backward, operator by operator through the C ABI (``koamodels/_ops.py``);
+    ``state_dict`` keys are the reference's, so the comparison loads one into the other."""
+    from oaprogressionmmf_b200.koamodels import Attention, FeedForward, Transformer
+
+    dim, heads, depth, b, n = 512, 8, 2, 3, 37
+    torch.manual_seed(5)
+    mine = Transformer(dim, depth, heads, dim, 0.0).to(cuda)
+    sd = {k: v.detach().clone() for k, v in mine.state_dict().items()}
+
+    def ref_transformer(x):
+        attns = []
+        for d in range(depth):
+            p = lambda k: sd[k].requires_grad_(True)  # noqa: E731
+            o = F.layer_norm(x, (dim,), p(f"prenorm_0_{d}.weight"), p(f"prenorm_0_{d}.bias"))
+            qkv = F.linear(o, p(f"attn_{d}.to_qkv.weight"))
+            q, k, v = qkv.view(b, n, 3, heads, dim // heads).permute(2, 0, 3, 1, 4)
+            attn = torch.softmax(q @ k.transpose(-1, -2) * dim ** -0.5, dim=-1)
+            o = (attn @ v).permute(0, 2, 1, 3).reshape(b, n, dim)
+            x = F.linear(o, p(f"attn_{d}.to_out.0.weight"), p(f"attn_{d}.to_out.0.bias")) + x
+            attns.append(attn)
+            o = F.layer_norm(x, (dim,), p(f"prenorm_1_{d}.weight"), p(f"prenorm_1_{d}.bias"))
+            o = F.linear(F.gelu(F.linear(o, p(f"ff_{d}.net.0.weight"), p(f"ff_{d}.net.0.bias"))), p(f"ff_{d}.net.3.weight"),
+                         p(f"ff_{d}.net.3.bias"))
+            x = o + x
+        return x, attns
+
+    x = _randn(b, n, dim, seed=3).requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    out, attns = mine(x)
+    ref, rattns = ref_transformer(xr)
+    assert len(attns) == depth and attns[0].shape == (b, heads, n, n)
+    assert rel(out, ref) < 2e-3 and rel(attns[1], rattns[1]) < 2e-3, (rel(out, ref), rel(attns[1], rattns[1]))
+    g = _randn(*out.shape, seed=4)
+    (out * g).sum().backward()
+    (ref * g).sum().backward()
+    assert rel(x.grad, xr.grad) < 1e-2, rel(x.grad, xr.grad)
+    for k, p in mine.named_parameters():
+        assert rel(p.grad, sd[k].grad) < 1.5e-2, (k, rel(p.grad, sd[k].grad))
+    # the two smaller building blocks, and the errors of the interface
+    ff = FeedForward(dim, 2 * dim).to(cuda)
+    y = ff(x.detach())
+    assert rel(y, F.linear(F.gelu(F.linear(x.detach(), ff.net[0].weight, ff.net[0].bias)), ff.net[3].weight, ff.net[3].bias)) < 2e-3
+    at = Attention(dim, heads).to(cuda)
+    o, a = at(x.detach())
+    assert o.shape == (b, n, dim) and a.shape == (b, heads, n, n) and abs(float(a.sum(-1).mean()) - 1) < 1e-5
+    with pytest.raises(ValueError):
+        at(x.detach(), mask=torch.ones(b, n - 1, dtype=torch.bool, device=cuda))
+    with pytest.raises(_lib.KoaError):
+        ff(x.detach().cpu())
+
+
+def test_resnet_classifier_forward(cuda):
+    """``dict_fes[arch]()`` is a complete classifier in the reference (``_torchvision.py:227-242``): here its ``forward``
+    runs the CUDA extractor + the fp32 ``fc`` kernel and matches the oracle's extractor followed by ``F.linear``."""
+    from oaprogressionmmf_b200.koamodels import dict_fes
+
+    sd, enc = _fe_pair("resnet18", cuda)
+    net = dict_fes["resnet18"](pretrained=False).to(cuda).eval()
+    # the oracle's keys are those of nn.Sequential(*children): position -> attribute name of the full network
+    remap = {"0": "conv1", "1": "bn1", "4": "layer1", "5": "layer2", "6": "layer3", "7": "layer4"}
+    net.load_state_dict({**net.state_dict(), **{remap[k[len("_fe."):].split(".")[0]] + k[len("_fe."):][1:]: v for k, v in sd.items()}})
+    x = _randn(3, 1, 64, 64, seed=6).expand(-1, 3, -1, -1)
+    with torch.no_grad():
+        got = net(x)
+        feat = ko.fe_forward(sd, "_fe", "resnet18", x, False, True).flatten(1)
+        ref = F.linear(feat, net.fc.weight, net.fc.bias)
+    assert got.shape == (3, 1000) and rel(got, ref) < LOGIT_TOL
+
+
 def test_feat_dropout_matches_oracle_with_the_same_masks(cuda):
     """nn.Dropout inside FeaT (emb_dropout after the positional embedding, mlp_dropout after to_out / GELU / ff out /
     head GELU; _core_trf.py:105,127,146-149,164). The engine draws counter-based Philox masks; koa_dropout_mask

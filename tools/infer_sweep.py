@@ -5,6 +5,7 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from oaprogressionmmf_b200.koamodels import dict_models
+from oaprogressionmmf_b200.evalpath import predict_batched
 from oaprogressionmmf_b200.synthetic import model_config, synthetic_batch, to_attr
 
 ap = argparse.ArgumentParser()
@@ -33,12 +34,8 @@ for b in [int(x) for x in args.batches.split(",")]:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.iters):
-                ins = [t.to(dev, non_blocking=True) for t in ins_h]   # host -> device inside the timed region
-                # every micro-batch hands its predictions to the host, as the reference's eval loop does per batch
-                # (koafusion/run/eval_prog_fus.py): this also keeps the host from queueing workspaces of several
-                # micro-batches ahead of the device
-                outs = [model(*[t[i:i + args.chunk] for t in ins])["main"].argmax(1).cpu() for i in range(0, b, args.chunk)]
-                pred = torch.cat(outs)
+                # host -> device inside the timed region, pipelined per micro-batch; predictions read back once per batch
+                pred, _ = predict_batched(model, ins_h, dev, micro_batch=args.chunk)
             e1.record()
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
