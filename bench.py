@@ -142,6 +142,49 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def _phase(msg):
+    """Progress marker on stderr (the JSON line is the only thing on stdout): tells where a run that never finished stopped."""
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+class Watchdog:
+    """The JSON line must come out even if one of the optional legs after the main measurement (end-to-end pass, CPU
+    baseline, full step, inference) never returns: once `arm` has been called with the line measured so far, a daemon thread
+    prints it and ends the process when the deadline passes. `disarm` before the normal print."""
+
+    def __init__(self):
+        self.line = None
+        self.deadline = None
+        self.lock = threading.Lock()
+        self.done = False
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def arm(self, line, seconds):
+        with self.lock:
+            self.line = dict(line)
+            self.deadline = time.time() + seconds
+
+    def update(self, **kv):
+        with self.lock:
+            if self.line is not None:
+                self.line.update(kv)
+
+    def disarm(self):
+        with self.lock:
+            self.done = True
+
+    def _run(self):
+        while True:
+            time.sleep(1.0)
+            with self.lock:
+                if self.done:
+                    return
+                if self.deadline is not None and time.time() > self.deadline:
+                    self.line["watchdog"] = "an optional leg exceeded its time budget: fields measured after `value` may be missing"
+                    print(json.dumps(self.line), flush=True)
+                    os._exit(0)
+
+
 def dist_info():
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -345,6 +388,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----------------------------------------------------------------------
+    _phase("warm-up")
     for i in range(args.warmup):
         step(*dev_batches[i % 2])
     barrier()
@@ -354,6 +398,7 @@ def run_ours(args):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    _phase("timed steps")
     ev0.record()
     for i in range(args.steps):
         loss = step(*dev_batches[i % 2])
@@ -368,12 +413,24 @@ def run_ours(args):
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = ws * B * args.steps / (ms_total / 1e3)
+    # from here on the measured line exists: whatever follows only adds fields to it (Watchdog)
+    wd = Watchdog() if rank == 0 else None
+    if wd is not None:
+        peaks0 = measured_peaks()
+        step_tf = value / ws * FLOPS_FWD_BWD[args.workload] / 1e12
+        wd.arm(dict(metric=METRIC, value=value, unit="knees/s", n_gpus=ws, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                    data="synthetic", config=dict(workload=args.workload, knees_per_gpu=B, global_batch=B * ws),
+                    roofline=dict(bound="tensor", kernel="whole training step", achieved=step_tf, peak=peaks0["tflops"],
+                                  unit="TFLOP/s", frac=step_tf / peaks0["tflops"], traffic=None),
+                    gpu_launches=int(launches), clocks=clocks), 600 if args.no_cpu_baseline else 900)
 
     # ---- per-launch pass for the roofline: the modality branches run one after the other here (with concurrent
     # branches the CUDA events around a launch also cover the time it waits for SMs held by another branch's kernel),
     # every tcgen05 launch is bracketed by events on its stream. Same model, same batches, still inside a long step.
     from oaprogressionmmf_b200.koamodels import set_branch_streams
 
+    _phase("per-launch roofline pass")
     prof_steps = 0 if args.no_roofline_pass else max(1, min(3, args.steps))
     set_branch_streams(False)
     if not args.skip_e2e:  # (profiler runs replay every launch: no extra warm-up step for them)
@@ -404,6 +461,7 @@ def run_ours(args):
         ins, tgt = next(it)
         return float(step(ins, tgt).item())
 
+    _phase("end-to-end pass")
     if args.skip_e2e:  # profiler runs only (ncu replays every launch): the line then carries no end-to-end number
         last_loss, e2e_value = float(loss.item()), None
         e2e_blocking, e2e_mode = None, None
@@ -462,6 +520,7 @@ def run_ours(args):
     # ---- N > 1: what the gradient all-reduce costs. The same K steps with the synchronisation switched off (every rank
     # then trains on its own: timing only); exposed = time with the all-reduce - time without it.
     comm = None
+    _phase("communication / inference legs")
     if ws > 1:
         from oaprogressionmmf_b200 import dataparallel as _dp
 
@@ -545,6 +604,7 @@ def run_ours(args):
                                           "`value` is measured with the branches on concurrent streams"))
     roofline["by_bound"] = split_by_bound(dump_path, peaks, ms_serial_total)
     cpu = None
+    _phase("cpu baseline")
     if ws == 1 and not args.no_cpu_baseline:
         # 1 warm-up + 3 timed steps, median and minimum, of the bench workload at 2 knees and of
         # BASELINE.json's config 1 (XR1Cnn, batch 8), on all host cores
@@ -558,6 +618,7 @@ def run_ours(args):
     # configuration (Adam, lr 1e-4, weight decay 1e-4: conf/prog_fus.yaml:47-48) through koa_adam_step. Reported next to
     # `value`, never instead of it; single GPU only and last, so that nothing above depends on it.
     full_step = None
+    _phase("cpu baseline done; full step")
     if ws == 1 and not args.skip_e2e and not args.no_full_step:
         try:
             full_step = measure_full_step(step, model, dev_batches, args.steps, B, peaks)
@@ -579,6 +640,8 @@ def run_ours(args):
                          loss_readback=e2e_mode, blocking_value=e2e_blocking),
                 gpu_launches=int(launches), clocks=clocks, last_loss=last_loss, debug_flag=flag, full_step=full_step, comm=comm,
                 inference=inference, switches={k: v for k, v in sorted(os.environ.items()) if k.startswith("KOA_")})
+    if wd is not None:
+        wd.disarm()
     print(json.dumps(line), flush=True)
     if ws > 1:
         dist.destroy_process_group()

@@ -64,26 +64,39 @@ def predict_batched(model, inputs_host: Sequence[torch.Tensor], device, micro_ba
     n = inputs_host[0].shape[0]
     main = torch.cuda.current_stream(device)
     copy = torch.cuda.Stream(device)
+    # two sets of device input buffers, allocated once on the compute stream (no tensor ever changes streams: the model
+    # runs its modality branches on several streams, and blocks that migrate between per-stream allocator pools stall it):
+    # the copy stream fills set k while the compute streams read set 1 - k; events order the two
+    mb = min(micro_batch, n)
+    bufs = [[torch.empty((mb,) + tuple(t.shape[1:]), dtype=t.dtype, device=device) for t in inputs_host] for _ in range(2)]
+    filled = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    starts = list(range(0, n, mb))
 
-    def fetch(i):
+    def fetch(j):
+        k, i = j & 1, starts[j]
+        m = min(mb, n - i)
         with torch.cuda.stream(copy):
-            chunk = [t[i:i + micro_batch].to(device, non_blocking=True) for t in inputs_host]
-            ev = torch.cuda.Event()
-            ev.record(copy)
-        return chunk, ev
+            if j >= 2:
+                copy.wait_event(consumed[k])
+            else:
+                copy.wait_stream(main)  # the buffers exist from here
+            for dst, src in zip(bufs[k], inputs_host):
+                dst[:m].copy_(src[i:i + m], non_blocking=True)
+            filled[k].record(copy)
+        return m
 
-    nxt = fetch(0)
+    sizes = {0: fetch(0)}
     probas, preds = [], []
-    for i in range(0, n, micro_batch):
-        chunk, ev = nxt
-        if i + micro_batch < n:
-            nxt = fetch(i + micro_batch)
-        main.wait_event(ev)
-        for t in chunk:
-            t.record_stream(main)
-        out = model(*chunk)
+    for j in range(len(starts)):
+        if j + 1 < len(starts):
+            sizes[j + 1] = fetch(j + 1)
+        k = j & 1
+        main.wait_event(filled[k])
+        out = model(*[t[:sizes[j]] for t in bufs[k]])
         logits = out["main"] if isinstance(out, dict) else out
         proba, pred = predict(logits.reshape(logits.shape[0], -1))
+        consumed[k].record(main)
         probas.append(proba)
         preds.append(pred)
     return torch.cat(preds).cpu(), torch.cat(probas).cpu()

@@ -102,32 +102,47 @@ class SyntheticKneeLoader:
 class DevicePrefetcher:
     """Host batches -> device batches with the copy of batch i+1 issued on a copy stream while step i computes (what
     the reference's ``DataLoader(pin_memory=True)`` + ``.to(device, non_blocking=True)`` loop amounts to,
-    ``koafusion/run/train_prog_fus.py:136-140``). Every batch is copied from pinned host memory, none is reused."""
+    ``koafusion/run/train_prog_fus.py:136-140``). Every batch is copied from pinned host memory inside the step that
+    precedes its use; the device tensors handed out are two alternating buffer sets."""
 
     def __init__(self, loader, device):
         self.loader = iter(loader)
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        self.next = None
+        # Two sets of device buffers allocated once on the compute stream and filled in turn by the copy stream (no tensor
+        # changes streams; blocks migrating between the per-stream pools of the caching allocator stall a model that
+        # runs its branches on several streams). The batch handed out by __next__ stays valid until the call after next.
+        self.bufs = [None, None]
+        self.filled = [torch.cuda.Event(), torch.cuda.Event()]
+        self.k = 0
+        self.calls = 0
         self._issue()
 
     def _issue(self):
         ins_h, tgt_h = next(self.loader)
+        k = self.k
+        cur = torch.cuda.current_stream(self.device)
+        if self.bufs[k] is None or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(self.bufs[k][0], ins_h)):
+            self.bufs[k] = ([torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in ins_h],
+                            torch.empty(tgt_h.shape, dtype=tgt_h.dtype, device=self.device))
+        # everything queued on the compute stream so far (the step that read this set two calls ago) precedes the refill
+        self.copy_stream.wait_stream(cur)
         with torch.cuda.stream(self.copy_stream):
-            ins = [t.to(self.device, non_blocking=True) for t in ins_h]
-            tgt = tgt_h.to(self.device, non_blocking=True)
-        self.next = (ins, tgt)
+            for dst, src in zip(self.bufs[k][0], ins_h):
+                dst.copy_(src, non_blocking=True)
+            self.bufs[k][1].copy_(tgt_h, non_blocking=True)
+            self.filled[k].record(self.copy_stream)
 
     def __iter__(self):
         return self
 
     def __next__(self):
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_stream(self.copy_stream)
-        ins, tgt = self.next
-        for t in ins + [tgt]:
-            t.record_stream(cur)  # allocated on the copy stream, consumed on the compute stream
-        self._issue()
+        k = self.k
+        cur.wait_event(self.filled[k])
+        ins, tgt = self.bufs[k]
+        self.k ^= 1
+        self._issue()  # the next batch goes into the other set while this one is consumed
         return ins, tgt
 
 
