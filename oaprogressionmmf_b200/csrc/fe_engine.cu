@@ -897,13 +897,16 @@ extern "C" int koa_fe_backward_range(const koa_fe_desc_t* d, const void* const* 
       // dz2 = ([G | a2] . wext^T + bias) * (a2 > 0) in ONE GEMM.
       const int w = u2.cout, c = u3->cout;
       const double count = (double)u3->rows_out;
-      if (!g_stats_done)  // sum(G) per channel (the producer of G did not reduce it)
+      // sum(G) per channel: from the producer of G when it reduced it (into the downsample unit's slots when the block has
+      // one: that BatchNorm needs sum(G * xhat_d) from the same epilogue, and sum(G) is the same for both), else by a pass
+      const float* sdz = bn_slot(ws, (ud && g_stats_done) ? *ud : *u3, S_SDZ);
+      if (!g_stats_done)
         KOA_TRY(koa_k_col_stats(g_out, bn_slot(ws, *u3, S_SDZ), bn_slot(ws, *u3, S_SDZX), u3->rows_out, c, st));
-      if (ud) KOA_TRY(bn_backward(*ud, nullptr, pv, grads, ws, g_out, nullptr, dy_down, nullptr, training, false, st));
+      if (ud) KOA_TRY(bn_backward(*ud, nullptr, pv, grads, ws, g_out, nullptr, dy_down, nullptr, training, g_stats_done, st));
       float* tq = (float*)at(ws, b.tq);
       KOA_TRY(koa_gemm_wgrad_launch(g_out, at(ws, b.a2_bf), tq, (int)u3->rows_out, c, w, 0, st));
       KOA_TRY(koa_k_bn_gram_bwd(tq, at(ws, u3->w_fwd), pv.w(*u3), (const float*)at(ws, b.sa2), (const float*)at(ws, b.q),
-                                bn_slot(ws, *u3, S_SDZ), pv.gamma(*u3), bn_slot(ws, *u3, S_MEAN), bn_slot(ws, *u3, S_INVSTD),
+                                sdz, pv.gamma(*u3), bn_slot(ws, *u3, S_MEAN), bn_slot(ws, *u3, S_INVSTD),
                                 (float*)grads[u3->idx * 3 + 1], (float*)grads[u3->idx * 3 + 2], (float*)grads[u3->idx * 3 + 0],
                                 at(ws, b.wext), at(ws, b.k2w), bn_slot(ws, *u3, S_K0), bn_slot(ws, *u3, S_K1),
                                 bn_slot(ws, *u3, S_K2), c, w, c + w, count, st));
@@ -981,8 +984,11 @@ extern "C" int koa_fe_backward_range(const koa_fe_desc_t* d, const void* const* 
     const bool fuse_prev = prev != nullptr && producer_reduces_g(p, bi - 1, fuse);
     (void)single_producer;
     auto gate_prev = [&](koa_epilogue_t& e) {
-      if (p.gram) gate_and_colsum(e, ws, b.in, prev_last, fuse_prev);
-      else gate_and_stats(e, ws, b.in, prev_last, fuse_prev);
+      if (!p.gram) gate_and_stats(e, ws, b.in, prev_last, fuse_prev);
+      // y-free tail: the last BatchNorm of the previous block only needs sum(G); the statistics slot of the epilogue is
+      // free for the BatchNorm of its downsample branch (sum(G) and sum(G * xhat_d), both into that unit's slots)
+      else if (prev != nullptr && prev->ud >= 0) gate_and_stats(e, ws, b.in, &p.units[prev->ud], fuse_prev);
+      else gate_and_colsum(e, ws, b.in, prev_last, fuse_prev);
     };
     if (!ud) {
       koa_epilogue_t ep{};

@@ -764,16 +764,20 @@ def test_fe_train_at_bf16_floor(cuda, arch, res_gain, b, s, size):
             assert int(msd[k[len("_fe."):]]) == int(v) == 1
 
 
+@pytest.mark.parametrize("train", [False, True])
 @pytest.mark.parametrize("arch,size,s", [("resnet50", 64, 3), ("resnext50_32x4d", 64, 0), ("resnet18", 64, 2)])
-def test_fe_backward_in_stages_equals_one_call(cuda, arch, size, s):
+def test_fe_backward_in_stages_equals_one_call(cuda, arch, size, s, train):
     """koa_fe_backward_range over adjacent block ranges (how the data-parallel wrapper runs the backward pass, one
-    gradient all-reduce per finished stage) computes what koa_fe_backward computes: same gradients up to the summation
-    order of the split-K atomics, for any split of the block list."""
+    gradient all-reduce per finished stage) computes what koa_fe_backward computes, for any split of the block list.
+    With BatchNorm in eval mode the backward pass is well conditioned: equal up to the summation order of the split-K
+    atomics (1e-5). In train mode on this tiny batch (2 x 2 pixels in layer4) the BatchNorm backward amplifies the
+    summation-order noise of its statistics from layer to layer, and that noise depends on the launch timing: there the
+    yardstick is the scatter between two identical runs, with a 2e-2 allowance."""
     from oaprogressionmmf_b200 import dataparallel
 
     lib = _lib.load()
     sd, enc = _fe_pair(arch, cuda)
-    enc.train()
+    enc.train(train)
     x = _randn(2, 1, size, size, max(s, 1), seed=5) if s else _randn(3, 1, size, size, seed=5)
     tok = enc.encode_volume(x) if s else enc.encode_image(x)
     gy = _randn(*tok.shape, seed=7)
@@ -803,8 +807,8 @@ def test_fe_backward_in_stages_equals_one_call(cuda, arch, size, s):
     assert stages[0][1] == n_blocks and stages[-1][0] == 0 and stages[-1][2] == 1
     for ranges in (stages, [(bi, bi + 1, 1 if bi == 0 else 0) for bi in range(n_blocks - 1, -1, -1)]):
         got = run(ranges)
-        assert rel(got, whole) < 2 * scatter + 1e-5, (rel(got, whole), scatter)
-    assert scatter < 3e-2, scatter
+        assert rel(got, whole) < (max(3 * scatter, 2e-2) if train else 1e-5), (rel(got, whole), scatter)
+    assert scatter < (3e-2 if train else 1e-5), scatter
     # the slices the wrapper hands to the all-reduce cover every gradient exactly once
     grads, flat = _lib.zeros_like_flat(params)
     covered = torch.zeros_like(flat, dtype=torch.int32)
