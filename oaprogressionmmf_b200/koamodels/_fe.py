@@ -199,6 +199,7 @@ class SliceEncoder(nn.Sequential):
         super().__init__(*(children[:-1] if with_gap else children[:-2]))
         self.arch = resnet.arch
         self.with_gap = with_gap
+        self._channels_checked = False
 
     # -- parameter plumbing -----------------------------------------------------------------------
     def _units(self):
@@ -266,6 +267,16 @@ class SliceEncoder(nn.Sequential):
         if x.dim() != 4 or x.shape[1] not in (1, 3):
             raise ValueError(f"SliceEncoder expects (N, 1|3, H, W), got {tuple(x.shape)}")
         n, _, h, w = x.shape
+        if x.shape[1] == 3 and not self._channels_checked:
+            # The stem folds the three input channels into one (the reference always feeds `repeat(x, k=3)` of a grey
+            # image, _xrNmrMcP.py:211-213): a genuine 3-channel image would silently lose two of them. Checked on the first
+            # call of every encoder (one device read-back), and on every call with KOA_CHECK_CHANNELS=1.
+            import os
+
+            if x.stride(1) != 0 and not bool(((x[:, 0] == x[:, 1]) & (x[:, 0] == x[:, 2])).all()):
+                raise ValueError("SliceEncoder folds the three input channels into one grey channel: the channels of this "
+                                 "input differ (koafusion feeds repeat(x, k=3); colour images are not supported)")
+            self._channels_checked = os.environ.get("KOA_CHECK_CHANNELS", "0") != "1"
         img = x[:, 0].contiguous().float()
         feat = self._run(img, n, h, w, 0)
         if self.with_gap:

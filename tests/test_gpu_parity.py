@@ -1450,3 +1450,18 @@ def test_branch_streams_do_not_change_the_results(cuda, golden_dir):
     finally:
         set_branch_streams(None)
     assert _lib.debug_flag() == 0
+
+
+def test_slice_encoder_rejects_a_colour_image(cuda):
+    """The stem folds the three identical channels the reference feeds (`repeat(x, k=3)`, _xrNmrMcP.py:211-213) into one:
+    an input whose channels differ is an error, not a silent use of channel 0."""
+    sd, enc = _fe_pair("resnet18", cuda)
+    enc.eval()
+    grey = _randn(2, 1, 64, 64, seed=6)
+    with torch.no_grad():
+        a = enc(grey.expand(-1, 3, -1, -1))
+        b = enc(grey.repeat(1, 3, 1, 1))
+        assert torch.equal(a, b)
+        enc2 = _fe_pair("resnet18", cuda)[1].eval()
+        with pytest.raises(ValueError):
+            enc2(_randn(2, 3, 64, 64, seed=7))
