@@ -146,6 +146,17 @@ class _Base(nn.Module):
         if self.config["restore_weights"]:
             self.load_state_dict(torch.load(path_weights))
 
+    def _replicate_for_data_parallel(self):
+        """``nn.DataParallel`` over SEVERAL devices (the reference's wrapper, ``run/train_prog_fus.py:84``) replicates the
+        module into one Python thread per GPU of one process. This path scales as one process per GPU instead
+        (``oaprogressionmmf_b200.dataparallel.wrap`` after ``torch.distributed`` initialisation: same per-replica BatchNorm
+        semantics, gradient all-reduce over NCCL overlapped with backward); a multi-device replication is refused here rather
+        than left to fail inside a kernel (measured in round 2: misaligned-address fault). ``nn.DataParallel`` with ONE device
+        never replicates and works as before."""
+        raise TypeError("koafusion-b200 models do not support nn.DataParallel over several devices: launch one process per GPU "
+                        "(torchrun) and wrap the model with oaprogressionmmf_b200.dataparallel.wrap(model) instead "
+                        "(INTEGRATION.md section 1)")
+
     def _make_feat(self, num_patches, with_cls=True):
         agg = self.config["agg"]
         return FeaT(num_patches=num_patches, patch_dim=self.vs["agg_in_depth"], emb_dim=self.vs["agg_in_depth"],

@@ -102,3 +102,17 @@ def test_cpu_forward_fails_loudly_instead_of_falling_back():
     enc = koamodels.SliceEncoder(koamodels.dict_fes["resnet18"](), with_gap=True)
     with pytest.raises(ValueError):
         enc(torch.zeros(1, 2, 64, 64))
+
+
+def test_multi_device_dataparallel_is_refused_with_guidance():
+    """The reference wraps its model in single-process nn.DataParallel (run/train_prog_fus.py:84). Over one device that
+    wrapper never replicates and works; over several devices this path is one process per GPU (dataparallel.wrap), and the
+    replication hook says so instead of failing inside a kernel."""
+    import pytest
+    from oaprogressionmmf_b200.koamodels import dict_models
+    from oracle import koa_oracle as ko
+    from tests.util import to_attr
+
+    model = dict_models["XR1Cnn"](to_attr(ko.make_config("XR1Cnn", xr_size=64, xr_arch="resnet18")), None)
+    with pytest.raises(TypeError, match="one process per GPU"):
+        model._replicate_for_data_parallel()
