@@ -423,7 +423,7 @@ def run_ours(args):
                     data="synthetic", config=dict(workload=args.workload, knees_per_gpu=B, global_batch=B * ws),
                     roofline=dict(bound="tensor", kernel="whole training step", achieved=step_tf, peak=peaks0["tflops"],
                                   unit="TFLOP/s", frac=step_tf / peaks0["tflops"], traffic=None),
-                    gpu_launches=int(launches), clocks=clocks), 600 if args.no_cpu_baseline else 900)
+                    gpu_launches=int(launches), clocks=clocks), 240 if args.no_cpu_baseline else 420)
 
     # ---- per-launch pass for the roofline: the modality branches run one after the other here (with concurrent
     # branches the CUDA events around a launch also cover the time it waits for SMs held by another branch's kernel),

@@ -116,3 +116,39 @@ def test_multi_device_dataparallel_is_refused_with_guidance():
     model = dict_models["XR1Cnn"](to_attr(ko.make_config("XR1Cnn", xr_size=64, xr_arch="resnet18")), None)
     with pytest.raises(TypeError, match="one process per GPU"):
         model._replicate_for_data_parallel()
+
+
+def test_backward_stage_bounds_partition_the_flat_gradient_buffer():
+    """Host logic of the staged backward pass (koamodels/_fe.py::_stage_bounds, used by the data-parallel wrapper): the four
+    stages (layer4, layer3, layer2, layer1 + stem) cover every block once, in backward order, and their flat-buffer
+    slices cover every gradient tensor exactly once without overlapping."""
+    import torch
+    from oaprogressionmmf_b200 import _lib
+    from oaprogressionmmf_b200.koamodels import SliceEncoder, dict_fes
+
+    for arch, layers in (("resnet50", (3, 4, 6, 3)), ("resnext50_32x4d", (3, 4, 6, 3)), ("resnet18", (2, 2, 2, 2))):
+        enc = SliceEncoder(dict_fes[arch](pretrained=False))
+        params = enc._trainable()
+        grads, flat = _lib.zeros_like_flat(params)
+        stages = enc._stage_bounds(params, grads, flat)
+        assert [(b, e, s) for b, e, s, *_ in stages] == [
+            (sum(layers[:3]), sum(layers), 0), (sum(layers[:2]), sum(layers[:3]), 0), (layers[0], sum(layers[:2]), 0),
+            (0, layers[0], 1)]
+        covered = torch.zeros(flat.numel(), dtype=torch.int32)
+        seen = []
+        prev_lo = flat.numel()
+        for _, _, _, lo, hi, ps in stages:
+            assert 0 <= lo < hi <= prev_lo      # earlier layers sit earlier in the buffer: stages walk it backwards
+            prev_lo = lo
+            covered[lo:hi] += 1
+            seen += ps
+        assert int(covered.max()) == 1
+        assert len(seen) == len(params) and {id(p) for p in seen} == {id(p) for p in params}
+        for g in grads:
+            off = (g.data_ptr() - flat.data_ptr()) // 4
+            assert bool((covered[off:off + g.numel()] == 1).all())
+        # a frozen tensor simply drops out of its stage
+        params[5].requires_grad_(False)
+        grads2, flat2 = _lib.zeros_like_flat([p if p.requires_grad else None for p in params])
+        stages2 = enc._stage_bounds(params, grads2, flat2)
+        assert sum(len(ps) for *_, ps in stages2) == len(params) - 1

@@ -4,10 +4,19 @@
 import csv, sys, json, collections, re
 
 path, out = sys.argv[1], sys.argv[2]
-lines = [l for l in open(path) if not l.startswith("==")]
+import gzip
+
+opener = gzip.open if path.endswith(".gz") else open
+lines = [l for l in opener(path, "rt") if not l.startswith("==")]
 acc = collections.OrderedDict()
 cur = {}
-for r in csv.DictReader(lines):
+rows_all = list(csv.DictReader(lines))
+# one training step = from the fourth-from-last pack_fe_weights_kernel (one per extractor, first kernel of a forward) on
+starts = [r["ID"] for r in rows_all if "pack_fe_weights_kernel" in r["Kernel Name"] and r["Metric Name"] == "gpu__time_duration.sum"]
+first_id = int(starts[-4]) if len(starts) >= 4 else -1
+for r in rows_all:
+    if int(r["ID"]) < first_id:
+        continue
     name = re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", r["Kernel Name"])
     fam = re.sub(r"[<(].*", "", name).replace("void ", "").strip()
     v = float(r["Metric Value"].replace(",", ""))
