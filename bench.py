@@ -144,7 +144,10 @@ class ClockSampler:
 
 def _phase(msg):
     """Progress marker on stderr (the JSON line is the only thing on stdout): tells where a run that never finished stopped."""
-    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+    mem = ""
+    if torch.cuda.is_available() and torch.cuda.is_initialized():
+        mem = f" [reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB, allocated {torch.cuda.memory_allocated() / 2**30:.1f} GiB]"
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}{mem}", file=sys.stderr, flush=True)
 
 
 class Watchdog:
@@ -155,6 +158,8 @@ class Watchdog:
     def __init__(self):
         self.line = None
         self.deadline = None
+        self.stall_seconds = None  # hunt mode: fire when `beat` has not been called for this long
+        self.last_beat = time.time()
         self.lock = threading.Lock()
         self.done = False
         threading.Thread(target=self._run, daemon=True).start()
@@ -169,6 +174,9 @@ class Watchdog:
             if self.line is not None:
                 self.line.update(kv)
 
+    def beat(self):
+        self.last_beat = time.time()
+
     def disarm(self):
         with self.lock:
             self.done = True
@@ -179,10 +187,34 @@ class Watchdog:
             with self.lock:
                 if self.done:
                     return
-                if self.deadline is not None and time.time() > self.deadline:
+                stalled = self.stall_seconds is not None and time.time() - self.last_beat > self.stall_seconds
+                if self.deadline is not None and (time.time() > self.deadline or stalled):
                     self.line["watchdog"] = "an optional leg exceeded its time budget: fields measured after `value` may be missing"
                     print(json.dumps(self.line), flush=True)
+                    self._post_mortem()
                     os._exit(0)
+
+    @staticmethod
+    def _post_mortem():
+        """Where every Python thread stands and what the GPU is doing, on stderr (the JSON line is already out)."""
+        try:
+            import faulthandler
+
+            faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+            from oaprogressionmmf_b200 import _lib
+
+            latest, first = _lib.debug_flag_peek()
+            print(f"[bench watchdog] barrier time-out codes: latest {latest:#x}, first {first:#x}", file=sys.stderr, flush=True)
+            buf = C.create_string_buffer(1 << 16)
+            n = _lib.load().koa_profile_pending(buf, len(buf))
+            print(f"[bench watchdog] {n} profiled launch(es) started but not finished (cls tag m n k):\n"
+                  f"{buf.value.decode()}", file=sys.stderr, flush=True)
+            q = "utilization.gpu,memory.used,memory.total,clocks.sm"
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader"], capture_output=True, text=True,
+                                 timeout=10).stdout
+            print(f"[bench watchdog] nvidia-smi {q}: {out.strip()}", file=sys.stderr, flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench watchdog] post-mortem failed: {e}", file=sys.stderr, flush=True)
 
 
 def dist_info():
@@ -423,7 +455,8 @@ def run_ours(args):
                     data="synthetic", config=dict(workload=args.workload, knees_per_gpu=B, global_batch=B * ws),
                     roofline=dict(bound="tensor", kernel="whole training step", achieved=step_tf, peak=peaks0["tflops"],
                                   unit="TFLOP/s", frac=step_tf / peaks0["tflops"], traffic=None),
-                    gpu_launches=int(launches), clocks=clocks), 240 if args.no_cpu_baseline else 420)
+                    gpu_launches=int(launches), clocks=clocks),
+               args.watchdog_seconds or (240 if args.no_cpu_baseline else 420))
 
     # ---- per-launch pass for the roofline: the modality branches run one after the other here (with concurrent
     # branches the CUDA events around a launch also cover the time it waits for SMs held by another branch's kernel),
@@ -470,11 +503,27 @@ def run_ours(args):
         for i in range(min(2, args.warmup)):
             e2e_step(feed)
         barrier()
-        ev0.record()
-        for i in range(args.steps):
-            last_loss = e2e_step(feed)
-        ev1.record()
-        barrier()
+        _phase("end-to-end pass: warm-up done")
+        if args.hunt and wd is not None:
+            _lib.debug_flag_peek()  # creates the watchdog's stream and pinned buffer while the device is idle
+            wd.stall_seconds = 20
+        for rep in range(max(1, args.e2e_repeat)):  # (> 1: soak runs of this leg only, tools/README.md)
+            ev0.record()
+            for i in range(args.steps):
+                if args.hunt_events:  # every tcgen05 launch bracketed by events: koa_profile_pending names a stuck one
+                    lib.koa_profile_enable(1)
+                if args.hunt and wd is not None:
+                    wd.beat()
+                last_loss = e2e_step(feed)
+            ev1.record()
+            barrier()
+            if args.e2e_repeat > 1:
+                _phase(f"end-to-end pass: repeat {rep}: {ev0.elapsed_time(ev1) / args.steps:.1f} ms per step")
+        if args.hunt:
+            lib.koa_profile_enable(0)
+            if wd is not None:
+                wd.stall_seconds = None
+        _phase("end-to-end pass: blocking read-back done")
         t = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
         if ws > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -502,12 +551,16 @@ def run_ours(args):
                 for i in range(n_warm):
                     piped_step(i)
                 torch.cuda.synchronize()
-                ev0.record()
-                for i in range(n_warm, n_warm + args.steps):
-                    piped_step(i)
-                marks[-1].synchronize()
-                ev1.record()
-                torch.cuda.synchronize()
+                for rep in range(1 if args.hunt else max(1, args.e2e_repeat)):
+                    ev0.record()
+                    for i in range(n_warm, n_warm + args.steps):
+                        piped_step(i)
+                    marks[-1].synchronize()
+                    ev1.record()
+                    torch.cuda.synchronize()
+                    if args.e2e_repeat > 1:
+                        _phase(f"end-to-end pass: pipelined repeat {rep}: {ev0.elapsed_time(ev1) / args.steps:.1f} ms per step")
+                        del marks[n_warm:]
                 losses = host[n_warm:].tolist()
                 if len(losses) == args.steps and all(v == v and abs(v) < 1e6 for v in losses):
                     e2e_value = B * args.steps / (ev0.elapsed_time(ev1) / 1e3)
@@ -662,6 +715,13 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true", help="profiler runs: skip the end-to-end pass")
     ap.add_argument("--no-full-step", action="store_true", help="skip the forward+backward+Adam measurement")
     ap.add_argument("--no-roofline-pass", action="store_true", help="profiler runs: skip the per-launch CUDA-event pass")
+    ap.add_argument("--e2e-repeat", type=int, default=1, help="soak test: repeat the timed end-to-end loops this many times")
+    ap.add_argument("--hunt", action="store_true",
+                    help="soak test: the watchdog fires after 20 s without a finished step of the blocking end-to-end loop and "
+                         "reports the barrier time-out codes")
+    ap.add_argument("--hunt-events", action="store_true",
+                    help="with --hunt: every tcgen05 launch bracketed by events, the watchdog also names the launches in flight")
+    ap.add_argument("--watchdog-seconds", type=int, default=0, help="override the time budget of the legs after `value`")
     ap.add_argument("--profile-dump", default=None, help="write the per-shape tcgen05 kernel timing table to this file")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -39,6 +39,9 @@ const char* koa_last_error(void);
 int koa_version(void);
 /* Reads and clears the device-side diagnostic word (non-zero: a pipeline barrier timed out). */
 int koa_debug_flag(unsigned int* out);
+/* The same word (and the code of the FIRST barrier that timed out since the last koa_debug_flag) read without waiting for
+ * the work in flight and without clearing: for a watchdog that wants to know why a stream does not drain. */
+int koa_debug_flag_peek(unsigned int* latest, unsigned int* first);
 /* Kernels launched by this library in this process so far. */
 long long koa_launch_count(void);
 /* Optional per-launch CUDA-event timing of the tcgen05 kernel family (used by bench.py for the roofline):
@@ -48,6 +51,9 @@ int koa_profile_enable(int on);
 int koa_profile_read(double* out);
 /* Writes a per-shape breakdown of the recorded launches to a text file (does not clear the records). */
 int koa_profile_dump(const char* path);
+/* Recorded launches that have started but not finished, as text lines "cls tag m n k" (never waits: for a watchdog that
+ * wants to name the kernel a stream is stuck in). Returns their number. */
+int koa_profile_pending(char* buf, int cap);
 
 /* ---- fused GEMM epilogue --------------------------------------------------------------------- */
 enum { KOA_ACT_NONE = 0, KOA_ACT_RELU = 1, KOA_ACT_GELU = 2, KOA_ACT_GELU_GRAD = 3 };

@@ -149,11 +149,13 @@ SIGNATURES = {
     "koa_last_error": (C.c_char_p, []),
     "koa_version": (_I, []),
     "koa_debug_flag": (_I, [C.POINTER(C.c_uint)]),
+    "koa_debug_flag_peek": (_I, [C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "koa_debug_set_wgrad_desc": (_I, [C.c_uint, C.c_uint, C.c_uint]),
     "koa_launch_count": (C.c_longlong, []),
     "koa_profile_enable": (_I, [_I]),
     "koa_profile_read": (_I, [C.POINTER(C.c_double)]),
     "koa_profile_dump": (_I, [C.c_char_p]),
+    "koa_profile_pending": (_I, [C.c_char_p, _I]),
     "koa_gemm_bf16": (_I, [_P, _P, _I, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_gemm_kcat_bf16": (_I, [_P, _I, _P, _I, _P, _I, _I, C.POINTER(Epilogue), _P]),
     "koa_conv_fprop_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(Epilogue), _P]),
@@ -287,6 +289,13 @@ def debug_flag() -> int:
     v = C.c_uint(0)
     check(load().koa_debug_flag(C.byref(v)), "koa_debug_flag")
     return int(v.value)
+
+
+def debug_flag_peek() -> tuple[int, int]:
+    """(latest, first) barrier time-out codes without waiting for the device and without clearing them."""
+    v, f = C.c_uint(0), C.c_uint(0)
+    check(load().koa_debug_flag_peek(C.byref(v), C.byref(f)), "koa_debug_flag_peek")
+    return int(v.value), int(f.value)
 
 
 def ptr(t) -> int | None:

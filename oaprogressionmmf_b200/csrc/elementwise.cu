@@ -1441,8 +1441,9 @@ int koa_k_layernorm_bwd(const float* dy, const float* x, const float* gamma, con
                         const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta, int rows, int d,
                         long long x_row_stride, long long dx_row_stride, cudaStream_t st) {
   KOA_REQUIRE(d % 256 == 0 && d <= 2048, "LayerNorm backward width %d must be a multiple of 256 and <= 2048", d);
-  int blocks = koa_cdiv(rows, kThreads / 32);
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  // every block ends with 2 * d global atomics (dgamma / dbeta): at least two rows per warp, at most one block per SM
+  int blocks = koa_cdiv(rows, 2 * (kThreads / 32));
+  if (blocks > 148) blocks = 148;
   layernorm_bwd_kernel<8><<<blocks, kThreads, 2 * d * sizeof(float), st>>>(dy, x, gamma, mean, rstd, dres, dx,
                                                                              (bf16*)dx_bf16, dgamma, dbeta, rows, d,
                                                                              x_row_stride, dx_row_stride);
@@ -1564,12 +1565,6 @@ int koa_k_dropout_apply(float* x_inplace, const float* x, void* out_bf16, unsign
   KOA_REQUIRE(n > 0 && n % 4 == 0 && p >= 0.0f && p < 1.0f && (x_inplace != nullptr || x != nullptr), "bad dropout request");
   dropout_apply_kernel<<<grid_for(n / 4), kThreads, 0, st>>>(make_drop_spec(seed, site, p), n / 4, x_inplace, x, (bf16*)out_bf16);
   KOA_LAUNCH_CHECK();
-  return 0;
-}
-int koa_k_debug_flag_elementwise(unsigned int* out) {
-  unsigned int zero = 0;
-  KOA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_koa_debug_flag, sizeof(unsigned int)));
-  KOA_CHECK_CUDA(cudaMemcpyToSymbol(g_koa_debug_flag, &zero, sizeof(unsigned int)));
   return 0;
 }
 int koa_k_focal_loss(const float* logits, const long long* target, float* loss, float* dlogits, int batch, int classes,

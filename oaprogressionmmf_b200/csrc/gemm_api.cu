@@ -1,4 +1,5 @@
 // gemm_api.cu — host launchers + C-ABI entry points for the tcgen05 GEMM / implicit-GEMM kernels.
+#include <cstdio>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -60,6 +61,21 @@ extern "C" int koa_profile_enable(int on) {
   s_prof.clear();
   return 0;
 }
+// The recorded launches that have STARTED but not finished, as text lines "cls tag m n k" (cudaEventQuery only: never
+// waits). With profiling enabled, this names the kernel(s) a stream is stuck in. Returns the number of such launches.
+extern "C" int koa_profile_pending(char* buf, int cap) {
+  std::lock_guard<std::mutex> lk(s_prof_mu);
+  int n = 0, used = 0;
+  if (buf != nullptr && cap > 0) buf[0] = 0;
+  for (auto& r : s_prof) {
+    if (cudaEventQuery(r.a) != cudaSuccess) continue;
+    if (cudaEventQuery(r.b) == cudaSuccess) continue;
+    ++n;
+    if (buf != nullptr && used < cap - 80) used += snprintf(buf + used, cap - used, "%d %d %d %d %d\n", r.cls, r.tag, r.m, r.n, r.k);
+  }
+  (void)cudaGetLastError();  // cudaErrorNotReady is not an error here
+  return n;
+}
 // Per-shape breakdown of the recorded launches as text lines "cls tag m n k launches ms tflops" (does not clear).
 extern "C" int koa_profile_dump(const char* path) {
   KOA_CHECK_CUDA(cudaDeviceSynchronize());
@@ -101,15 +117,67 @@ extern "C" int koa_profile_read(double* out) {
 
 extern "C" int koa_version(void) { return 1; }
 
+namespace {
+struct DebugWords { const void* flag; const void* first; };
+std::vector<DebugWords>& debug_words() {  // function-local: constructed before the first registrar runs
+  static std::vector<DebugWords> v;
+  return v;
+}
+}  // namespace
+void koa_register_debug_words(const void* flag_symbol, const void* first_symbol) {
+  debug_words().push_back({flag_symbol, first_symbol});
+}
+
 extern "C" int koa_debug_flag(unsigned int* out) {
-  unsigned int zero = 0, other = 0;
-  KOA_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_koa_debug_flag, sizeof(unsigned int)));
-  KOA_CHECK_CUDA(cudaMemcpyToSymbol(g_koa_debug_flag, &zero, sizeof(unsigned int)));
-  // the diagnostic word is one variable per translation unit: fold in the element-wise kernels' copy (focal-loss targets)
-  int rc = koa_k_debug_flag_elementwise(&other);
-  if (rc) return rc;
-  *out |= other;
+  const unsigned int zero = 0;
+  *out = 0;
+  for (const DebugWords& w : debug_words()) {
+    unsigned int v = 0;
+    KOA_CHECK_CUDA(cudaMemcpyFromSymbol(&v, w.flag, sizeof(unsigned int)));
+    KOA_CHECK_CUDA(cudaMemcpyToSymbol(w.flag, &zero, sizeof(unsigned int)));
+    KOA_CHECK_CUDA(cudaMemcpyToSymbol(w.first, &zero, sizeof(unsigned int)));
+    *out |= v;
+  }
   return 0;
+}
+
+// The same words read WITHOUT waiting for the work in flight (a copy on a non-blocking stream of its own) and without
+// clearing them: what a watchdog calls while a kernel is still spinning on a barrier.
+extern "C" int koa_debug_flag_peek(unsigned int* latest, unsigned int* first) {
+  int dev = 0;
+  KOA_CHECK_CUDA(cudaGetDevice(&dev));
+  // the stream and the pinned landing buffer are created by the FIRST call on a device (make it while the device is idle:
+  // creating them can itself wait for running kernels)
+  struct Peek { cudaStream_t st; unsigned int* host; };
+  static std::mutex mu;
+  static std::map<int, Peek> peeks;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = peeks.find(dev);
+  if (it == peeks.end()) {
+    Peek pk{};
+    KOA_CHECK_CUDA(cudaStreamCreateWithFlags(&pk.st, cudaStreamNonBlocking));
+    KOA_CHECK_CUDA(cudaMallocHost(&pk.host, 2 * sizeof(unsigned int)));
+    it = peeks.emplace(dev, pk).first;
+  }
+  cudaStream_t st = it->second.st;
+  unsigned int* host = it->second.host;
+  *latest = 0;
+  *first = 0;
+  int rc = 0;
+  for (const DebugWords& w : debug_words()) {
+    void *df = nullptr, *d1 = nullptr;
+    if (cudaGetSymbolAddress(&df, w.flag) != cudaSuccess || cudaGetSymbolAddress(&d1, w.first) != cudaSuccess ||
+        cudaMemcpyAsync(host, df, sizeof(unsigned int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(host + 1, d1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      rc = KOA_ERR_CUDA;
+      break;
+    }
+    *latest |= host[0];
+    if (*first == 0) *first = host[1];
+  }
+  if (rc) koa_set_error("koa_debug_flag_peek: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
 }
 
 extern "C" int koa_debug_set_wgrad_desc(unsigned int lbo, unsigned int sbo, unsigned int k_adv) {
@@ -400,7 +468,9 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
                         const ConvGeom& g, float* dw, int x_f16, cudaStream_t st) {
   if (!XCVT && !CTA2 && x_f16 == 2) return launch_wgrad<BN, STAGES, IM2COL, true, false>(ta, tb, cout, cin, pixels, taps, g, dw, 0, st);
   const int a_f16 = x_f16, b_f16 = x_f16;  // dY, X
-  constexpr size_t smem = wgrad_smem_bytes<CTA2 ? BN / 2 : BN, STAGES>();
+  // (a CTA pair allocates tensor memory collectively: it must not share its SMs with other allocating CTAs, see wgrad_cta2)
+  constexpr size_t smem = CTA2 ? (size_t)227 * 1024 : wgrad_smem_bytes<BN, STAGES>();
+  static_assert(wgrad_smem_bytes<CTA2 ? BN / 2 : BN, STAGES>() <= smem, "shared memory of the weight-gradient kernel");
   auto kern = gemm_wgrad_kernel<BN, STAGES, IM2COL, XCVT, CTA2>;
   static std::atomic<unsigned long long> attr_done{0};
   KOA_CHECK_CUDA(koa_ensure_dyn_smem(kern, (int)smem, attr_done));
@@ -446,12 +516,18 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
   return 0;
 }
 
-// CTA pairs for weight gradients. KOA_WGRAD_CTA2: 0 never, 1 (default) where measured faster on B200, 2 wherever the
-// shape allows (Cout and Cin multiples of 256). Measured (tools/prof_wgrad.py): 3x3 with 256 channels 79.9 -> 68.6 us;
-// 3x3 with 512 channels 80.9 -> 85.0 us; 1x1 layers 50 -> 61 us and the transformer Linears 34-46 -> 39-69 us: with
-// half as many, twice as large tiles the split-K count doubles and the kernel becomes bound by its fp32 atomics.
+// CTA pairs for weight gradients. KOA_WGRAD_CTA2: 0 (default) never, 1 the one shape where a pair measured faster on B200
+// (3x3, 256 -> 256 channels: 79.9 -> 68.6 us, tools/prof_wgrad.py), 2 wherever the shape allows (Cout and Cin multiples of
+// 256; slower: 3x3 with 512 channels 80.9 -> 85.0 us, 1x1 layers 50 -> 61 us, the transformer Linears 34-46 -> 39-69 us -
+// with half as many, twice as large tiles the split-K count doubles and the kernel becomes bound by its fp32 atomics).
+// OFF by default since round 2: with 97 KB of shared memory two CTAs of DIFFERENT pairs (and CTAs of the other
+// weight-gradient kernels) shared an SM, and about once per 500 training steps a step never finished - GPU at 100 %, no
+// mbarrier time-out code, i.e. a warp sitting in a blocking instruction; the collective tcgen05.alloc.cta_group::2 of two
+// pairs that each hold one SM's allocation permit is the suspect. 1200 steps with the pair kernel off, and every other
+// cta_group::2 kernel of the library (206 KB: alone on its SM), never showed it (tools/r2_hunt.sh). When the
+// switch is on the pair kernel now asks for the whole shared memory of its SM, so that it never shares one.
 static bool wgrad_cta2(int cout, int cin, int x_f16, bool conv3x3) {
-  static const int mode = env_int("KOA_WGRAD_CTA2", 1);
+  static const int mode = env_int("KOA_WGRAD_CTA2", 0);
   if (mode == 0 || x_f16 == 2 || koa_num_sms() < 2 || cout % 256 != 0 || cin % 256 != 0) return false;
   return mode >= 2 || (conv3x3 && cout == 256 && cin == 256);
 }

@@ -56,11 +56,20 @@ void koa_count_launch();
 
 static inline int koa_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// Device-side diagnostic word, one per translation unit that waits on mbarriers. A barrier
-// wait that exceeds its time budget records a code here instead of hanging the GPU.
-// Read and cleared by koa_debug_flag() (gemm_api.cu).
+// Device-side diagnostic words, one pair per translation unit (no relocatable device code): a barrier wait that exceeds
+// its time budget records its code here instead of hanging the GPU ([0]: the latest code, [1]: the FIRST one since the last
+// read). Every translation unit registers its pair at load time; koa_debug_flag() / koa_debug_flag_peek() (gemm_api.cu)
+// walk the registry.
 #ifdef __CUDACC__
 static __device__ unsigned int g_koa_debug_flag = 0;
+static __device__ unsigned int g_koa_debug_first = 0;
+void koa_register_debug_words(const void* flag_symbol, const void* first_symbol);
+namespace {
+struct KoaDebugWordsRegistrar {
+  KoaDebugWordsRegistrar() { koa_register_debug_words(&g_koa_debug_flag, &g_koa_debug_first); }
+};
+static KoaDebugWordsRegistrar s_koa_debug_words_registrar;
+}  // namespace
 #endif
 
 #ifdef __CUDACC__
@@ -136,6 +145,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   while (!mbar_try_wait(bar, parity)) {
     if (globaltimer_ns() - t0 > 2000000000ull) {  // 2 s
       atomicExch(&g_koa_debug_flag, code);
+      atomicCAS(&g_koa_debug_first, 0u, code);
       return;
     }
   }

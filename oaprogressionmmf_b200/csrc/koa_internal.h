@@ -13,8 +13,6 @@ struct KoaFlopScale {  // RAII form
   explicit KoaFlopScale(double s) : old(koa_profile_flop_scale(s)) {}
   ~KoaFlopScale() { koa_profile_flop_scale(old); }
 };
-// reads and clears the diagnostic word of elementwise.cu (koa_debug_flag() in gemm_api.cu folds it into its own)
-int koa_k_debug_flag_elementwise(unsigned int* out);
 
 int koa_gemm_launch(const void* a, const void* b, int m, int n, int k, const koa_epilogue_t* ep, cudaStream_t st);
 int koa_gemm_kcat_launch(const void* a1, int k1, const void* a2, int k2, const void* b, int m, int n,
