@@ -524,7 +524,7 @@ static int launch_wgrad(const CUtensorMap& ta, const CUtensorMap& tb, int cout, 
 // weight-gradient kernels) shared an SM, and about once per 500 training steps a step never finished - GPU at 100 %, no
 // mbarrier time-out code, i.e. a warp sitting in a blocking instruction; the collective tcgen05.alloc.cta_group::2 of two
 // pairs that each hold one SM's allocation permit is the suspect. 2500 steps with the pair kernel off, and every other
-// cta_group::2 kernel of the library (206 KB: alone on its SM), never showed it (tools/r2_hunt.sh, DESIGN.md 4.2). When the
+// cta_group::2 kernel of the library (206 KB: alone on its SM), never showed it (tools/r2_hunt.sh, DESIGN.md 4.1). When the
 // switch is on the pair kernel now asks for the whole shared memory of its SM, so that it never shares one.
 static bool wgrad_cta2(int cout, int cin, int x_f16, bool conv3x3) {
   static const int mode = env_int("KOA_WGRAD_CTA2", 0);
