@@ -40,3 +40,49 @@ def test_measured_peaks_fallback_and_file():
     b = _bench()
     p = b.measured_peaks()
     assert p["tflops"] > 100 and p["hbm"] > 1000 and isinstance(p["source"], str)
+
+
+def _run_watchdog_script(body):
+    import subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = "import sys, time\nsys.path.insert(0, %r)\nimport bench\n" % root + textwrap.dedent(body)
+    return subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=120)
+
+
+def test_watchdog_prints_the_measured_line_when_a_later_leg_never_returns():
+    """bench.py's contract: once `value` exists the JSON line comes out, whatever the optional legs after it do."""
+    import json
+    r = _run_watchdog_script("""
+        wd = bench.Watchdog()
+        wd.arm(dict(metric="m", value=1.5, unit="knees/s"), 1)
+        wd.update(e2e=dict(value=1.0))
+        time.sleep(60)          # a leg that never returns
+        print("not reached")
+    """)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and "not reached" not in r.stdout
+    line = json.loads(lines[0])
+    assert line["value"] == 1.5 and line["e2e"] == {"value": 1.0} and "watchdog" in line
+    assert "most recent call first" in r.stderr      # the post-mortem names where every thread stood
+
+
+def test_watchdog_stall_detector_and_disarm():
+    import json
+    r = _run_watchdog_script("""
+        wd = bench.Watchdog()
+        wd.arm(dict(metric="m", value=2.0), 3600)
+        wd.stall_seconds = 1
+        for _ in range(3):      # steps that finish keep it quiet
+            wd.beat(); time.sleep(0.4)
+        time.sleep(30)          # a step that does not finish
+    """)
+    assert r.returncode == 0 and json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])["value"] == 2.0
+    r = _run_watchdog_script("""
+        wd = bench.Watchdog()
+        wd.arm(dict(metric="m", value=2.0), 1)
+        wd.disarm()
+        time.sleep(2.5)
+        print("finished normally")
+    """)
+    assert r.returncode == 0 and "finished normally" in r.stdout and "{" not in r.stdout
