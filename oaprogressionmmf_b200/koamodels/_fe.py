@@ -17,6 +17,24 @@ from torch import nn
 
 from .. import _lib, dataparallel
 
+_FP16_MAX = 65504.0
+
+
+def poison_if_out_of_fp16_range(x: torch.Tensor, stem_weight: torch.Tensor, feat: torch.Tensor) -> torch.Tensor:
+    """The raw output of the stem convolution is stored in fp16; every later tensor sits behind a BatchNorm. Its magnitude
+    is at most ``max|x| * max_c sum|w_c|`` (the three input channels are folded into the 7x7 weights). Where that bound
+    reaches the fp16 range the result cannot be trusted (measured: 1e7-scale inputs came back finite and wrong, because the
+    ReLU kernels turn NaN into 0), so the features are replaced by NaN: the training loop sees a NaN loss, as it would after
+    an overflow in PyTorch. Device-side (a min / max pass over the input, a few scalar kernels, one select): no host
+    read-back. Inputs the reference's transform chain delivers (|x| < 5) or raw 8-bit data are far below the limit
+    (about 2e4 with Kaiming-initialised weights)."""
+    with torch.no_grad():
+        lo, hi = torch.aminmax(x)
+        bound = torch.maximum(hi, -lo) * stem_weight.abs().sum(dim=(1, 2, 3)).amax()
+        ok = bound < _FP16_MAX  # False for NaN / inf inputs too
+    return torch.where(ok, feat, feat.new_full((), float("nan")))
+
+
 _BLOCKS = {
     "resnet18": ("basic", (2, 2, 2, 2), 1, 64),
     "resnet34": ("basic", (3, 4, 6, 3), 1, 64),
@@ -261,7 +279,8 @@ class SliceEncoder(nn.Sequential):
         # (n_img, C) with GAP, (n_img, h_out*w_out, C) without
         params = self._trainable()
         need_bw = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _FEFunction.apply(self, x, n_img, h, w, slices, need_bw, *params)
+        feat = _FEFunction.apply(self, x, n_img, h, w, slices, need_bw, *params)
+        return poison_if_out_of_fp16_range(x, self[0].weight, feat)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 4 or x.shape[1] not in (1, 3):

@@ -764,6 +764,54 @@ def test_fe_train_at_bf16_floor(cuda, arch, res_gain, b, s, size):
             assert int(msd[k[len("_fe."):]]) == int(v) == 1
 
 
+@pytest.mark.parametrize("kind", ["loader_range", "raw_0_255"])
+def test_fe_input_ranges(cuda, kind):
+    """Inputs in the ranges a real loader produces, not N(0, 1): (a) what the reference's transform chain delivers,
+    uniform [0, 1] voxels -> (x - mean) / std with the DESS statistics (SURVEY.md 8d, `_data_provider.py:297-334`);
+    (b) what a loader that skipped PTToUnitRange / PTNormalize would deliver, 0 .. 255. The forward activations are fp16
+    (max 65504); every tensor but the stem's raw convolution output sits behind a BatchNorm, and the stem sees
+    |x| * |w| * 147 taps, far below the fp16 range for 8-bit data. Train mode (batch statistics): features finite and at the
+    same 16-bit floor as with N(0, 1) inputs."""
+    g = torch.Generator().manual_seed(21)
+    u = torch.rand(4, 1, 64, 64, 4, generator=g)
+    x = ((u - 0.257) / 0.235 if kind == "loader_range" else torch.floor(u * 256.0).clamp(max=255.0)).to(cuda)
+    imgs = ko._slices_to_images(x)
+    runs = {}
+    with torch.no_grad():
+        for tag in ("fp32", "emu"):
+            sd, _ = _fe_pair("resnet50", cuda)
+            runs[tag] = ko.fe_forward(sd, "_fe", "resnet50", imgs, True, True, None, emulate_16bit=(tag == "emu")).flatten(1)
+    sd, enc = _fe_pair("resnet50", cuda)
+    enc.train()
+    tok = enc.encode_volume(x)
+    got = tok.detach().reshape(-1, tok.shape[-1])
+    assert torch.isfinite(got).all()
+    floor_f, mine_f = rel(runs["emu"], runs["fp32"]), rel(got, runs["fp32"])
+    assert mine_f <= 1.5 * floor_f + 2e-3, (kind, mine_f, floor_f)
+    assert _lib.debug_flag() == 0
+
+
+def test_fe_fp16_overflow_is_loud(cuda):
+    """The stem's raw convolution output is stored in fp16: inputs of magnitude 1e7 (nothing a loader produces) exceed its
+    range. Without a guard the features came back FINITE and wrong (0.49 relative; the ReLU kernels turn NaN into 0); the
+    encoder therefore replaces them by NaN wherever max|x| * max_c sum|w_c| reaches the fp16 range (`_fe.py`), and leaves
+    ordinary inputs bit for bit alone."""
+    from oaprogressionmmf_b200.koamodels._fe import poison_if_out_of_fp16_range
+
+    x = _randn(2, 1, 64, 64, 3, seed=9)
+    sd, enc = _fe_pair("resnet50", cuda)
+    enc.train()
+    tok = enc.encode_volume(x * 1e7)
+    assert bool(torch.isnan(tok).all())
+    enc.eval()
+    with torch.no_grad():
+        good = enc.encode_volume(x)
+        assert torch.isfinite(good).all()
+        assert torch.equal(poison_if_out_of_fp16_range(x, enc[0].weight, good), good)
+        assert bool(torch.isnan(enc.encode_volume(torch.full_like(x, float("nan")))).all())
+    _lib.debug_flag()
+
+
 @pytest.mark.parametrize("train", [False, True])
 @pytest.mark.parametrize("arch,size,s", [("resnet50", 64, 3), ("resnext50_32x4d", 64, 0), ("resnet18", 64, 2)])
 def test_fe_backward_in_stages_equals_one_call(cuda, arch, size, s, train):

@@ -152,3 +152,29 @@ def test_backward_stage_bounds_partition_the_flat_gradient_buffer():
         grads2, flat2 = _lib.zeros_like_flat([p if p.requires_grad else None for p in params])
         stages2 = enc._stage_bounds(params, grads2, flat2)
         assert sum(len(ps) for *_, ps in stages2) == len(params) - 1
+
+
+def test_fp16_range_guard_of_the_slice_encoder():
+    """`poison_if_out_of_fp16_range` (pure torch, device-side in production): features pass through untouched while
+    max|x| * max_c sum|w_c| is below the fp16 range, become NaN beyond it and for non-finite inputs, and stay differentiable."""
+    from oaprogressionmmf_b200.koamodels._fe import poison_if_out_of_fp16_range
+
+    torch.manual_seed(0)
+    w = torch.randn(64, 3, 7, 7) * 0.025
+    l1 = float(w.abs().sum(dim=(1, 2, 3)).max())
+    feat = torch.randn(6, 2048, requires_grad=True)
+    x = torch.randn(6, 32, 32)
+    out = poison_if_out_of_fp16_range(x, w, feat)
+    assert torch.equal(out, feat)
+    out.sum().backward()
+    assert torch.equal(feat.grad, torch.ones_like(feat))
+    just_below = x / x.abs().max() * (65504.0 / l1) * 0.999
+    assert torch.equal(poison_if_out_of_fp16_range(just_below, w, feat), feat)
+    assert torch.isnan(poison_if_out_of_fp16_range(just_below * 1.01, w, feat)).all()
+    assert torch.isnan(poison_if_out_of_fp16_range(-just_below * 1.01, w, feat)).all()
+    bad = x.clone()
+    bad[0, 0, 0] = float("nan")
+    assert torch.isnan(poison_if_out_of_fp16_range(bad, w, feat)).all()
+    bad[0, 0, 0] = float("inf")
+    assert torch.isnan(poison_if_out_of_fp16_range(bad, w, feat)).all()
+    assert torch.equal(poison_if_out_of_fp16_range(torch.rand(2, 8, 8) * 255.0, w, feat), feat)  # raw 8-bit data
